@@ -57,10 +57,10 @@ def lib():
         L.or_uniform53.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
         L.or_rand_categorical.restype = C.c_int64
         L.or_rand_categorical.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.POINTER(C.c_int)]
-        L.or_qfix_f64.restype = C.c_uint64
-        L.or_qfix_f64.argtypes = [C.c_double]
-        L.or_qfix_f32.restype = C.c_uint64
-        L.or_qfix_f32.argtypes = [C.c_float]
+        L.or_q31_f64.restype = C.c_uint32
+        L.or_q31_f64.argtypes = [C.c_double]
+        L.or_q31_f32.restype = C.c_uint32
+        L.or_q31_f32.argtypes = [C.c_float]
         L.or_logsumexp.restype = C.c_double
         L.or_logsumexp.argtypes = [C.c_void_p, C.c_int64]
         L.or_bnet_score.restype = C.c_double

@@ -134,8 +134,8 @@ static inline double pow2i(int k) {       /* 2^k for -1022 <= k <= 1023 */
     return v.d;
 }
 
-uint64_t or_qfix_f64(double d) {
-    if (!(d > -51.0)) return 0;           /* also catches -inf and NaN */
+uint32_t or_q31_f64(double d) {
+    if (!(d > -33.0)) return 0;           /* also catches -inf and NaN */
     double k = floor(d);
     double r = d - k;                     /* exact, in [0,1) */
     double t = (r - 0.5) * 0x1.62e42fefa39efp-1;   /* ln 2 */
@@ -153,11 +153,11 @@ uint64_t or_qfix_f64(double d) {
     p = fma(p, t, 1.0);
     p = fma(p, t, 1.0);
     p = p * 0x1.6a09e667f3bcdp+0;         /* sqrt 2 */
-    return (uint64_t)(p * pow2i(OR_QBITS + (int)k));
+    return (uint32_t)(uint64_t)(p * pow2i(OR_QBITS + (int)k));
 }
 
-uint64_t or_qfix_f32(float d) {
-    if (!(d > -51.0f)) return 0;
+uint32_t or_q31_f32(float d) {
+    if (!(d > -33.0f)) return 0;
     float k = floorf(d);
     float r = d - k;
     float t = (r - 0.5f) * 0x1.62e430p-1f;
@@ -170,7 +170,7 @@ uint64_t or_qfix_f32(float d) {
     p = fmaf(p, t, 1.0f);
     p = fmaf(p, t, 1.0f);
     p = p * 0x1.6a09e6p+0f;
-    return (uint64_t)((double)p * pow2i(OR_QBITS + (int)k));
+    return (uint32_t)(uint64_t)((double)p * pow2i(OR_QBITS + (int)k));
 }
 
 static inline int ceil_log2_i64(int64_t v) {
@@ -182,15 +182,10 @@ static inline int ceil_log2_i64(int64_t v) {
 #define LOG2E_D 0x1.71547652b82fep+0
 #define LOG2E_F 0x1.715476p+0f
 
-int or_grid_build(const void* data, int kind, int64_t n, or_grid* g) {
-    memset(g, 0, sizeof(*g));
-    if (n <= 0) return OR_EINVAL;
+/* Stage 1 of the grid: per tile of OR_TILE entries, a power-of-two exponent e_b >= every weight
+ * and 32-bit fixed-point weights w32_i = floor(w_i / 2^e_b * 2^31). */
+int or_grid_quantise(const void* data, int kind, int64_t n, uint32_t* w32, int32_t* e_out) {
     int64_t nt = (n + OR_TILE - 1) / OR_TILE;
-    g->n = n; g->n_tiles = nt;
-    g->e = (int32_t*)malloc(sizeof(int32_t) * (size_t)nt);
-    g->Q = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)nt);
-    g->P = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(nt + 1));
-    g->C = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)n);
     int bad = 0;
     const double* wd = (const double*)data;
     const float* wf = (const float*)data;
@@ -221,32 +216,51 @@ int or_grid_build(const void* data, int kind, int64_t n, or_grid* g) {
             }
             if (mx > -INFINITY) e = (int32_t)ceilf(mx);
         }
-        g->e[b] = e;
-        uint64_t c = 0;
+        e_out[b] = e;
         for (int64_t i = i0; i < i1; ++i) {
-            uint64_t q = 0;
-            if (e != OR_E_EMPTY) {
-                if (kind == 0)      q = (uint64_t)scalbn(wd[i], OR_QBITS - e);
-                else if (kind == 1) q = or_qfix_f64(wd[i] * LOG2E_D - (double)e);
-                else                q = or_qfix_f32(wf[i] * LOG2E_F - (float)e);
+            uint32_t q = 0;
+            if (e != OR_E_EMPTY && !bad) {
+                if (kind == 0)      q = (uint32_t)(uint64_t)scalbn(wd[i], OR_QBITS - e);
+                else if (kind == 1) q = or_q31_f64(wd[i] * LOG2E_D - (double)e);
+                else                q = or_q31_f32(wf[i] * LOG2E_F - (float)e);
             }
-            c += q;
-            g->C[i] = c;          /* tile-local for now */
+            w32[i] = q;
         }
+    }
+    return bad ? OR_ENAN : OR_OK;
+}
+
+/* Stage 2: exact integer CDF.  Tile-local inclusive sums c_i (<= 2^42), global exponent
+ * E = max e_b, left shift LS = 20 - ceil_log2(n_tiles), C_i = P_b + ((c_i << LS) >> (E - e_b)). */
+int or_grid_from_w32(const uint32_t* w32, const int32_t* e, int64_t n, or_grid* g) {
+    memset(g, 0, sizeof(*g));
+    if (n <= 0) return OR_EINVAL;
+    int64_t nt = (n + OR_TILE - 1) / OR_TILE;
+    if (nt > ((int64_t)1 << 20)) return OR_EINVAL;
+    g->n = n; g->n_tiles = nt;
+    g->e = (int32_t*)malloc(sizeof(int32_t) * (size_t)nt);
+    g->Q = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)nt);
+    g->P = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(nt + 1));
+    g->C = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)n);
+    memcpy(g->e, e, sizeof(int32_t) * (size_t)nt);
+    #pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < nt; ++b) {
+        int64_t i0 = b * OR_TILE, i1 = i0 + OR_TILE < n ? i0 + OR_TILE : n;
+        uint64_t c = 0;
+        for (int64_t i = i0; i < i1; ++i) { c += w32[i]; g->C[i] = c; }
         g->Q[b] = c;
     }
-    if (bad) { or_grid_free(g); return OR_ENAN; }
     int32_t E = OR_E_EMPTY;
-    for (int64_t b = 0; b < nt; ++b) if (g->e[b] > E) E = g->e[b];
+    for (int64_t b = 0; b < nt; ++b) if (g->Q[b] != 0 && g->e[b] > E) E = g->e[b];
     if (E == OR_E_EMPTY) { or_grid_free(g); return OR_EZEROMASS; }
-    int sh0 = ceil_log2_i64(nt) - 1; if (sh0 < 0) sh0 = 0;
-    g->E = E; g->sh0 = sh0;
+    int LS = 20 - ceil_log2_i64(nt);
+    g->E = E; g->sh0 = LS;
     uint64_t acc = 0;
     for (int64_t b = 0; b < nt; ++b) {
         g->P[b] = acc;
-        if (g->e[b] != OR_E_EMPTY) {
-            int64_t sh = (int64_t)sh0 + ((int64_t)E - g->e[b]);
-            acc += sh >= 64 ? 0 : (g->Q[b] >> sh);
+        if (g->Q[b] != 0) {
+            int64_t sh = (int64_t)E - g->e[b];
+            acc += sh >= 63 ? 0 : ((g->Q[b] << LS) >> sh);
         }
     }
     g->P[nt] = acc; g->total = acc;
@@ -254,11 +268,23 @@ int or_grid_build(const void* data, int kind, int64_t n, or_grid* g) {
     #pragma omp parallel for schedule(static)
     for (int64_t b = 0; b < nt; ++b) {
         int64_t i0 = b * OR_TILE, i1 = i0 + OR_TILE < n ? i0 + OR_TILE : n;
-        int64_t sh = g->e[b] == OR_E_EMPTY ? 64 : (int64_t)sh0 + ((int64_t)E - g->e[b]);
+        int64_t sh = g->Q[b] == 0 ? 63 : (int64_t)E - g->e[b];
         for (int64_t i = i0; i < i1; ++i)
-            g->C[i] = g->P[b] + (sh >= 64 ? 0 : (g->C[i] >> sh));
+            g->C[i] = g->P[b] + (sh >= 63 ? 0 : ((g->C[i] << LS) >> sh));
     }
     return OR_OK;
+}
+
+int or_grid_build(const void* data, int kind, int64_t n, or_grid* g) {
+    memset(g, 0, sizeof(*g));
+    if (n <= 0) return OR_EINVAL;
+    int64_t nt = (n + OR_TILE - 1) / OR_TILE;
+    uint32_t* w32 = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)n);
+    int32_t* e = (int32_t*)malloc(sizeof(int32_t) * (size_t)nt);
+    int rc = or_grid_quantise(data, kind, n, w32, e);
+    if (rc == OR_OK) rc = or_grid_from_w32(w32, e, n, g);
+    free(w32); free(e);
+    return rc;
 }
 
 void or_grid_free(or_grid* g) {
@@ -266,9 +292,9 @@ void or_grid_free(or_grid* g) {
     memset(g, 0, sizeof(*g));
 }
 
-/* log(mean weight) = log(total) + (E - QBITS + sh0) ln2 - log n   (log-weight kinds) */
+/* log(mean weight) = log(total) + (E - QBITS - LS) ln2 - log n   (log-weight kinds) */
 double or_grid_log_mean_weight(const or_grid* g) {
-    return log((double)g->total) + (double)(g->E - OR_QBITS + g->sh0) * 0x1.62e42fefa39efp-1
+    return log((double)g->total) + (double)(g->E - OR_QBITS - g->sh0) * 0x1.62e42fefa39efp-1
            - log((double)g->n);
 }
 

@@ -35,7 +35,7 @@ extern "C" {
 #define OR_EINVAL     3
 
 #define OR_TILE       2048
-#define OR_QBITS      50
+#define OR_QBITS      31
 
 /* resample modes (same numbering as include/stochy_b200.h) */
 #define OR_RESAMPLE_SYSTEMATIC   0
@@ -56,19 +56,21 @@ int or_resample_literal(const double* w, int64_t n, const double* r, int64_t m, 
 int or_resample_literal_fast(const double* w, int64_t n, const double* r, int64_t m, int64_t* anc);
 
 /* ---- weight grid (extension; see DESIGN.md "weight grid") ---- */
-uint64_t or_qfix_f64(double d);          /* floor(2^d * 2^50), d <= 0, deterministic IEEE-only */
-uint64_t or_qfix_f32(float d);
+uint32_t or_q31_f64(double d);           /* floor(2^d * 2^31), d <= 0, deterministic IEEE-only */
+uint32_t or_q31_f32(float d);
 typedef struct {
     int64_t   n, n_tiles;
     int32_t*  e;        /* [n_tiles] tile exponents (OR_E_EMPTY if tile has no mass) */
     uint64_t* Q;        /* [n_tiles] tile sums at tile scale */
     uint64_t* P;        /* [n_tiles+1] exclusive prefix of rescaled tile sums */
     uint64_t* C;        /* [n] inclusive global CDF on the grid */
-    int32_t   E, sh0;
+    int32_t   E, sh0;   /* sh0 = LS, the left shift applied before the per-tile right shift */
     uint64_t  total;
 } or_grid;
 #define OR_E_EMPTY (-0x40000000)
 /* kind: 0 = linear fp64 weights, 1 = fp64 log-weights, 2 = fp32 log-weights (data points to float) */
+int  or_grid_quantise(const void* data, int kind, int64_t n, uint32_t* w32, int32_t* e_out);
+int  or_grid_from_w32(const uint32_t* w32, const int32_t* e, int64_t n, or_grid* g);
 int  or_grid_build(const void* data, int kind, int64_t n, or_grid* g);
 void or_grid_free(or_grid* g);
 double or_grid_log_mean_weight(const or_grid* g);  /* log( sum w / n ) for kinds 1,2 */

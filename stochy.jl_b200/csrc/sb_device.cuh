@@ -1,0 +1,316 @@
+// sb_device.cuh -- device-side building blocks of libstochy_b200 (sm_100a).
+//
+// Everything here is HBM-bound integer / byte work plus a little fp64; there is no dense
+// contraction on this path, so no tensor cores (tcgen05) are used.  The rules that matter are
+// coalesced 128-bit accesses, grids sized in tiles of SB_TILE particles, shared-memory staging
+// of the per-tile scan, and keeping the bytes per particle-step at the algorithmic minimum.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define SB_TILE     2048          // particles per tile == per CTA
+#define SB_THREADS  256
+#define SB_ITEMS    8             // consecutive particles per thread (blocked arrangement)
+#define SB_WARPS    (SB_THREADS / 32)
+#define SB_QBITS    31
+#define SB_E_EMPTY  (-0x40000000)
+
+#define SB_ERRBIT_NAN   1u
+#define SB_ERRBIT_ZERO  2u
+
+#define SB_P_PROP     0u
+#define SB_P_RESAMPLE 1u
+#define SB_P_INIT     2u
+#define SB_P_PICK     3u
+#define SB_P_MH       4u
+
+#define SB_LN2     0x1.62e42fefa39efp-1
+#define SB_LOG2E_D 0x1.71547652b82fep+0
+#define SB_LOG2E_F 0x1.715476p+0f
+#define SB_SQRT2_D 0x1.6a09e667f3bcdp+0
+#define SB_SQRT2_F 0x1.6a09e6p+0f
+
+// Written by k_tilescan for the pool that is about to be resampled; read by every consumer.
+struct SbStepInfo {
+    unsigned long long total;   // sum of all grid weights (<= 2^62)
+    double inv;                 // m / total
+    double u;                   // systematic offset in [0,1)
+    long long n;                // pool size
+    long long m;                // children to draw
+    int E;                      // global exponent = max tile exponent
+    int LS;                     // left shift applied before the per-tile right shift
+    int nt;                     // tiles in the pool
+    int valid;
+};
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct SbU4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ SbU4 sb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                          uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0;
+        uint32_t n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return SbU4{c0, c1, c2, c3};
+}
+__device__ __forceinline__ SbU4 sb_stream4(unsigned long long seed, unsigned long long idx, uint32_t t,
+                                           uint32_t iter, uint32_t purpose) {
+    return sb_philox((uint32_t)idx, (uint32_t)(idx >> 32), t, (iter << 4) | purpose,
+                     (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+__device__ __forceinline__ unsigned long long sb_r53(uint32_t a, uint32_t b) {
+    return ((unsigned long long)a << 21) | (unsigned long long)(b >> 11);
+}
+__device__ __forceinline__ double sb_u53(uint32_t a, uint32_t b) {
+    return __dmul_rn((double)sb_r53(a, b), 0x1p-53);
+}
+
+// ---------------------------------------------------------------- deterministic 2^d on the 31-bit grid
+// Same IEEE operation sequence as the CPU checker used by the tests (which restates
+// this definition independently); intrinsics forbid the compiler from contracting mul+add.
+__device__ __forceinline__ uint32_t sb_q31_f64(double d) {
+    if (!(d > -33.0)) return 0u;
+    double k = floor(d);
+    double r = __dsub_rn(d, k);
+    double t = __dmul_rn(__dsub_rn(r, 0.5), SB_LN2);
+    double p = 1.0 / 39916800.0;
+    p = __fma_rn(p, t, 1.0 / 3628800.0);
+    p = __fma_rn(p, t, 1.0 / 362880.0);
+    p = __fma_rn(p, t, 1.0 / 40320.0);
+    p = __fma_rn(p, t, 1.0 / 5040.0);
+    p = __fma_rn(p, t, 1.0 / 720.0);
+    p = __fma_rn(p, t, 1.0 / 120.0);
+    p = __fma_rn(p, t, 1.0 / 24.0);
+    p = __fma_rn(p, t, 1.0 / 6.0);
+    p = __fma_rn(p, t, 0.5);
+    p = __fma_rn(p, t, 1.0);
+    p = __fma_rn(p, t, 1.0);
+    p = __dmul_rn(p, SB_SQRT2_D);
+    double s = __longlong_as_double((long long)(1023 + SB_QBITS + (int)k) << 52);
+    return (uint32_t)__double2ull_rz(__dmul_rn(p, s));
+}
+__device__ __forceinline__ uint32_t sb_q31_f32(float d) {
+    if (!(d > -33.0f)) return 0u;
+    float k = floorf(d);
+    float r = __fsub_rn(d, k);
+    float t = __fmul_rn(__fsub_rn(r, 0.5f), 0x1.62e430p-1f);
+    float p = 1.0f / 5040.0f;
+    p = __fmaf_rn(p, t, 1.0f / 720.0f);
+    p = __fmaf_rn(p, t, 1.0f / 120.0f);
+    p = __fmaf_rn(p, t, 1.0f / 24.0f);
+    p = __fmaf_rn(p, t, 1.0f / 6.0f);
+    p = __fmaf_rn(p, t, 0.5f);
+    p = __fmaf_rn(p, t, 1.0f);
+    p = __fmaf_rn(p, t, 1.0f);
+    p = __fmul_rn(p, SB_SQRT2_F);
+    // p * 2^(31+k) truncated: exact integer arithmetic on the float's 24-bit significand
+    int sh = SB_QBITS + (int)k - 23;                 // p = sig * 2^(ex-23)
+    uint32_t bits = __float_as_uint(p);
+    uint32_t sig = (bits & 0x7FFFFFu) | 0x800000u;
+    sh += (int)(bits >> 23) - 127;
+    if (sh >= 0) return sig << sh;                   // sh <= 8 because p*2^(31+k) <= 2^31 (+1 ulp)
+    return sh > -24 ? (sig >> (-sh)) : 0u;
+}
+
+// child index function of systematic resampling: number of children c in [0,m) whose threshold
+// (c+u)/m * total is strictly below C (strict `<` as in src/rand.jl:9).  Monotone in C.
+__device__ __forceinline__ int sb_sys_F(unsigned long long C, const SbStepInfo& si) {
+    if (C >= si.total) return (int)si.m;
+    double v = __dmul_rn(__ull2double_rn(C), si.inv);
+    v = ceil(__dsub_rn(v, si.u));
+    if (v <= 0.0) return 0;
+    if (v >= (double)si.m) return (int)si.m;
+    return (int)v;
+}
+
+// ---------------------------------------------------------------- block-level primitives (256 threads)
+__device__ __forceinline__ unsigned long long sb_shfl_up_u64(unsigned long long v, int d) {
+    uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);
+    uint32_t hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// exclusive prefix of one u64 per thread across the CTA; *total gets the CTA sum.  smem: SB_WARPS+1 u64
+__device__ __forceinline__ unsigned long long sb_block_excl_scan_u64(unsigned long long v, unsigned long long* sm,
+                                                                     unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = sb_shfl_up_u64(inc, d);
+        if (lane >= d) inc += o;
+    }
+    __syncthreads();                       // protects sm reuse across calls
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SB_WARPS; ++w) {
+        unsigned long long s = sm[w];
+        if (w < warp) base += s;
+        tot += s;
+    }
+    *total = tot;
+    return base + inc - v;
+}
+
+__device__ __forceinline__ int sb_block_max_i32(int v, int* sm) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = sm[0];
+#pragma unroll
+    for (int w = 1; w < SB_WARPS; ++w) r = max(r, sm[w]);
+    return r;
+}
+__device__ __forceinline__ double sb_block_max_f64(double v, double* sm) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = sm[0];
+#pragma unroll
+    for (int w = 1; w < SB_WARPS; ++w) r = fmax(r, sm[w]);
+    return r;
+}
+__device__ __forceinline__ float sb_block_max_f32(float v, float* sm) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = sm[0];
+#pragma unroll
+    for (int w = 1; w < SB_WARPS; ++w) r = fmaxf(r, sm[w]);
+    return r;
+}
+__device__ __forceinline__ unsigned long long sb_block_sum_u64(unsigned long long v, unsigned long long* sm) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, d);
+        uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+        v += ((unsigned long long)hi << 32) | lo;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long r = 0;
+#pragma unroll
+    for (int w = 0; w < SB_WARPS; ++w) r += sm[w];
+    return r;
+}
+
+// 128-bit streaming accesses (each thread owns 8 consecutive 4-byte items = two 16-byte vectors)
+__device__ __forceinline__ void sb_load8_u32(const uint32_t* __restrict__ p, uint32_t v[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void sb_store8_u32(uint32_t* p, const uint32_t v[8]) {
+    reinterpret_cast<uint4*>(p)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<uint4*>(p)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+
+// ---------------------------------------------------------------- the pull: ancestors of one children tile
+struct SbPullSmem {
+    int marker[SB_TILE];
+    unsigned long long scan[SB_WARPS + 1];
+    int wmax[SB_WARPS];
+    int range[4];
+};
+
+// #{ b in [0, nt] : child_start[b] <= x } by cooperative 256-ary narrowing (2-3 dependent loads
+// instead of log2(nt) on one thread).  child_start is non-decreasing, child_start[0] = 0.
+__device__ __forceinline__ int sb_count_le(const int* __restrict__ child_start, int nt, int x) {
+    int lo = 0, hi = nt + 1;                 // answer in (lo, hi]: child_start[lo] <= x known (lo = 0)
+    // invariant: count of entries <= x lies in [lo+1, hi]
+    while (hi - lo > 1) {
+        int span = hi - lo - 1;              // candidates lo+1 .. hi-1
+        int step = (span + SB_THREADS - 1) / SB_THREADS;
+        int idx = lo + 1 + (int)threadIdx.x * step;
+        int pred = (idx < hi) && (__ldg(child_start + idx) <= x);
+        int k = __syncthreads_count(pred);   // predicates true form a prefix of the threads
+        int nlo = lo + (k ? 1 + (k - 1) * step : 0);
+        int nhi = min(hi, lo + 1 + k * step);
+        lo = nlo; hi = nhi;
+    }
+    return lo + 1;
+}
+
+// Computes, for the children [c0, c0+SB_TILE) of this CTA, the pool index of each child's parent
+// under systematic resampling on the weight grid; thread `tid` receives children c0+8*tid .. +7.
+// w32 / e / P / child_start describe the POOL (previous step); all loads are coalesced tile reads.
+__device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const uint32_t* __restrict__ w32,
+                                                  const int* __restrict__ e, const unsigned long long* __restrict__ P,
+                                                  const int* __restrict__ child_start, int c0, SbPullSmem& sm,
+                                                  int anc[SB_ITEMS]) {
+    const int tid = threadIdx.x;
+    const int m = (int)si.m;
+    const int c1 = min(c0 + SB_TILE, m);
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) sm.marker[tid + j * SB_THREADS] = -1;
+    const int b_lo = sb_count_le(child_start, si.nt, c0) - 1;
+    const int b_hi = sb_count_le(child_start, si.nt, c1 - 1) - 1;
+    for (int b = b_lo; b <= b_hi; ++b) {
+        const int cs = __ldg(child_start + b), ce = __ldg(child_start + b + 1);
+        if (ce == cs) continue;                                  // tile without offspring (uniform branch)
+        uint32_t w[SB_ITEMS];
+        sb_load8_u32(w32 + (size_t)b * SB_TILE + tid * SB_ITEMS, w);
+        unsigned long long tsum = 0;
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) tsum += w[j];
+        unsigned long long tot;
+        unsigned long long c = sb_block_excl_scan_u64(tsum, sm.scan, &tot);
+        if (tsum != 0) {
+            const int sh = si.E - __ldg(e + b);
+            const unsigned long long Pb = __ldg(P + b);
+            const int LS = si.LS;
+            int lo = sb_sys_F(Pb + (sh >= 63 ? 0ull : ((c << LS) >> sh)), si);
+            const int base = b * SB_TILE + tid * SB_ITEMS;
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) {
+                if (w[j] == 0u) continue;
+                c += w[j];
+                const int hi = sb_sys_F(Pb + (sh >= 63 ? 0ull : ((c << LS) >> sh)), si);
+                const int s = max(lo, c0), t = min(hi, c1);
+                if (s < t) sm.marker[s - c0] = base + j;
+                lo = hi;
+            }
+        }
+    }
+    __syncthreads();
+    // inclusive max-scan of the head markers fills every child slot with its parent
+    int v[SB_ITEMS];
+    {
+        const int4 a = reinterpret_cast<const int4*>(sm.marker)[tid * 2];
+        const int4 b = reinterpret_cast<const int4*>(sm.marker)[tid * 2 + 1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+#pragma unroll
+    for (int j = 1; j < SB_ITEMS; ++j) v[j] = max(v[j], v[j - 1]);
+    int inc = v[SB_ITEMS - 1];
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc = max(inc, o);
+    }
+    if (lane == 31) sm.wmax[warp] = inc;
+    int prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) prev = -1;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < SB_WARPS; ++w) if (w < warp) prev = max(prev, sm.wmax[w]);
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(v[j], prev);
+    __syncthreads();                                             // marker may be reused by the caller
+}

@@ -1,0 +1,976 @@
+// sb_kernels.cuh -- the kernels of libstochy_b200 (sm_100a).  See DESIGN.md for the per-kernel
+// byte counts and rooflines.  Reference lines each kernel replaces are cited at the kernel.
+#pragma once
+#include "sb_device.cuh"
+#include <cfloat>
+#include <cmath>
+#include <type_traits>
+
+// =====================================================================================
+// k_quantise: host/device supplied weights -> (w32, tile exponent, tile sum).
+// Replaces `weights = Float64[exp(p.path[end].score) ...]` (src/pmcmc.jl:55,64) for the hooks.
+// KIND 0: linear fp64, 1: fp64 log-weights, 2: fp32 log-weights.   Bytes: read W, write 4.
+// =====================================================================================
+template <int KIND>
+__global__ void __launch_bounds__(SB_THREADS)
+k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w32, int* __restrict__ e_out,
+           unsigned long long* __restrict__ Q_out, unsigned* __restrict__ err) {
+    __shared__ unsigned long long s_u64[SB_WARPS + 1];
+    __shared__ double s_f64[SB_WARPS];
+    __shared__ int s_i32[SB_WARPS];
+    const int tid = threadIdx.x;
+    const long long base = (long long)blockIdx.x * SB_TILE + tid * SB_ITEMS;
+    double vd[SB_ITEMS];
+    float vf[SB_ITEMS];
+    bool bad = false;
+    int e = SB_E_EMPTY;
+    const bool full = base + SB_ITEMS <= n;
+    if (KIND == 2) {
+        const float* p = (const float*)data;
+        float mx = -INFINITY;
+        float in[SB_ITEMS];
+        if (full) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p + base));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p + base) + 1);
+            in[0] = a.x; in[1] = a.y; in[2] = a.z; in[3] = a.w; in[4] = b.x; in[5] = b.y; in[6] = b.z; in[7] = b.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) in[j] = (base + j < n) ? __ldg(p + base + j) : -INFINITY;
+        }
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) {
+            float lw = in[j];
+            float l2 = __fmul_rn(lw, SB_LOG2E_F);
+            if (isnan(l2) || l2 == INFINITY) { bad = true; l2 = -INFINITY; }
+            vf[j] = l2;
+            mx = fmaxf(mx, l2);
+        }
+        mx = sb_block_max_f32(mx, (float*)s_f64);
+        if (mx > -INFINITY) e = (int)ceilf(mx);
+    } else {
+        const double* p = (const double*)data;
+        double in[SB_ITEMS];
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; j += 2) {
+                const double2 a = __ldg(reinterpret_cast<const double2*>(p + base + j));
+                in[j] = a.x; in[j + 1] = a.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) in[j] = (base + j < n) ? __ldg(p + base + j) : (KIND == 1 ? -INFINITY : 0.0);
+        }
+        if (KIND == 1) {
+            double mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) {
+                double lw = in[j];
+                double l2 = __dmul_rn(lw, SB_LOG2E_D);
+                if (isnan(l2) || l2 == INFINITY) { bad = true; l2 = -INFINITY; }
+                vd[j] = l2;
+                mx = fmax(mx, l2);
+            }
+            mx = sb_block_max_f64(mx, s_f64);
+            if (mx > -INFINITY) e = (int)ceil(mx);
+        } else {
+            int me = SB_E_EMPTY;
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) {
+                double w = in[j];
+                if (!(w >= 0.0) || isinf(w)) { bad = true; w = 0.0; }
+                vd[j] = w;
+                if (w > 0.0) { int ex; frexp(w, &ex); me = max(me, ex); }
+            }
+            e = sb_block_max_i32(me, s_i32);
+        }
+    }
+    uint32_t q[SB_ITEMS];
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) {
+        uint32_t v = 0;
+        if (e != SB_E_EMPTY) {
+            if (KIND == 0)      v = (uint32_t)__double2ull_rz(scalbn(vd[j], SB_QBITS - e));
+            else if (KIND == 1) v = sb_q31_f64(__dsub_rn(vd[j], (double)e));
+            else                v = sb_q31_f32(__fsub_rn(vf[j], (float)e));
+        }
+        q[j] = v;
+        tsum += v;
+    }
+    sb_store8_u32(w32 + base, q);                 // w32 is padded to whole tiles
+    unsigned long long tot = sb_block_sum_u64(tsum, s_u64);
+    if (tid == 0) { e_out[blockIdx.x] = e; Q_out[blockIdx.x] = tot; }
+    if (bad) atomicOr(err, SB_ERRBIT_NAN);
+}
+
+// =====================================================================================
+// k_tilescan: exact integer exclusive scan of the rescaled tile sums; the systematic offset u;
+// first child of every tile; log(mean weight) of the pool.  One CTA (latency-bound, O(n/2048)).
+// Replaces `ps = weights/sum(weights)` (src/pmcmc.jl:50); the log-evidence term is the north-star
+// extension.  Deterministic: integer adds only.
+// =====================================================================================
+#define SB_SCAN_THREADS 1024
+__global__ void __launch_bounds__(SB_SCAN_THREADS)
+k_tilescan(const int* __restrict__ e, const unsigned long long* __restrict__ Q, int nt, long long n, long long m,
+           unsigned long long seed, unsigned t, unsigned iter, double u_override, SbStepInfo* __restrict__ info,
+           unsigned long long* __restrict__ P, int* __restrict__ child_start, double* __restrict__ logZ_acc,
+           double* __restrict__ logZ_step, unsigned* __restrict__ err) {
+    __shared__ int s_e[32];
+    __shared__ unsigned long long s_w[32];
+    __shared__ SbStepInfo s_info;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (nt + SB_SCAN_THREADS - 1) / SB_SCAN_THREADS;
+    const int b0 = min(nt, tid * per), b1 = min(nt, b0 + per);
+    int E = SB_E_EMPTY;
+    for (int b = b0; b < b1; ++b) if (Q[b] != 0ull) E = max(E, e[b]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) E = max(E, __shfl_xor_sync(0xffffffffu, E, d));
+    if (lane == 0) s_e[warp] = E;
+    __syncthreads();
+    E = s_e[0];
+#pragma unroll
+    for (int w = 1; w < 32; ++w) E = max(E, s_e[w]);
+    int LS = 20;
+    while (LS > 0 && (1 << (20 - LS)) < nt) --LS;            // LS = 20 - ceil_log2(nt)
+    unsigned long long loc = 0;
+    for (int b = b0; b < b1; ++b) {
+        const unsigned long long q = Q[b];
+        if (q != 0ull) { const int sh = E - e[b]; loc += sh >= 63 ? 0ull : ((q << LS) >> sh); }
+    }
+    unsigned long long inc = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = sb_shfl_up_u64(inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    unsigned long long base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) { const unsigned long long s = s_w[w]; if (w < warp) base += s; total += s; }
+    unsigned long long run = base + inc - loc;
+    if (tid == 0) {
+        SbStepInfo si;
+        si.total = total; si.n = n; si.m = m; si.E = E; si.LS = LS; si.nt = nt;
+        si.valid = (E != SB_E_EMPTY && total != 0ull) ? 1 : 0;
+        si.inv = total ? __ddiv_rn((double)m, __ull2double_rn(total)) : 0.0;
+        if (u_override >= 0.0) si.u = u_override;
+        else { const SbU4 o = sb_stream4(seed, 0ull, t, iter, SB_P_RESAMPLE); si.u = sb_u53(o.x, o.y); }
+        s_info = si;
+        *info = si;
+        if (!si.valid) atomicOr(err, SB_ERRBIT_ZERO);
+        else {
+            const double lm = log(__ull2double_rn(total)) + (double)(E - SB_QBITS - LS) * SB_LN2 - log((double)n);
+            if (logZ_acc) *logZ_acc += lm;
+            if (logZ_step) logZ_step[t] = lm;
+        }
+    }
+    __syncthreads();
+    const SbStepInfo si = s_info;
+    for (int b = b0; b < b1; ++b) {
+        P[b] = run;
+        child_start[b] = si.valid ? sb_sys_F(run, si) : 0;
+        const unsigned long long q = Q[b];
+        if (q != 0ull) { const int sh = E - e[b]; run += sh >= 63 ? 0ull : ((q << LS) >> sh); }
+    }
+    if (tid == 0) { P[nt] = total; child_start[nt] = (int)m; }
+}
+
+// =====================================================================================
+// k_pull: ancestors only (hooks, and the final resample of a sweep).
+// Replaces the N calls of rand(ps) (src/rand.jl:2-13 via src/pmcmc.jl:51) by ONE merge of the
+// sorted child thresholds with the integer CDF.  Bytes per child: read 4 (w32), write 4 (anc).
+// =====================================================================================
+__global__ void __launch_bounds__(SB_THREADS)
+k_pull(const SbStepInfo* __restrict__ info, const uint32_t* __restrict__ w32, const int* __restrict__ e,
+       const unsigned long long* __restrict__ P, const int* __restrict__ child_start, int* __restrict__ anc_out) {
+    __shared__ SbPullSmem ps;
+    const SbStepInfo si = *info;
+    const int c0 = blockIdx.x * SB_TILE;
+    if (c0 >= (int)si.m) return;
+    int anc[SB_ITEMS];
+    sb_pull_ancestors(si, w32, e, P, child_start, c0, ps, anc);
+    const int base = c0 + threadIdx.x * SB_ITEMS;
+    if (base + SB_ITEMS <= (int)si.m) {
+        reinterpret_cast<int4*>(anc_out + base)[0] = make_int4(anc[0], anc[1], anc[2], anc[3]);
+        reinterpret_cast<int4*>(anc_out + base)[1] = make_int4(anc[4], anc[5], anc[6], anc[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < (int)si.m) anc_out[base + j] = anc[j];
+    }
+}
+
+// =====================================================================================
+// Multinomial on the grid: materialise the integer CDF, then one upper_bound per draw.
+// Same semantics as src/rand.jl:2-13 (first i with r < acc_i, last index as fallback).
+// =====================================================================================
+__global__ void __launch_bounds__(SB_THREADS)
+k_cdf(const SbStepInfo* __restrict__ info, const uint32_t* __restrict__ w32, const int* __restrict__ e,
+      const unsigned long long* __restrict__ P, unsigned long long* __restrict__ cdf) {
+    __shared__ unsigned long long s_scan[SB_WARPS + 1];
+    const SbStepInfo si = *info;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    uint32_t w[SB_ITEMS];
+    sb_load8_u32(w32 + (size_t)b * SB_TILE + tid * SB_ITEMS, w);
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) tsum += w[j];
+    unsigned long long tot;
+    unsigned long long c = sb_block_excl_scan_u64(tsum, s_scan, &tot);
+    const int sh = tot ? si.E - e[b] : 63;
+    const unsigned long long Pb = P[b];
+    const long long base = (long long)b * SB_TILE + tid * SB_ITEMS;
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) {
+        c += w[j];
+        if (base + j < si.n) cdf[base + j] = Pb + (sh >= 63 ? 0ull : ((c << si.LS) >> sh));
+    }
+}
+
+// r_in != nullptr: caller-supplied 53-bit uniforms (hook); else Philox stream (purpose RESAMPLE).
+__global__ void __launch_bounds__(256)
+k_multinomial_search(const SbStepInfo* __restrict__ info, const unsigned long long* __restrict__ cdf,
+                     const double* __restrict__ r_in, unsigned long long seed, unsigned t, unsigned iter,
+                     int* __restrict__ anc_out) {
+    const SbStepInfo si = *info;
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= si.m) return;
+    unsigned long long R;
+    if (r_in) R = __double2ull_rz(__dmul_rn(r_in[j], 0x1p53));
+    else {
+        const SbU4 o = sb_stream4(seed, (unsigned long long)j >> 1, t, iter, SB_P_RESAMPLE);
+        R = (j & 1) ? sb_r53(o.z, o.w) : sb_r53(o.x, o.y);
+    }
+    // thr = floor(R * total / 2^53), exact in 128 bits
+    const unsigned long long hi = __umul64hi(R, si.total), lo = R * si.total;
+    const unsigned long long thr = (hi << 11) | (lo >> 53);
+    long long a = 0, b = si.n - 1;
+    while (a < b) {
+        const long long mid = a + ((b - a) >> 1);
+        if (thr < __ldg(cdf + mid)) b = mid; else a = mid + 1;
+    }
+    anc_out[j] = (int)a;
+}
+
+// =====================================================================================
+// Literal reference numerics (src/pmcmc.jl:48-52 + src/rand.jl:2-13): sequentially rounded fp64
+// sum, ps = w/sum, sequentially rounded running sum.  One CTA; thread 0 owns the two dependent
+// add chains, the other threads only stage data through shared memory.  Parity path (small N).
+// =====================================================================================
+#define SB_LIT_CHUNK 2048
+__global__ void __launch_bounds__(256)
+k_literal_cdf(const double* __restrict__ w, long long n, double* __restrict__ acc_out, unsigned* __restrict__ err) {
+    __shared__ double buf[SB_LIT_CHUNK];
+    __shared__ double s_sum;
+    const int tid = threadIdx.x;
+    double s = 0.0;
+    for (long long c0 = 0; c0 < n; c0 += SB_LIT_CHUNK) {
+        const int len = (int)min((long long)SB_LIT_CHUNK, n - c0);
+        for (int i = tid; i < len; i += blockDim.x) buf[i] = w[c0 + i];
+        __syncthreads();
+        if (tid == 0) for (int i = 0; i < len; ++i) s = __dadd_rn(s, buf[i]);
+        __syncthreads();
+    }
+    if (tid == 0) s_sum = s;
+    __syncthreads();
+    s = s_sum;
+    double a = 0.0;
+    bool bad = false;
+    for (long long c0 = 0; c0 < n; c0 += SB_LIT_CHUNK) {
+        const int len = (int)min((long long)SB_LIT_CHUNK, n - c0);
+        for (int i = tid; i < len; i += blockDim.x) buf[i] = __ddiv_rn(w[c0 + i], s);   // pmcmc.jl:50
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < len; ++i) {
+                a = __dadd_rn(a, buf[i]);                                             // rand.jl:7
+                if (isnan(a) && (c0 + i < n - 1 || n == 1)) bad = true;               // rand.jl:8,11
+                buf[i] = a;
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < len; i += blockDim.x) acc_out[c0 + i] = buf[i];
+        __syncthreads();
+    }
+    if (tid == 0 && bad) atomicOr(err, SB_ERRBIT_NAN);
+}
+
+__global__ void __launch_bounds__(256)
+k_literal_search(const double* __restrict__ acc, long long n, const double* __restrict__ r_in, long long m,
+                 unsigned long long seed, unsigned t, unsigned iter, int* __restrict__ anc_out) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double r;
+    if (r_in) r = r_in[j];
+    else {
+        const SbU4 o = sb_stream4(seed, (unsigned long long)j >> 1, t, iter, SB_P_RESAMPLE);
+        r = (j & 1) ? sb_u53(o.z, o.w) : sb_u53(o.x, o.y);
+    }
+    long long a = 0, b = n - 1;                       // first i in [0, n-1) with r < acc[i], else n-1
+    while (a < b) {
+        const long long mid = a + ((b - a) >> 1);
+        if (r < __ldg(acc + mid)) b = mid; else a = mid + 1;
+    }
+    anc_out[j] = (int)a;
+}
+
+// =====================================================================================
+// k_gather: dst[i] = src[anc[i]]  (deepcopy(particles[...]) src/pmcmc.jl:51).
+// Bytes per child: read 4 (anc) + S (state, monotone for systematic) + write S.
+// =====================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_gather(const T* __restrict__ src, const int* __restrict__ anc, long long m, T* __restrict__ dst) {
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 + 4 <= m) {
+        const int4 a = __ldg(reinterpret_cast<const int4*>(anc + i0));
+        T v0 = __ldg(src + a.x), v1 = __ldg(src + a.y), v2 = __ldg(src + a.z), v3 = __ldg(src + a.w);
+        dst[i0] = v0; dst[i0 + 1] = v1; dst[i0 + 2] = v2; dst[i0 + 3] = v3;
+    } else {
+        for (long long i = i0; i < m; ++i) dst[i] = src[anc[i]];
+    }
+}
+template <>
+__global__ void __launch_bounds__(256)
+k_gather<uint32_t>(const uint32_t* __restrict__ src, const int* __restrict__ anc, long long m, uint32_t* __restrict__ dst) {
+    const long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i0 + 4 <= m) {
+        const int4 a = __ldg(reinterpret_cast<const int4*>(anc + i0));
+        uint4 v;
+        v.x = __ldg(src + a.x); v.y = __ldg(src + a.y); v.z = __ldg(src + a.z); v.w = __ldg(src + a.w);
+        *reinterpret_cast<uint4*>(dst + i0) = v;
+    } else {
+        for (long long i = i0; i < m; ++i) dst[i] = src[anc[i]];
+    }
+}
+
+// =====================================================================================
+// Log-sum-exp: warp-shuffle + shared-memory reduction of (max, sum exp(x - max)) pairs.
+// Stabilised replacement for `sum(exp(score))` (src/pmcmc.jl:50,55); extension D2/H3.
+// =====================================================================================
+struct SbLse { double m, s; };
+__device__ __forceinline__ SbLse sb_lse_combine(SbLse a, SbLse b) {
+    if (a.m == -INFINITY) return b;
+    if (b.m == -INFINITY) return a;
+    if (a.m >= b.m) return SbLse{a.m, a.s + b.s * exp(b.m - a.m)};
+    return SbLse{b.m, b.s + a.s * exp(a.m - b.m)};
+}
+__device__ __forceinline__ SbLse sb_lse_block(SbLse v, SbLse* sm) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        SbLse o;
+        o.m = __shfl_xor_sync(0xffffffffu, v.m, d);
+        o.s = __shfl_xor_sync(0xffffffffu, v.s, d);
+        v = sb_lse_combine(v, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    SbLse r = sm[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = sb_lse_combine(r, sm[w]);
+    return r;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_lse_partial(const T* __restrict__ lw, long long n, SbLse* __restrict__ partial, unsigned* __restrict__ err) {
+    __shared__ SbLse sm[8];
+    // two passes over this CTA's contiguous slab: max first, then the sum (slab stays in L1/L2)
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long i0 = (long long)blockIdx.x * per, i1 = min(n, i0 + per);
+    double mx = -INFINITY;
+    bool bad = false;
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const double v = (double)__ldg(lw + i);
+        if (isnan(v) || v == INFINITY) bad = true;
+        mx = fmax(mx, v);
+    }
+    __shared__ double s_mx[8];
+    mx = sb_block_max_f64(mx, s_mx);
+    double s = 0.0;
+    if (mx > -INFINITY)
+        for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) s += exp((double)__ldg(lw + i) - mx);
+    SbLse r = sb_lse_block(SbLse{mx > -INFINITY ? mx : -INFINITY, s}, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+    if (bad) atomicOr(err, SB_ERRBIT_NAN);
+}
+__global__ void __launch_bounds__(256)
+k_lse_final(const SbLse* __restrict__ partial, int np, double* __restrict__ out) {
+    __shared__ SbLse sm[8];
+    SbLse v{-INFINITY, 0.0};
+    for (int i = threadIdx.x; i < np; i += blockDim.x) v = sb_lse_combine(v, partial[i]);
+    v = sb_lse_block(v, sm);
+    if (threadIdx.x == 0) *out = v.m == -INFINITY ? -INFINITY : v.m + log(v.s);
+}
+
+// =====================================================================================
+// The fused step kernels.  One CTA = one tile of 2048 children:
+//   (1) resample: pull this tile's ancestors from the previous pool (or explicit / identity),
+//   (2) gather the parents' states,
+//   (3) propagate through the model's ERP draw with a counter-based Philox stream,
+//   (4) weight with the step's factor / observe score,
+//   (5) quantise the weights onto the grid and emit the tile exponent and tile sum.
+// Replaces, per particle-step: sample -> rand(e) (src/pmcmc.jl:32-34), the model body,
+// factor's Step push (src/pmcmc.jl:37), and resample + deepcopy (src/pmcmc.jl:42,48-66).
+// Algorithmic bytes per particle-step: read w32 (4) + read parent state (S) + write state (S)
+// + write w32 (4) [+ 4 for the ancestor row when history is kept].
+// =====================================================================================
+#define SB_ANC_NONE     0   // first step: no parents
+#define SB_ANC_PULL     1   // systematic resampling fused in
+#define SB_ANC_EXPLICIT 2   // ancestors already materialised (multinomial / literal)
+#define SB_ANC_IDENTITY 3   // previous step had no factor statement
+
+struct SbHmmStepArgs {
+    // previous pool
+    const int* x_prev;
+    const uint32_t* w32_prev;
+    const int* e_prev;
+    const unsigned long long* P;
+    const int* child_start;
+    const SbStepInfo* info_prev;
+    const int* anc_in;
+    int* anc_out;               // history row of the resample after step t-1 (or nullptr)
+    // this step's outputs
+    int* x_out;
+    uint32_t* w32_out;
+    int* e_out;
+    unsigned long long* Q_out;
+    double* lw_out;             // optional (store_logw)
+    double* wlit_out;           // optional (literal mode): exp(score) from the host-built table
+    // model tables (global memory; staged into shared memory)
+    const double* cum;          // [rows*K] sequential running sums of the transition rows
+    const double* logF_t;       // [K]
+    const double* expF_t;       // [K] or nullptr
+    const int* xstar;           // retained trajectory [T] or nullptr
+    long long N;
+    int n_out;                  // N (+1 with a retained particle)
+    int K, rows, t;
+    unsigned iter;
+    unsigned long long seed;
+    unsigned* err;
+};
+
+template <int ANC, bool FP32>
+__global__ void __launch_bounds__(SB_THREADS)
+k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    double* s_cum = reinterpret_cast<double*>(dyn);                 // rows*K
+    double* s_l2 = s_cum + a.rows * a.K;                            // K   (float view when FP32)
+    uint32_t* s_q = reinterpret_cast<uint32_t*>(s_l2 + a.K);        // K
+    __shared__ SbPullSmem ps;
+    __shared__ double s_red[SB_WARPS];
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * SB_TILE;
+    const int base = c0 + tid * SB_ITEMS;
+    const int K = a.K;
+    for (int i = tid; i < a.rows * K; i += SB_THREADS) s_cum[i] = a.cum[i];
+    if (tid < K) {
+        if (FP32) reinterpret_cast<float*>(s_l2)[tid] = __fmul_rn((float)a.logF_t[tid], SB_LOG2E_F);
+        else      s_l2[tid] = __dmul_rn(a.logF_t[tid], SB_LOG2E_D);
+    }
+    // (1) ancestors
+    int anc[SB_ITEMS];
+    if (ANC == SB_ANC_PULL) {
+        const SbStepInfo si = *a.info_prev;
+        if (c0 < (int)si.m) sb_pull_ancestors(si, a.w32_prev, a.e_prev, a.P, a.child_start, c0, ps, anc);
+        else {
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) anc[j] = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(anc[j], 0);
+    } else if (ANC == SB_ANC_EXPLICIT) {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < a.N) ? __ldg(a.anc_in + base + j) : 0;
+    } else {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;
+    }
+    if (ANC != SB_ANC_NONE && ANC != SB_ANC_EXPLICIT && a.anc_out) {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) {
+            const int i = base + j;
+            if (i < a.N) a.anc_out[i] = anc[j];
+            else if (i == a.N) a.anc_out[i] = (int)a.N;      // the retained slot descends from itself
+        }
+    }
+    // (2) gather parents
+    int xp[SB_ITEMS];
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j)
+        xp[j] = (ANC != SB_ANC_NONE && base + j < a.N) ? __ldg(a.x_prev + anc[j]) : 0;
+    __syncthreads();                                              // tables staged
+    // (3) propagate: one Philox call per particle PAIR, one 53-bit uniform per particle
+    int x[SB_ITEMS];
+#pragma unroll
+    for (int p = 0; p < SB_ITEMS / 2; ++p) {
+        const SbU4 o = sb_stream4(a.seed, (unsigned long long)((base >> 1) + p), (unsigned)a.t, a.iter, SB_P_PROP);
+        const double u0 = sb_u53(o.x, o.y), u1 = sb_u53(o.z, o.w);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = 2 * p + h;
+            const double u = h ? u1 : u0;
+            const double* row = s_cum + (a.rows > 1 ? xp[j] * K : 0);
+            int lo = 0, hi = K - 1;                              // src/rand.jl:6-12 on a monotone row
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (u < row[mid]) hi = mid; else lo = mid + 1;
+            }
+            x[j] = lo;
+        }
+    }
+    // retained particle (src/pmcmc.jl:59-66) and padding
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) {
+        const int i = base + j;
+        if (i >= a.N) x[j] = (i == a.N && a.xstar) ? __ldg(a.xstar + a.t) : 0;
+    }
+    // (4)+(5) weight and quantise.  Only K distinct scores exist, so 2^(l2 - e) is evaluated K times.
+    int e;
+    if (FP32) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) mx = fmaxf(mx, reinterpret_cast<float*>(s_l2)[x[j]]);
+        mx = sb_block_max_f32(mx, reinterpret_cast<float*>(s_red));
+        e = mx > -INFINITY ? (int)ceilf(mx) : SB_E_EMPTY;
+        if (tid < K) {
+            const float l2 = reinterpret_cast<float*>(s_l2)[tid];
+            if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
+            s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f32(__fsub_rn(l2, (float)e));
+        }
+    } else {
+        double mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) mx = fmax(mx, s_l2[x[j]]);
+        mx = sb_block_max_f64(mx, s_red);
+        e = mx > -INFINITY ? (int)ceil(mx) : SB_E_EMPTY;
+        if (tid < K) {
+            const double l2 = s_l2[tid];
+            if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
+            s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f64(__dsub_rn(l2, (double)e));
+        }
+    }
+    __syncthreads();
+    uint32_t q[SB_ITEMS];
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) {
+        q[j] = (base + j < a.n_out) ? s_q[x[j]] : 0u;
+        tsum += q[j];
+    }
+    sb_store8_u32(reinterpret_cast<uint32_t*>(a.x_out) + base, reinterpret_cast<const uint32_t*>(x));
+    sb_store8_u32(a.w32_out + base, q);
+    if (a.lw_out) {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.lw_out[base + j] = a.logF_t[x[j]];
+    }
+    if (a.wlit_out) {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.wlit_out[base + j] = a.expF_t[x[j]];
+    }
+    const unsigned long long tot = sb_block_sum_u64(tsum, ps.scan);
+    if (tid == 0) { a.e_out[blockIdx.x] = e; a.Q_out[blockIdx.x] = tot; }
+}
+
+// ---------------------------------------------------------------- linear-Gaussian step
+struct SbLgStepArgs {
+    const void* x_prev;         // REAL[n]
+    const uint32_t* w32_prev;
+    const int* e_prev;
+    const unsigned long long* P;
+    const int* child_start;
+    const SbStepInfo* info_prev;
+    const int* anc_in;
+    int* anc_out;
+    void* x_out;
+    uint32_t* w32_out;
+    int* e_out;
+    unsigned long long* Q_out;
+    double* lw_out;
+    long long N;
+    int t;
+    unsigned iter;
+    unsigned long long seed;
+    double a, sq, sp, c, r, m0, y, lc;   // sq = sqrt(q), sp = sqrt(P0), lc = -0.5 log(2 pi r)
+    unsigned* err;
+};
+
+#define SB_TWO_PI 6.283185307179586476925286766559
+
+template <int ANC, bool FP32>
+__global__ void __launch_bounds__(SB_THREADS)
+k_step_lg(const __grid_constant__ SbLgStepArgs a) {
+    typedef typename std::conditional<FP32, float, double>::type REAL;
+    __shared__ SbPullSmem ps;
+    __shared__ double s_red[SB_WARPS];
+    const int tid = threadIdx.x;
+    const int c0 = blockIdx.x * SB_TILE;
+    const int base = c0 + tid * SB_ITEMS;
+    int anc[SB_ITEMS];
+    if (ANC == SB_ANC_PULL) {
+        const SbStepInfo si = *a.info_prev;
+        sb_pull_ancestors(si, a.w32_prev, a.e_prev, a.P, a.child_start, c0, ps, anc);
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(anc[j], 0);
+    } else if (ANC == SB_ANC_EXPLICIT) {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < a.N) ? __ldg(a.anc_in + base + j) : 0;
+    } else {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;
+    }
+    if (ANC == SB_ANC_PULL && a.anc_out) {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.N) a.anc_out[base + j] = anc[j];
+    }
+    REAL x[SB_ITEMS];
+    REAL l2[SB_ITEMS];
+    REAL mx = -INFINITY;
+    bool bad = false;
+    const REAL* xprev = reinterpret_cast<const REAL*>(a.x_prev);
+    if (FP32) {
+        const float fa = (float)a.a, fsq = (float)a.sq, fsp = (float)a.sp, fc = (float)a.c, fy = (float)a.y;
+        const float hr = -0.5f / (float)a.r, flc = (float)a.lc, fm0 = (float)a.m0;
+#pragma unroll
+        for (int p = 0; p < SB_ITEMS / 2; ++p) {
+            const SbU4 o = sb_stream4(a.seed, (unsigned long long)((base >> 1) + p), (unsigned)a.t, a.iter, SB_P_PROP);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * p + h;
+                const float u1 = (float)((h ? o.z : o.x) >> 8) * 0x1p-24f;
+                const float u2 = (float)((h ? o.w : o.y) >> 8) * 0x1p-24f;
+                const float z = sqrtf(-2.0f * logf(1.0f - u1)) * cosf((float)SB_TWO_PI * u2);
+                float xv;
+                if (ANC == SB_ANC_NONE) xv = fm0 + fsp * z;
+                else xv = fa * ((base + j < a.N) ? (float)__ldg(xprev + anc[j]) : 0.0f) + fsq * z;
+                const float d = fy - fc * xv;
+                const float lw = hr * d * d + flc;
+                const bool live = base + j < a.N;
+                float v = live ? __fmul_rn(lw, SB_LOG2E_F) : -INFINITY;
+                if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
+                x[j] = (REAL)xv; l2[j] = (REAL)v;
+                mx = (REAL)fmaxf((float)mx, v);
+                if (a.lw_out && live) a.lw_out[base + j] = (double)lw;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) {
+            const SbU4 o = sb_stream4(a.seed, (unsigned long long)(base + j), (unsigned)a.t, a.iter, SB_P_PROP);
+            const double u1 = sb_u53(o.x, o.y), u2 = sb_u53(o.z, o.w);
+            const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(SB_TWO_PI * u2);
+            double xv;
+            if (ANC == SB_ANC_NONE) xv = a.m0 + a.sp * z;
+            else xv = a.a * ((base + j < a.N) ? (double)__ldg(xprev + anc[j]) : 0.0) + a.sq * z;
+            const double d = a.y - a.c * xv;
+            const double lw = -0.5 * d * d / a.r + a.lc;
+            const bool live = base + j < a.N;
+            double v = live ? __dmul_rn(lw, SB_LOG2E_D) : -INFINITY;
+            if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
+            x[j] = (REAL)xv; l2[j] = (REAL)v;
+            mx = (REAL)fmax((double)mx, v);
+            if (a.lw_out && live) a.lw_out[base + j] = lw;
+        }
+    }
+    int e;
+    if (FP32) { const float m2 = sb_block_max_f32((float)mx, reinterpret_cast<float*>(s_red)); e = m2 > -INFINITY ? (int)ceilf(m2) : SB_E_EMPTY; }
+    else      { const double m2 = sb_block_max_f64((double)mx, s_red); e = m2 > -INFINITY ? (int)ceil(m2) : SB_E_EMPTY; }
+    uint32_t q[SB_ITEMS];
+    unsigned long long tsum = 0;
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) {
+        uint32_t v = 0;
+        if (e != SB_E_EMPTY) v = FP32 ? sb_q31_f32(__fsub_rn((float)l2[j], (float)e)) : sb_q31_f64(__dsub_rn((double)l2[j], (double)e));
+        q[j] = v; tsum += v;
+    }
+    REAL* xo = reinterpret_cast<REAL*>(a.x_out) + base;
+    if (FP32) {
+        reinterpret_cast<float4*>(xo)[0] = make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
+        reinterpret_cast<float4*>(xo)[1] = make_float4((float)x[4], (float)x[5], (float)x[6], (float)x[7]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; j += 2) reinterpret_cast<double2*>(xo)[j / 2] = make_double2((double)x[j], (double)x[j + 1]);
+    }
+    sb_store8_u32(a.w32_out + base, q);
+    const unsigned long long tot = sb_block_sum_u64(tsum, ps.scan);
+    if (tid == 0) { a.e_out[blockIdx.x] = e; a.Q_out[blockIdx.x] = tot; }
+    if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
+}
+
+// =====================================================================================
+// Value accounting for pmcmc: counts[p.value] += 1 for ALL N particles (src/pmcmc.jl:90-92).
+// Per-time marginals by propagating offspring counts backwards through the ancestor rows
+// (coalesced, 12 B per particle-step) instead of N pointer chases of length T.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+k_count_final(const int* __restrict__ anc_last, long long N, int* __restrict__ cnt) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) atomicAdd(cnt + anc_last[i], 1);
+}
+// cnt_t[j] lineages pass through pool entry j at step t.  anc_prev = ancestors drawn after step
+// t-1 (nullptr at t == 0; identity when that step had no factor).  Also walks the retained
+// lineage one step (thread 0 of block 0) so no separate pointer chase is needed.
+__global__ void __launch_bounds__(256)
+k_count_back(const int* __restrict__ x_t, const int* __restrict__ cnt_t, const int* __restrict__ anc_prev,
+             int identity_prev, long long n_pool, long long N, int K, int t,
+             int* __restrict__ cnt_prev, unsigned long long* __restrict__ marg,
+             int* __restrict__ lineage, int* __restrict__ xstar_out) {
+    extern __shared__ unsigned int s_hist[];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) s_hist[k] = 0u;
+    __syncthreads();
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_pool) {
+        const int c = cnt_t[j];
+        if (c) {
+            atomicAdd(&s_hist[x_t[j]], (unsigned)c);
+            if (cnt_prev) {
+                const int pj = (j >= N || identity_prev) ? (int)j : anc_prev[j];
+                atomicAdd(cnt_prev + pj, c);
+            }
+        }
+    }
+    __syncthreads();
+    if (marg)
+        for (int k = threadIdx.x; k < K; k += blockDim.x)
+            if (s_hist[k]) atomicAdd(marg + (size_t)t * K + k, (unsigned long long)s_hist[k]);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && lineage) {
+        const int r = *lineage;
+        xstar_out[t] = x_t[r];
+        if (t > 0) *lineage = (r >= N || identity_prev) ? r : anc_prev[r];
+    }
+}
+// start of the retained lineage: child c* of the final resample (src/pmcmc.jl:89 or uniform pick, H4)
+__global__ void k_lineage_start(const int* __restrict__ anc_last, long long N, int pick_uniform,
+                                unsigned long long seed, unsigned T, unsigned iter, int* __restrict__ lineage) {
+    long long c = 0;
+    if (pick_uniform) {
+        const SbU4 o = sb_stream4(seed, 0ull, T, iter, SB_P_PICK);
+        c = (long long)__double2ll_rz(__dmul_rn(sb_u53(o.x, o.y), (double)N));
+        if (c >= N) c = N - 1;
+    }
+    *lineage = anc_last[c];
+}
+// joint trajectory histogram for small K^T: one walk of length T per final particle
+__global__ void __launch_bounds__(256)
+k_joint_hist(const int* __restrict__ x_hist, const int* __restrict__ anc_hist, const unsigned char* __restrict__ has_factor,
+             long long S, long long N, int K, int T, unsigned long long* __restrict__ joint) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    long long j = anc_hist[(size_t)(T - 1) * S + c];
+    unsigned long long code = 0;
+    for (int t = T - 1; t >= 0; --t) {
+        code = code * (unsigned long long)K + (unsigned long long)x_hist[(size_t)t * S + j];
+        if (t > 0 && j < N && has_factor[t - 1]) j = anc_hist[(size_t)(t - 1) * S + j];
+    }
+    atomicAdd(joint + code, 1ull);
+}
+__global__ void k_fill_identity(int* __restrict__ a, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (int)i;
+}
+
+// =====================================================================================
+// Batched single-site MH on a binary Bayes net: one thread = one chain, state in registers,
+// tables in shared memory, warp-aggregated histogram.  Replaces the loop src/mh.jl:61-88 and
+// log_mh_ratio src/mh.jl:95-111 for fixed-structure traces.  Not HBM-bound (INT/FP64 pipes).
+// =====================================================================================
+struct SbBnetArgs {
+    int D, F, stride;
+    unsigned query_mask;
+    const unsigned* site_parents;
+    const double* site_cpt;     // P(site = 1 | parents)
+    const double* site_lp1;     // log p
+    const double* site_lp0;     // log(1 - p)
+    const unsigned* fac_parents;
+    const double* fac_logf;
+    unsigned long long seed;
+    long long chains, steps, chain0;
+    unsigned long long* counts;
+    unsigned long long* accepts;
+};
+__device__ __forceinline__ unsigned sb_pack_bits(unsigned state, unsigned mask) {
+    unsigned idx = 0, pos = 0;
+    while (mask) {
+        const unsigned b = mask & (0u - mask);
+        if (state & b) idx |= 1u << pos;
+        ++pos; mask ^= b;
+    }
+    return idx;
+}
+#define SB_MH_MAXD 16
+__global__ void __launch_bounds__(128)
+k_mh_bnet(const __grid_constant__ SbBnetArgs a) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const int D = a.D, F = a.F, st = a.stride;
+    double* s_cpt = reinterpret_cast<double*>(dyn);         // D*st
+    double* s_lp1 = s_cpt + D * st;
+    double* s_lp0 = s_lp1 + D * st;
+    double* s_fac = s_lp0 + D * st;                         // F*st
+    unsigned* s_sp = reinterpret_cast<unsigned*>(s_fac + F * st);   // D
+    unsigned* s_fp = s_sp + D;                              // F
+    unsigned* s_hist = s_fp + F;                            // warps * nv
+    int nq = __popc(a.query_mask);
+    const int nv = 1 << nq;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < D * st; i += blockDim.x) { s_cpt[i] = a.site_cpt[i]; s_lp1[i] = a.site_lp1[i]; s_lp0[i] = a.site_lp0[i]; }
+    for (int i = threadIdx.x; i < F * st; i += blockDim.x) s_fac[i] = a.fac_logf[i];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s_sp[i] = a.site_parents[i];
+    for (int i = threadIdx.x; i < F; i += blockDim.x) s_fp[i] = a.fac_parents[i];
+    for (int i = threadIdx.x; i < nwarps * nv; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = ch < a.chains;
+    const unsigned long long gch = (unsigned long long)(a.chain0 + ch);
+    unsigned state = 0;
+    double cs_old[SB_MH_MAXD];
+    double score_old = 0.0;
+    unsigned long long acc = 0;
+    // src/mh.jl:57 -- run once from the prior; choicescores in program order
+#pragma unroll 1
+    for (int d = 0; d < D; ++d) {
+        const SbU4 o = sb_stream4(a.seed, gch, (unsigned)d, 0u, SB_P_INIT);
+        const double u = __dmul_rn((double)o.x, 0x1p-32);
+        const unsigned idx = sb_pack_bits(state, s_sp[d]);
+        if (u < s_cpt[d * st + idx]) state |= 1u << d;
+    }
+#pragma unroll
+    for (int d = 0; d < SB_MH_MAXD; ++d) {
+        if (d < D) {
+            const unsigned idx = sb_pack_bits(state, s_sp[d]);
+            const double c = ((state >> d) & 1u) ? s_lp1[d * st + idx] : s_lp0[d * st + idx];
+            cs_old[d] = c;
+            score_old = __dadd_rn(score_old, c);
+        }
+    }
+    for (int f = 0; f < F; ++f) score_old = __dadd_rn(score_old, s_fac[f * st + sb_pack_bits(state, s_fp[f])]);
+    unsigned* hist = s_hist + warp * nv;
+    for (long long s = 0; s < a.steps; ++s) {
+        const SbU4 o = sb_stream4(a.seed, gch, (unsigned)s, (unsigned)(s >> 32), SB_P_MH);
+        const int j = (int)__umulhi(o.x, (unsigned)D);                               // mh.jl:62
+        const double up = __dmul_rn((double)o.y, 0x1p-32), ua = __dmul_rn((double)o.z, 0x1p-32);
+        const unsigned prefix = state & ((1u << j) - 1u);
+        unsigned prop = state & ~(1u << j);
+        if (up < s_cpt[j * st + sb_pack_bits(prefix, s_sp[j])]) prop |= 1u << j;     // mh.jl:70-76
+        double cs_new[SB_MH_MAXD];
+        double score_new = 0.0;
+#pragma unroll
+        for (int d = 0; d < SB_MH_MAXD; ++d) {
+            if (d < D) {
+                const unsigned idx = sb_pack_bits(prop, s_sp[d]);
+                const double c = ((prop >> d) & 1u) ? s_lp1[d * st + idx] : s_lp0[d * st + idx];
+                cs_new[d] = c;
+                score_new = __dadd_rn(score_new, c);
+            }
+        }
+        for (int f = 0; f < F; ++f) score_new = __dadd_rn(score_new, s_fac[f * st + sb_pack_bits(prop, s_fp[f])]);
+        double fw = 0.0, bw = 0.0;
+#pragma unroll
+        for (int d = 0; d < SB_MH_MAXD; ++d) if (d == j) { fw = cs_new[d]; bw = cs_old[d]; }
+        const double lr = __dsub_rn(__dadd_rn(__dsub_rn(score_new, score_old), bw), fw);   // mh.jl:110
+        const double ar = exp(lr);
+        const bool accept = !isnan(ar) && ua < (ar < 1.0 ? ar : 1.0);                // mh.jl:78
+        if (accept) {
+            state = prop; score_old = score_new; ++acc;
+#pragma unroll
+            for (int d = 0; d < SB_MH_MAXD; ++d) cs_old[d] = cs_new[d];
+        }
+        // mh.jl:87 -- count the current value after every step (warp-aggregated)
+        const unsigned v = sb_pack_bits(state, a.query_mask);
+        const unsigned act = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const unsigned peers = __match_any_sync(act, v);
+            if (lane == __ffs(peers) - 1) hist[v] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        unsigned long long t = 0;
+        for (int w = 0; w < nwarps; ++w) t += s_hist[w * nv + v];
+        if (t) atomicAdd(a.counts + v, t);
+    }
+    if (live && acc) atomicAdd(a.accepts, acc);
+}
+
+// =====================================================================================
+// ERP vocabulary (src/erp.jl:1-30): samplers and log-densities.  Distributions.jl 0.6.3 is not
+// in the reference tree, so these are the textbook algorithms; validated statistically.
+// =====================================================================================
+struct SbRng {           // sequential draws from one Philox counter stream (for rejection samplers)
+    unsigned long long seed, idx;
+    unsigned n;
+    __device__ double next() {
+        const SbU4 o = sb_stream4(seed, idx, n >> 1, 0u, 5u);
+        const double u = (n & 1) ? sb_u53(o.z, o.w) : sb_u53(o.x, o.y);
+        ++n;
+        return u;
+    }
+    __device__ double normal() {
+        const double u1 = next(), u2 = next();
+        return sqrt(-2.0 * log(1.0 - u1)) * cos(SB_TWO_PI * u2);
+    }
+    // Marsaglia-Tsang (2000); shape < 1 boosted by u^(1/shape)
+    __device__ double gamma(double shape) {
+        double boost = 1.0;
+        if (shape < 1.0) { boost = pow(1.0 - next(), 1.0 / shape); shape += 1.0; }
+        const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        for (int it = 0; it < 1000; ++it) {
+            const double z = normal();
+            double v = 1.0 + c * z;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            const double u = 1.0 - next();
+            if (log(u) < 0.5 * z * z + d - d * v + d * log(v)) return boost * d * v;
+        }
+        return boost * d;
+    }
+};
+
+__global__ void __launch_bounds__(256)
+k_erp_sample(int erp, double p0, double p1, long long n, unsigned long long seed, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SbRng g{seed, (unsigned long long)i, 0u};
+    double v = 0.0;
+    switch (erp) {
+        case 0: v = g.next() < p0 ? 1.0 : 0.0; break;                                  // flip: (false,true)[Bernoulli+1]
+        case 1: { double k = floor(g.next() * p0); v = (k >= p0 ? p0 - 1.0 : k) + 1.0; } break;   // randominteger: 1..k
+        case 2: v = p0 + p1 * g.normal(); break;
+        case 3: { const double x = g.gamma(p0), y = g.gamma(p1); v = x / (x + y); } break;
+        case 4: v = p1 * g.gamma(p0); break;
+        case 5: v = p0 + (p1 - p0) * g.next(); break;
+    }
+    out[i] = v;
+}
+__global__ void __launch_bounds__(256)
+k_erp_logpdf(int erp, double p0, double p1, const double* __restrict__ x, long long n, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    double lp = -INFINITY;
+    switch (erp) {
+        case 0: lp = v == 1.0 ? log(p0) : (v == 0.0 ? log(1.0 - p0) : -INFINITY); break;
+        case 1: lp = (v >= 1.0 && v <= p0 && v == floor(v)) ? -log(p0) : -INFINITY; break;
+        case 2: { const double z = (v - p0) / p1; lp = -0.5 * z * z - log(p1) - 0.5 * log(SB_TWO_PI); } break;
+        case 3: lp = (v > 0.0 && v < 1.0) ? (p0 - 1.0) * log(v) + (p1 - 1.0) * log1p(-v) + lgamma(p0 + p1) - lgamma(p0) - lgamma(p1) : -INFINITY; break;
+        case 4: lp = v > 0.0 ? (p0 - 1.0) * log(v) - v / p1 - lgamma(p0) - p0 * log(p1) : -INFINITY; break;
+        case 5: lp = (v >= p0 && v <= p1) ? -log(p1 - p0) : -INFINITY; break;
+    }
+    out[i] = lp;
+}
+#define SB_DIR_MAXK 32
+__global__ void __launch_bounds__(256)
+k_dirichlet_sample(const double* __restrict__ alpha, int k, long long n, unsigned long long seed, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SbRng g{seed, (unsigned long long)i, 0u};
+    double s = 0.0;
+    for (int j = 0; j < k; ++j) { const double v = g.gamma(alpha[j]); out[i * k + j] = v; s += v; }
+    for (int j = 0; j < k; ++j) out[i * k + j] /= s;
+}
+__global__ void __launch_bounds__(256)
+k_dirichlet_logpdf(const double* __restrict__ alpha, int k, const double* __restrict__ x, long long n, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a0 = 0.0, lp = 0.0;
+    for (int j = 0; j < k; ++j) { a0 += alpha[j]; lp += (alpha[j] - 1.0) * log(x[i * k + j]) - lgamma(alpha[j]); }
+    out[i] = lp + lgamma(a0);
+}

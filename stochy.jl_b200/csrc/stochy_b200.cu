@@ -1,0 +1,930 @@
+// stochy_b200.cu -- C ABI of libstochy_b200.so (see include/stochy_b200.h).
+// Host orchestration of the sm_100a kernels in sb_kernels.cuh.  No CPU fallback exists: every
+// entry point that computes launches CUDA kernels and fails with SB_ECUDA when it cannot.
+#include "../../include/stochy_b200.h"
+#include "sb_kernels.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t rc = cudaMalloc(&p, want);
+        if (rc == cudaSuccess) cap = want;
+        return rc;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum ModelKind { MODEL_NONE = 0, MODEL_HMM = 1, MODEL_LG = 2, MODEL_BNET = 3 };
+
+}  // namespace
+
+struct sb_handle {
+    sb_options opt;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    std::string err;
+    sb_stats stats;
+    int64_t launches = 0;
+
+    // error word, logZ accumulators, lineage index, step infos
+    unsigned* d_err = nullptr;
+    DevBuf d_logZ;        // [0] accumulator, [1..T] per step
+    DevBuf d_info;        // SbStepInfo[max(T,1)]
+    DevBuf d_misc;        // int lineage
+
+    // grid scratch
+    DevBuf w32[2], tile_e[2], tile_Q[2], P, child_start, cdf, lit_acc, lse_part;
+    // hook staging
+    DevBuf hk_in, hk_r, hk_anc, hk_out, hk_src;
+
+    // model
+    int model = MODEL_NONE;
+    // HMM
+    int K = 0, T = 0, x0 = -1;
+    std::vector<uint8_t> has_factor;
+    DevBuf hmm_cumA, hmm_cumpi, hmm_logF, hmm_expF, hmm_hasf;
+    // LG
+    double lg_a = 0, lg_q = 0, lg_c = 0, lg_r = 0, lg_m0 = 0, lg_P0 = 0;
+    std::vector<double> lg_y;
+    // BNET
+    int bn_D = 0, bn_F = 0, bn_stride = 0;
+    unsigned bn_query = 0;
+    DevBuf bn_sp, bn_cpt, bn_lp1, bn_lp0, bn_fp, bn_fac, bn_counts;
+
+    // sweep state
+    DevBuf xbuf, ancbuf, lwbuf, wlit, cnt[2], xstar[2], marg, joint;
+    int64_t sw_N = 0, sw_S = 0;       // particles and row stride of the last sweep
+    int sw_hist = 0;                  // history rows kept
+    int sw_cond = 0;
+    int xstar_cur = 0;
+    bool have_retained = false;
+};
+
+namespace {
+
+int fail(sb_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(h, _e == cudaErrorMemoryAllocation ? SB_ENOMEM : SB_ECUDA,             \
+                        std::string(#call) + ": " + cudaGetErrorString(_e));                   \
+    } while (0)
+#define LAUNCH_CHECK()                                                                         \
+    do {                                                                                       \
+        ++h->launches;                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) return fail(h, SB_ECUDA, std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+    } while (0)
+
+inline int64_t tiles_of(int64_t n) { return (n + SB_TILE - 1) / SB_TILE; }
+
+int check_err_word(sb_handle* h) {
+    unsigned w = 0;
+    CK(cudaMemcpyAsync(&w, h->d_err, sizeof(w), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (w) {
+        cudaMemsetAsync(h->d_err, 0, sizeof(unsigned), h->stream);
+        if (w & SB_ERRBIT_NAN) return fail(h, SB_ENAN, "unexpected nan in rand");
+        return fail(h, SB_EZEROMASS, "Distribution has zero probability mass.");
+    }
+    return SB_OK;
+}
+
+int ensure_grid(sb_handle* h, int64_t n_pool, int64_t m) {
+    const int64_t nt = tiles_of(n_pool);
+    if (nt > (1 << 20) || m > 0x7fffffffLL - SB_TILE) return fail(h, SB_EINVAL, "pool too large (max 2^31 particles)");
+    for (int i = 0; i < 2; ++i) {
+        CK(h->w32[i].ensure((size_t)nt * SB_TILE * 4));
+        CK(h->tile_e[i].ensure((size_t)nt * 4));
+        CK(h->tile_Q[i].ensure((size_t)nt * 8));
+    }
+    CK(h->P.ensure((size_t)(nt + 1) * 8));
+    CK(h->child_start.ensure((size_t)(nt + 1) * 4));
+    return SB_OK;
+}
+
+// quantise (device data) into grid buffer `slot`
+int launch_quantise(sb_handle* h, const void* d_data, int kind, int64_t n, int slot) {
+    const int nt = (int)tiles_of(n);
+    uint32_t* w32 = h->w32[slot].as<uint32_t>();
+    int* e = h->tile_e[slot].as<int>();
+    unsigned long long* Q = h->tile_Q[slot].as<unsigned long long>();
+    if (kind == SB_W_LINEAR_F64) k_quantise<0><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, h->d_err);
+    else if (kind == SB_W_LOG_F64) k_quantise<1><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, h->d_err);
+    else if (kind == SB_W_LOG_F32) k_quantise<2><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, h->d_err);
+    else return fail(h, SB_EINVAL, "unknown weight kind");
+    LAUNCH_CHECK();
+    return SB_OK;
+}
+
+int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, unsigned t, unsigned iter, double u_override,
+                    SbStepInfo* info, double* logZ_acc, double* logZ_step) {
+    k_tilescan<<<1, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(),
+                                                     (int)tiles_of(n), n, m, h->opt.seed, t, iter, u_override, info,
+                                                     h->P.as<unsigned long long>(), h->child_start.as<int>(),
+                                                     logZ_acc, logZ_step, h->d_err);
+    LAUNCH_CHECK();
+    return SB_OK;
+}
+
+int launch_pull(sb_handle* h, int slot, const SbStepInfo* info, int64_t m, int* d_anc) {
+    k_pull<<<(unsigned)tiles_of(m), SB_THREADS, 0, h->stream>>>(info, h->w32[slot].as<uint32_t>(), h->tile_e[slot].as<int>(),
+                                                                h->P.as<unsigned long long>(), h->child_start.as<int>(), d_anc);
+    LAUNCH_CHECK();
+    return SB_OK;
+}
+
+// grid multinomial on pool `slot`: CDF + search.  d_r may be nullptr (Philox stream)
+int launch_grid_multinomial(sb_handle* h, int slot, const SbStepInfo* info, int64_t n, int64_t m, const double* d_r,
+                            unsigned t, unsigned iter, int* d_anc) {
+    CK(h->cdf.ensure((size_t)n * 8));
+    k_cdf<<<(unsigned)tiles_of(n), SB_THREADS, 0, h->stream>>>(info, h->w32[slot].as<uint32_t>(), h->tile_e[slot].as<int>(),
+                                                               h->P.as<unsigned long long>(), h->cdf.as<unsigned long long>());
+    LAUNCH_CHECK();
+    k_multinomial_search<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(info, h->cdf.as<unsigned long long>(), d_r,
+                                                                           h->opt.seed, t, iter, d_anc);
+    LAUNCH_CHECK();
+    return SB_OK;
+}
+
+int launch_literal(sb_handle* h, const double* d_w, int64_t n, int64_t m, const double* d_r, unsigned t, unsigned iter,
+                   int* d_anc) {
+    CK(h->lit_acc.ensure((size_t)n * 8));
+    k_literal_cdf<<<1, 256, 0, h->stream>>>(d_w, n, h->lit_acc.as<double>(), h->d_err);
+    LAUNCH_CHECK();
+    k_literal_search<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(h->lit_acc.as<double>(), n, d_r, m, h->opt.seed,
+                                                                       t, iter, d_anc);
+    LAUNCH_CHECK();
+    return SB_OK;
+}
+
+inline size_t kind_bytes(int kind) { return kind == SB_W_LOG_F32 ? 4 : 8; }
+
+int begin_timed(sb_handle* h) {
+    h->launches = 0;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    return SB_OK;
+}
+int end_timed(sb_handle* h) {
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.device_ms = ms;
+    h->stats.kernel_launches = h->launches;
+    return SB_OK;
+}
+
+}  // namespace
+
+// ======================================================================= lifecycle
+extern "C" int32_t sb_version(void) { return SB_VERSION; }
+
+extern "C" void sb_options_default(sb_options* o) {
+    if (!o) return;
+    o->device = 0;
+    o->precision = SB_FP32;
+    o->resample_mode = SB_RESAMPLE_SYSTEMATIC;
+    o->retained_pick = -1;
+    o->store_logw = 0;
+    o->use_graph = 0;
+    o->seed = 1;
+}
+
+static thread_local std::string g_create_err;
+
+extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
+    if (!out) return SB_EINVAL;
+    *out = nullptr;
+    sb_options opt;
+    if (o) opt = *o; else sb_options_default(&opt);
+    if (opt.precision != SB_FP32 && opt.precision != SB_FP64) { g_create_err = "bad precision"; return SB_EINVAL; }
+    if (opt.resample_mode < 0 || opt.resample_mode > 2) { g_create_err = "bad resample_mode"; return SB_EINVAL; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libstochy_b200 has no CPU fallback)";
+        return SB_ECUDA;
+    }
+    if (opt.device < 0 || opt.device >= ndev) { g_create_err = "device ordinal out of range"; return SB_EINVAL; }
+    if ((e = cudaSetDevice(opt.device)) != cudaSuccess) { g_create_err = cudaGetErrorString(e); return SB_ECUDA; }
+    sb_handle* h = new sb_handle();
+    h->opt = opt;
+    memset(&h->stats, 0, sizeof(h->stats));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+        cudaEventCreate(&h->evt0) != cudaSuccess || cudaEventCreate(&h->evt1) != cudaSuccess ||
+        cudaMalloc(&h->d_err, sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(h->d_err, 0, sizeof(unsigned)) != cudaSuccess ||
+        h->d_misc.ensure(64) != cudaSuccess) {
+        g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
+        sb_destroy(h);
+        return SB_ECUDA;
+    }
+    *out = h;
+    return SB_OK;
+}
+
+extern "C" void sb_destroy(sb_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->opt.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->d_logZ, &h->d_info, &h->d_misc, &h->w32[0], &h->w32[1], &h->tile_e[0], &h->tile_e[1],
+                      &h->tile_Q[0], &h->tile_Q[1], &h->P, &h->child_start, &h->cdf, &h->lit_acc, &h->lse_part,
+                      &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
+                      &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
+                      &h->bn_fp, &h->bn_fac, &h->bn_counts, &h->xbuf, &h->ancbuf, &h->lwbuf, &h->wlit, &h->cnt[0],
+                      &h->cnt[1], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint};
+    for (DevBuf* b : bufs) b->release();
+    if (h->d_err) cudaFree(h->d_err);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evt0) cudaEventDestroy(h->evt0);
+    if (h->evt1) cudaEventDestroy(h->evt1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" const char* sb_last_error(const sb_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int32_t sb_get_stats(const sb_handle* h, sb_stats* out) {
+    if (!h || !out) return SB_EINVAL;
+    *out = h->stats;
+    return SB_OK;
+}
+
+extern "C" int32_t sb_sync(sb_handle* h) {
+    if (!h) return SB_EINVAL;
+    CK(cudaSetDevice(h->opt.device));
+    CK(cudaStreamSynchronize(h->stream));
+    return check_err_word(h);
+}
+extern "C" int32_t sb_timer_start(sb_handle* h) {
+    if (!h) return SB_EINVAL;
+    CK(cudaEventRecord(h->evt0, h->stream));
+    return SB_OK;
+}
+extern "C" int32_t sb_timer_stop(sb_handle* h, double* ms) {
+    if (!h || !ms) return SB_EINVAL;
+    CK(cudaEventRecord(h->evt1, h->stream));
+    CK(cudaEventSynchronize(h->evt1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, h->evt0, h->evt1));
+    *ms = f;
+    return SB_OK;
+}
+
+// ======================================================================= models
+extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int32_t x0, const double* pi,
+                                         const double* A, const double* logF, const uint8_t* has_factor) {
+    if (!h) return SB_EINVAL;
+    if (!A || !logF || K < 1 || T < 1) return fail(h, SB_EINVAL, "discrete_hmm: bad arguments");
+    if (K > 64) return fail(h, SB_EUNSUPPORTED, "discrete_hmm: K > 64 is not supported on the GPU path (no CPU fallback)");
+    if (x0 >= K) return fail(h, SB_EINVAL, "discrete_hmm: x0 out of range");
+    if (x0 < 0 && !pi) return fail(h, SB_EINVAL, "discrete_hmm: pi required when x0 < 0");
+    CK(cudaSetDevice(h->opt.device));
+    // sequential running sums, exactly the accumulation of src/rand.jl:3-7
+    std::vector<double> cumA((size_t)K * K), cumpi((size_t)K, 0.0), expF((size_t)T * K);
+    for (int r = 0; r < K; ++r) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double p = A[(size_t)r * K + k];
+            if (!(p >= 0.0)) return fail(h, SB_EINVAL, "discrete_hmm: negative or NaN transition probability");
+            acc += p; cumA[(size_t)r * K + k] = acc;
+        }
+    }
+    if (x0 < 0) { double acc = 0.0; for (int k = 0; k < K; ++k) { acc += pi[k]; cumpi[k] = acc; } }
+    for (size_t i = 0; i < (size_t)T * K; ++i) expF[i] = exp(logF[i]);       // src/pmcmc.jl:55 (literal mode)
+    h->has_factor.assign((size_t)T, 1);
+    if (has_factor) for (int t = 0; t < T; ++t) h->has_factor[t] = has_factor[t] ? 1 : 0;
+    CK(h->hmm_cumA.ensure(cumA.size() * 8));
+    CK(h->hmm_cumpi.ensure(cumpi.size() * 8));
+    CK(h->hmm_logF.ensure((size_t)T * K * 8));
+    CK(h->hmm_expF.ensure((size_t)T * K * 8));
+    CK(h->hmm_hasf.ensure((size_t)T));
+    CK(cudaMemcpyAsync(h->hmm_cumA.p, cumA.data(), cumA.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->hmm_cumpi.p, cumpi.data(), cumpi.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->hmm_logF.p, logF, (size_t)T * K * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->hmm_expF.p, expF.data(), (size_t)T * K * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->hmm_hasf.p, h->has_factor.data(), (size_t)T, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->model = MODEL_HMM; h->K = K; h->T = T; h->x0 = x0;
+    h->have_retained = false;
+    return SB_OK;
+}
+
+extern "C" int32_t sb_model_linear_gaussian(sb_handle* h, int32_t T, double a, double q, double c, double r,
+                                            double m0, double P0, const double* y) {
+    if (!h) return SB_EINVAL;
+    if (!y || T < 1 || !(q > 0) || !(r > 0) || !(P0 > 0)) return fail(h, SB_EINVAL, "linear_gaussian: bad arguments");
+    h->model = MODEL_LG; h->T = T; h->K = 0;
+    h->lg_a = a; h->lg_q = q; h->lg_c = c; h->lg_r = r; h->lg_m0 = m0; h->lg_P0 = P0;
+    h->lg_y.assign(y, y + T);
+    h->have_retained = false;
+    return SB_OK;
+}
+
+extern "C" int32_t sb_model_bayesnet(sb_handle* h, int32_t D, int32_t F, const uint32_t* site_parents,
+                                     const double* site_cpt, const uint32_t* fac_parents, const double* fac_logf,
+                                     int32_t cpt_stride, uint32_t query_mask) {
+    if (!h) return SB_EINVAL;
+    if (D < 1 || D > SB_MH_MAXD || F < 0 || !site_parents || !site_cpt || cpt_stride < 1 || (F > 0 && (!fac_parents || !fac_logf)))
+        return fail(h, SB_EINVAL, "bayesnet: bad arguments (1 <= D <= 16)");
+    if (query_mask == 0 || (query_mask >> D) != 0 || __builtin_popcount(query_mask) > 10)
+        return fail(h, SB_EINVAL, "bayesnet: query_mask must select 1..10 of the D sites");
+    for (int d = 0; d < D; ++d) {
+        if (site_parents[d] >> d) return fail(h, SB_EUNSUPPORTED, "bayesnet: sites must be in topological order (fixed structure)");
+        if ((1 << __builtin_popcount(site_parents[d])) > cpt_stride) return fail(h, SB_EINVAL, "bayesnet: cpt_stride too small");
+    }
+    for (int f = 0; f < F; ++f) {
+        if (fac_parents[f] >> D) return fail(h, SB_EINVAL, "bayesnet: factor parent outside the sites");
+        if ((1 << __builtin_popcount(fac_parents[f])) > cpt_stride) return fail(h, SB_EINVAL, "bayesnet: cpt_stride too small");
+    }
+    CK(cudaSetDevice(h->opt.device));
+    const size_t ns = (size_t)D * cpt_stride, nf = (size_t)(F > 0 ? F : 1) * cpt_stride;
+    std::vector<double> lp1(ns), lp0(ns), fac(nf, 0.0);
+    for (size_t i = 0; i < ns; ++i) { lp1[i] = log(site_cpt[i]); lp0[i] = log(1.0 - site_cpt[i]); }   // logpdf(Bernoulli(p), x)
+    for (size_t i = 0; i < (size_t)F * cpt_stride; ++i) fac[i] = fac_logf[i];
+    std::vector<unsigned> fp((size_t)(F > 0 ? F : 1), 0u);
+    for (int f = 0; f < F; ++f) fp[f] = fac_parents[f];
+    CK(h->bn_sp.ensure((size_t)D * 4)); CK(h->bn_cpt.ensure(ns * 8)); CK(h->bn_lp1.ensure(ns * 8)); CK(h->bn_lp0.ensure(ns * 8));
+    CK(h->bn_fp.ensure(fp.size() * 4)); CK(h->bn_fac.ensure(nf * 8));
+    CK(cudaMemcpyAsync(h->bn_sp.p, site_parents, (size_t)D * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->bn_cpt.p, site_cpt, ns * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->bn_lp1.p, lp1.data(), ns * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->bn_lp0.p, lp0.data(), ns * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->bn_fp.p, fp.data(), fp.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->bn_fac.p, fac.data(), nf * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->model = MODEL_BNET; h->bn_D = D; h->bn_F = F; h->bn_stride = cpt_stride; h->bn_query = query_mask;
+    return SB_OK;
+}
+
+// ======================================================================= sweeps
+namespace {
+
+template <bool FP32>
+int launch_step_hmm(sb_handle* h, int anc_mode, const SbHmmStepArgs& a, unsigned grid) {
+    const size_t smem = (size_t)(a.rows * a.K + a.K) * 8 + (size_t)a.K * 4;
+    switch (anc_mode) {
+        case SB_ANC_NONE:     k_step_hmm<SB_ANC_NONE, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
+        case SB_ANC_PULL:     k_step_hmm<SB_ANC_PULL, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
+        case SB_ANC_EXPLICIT: k_step_hmm<SB_ANC_EXPLICIT, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
+        default:              k_step_hmm<SB_ANC_IDENTITY, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
+    }
+    LAUNCH_CHECK();
+    return SB_OK;
+}
+template <bool FP32>
+int launch_step_lg(sb_handle* h, int anc_mode, const SbLgStepArgs& a, unsigned grid) {
+    switch (anc_mode) {
+        case SB_ANC_NONE:     k_step_lg<SB_ANC_NONE, FP32><<<grid, SB_THREADS, 0, h->stream>>>(a); break;
+        case SB_ANC_PULL:     k_step_lg<SB_ANC_PULL, FP32><<<grid, SB_THREADS, 0, h->stream>>>(a); break;
+        default:              k_step_lg<SB_ANC_EXPLICIT, FP32><<<grid, SB_THREADS, 0, h->stream>>>(a); break;
+    }
+    LAUNCH_CHECK();
+    return SB_OK;
+}
+
+// resample pool `slot` of step t explicitly (multinomial / literal modes) into d_anc
+int explicit_resample(sb_handle* h, int slot, int t, unsigned iter, int64_t n_pool, int64_t N, int* d_anc) {
+    SbStepInfo* info = h->d_info.as<SbStepInfo>() + t;
+    if (h->opt.resample_mode == SB_RESAMPLE_MULTINOMIAL)
+        return launch_grid_multinomial(h, slot, info, n_pool, N, nullptr, (unsigned)t, iter, d_anc);
+    return launch_literal(h, h->wlit.as<double>(), n_pool, N, nullptr, (unsigned)t, iter, d_anc);
+}
+
+// One sweep of the discrete model.  conditional: pool of N+1 with the retained particle appended.
+int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool history, bool final_anc) {
+    const int T = h->T, K = h->K;
+    const int64_t S = tiles_of(N + 1) * SB_TILE;                       // row stride (slot N = retained)
+    const int n_out = (int)(N + (conditional ? 1 : 0));
+    const bool fp32 = h->opt.precision == SB_FP32;
+    const int mode = h->opt.resample_mode;
+    const bool literal = mode == SB_RESAMPLE_LITERAL;
+    int rc;
+    if ((rc = ensure_grid(h, N + 1, N)) != SB_OK) return rc;
+    const int xrows = history ? T : 2;
+    const int arows = history ? T : 1;
+    CK(h->xbuf.ensure((size_t)xrows * S * 4));
+    CK(h->ancbuf.ensure((size_t)arows * S * 4));
+    CK(h->d_info.ensure(sizeof(SbStepInfo) * (size_t)T));
+    CK(h->d_logZ.ensure(sizeof(double) * (size_t)(T + 1)));
+    if (h->opt.store_logw) CK(h->lwbuf.ensure((size_t)T * S * 8));
+    if (literal) CK(h->wlit.ensure((size_t)S * 8));
+    CK(cudaMemsetAsync(h->d_logZ.p, 0, sizeof(double) * (size_t)(T + 1), h->stream));
+    h->sw_N = N; h->sw_S = S; h->sw_hist = history ? 1 : 0; h->sw_cond = conditional ? 1 : 0;
+    int* xb = h->xbuf.as<int>();
+    int* ab = h->ancbuf.as<int>();
+    const unsigned grid = (unsigned)tiles_of(n_out);
+    for (int t = 0; t < T; ++t) {
+        const int cur = t & 1, prev = cur ^ 1;
+        int anc_mode = SB_ANC_NONE;
+        int* anc_row_prev = t ? ab + (size_t)(history ? (t - 1) : 0) * S : nullptr;
+        if (t > 0) {
+            if (!h->has_factor[t - 1]) anc_mode = SB_ANC_IDENTITY;
+            else if (mode == SB_RESAMPLE_SYSTEMATIC) anc_mode = SB_ANC_PULL;
+            else {
+                anc_mode = SB_ANC_EXPLICIT;
+                const int64_t n_pool = N + (conditional ? 1 : 0);
+                if ((rc = explicit_resample(h, prev, t - 1, iter, n_pool, N, anc_row_prev)) != SB_OK) return rc;
+            }
+        }
+        SbHmmStepArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x_prev = t ? xb + (size_t)(history ? (t - 1) : prev) * S : nullptr;
+        a.w32_prev = h->w32[prev].as<uint32_t>();
+        a.e_prev = h->tile_e[prev].as<int>();
+        a.P = h->P.as<unsigned long long>();
+        a.child_start = h->child_start.as<int>();
+        a.info_prev = t ? h->d_info.as<SbStepInfo>() + (t - 1) : nullptr;
+        a.anc_in = anc_row_prev;
+        a.anc_out = (history && t) ? anc_row_prev : nullptr;
+        a.x_out = xb + (size_t)(history ? t : cur) * S;
+        a.w32_out = h->w32[cur].as<uint32_t>();
+        a.e_out = h->tile_e[cur].as<int>();
+        a.Q_out = h->tile_Q[cur].as<unsigned long long>();
+        a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
+        a.wlit_out = literal ? h->wlit.as<double>() : nullptr;
+        if (t == 0) { a.cum = h->x0 >= 0 ? h->hmm_cumA.as<double>() + (size_t)h->x0 * K : h->hmm_cumpi.as<double>(); a.rows = 1; }
+        else        { a.cum = h->hmm_cumA.as<double>(); a.rows = K; }
+        a.logF_t = h->hmm_logF.as<double>() + (size_t)t * K;
+        a.expF_t = h->hmm_expF.as<double>() + (size_t)t * K;
+        a.xstar = conditional ? h->xstar[h->xstar_cur].as<int>() : nullptr;
+        a.N = N; a.n_out = n_out; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.err = h->d_err;
+        rc = fp32 ? launch_step_hmm<true>(h, anc_mode, a, grid) : launch_step_hmm<false>(h, anc_mode, a, grid);
+        if (rc != SB_OK) return rc;
+        if (h->has_factor[t]) {
+            // literal mode still runs the tile scan: it supplies the log-evidence term
+            if ((rc = launch_tilescan(h, cur, n_out, N, (unsigned)t, iter, -1.0, h->d_info.as<SbStepInfo>() + t,
+                                      h->d_logZ.as<double>(), h->d_logZ.as<double>() + 1)) != SB_OK) return rc;
+        }
+    }
+    if (final_anc) {
+        const int t = T - 1, cur = t & 1;
+        int* row = ab + (size_t)(history ? t : 0) * S;
+        if (!h->has_factor[t]) {
+            k_fill_identity<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(row, N);
+            LAUNCH_CHECK();
+        } else if (mode == SB_RESAMPLE_SYSTEMATIC) {
+            if ((rc = launch_pull(h, cur, h->d_info.as<SbStepInfo>() + t, N, row)) != SB_OK) return rc;
+        } else {
+            if ((rc = explicit_resample(h, cur, t, iter, n_out, N, row)) != SB_OK) return rc;
+        }
+    }
+    return SB_OK;
+}
+
+int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
+    const int T = h->T;
+    const bool fp32 = h->opt.precision == SB_FP32;
+    const size_t sz = fp32 ? 4 : 8;
+    const int64_t S = tiles_of(N) * SB_TILE;
+    const int mode = h->opt.resample_mode;
+    if (mode == SB_RESAMPLE_LITERAL)
+        return fail(h, SB_EUNSUPPORTED, "literal resampling is a parity mode of the discrete model only");
+    int rc;
+    if ((rc = ensure_grid(h, N, N)) != SB_OK) return rc;
+    CK(h->xbuf.ensure((size_t)2 * S * sz));
+    CK(h->ancbuf.ensure((size_t)S * 4));
+    CK(h->d_info.ensure(sizeof(SbStepInfo) * (size_t)T));
+    CK(h->d_logZ.ensure(sizeof(double) * (size_t)(T + 1)));
+    if (h->opt.store_logw) CK(h->lwbuf.ensure((size_t)T * S * 8));
+    CK(cudaMemsetAsync(h->d_logZ.p, 0, sizeof(double) * (size_t)(T + 1), h->stream));
+    h->sw_N = N; h->sw_S = S; h->sw_hist = 0; h->sw_cond = 0;
+    char* xb = h->xbuf.as<char>();
+    const unsigned grid = (unsigned)tiles_of(N);
+    for (int t = 0; t < T; ++t) {
+        const int cur = t & 1, prev = cur ^ 1;
+        int anc_mode = t ? (mode == SB_RESAMPLE_SYSTEMATIC ? SB_ANC_PULL : SB_ANC_EXPLICIT) : SB_ANC_NONE;
+        if (anc_mode == SB_ANC_EXPLICIT)
+            if ((rc = explicit_resample(h, prev, t - 1, iter, N, N, h->ancbuf.as<int>())) != SB_OK) return rc;
+        SbLgStepArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x_prev = xb + (size_t)prev * S * sz;
+        a.w32_prev = h->w32[prev].as<uint32_t>();
+        a.e_prev = h->tile_e[prev].as<int>();
+        a.P = h->P.as<unsigned long long>();
+        a.child_start = h->child_start.as<int>();
+        a.info_prev = t ? h->d_info.as<SbStepInfo>() + (t - 1) : nullptr;
+        a.anc_in = h->ancbuf.as<int>();
+        a.anc_out = nullptr;
+        a.x_out = xb + (size_t)cur * S * sz;
+        a.w32_out = h->w32[cur].as<uint32_t>();
+        a.e_out = h->tile_e[cur].as<int>();
+        a.Q_out = h->tile_Q[cur].as<unsigned long long>();
+        a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
+        a.N = N; a.t = t; a.iter = iter; a.seed = h->opt.seed;
+        a.a = h->lg_a; a.sq = sqrt(h->lg_q); a.sp = sqrt(h->lg_P0); a.c = h->lg_c; a.r = h->lg_r; a.m0 = h->lg_m0;
+        a.y = h->lg_y[t]; a.lc = -0.5 * log(SB_TWO_PI * h->lg_r);
+        a.err = h->d_err;
+        rc = fp32 ? launch_step_lg<true>(h, anc_mode, a, grid) : launch_step_lg<false>(h, anc_mode, a, grid);
+        if (rc != SB_OK) return rc;
+        if ((rc = launch_tilescan(h, cur, N, N, (unsigned)t, iter, -1.0, h->d_info.as<SbStepInfo>() + t,
+                                  h->d_logZ.as<double>(), h->d_logZ.as<double>() + 1)) != SB_OK) return rc;
+    }
+    return SB_OK;
+}
+
+int fetch_logZ(sb_handle* h, double* out) {
+    double v = 0.0;
+    CK(cudaMemcpyAsync(&v, h->d_logZ.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *out = v;
+    return SB_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t sb_smc_sweep(sb_handle* h, int64_t N, uint32_t iter, int32_t store_history, double* out_logZ) {
+    if (!h) return SB_EINVAL;
+    if (N < 1) return fail(h, SB_EINVAL, "smc: N must be >= 1");
+    if (h->model != MODEL_HMM && h->model != MODEL_LG)
+        return fail(h, SB_EUNSUPPORTED, "smc: no fixed-structure state-space model is loaded (no CPU fallback)");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    if (h->model == MODEL_HMM) rc = sweep_hmm(h, N, iter, false, store_history != 0, store_history != 0);
+    else rc = sweep_lg(h, N, iter);
+    if (rc != SB_OK) return rc;
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    h->stats.particle_steps = N * (int64_t)h->T;
+    double lz = 0.0;
+    if ((rc = fetch_logZ(h, &lz)) != SB_OK) return rc;
+    h->stats.logZ_first = h->stats.logZ_last = lz;
+    if (out_logZ) *out_logZ = lz;
+    return check_err_word(h);
+}
+
+extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t* marg, int64_t* joint) {
+    if (!h) return SB_EINVAL;
+    if (h->model != MODEL_HMM)
+        return fail(h, SB_EUNSUPPORTED, "pmcmc: only the fixed-structure discrete model is supported (no CPU fallback)");
+    if (iters < 1 || N < 1) return fail(h, SB_EINVAL, "pmcmc: numiterations and numparticles must be >= 1");
+    CK(cudaSetDevice(h->opt.device));
+    const int T = h->T, K = h->K;
+    int64_t njoint = 0;
+    if (joint) {
+        double lg = T * log2((double)K);
+        if (lg > 26.0) return fail(h, SB_EUNSUPPORTED, "pmcmc: joint histogram needs K^T <= 2^26; pass joint = NULL");
+        njoint = 1; for (int t = 0; t < T; ++t) njoint *= K;
+    }
+    const int64_t S = tiles_of(N + 1) * SB_TILE;
+    CK(h->xstar[0].ensure((size_t)T * 4)); CK(h->xstar[1].ensure((size_t)T * 4));
+    CK(h->cnt[0].ensure((size_t)S * 4)); CK(h->cnt[1].ensure((size_t)S * 4));
+    CK(h->marg.ensure((size_t)T * K * 8));
+    CK(cudaMemsetAsync(h->marg.p, 0, (size_t)T * K * 8, h->stream));
+    if (joint) { CK(h->joint.ensure((size_t)njoint * 8)); CK(cudaMemsetAsync(h->joint.p, 0, (size_t)njoint * 8, h->stream)); }
+    int pick = h->opt.retained_pick;
+    if (pick < 0) pick = h->opt.resample_mode == SB_RESAMPLE_SYSTEMATIC ? 1 : 0;
+    int rc;
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    int* lineage = h->d_misc.as<int>();
+    for (int64_t it = 0; it < iters; ++it) {
+        if ((rc = sweep_hmm(h, N, (unsigned)it, it > 0, true, true)) != SB_OK) return rc;
+        const int n_pool = (int)(N + (it > 0 ? 1 : 0));
+        int* xb = h->xbuf.as<int>();
+        int* ab = h->ancbuf.as<int>();
+        // src/pmcmc.jl:89 -- the next retained particle
+        k_lineage_start<<<1, 1, 0, h->stream>>>(ab + (size_t)(T - 1) * S, N, pick, h->opt.seed, (unsigned)T, (unsigned)it, lineage);
+        LAUNCH_CHECK();
+        // src/pmcmc.jl:90-92 -- count every particle's value
+        int* cnt_t = h->cnt[(T - 1) & 1].as<int>();
+        CK(cudaMemsetAsync(cnt_t, 0, (size_t)S * 4, h->stream));
+        k_count_final<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(ab + (size_t)(T - 1) * S, N, cnt_t);
+        LAUNCH_CHECK();
+        int* xs_next = h->xstar[h->xstar_cur ^ 1].as<int>();
+        for (int t = T - 1; t >= 0; --t) {
+            int* c_t = h->cnt[t & 1].as<int>();
+            int* c_p = t ? h->cnt[(t - 1) & 1].as<int>() : nullptr;
+            if (c_p) CK(cudaMemsetAsync(c_p, 0, (size_t)S * 4, h->stream));
+            k_count_back<<<(unsigned)((n_pool + 255) / 256), 256, (size_t)K * 4, h->stream>>>(
+                xb + (size_t)t * S, c_t, t ? ab + (size_t)(t - 1) * S : nullptr, t ? !h->has_factor[t - 1] : 0,
+                n_pool, N, K, t, c_p, h->marg.as<unsigned long long>(), lineage, xs_next);
+            LAUNCH_CHECK();
+        }
+        if (joint) {
+            k_joint_hist<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(xb, ab, h->hmm_hasf.as<unsigned char>(), S, N, K, T,
+                                                                            h->joint.as<unsigned long long>());
+            LAUNCH_CHECK();
+        }
+        h->xstar_cur ^= 1;
+        h->have_retained = true;
+        if (it == 0) {
+            double lz;
+            if ((rc = fetch_logZ(h, &lz)) != SB_OK) return rc;
+            h->stats.logZ_first = lz;
+            if ((rc = check_err_word(h)) != SB_OK) return rc;
+        }
+    }
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    h->stats.particle_steps = iters * N * (int64_t)T;
+    double lz;
+    if ((rc = fetch_logZ(h, &lz)) != SB_OK) return rc;
+    h->stats.logZ_last = lz;
+    if ((rc = check_err_word(h)) != SB_OK) return rc;
+    if (marg) {
+        std::vector<unsigned long long> tmp((size_t)T * K);
+        CK(cudaMemcpy(tmp.data(), h->marg.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) marg[i] += (int64_t)tmp[i];
+    }
+    if (joint) {
+        std::vector<unsigned long long> tmp((size_t)njoint);
+        CK(cudaMemcpy(tmp.data(), h->joint.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) joint[i] += (int64_t)tmp[i];
+    }
+    return SB_OK;
+}
+
+extern "C" int32_t sb_mh_run(sb_handle* h, int64_t chains, int64_t steps, int64_t chain0, int64_t* counts) {
+    if (!h) return SB_EINVAL;
+    if (h->model != MODEL_BNET)
+        return fail(h, SB_EUNSUPPORTED, "mh: only fixed-structure binary Bayes nets are supported (no CPU fallback)");
+    if (chains < 1 || steps < 0 || !counts) return fail(h, SB_EINVAL, "mh: bad arguments");
+    CK(cudaSetDevice(h->opt.device));
+    const int nv = 1 << __builtin_popcount(h->bn_query);
+    CK(h->bn_counts.ensure((size_t)(nv + 1) * 8));
+    CK(cudaMemsetAsync(h->bn_counts.p, 0, (size_t)(nv + 1) * 8, h->stream));
+    SbBnetArgs a;
+    a.D = h->bn_D; a.F = h->bn_F; a.stride = h->bn_stride; a.query_mask = h->bn_query;
+    a.site_parents = h->bn_sp.as<unsigned>(); a.site_cpt = h->bn_cpt.as<double>();
+    a.site_lp1 = h->bn_lp1.as<double>(); a.site_lp0 = h->bn_lp0.as<double>();
+    a.fac_parents = h->bn_fp.as<unsigned>(); a.fac_logf = h->bn_fac.as<double>();
+    a.seed = h->opt.seed; a.chains = chains; a.steps = steps; a.chain0 = chain0;
+    a.counts = h->bn_counts.as<unsigned long long>(); a.accepts = a.counts + nv;
+    const int threads = 128;
+    const size_t smem = (size_t)(3 * a.D + a.F) * a.stride * 8 + (size_t)(a.D + a.F) * 4 + (size_t)(threads / 32) * nv * 4;
+    int rc;
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    k_mh_bnet<<<(unsigned)((chains + threads - 1) / threads), threads, smem, h->stream>>>(a);
+    LAUNCH_CHECK();
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    std::vector<unsigned long long> tmp((size_t)nv + 1);
+    CK(cudaMemcpy(tmp.data(), h->bn_counts.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+    for (int v = 0; v < nv; ++v) counts[v] += (int64_t)tmp[v];
+    h->stats.accepts = (int64_t)tmp[nv];
+    h->stats.particle_steps = chains * steps;
+    return SB_OK;
+}
+
+// ======================================================================= hooks
+namespace {
+int stage_in(sb_handle* h, DevBuf& b, const void* src, size_t bytes) {
+    CK(b.ensure(bytes));
+    CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return SB_OK;
+}
+}  // namespace
+
+extern "C" int32_t sb_dev_resample_systematic(sb_handle* h, const void* d_weights, int32_t kind, int64_t n,
+                                              double u, int64_t m, int32_t* d_anc) {
+    if (!h) return SB_EINVAL;
+    if (!d_weights || !d_anc || n < 1 || m < 1 || !(u >= 0.0 && u < 1.0)) return fail(h, SB_EINVAL, "resample_systematic: bad arguments");
+    int rc;
+    if ((rc = ensure_grid(h, n, m)) != SB_OK) return rc;
+    CK(h->d_info.ensure(sizeof(SbStepInfo)));
+    if ((rc = launch_quantise(h, d_weights, kind, n, 0)) != SB_OK) return rc;
+    if ((rc = launch_tilescan(h, 0, n, m, 0, 0, u, h->d_info.as<SbStepInfo>(), nullptr, nullptr)) != SB_OK) return rc;
+    return launch_pull(h, 0, h->d_info.as<SbStepInfo>(), m, d_anc);
+}
+
+extern "C" int32_t sb_resample_systematic(sb_handle* h, const void* weights, int32_t kind, int64_t n,
+                                          double u, int64_t m, int32_t* anc_out) {
+    if (!h) return SB_EINVAL;
+    if (!weights || !anc_out || n < 1 || m < 1) return fail(h, SB_EINVAL, "resample_systematic: bad arguments");
+    if (kind < 0 || kind > 2) return fail(h, SB_EINVAL, "unknown weight kind");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    if ((rc = stage_in(h, h->hk_in, weights, (size_t)n * kind_bytes(kind))) != SB_OK) return rc;
+    CK(h->hk_anc.ensure((size_t)tiles_of(m) * SB_TILE * 4));
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    if ((rc = sb_dev_resample_systematic(h, h->hk_in.p, kind, n, u, m, h->hk_anc.as<int>())) != SB_OK) return rc;
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    if ((rc = check_err_word(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(anc_out, h->hk_anc.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+extern "C" int32_t sb_resample_multinomial(sb_handle* h, const void* weights, int32_t kind, int64_t n,
+                                           const double* r, int64_t m, int32_t* anc_out) {
+    if (!h) return SB_EINVAL;
+    if (!weights || !anc_out || !r || n < 1 || m < 1) return fail(h, SB_EINVAL, "resample_multinomial: bad arguments");
+    if (kind < 0 || kind > 2) return fail(h, SB_EINVAL, "unknown weight kind");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    if ((rc = stage_in(h, h->hk_in, weights, (size_t)n * kind_bytes(kind))) != SB_OK) return rc;
+    if ((rc = stage_in(h, h->hk_r, r, (size_t)m * 8)) != SB_OK) return rc;
+    CK(h->hk_anc.ensure((size_t)m * 4));
+    if ((rc = ensure_grid(h, n, m)) != SB_OK) return rc;
+    CK(h->d_info.ensure(sizeof(SbStepInfo)));
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    if ((rc = launch_quantise(h, h->hk_in.p, kind, n, 0)) != SB_OK) return rc;
+    if ((rc = launch_tilescan(h, 0, n, m, 0, 0, 0.0, h->d_info.as<SbStepInfo>(), nullptr, nullptr)) != SB_OK) return rc;
+    if ((rc = launch_grid_multinomial(h, 0, h->d_info.as<SbStepInfo>(), n, m, h->hk_r.as<double>(), 0, 0, h->hk_anc.as<int>())) != SB_OK) return rc;
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    if ((rc = check_err_word(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(anc_out, h->hk_anc.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+extern "C" int32_t sb_resample_literal(sb_handle* h, const double* w, int64_t n, const double* r, int64_t m,
+                                       int32_t* anc_out) {
+    if (!h) return SB_EINVAL;
+    if (!w || !anc_out || !r || n < 1 || m < 1) return fail(h, SB_EINVAL, "resample_literal: bad arguments");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    if ((rc = stage_in(h, h->hk_in, w, (size_t)n * 8)) != SB_OK) return rc;
+    if ((rc = stage_in(h, h->hk_r, r, (size_t)m * 8)) != SB_OK) return rc;
+    CK(h->hk_anc.ensure((size_t)m * 4));
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    if ((rc = launch_literal(h, h->hk_in.as<double>(), n, m, h->hk_r.as<double>(), 0, 0, h->hk_anc.as<int>())) != SB_OK) return rc;
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    if ((rc = check_err_word(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(anc_out, h->hk_anc.p, (size_t)m * 4, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+extern "C" int32_t sb_logsumexp(sb_handle* h, const void* lw, int32_t kind, int64_t n, double* out) {
+    if (!h) return SB_EINVAL;
+    if (!lw || !out || n < 1 || (kind != SB_W_LOG_F64 && kind != SB_W_LOG_F32)) return fail(h, SB_EINVAL, "logsumexp: bad arguments");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    if ((rc = stage_in(h, h->hk_in, lw, (size_t)n * kind_bytes(kind))) != SB_OK) return rc;
+    int np = (int)((n + 8191) / 8192);
+    if (np > 1184) np = 1184;                       // 148 SMs x 8 CTAs
+    CK(h->lse_part.ensure((size_t)np * sizeof(SbLse) + 8));
+    SbLse* part = h->lse_part.as<SbLse>();
+    double* d_out = reinterpret_cast<double*>(part + np);
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    if (kind == SB_W_LOG_F64) k_lse_partial<double><<<np, 256, 0, h->stream>>>(h->hk_in.as<double>(), n, part, h->d_err);
+    else k_lse_partial<float><<<np, 256, 0, h->stream>>>(h->hk_in.as<float>(), n, part, h->d_err);
+    LAUNCH_CHECK();
+    k_lse_final<<<1, 256, 0, h->stream>>>(part, np, d_out);
+    LAUNCH_CHECK();
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    if ((rc = check_err_word(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(out, d_out, 8, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+extern "C" int32_t sb_dev_gather(sb_handle* h, const void* d_src, int32_t elem_bytes, int64_t n,
+                                 const int32_t* d_anc, int64_t m, void* d_dst) {
+    if (!h) return SB_EINVAL;
+    if (!d_src || !d_anc || !d_dst || n < 1 || m < 1) return fail(h, SB_EINVAL, "gather: bad arguments");
+    const unsigned grid = (unsigned)((m + 1023) / 1024);
+    if (elem_bytes == 4) k_gather<uint32_t><<<grid, 256, 0, h->stream>>>((const uint32_t*)d_src, d_anc, m, (uint32_t*)d_dst);
+    else if (elem_bytes == 8) k_gather<unsigned long long><<<grid, 256, 0, h->stream>>>((const unsigned long long*)d_src, d_anc, m, (unsigned long long*)d_dst);
+    else return fail(h, SB_EINVAL, "gather: elem_bytes must be 4 or 8");
+    LAUNCH_CHECK();
+    return SB_OK;
+}
+
+extern "C" int32_t sb_gather(sb_handle* h, const void* src, int32_t elem_bytes, int64_t n, const int32_t* anc,
+                             int64_t m, void* dst) {
+    if (!h) return SB_EINVAL;
+    if (!src || !anc || !dst || n < 1 || m < 1 || (elem_bytes != 4 && elem_bytes != 8)) return fail(h, SB_EINVAL, "gather: bad arguments");
+    for (int64_t i = 0; i < m; ++i) if (anc[i] < 0 || anc[i] >= n) return fail(h, SB_EINVAL, "gather: ancestor index out of range");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    if ((rc = stage_in(h, h->hk_src, src, (size_t)n * elem_bytes)) != SB_OK) return rc;
+    if ((rc = stage_in(h, h->hk_anc, anc, (size_t)m * 4)) != SB_OK) return rc;
+    CK(h->hk_out.ensure((size_t)m * elem_bytes));
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    if ((rc = sb_dev_gather(h, h->hk_src.p, elem_bytes, n, h->hk_anc.as<int>(), m, h->hk_out.p)) != SB_OK) return rc;
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(dst, h->hk_out.p, (size_t)m * elem_bytes, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+// ======================================================================= ERP hooks
+extern "C" int32_t sb_erp_sample(sb_handle* h, int32_t erp, const double* params, int64_t n, uint64_t seed, double* out) {
+    if (!h) return SB_EINVAL;
+    if (!params || !out || n < 1 || erp < 0 || erp > 5) return fail(h, SB_EINVAL, "erp_sample: bad arguments");
+    CK(cudaSetDevice(h->opt.device));
+    CK(h->hk_out.ensure((size_t)n * 8));
+    int rc;
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    k_erp_sample<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(erp, params[0], erp == SB_ERP_FLIP || erp == SB_ERP_RANDOMINTEGER ? 0.0 : params[1], n, seed, h->hk_out.as<double>());
+    LAUNCH_CHECK();
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(out, h->hk_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+extern "C" int32_t sb_erp_logpdf(sb_handle* h, int32_t erp, const double* params, const double* x, int64_t n, double* out) {
+    if (!h) return SB_EINVAL;
+    if (!params || !x || !out || n < 1 || erp < 0 || erp > 5) return fail(h, SB_EINVAL, "erp_logpdf: bad arguments");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    if ((rc = stage_in(h, h->hk_in, x, (size_t)n * 8)) != SB_OK) return rc;
+    CK(h->hk_out.ensure((size_t)n * 8));
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    k_erp_logpdf<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(erp, params[0], erp == SB_ERP_FLIP || erp == SB_ERP_RANDOMINTEGER ? 0.0 : params[1], h->hk_in.as<double>(), n, h->hk_out.as<double>());
+    LAUNCH_CHECK();
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(out, h->hk_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+extern "C" int32_t sb_erp_sample_dirichlet(sb_handle* h, const double* alpha, int32_t k, int64_t n, uint64_t seed, double* out) {
+    if (!h) return SB_EINVAL;
+    if (!alpha || !out || n < 1 || k < 1 || k > SB_DIR_MAXK) return fail(h, SB_EINVAL, "dirichlet: bad arguments (k <= 32)");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    if ((rc = stage_in(h, h->hk_in, alpha, (size_t)k * 8)) != SB_OK) return rc;
+    CK(h->hk_out.ensure((size_t)n * k * 8));
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    k_dirichlet_sample<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->hk_in.as<double>(), k, n, seed, h->hk_out.as<double>());
+    LAUNCH_CHECK();
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(out, h->hk_out.p, (size_t)n * k * 8, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+extern "C" int32_t sb_erp_logpdf_dirichlet(sb_handle* h, const double* alpha, int32_t k, const double* x, int64_t n, double* out) {
+    if (!h) return SB_EINVAL;
+    if (!alpha || !x || !out || n < 1 || k < 1 || k > SB_DIR_MAXK) return fail(h, SB_EINVAL, "dirichlet: bad arguments (k <= 32)");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    if ((rc = stage_in(h, h->hk_in, alpha, (size_t)k * 8)) != SB_OK) return rc;
+    if ((rc = stage_in(h, h->hk_src, x, (size_t)n * k * 8)) != SB_OK) return rc;
+    CK(h->hk_out.ensure((size_t)n * 8));
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    k_dirichlet_logpdf<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->hk_in.as<double>(), k, h->hk_src.as<double>(), n, h->hk_out.as<double>());
+    LAUNCH_CHECK();
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(out, h->hk_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+// ======================================================================= state access
+extern "C" int32_t sb_get_history(sb_handle* h, int32_t t, int64_t count, void* x_out, int32_t* anc_out, double* lw_out) {
+    if (!h) return SB_EINVAL;
+    if (h->sw_N == 0 || t < 0 || t >= h->T || count < 1 || count > h->sw_S) return fail(h, SB_EINVAL, "get_history: no sweep / bad index");
+    CK(cudaSetDevice(h->opt.device));
+    CK(cudaStreamSynchronize(h->stream));
+    const int64_t S = h->sw_S;
+    if (x_out) {
+        if (h->model != MODEL_HMM || !h->sw_hist) return fail(h, SB_EINVAL, "get_history: state history was not kept");
+        CK(cudaMemcpy(x_out, h->xbuf.as<int>() + (size_t)t * S, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    }
+    if (anc_out) {
+        if (h->model != MODEL_HMM || !h->sw_hist) return fail(h, SB_EINVAL, "get_history: ancestor history was not kept");
+        CK(cudaMemcpy(anc_out, h->ancbuf.as<int>() + (size_t)t * S, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    }
+    if (lw_out) {
+        if (!h->opt.store_logw) return fail(h, SB_EINVAL, "get_history: store_logw was off");
+        CK(cudaMemcpy(lw_out, h->lwbuf.as<double>() + (size_t)t * S, (size_t)count * 8, cudaMemcpyDeviceToHost));
+    }
+    return SB_OK;
+}
+
+extern "C" int32_t sb_get_retained(sb_handle* h, int32_t* xstar_out) {
+    if (!h) return SB_EINVAL;
+    if (!xstar_out || !h->have_retained) return fail(h, SB_EINVAL, "get_retained: no retained particle");
+    CK(cudaSetDevice(h->opt.device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(xstar_out, h->xstar[h->xstar_cur].p, (size_t)h->T * 4, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+
+extern "C" int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out) {
+    if (!h) return SB_EINVAL;
+    if (!x_out || h->sw_N == 0 || count < 1 || count > h->sw_N) return fail(h, SB_EINVAL, "get_particles: no sweep / bad count");
+    CK(cudaSetDevice(h->opt.device));
+    CK(cudaStreamSynchronize(h->stream));
+    const int t = h->T - 1;
+    if (h->model == MODEL_HMM) {
+        const int row = h->sw_hist ? t : (t & 1);
+        CK(cudaMemcpy(x_out, h->xbuf.as<int>() + (size_t)row * h->sw_S, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    } else {
+        const size_t sz = h->opt.precision == SB_FP32 ? 4 : 8;
+        std::vector<char> tmp((size_t)count * sz);
+        CK(cudaMemcpy(tmp.data(), h->xbuf.as<char>() + (size_t)(t & 1) * h->sw_S * sz, tmp.size(), cudaMemcpyDeviceToHost));
+        double* o = (double*)x_out;
+        if (sz == 4) for (int64_t i = 0; i < count; ++i) o[i] = (double)((float*)tmp.data())[i];
+        else memcpy(o, tmp.data(), tmp.size());
+    }
+    return SB_OK;
+}
+
+// ======================================================================= multi-GPU (see sb_dist.cu)
+extern "C" int32_t sb_dist_unique_id(uint8_t out_id[128]) { (void)out_id; return SB_EUNSUPPORTED; }
+extern "C" int32_t sb_dist_init(sb_handle* h, int32_t, int32_t, const uint8_t*) { return fail(h, SB_EUNSUPPORTED, "multi-GPU path not built yet"); }
+extern "C" int32_t sb_dist_ipc_export(sb_handle* h, int64_t, uint8_t*) { return fail(h, SB_EUNSUPPORTED, "multi-GPU path not built yet"); }
+extern "C" int32_t sb_dist_ipc_import(sb_handle* h, const uint8_t*) { return fail(h, SB_EUNSUPPORTED, "multi-GPU path not built yet"); }

@@ -1,0 +1,94 @@
+"""CPU-side checks of the drop-in boundary: the shared library builds, loads without a GPU, exports
+every symbol include/stochy_b200.h declares, and refuses to compute without a CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sb():
+    import stochy_jl_b200 as sb
+    sb.build()
+    return sb
+
+
+def test_header_symbols_exported(sb):
+    hdr = open(os.path.join(ROOT, "include", "stochy_b200.h")).read()
+    declared = set(re.findall(r"\b(sb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"sb_handle"}
+    L = C.CDLL(sb._native.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(sb._native.EXPORTS) <= declared
+
+
+def test_version_and_defaults(sb):
+    L = sb.lib()
+    assert L.sb_version() == 100
+    o = sb._native.Options()
+    L.sb_options_default(C.byref(o))
+    assert (o.precision, o.resample_mode, o.retained_pick, o.seed) == (sb._native.FP32, sb._native.SYSTEMATIC, -1, 1)
+
+
+def test_no_cpu_fallback(sb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(sb.StochyError) as e:
+        sb.Engine()
+    assert e.value.code == sb._native.ECUDA
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(sb.StochyError):
+        sb.pmcmc(sb.hmm2_example(), 5, 5)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "stochy.jl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "stochy_oracle" not in txt, f
+
+
+def test_host_api_rejects_general_programs(sb):
+    # a closure (general CPS program) is not a fixed-structure descriptor
+    import torch
+    if torch.cuda.is_available():
+        with pytest.raises(sb.StochyError) as e:
+            sb.pmcmc(lambda: None, 1, 1)
+        assert e.value.code == sb._native.EUNSUPPORTED
+
+
+def test_discrete_result_type(sb):
+    # test/erptests.jl:1-10
+    import math
+    hist = {0: 2, 1: 3, 2: 5}
+    erp = sb.Discrete(hist)
+    assert sorted(sb.support(erp)) == [0, 1, 2]
+    for x in range(3):
+        assert sb.score(erp, x) == pytest.approx(math.log(hist[x] / 10))
+    with pytest.raises(sb.StochyError) as e:
+        sb.Discrete({1: 0})
+    assert "zero probability mass" in str(e.value)
+
+
+def test_hmm_example_descriptor_matches_enumerate(sb, enumref):
+    # the augmented-state table form of examples/hmm.jl has the same exact posterior (SURVEY §4 goldens)
+    m = sb.hmm_example(3)
+    Z, joint = enumref.hmm_enumerate_joint(m.A, m.logF, x0=m.x0, has_factor=m.has_factor)
+    assert Z == pytest.approx(0.12916, abs=1e-12)
+    post = {}
+    for code, p in enumerate(joint):
+        if p > 0:
+            xs = tuple((code // 4 ** t) % 4 for t in range(3))
+            v = m.value(xs)
+            post[v] = post.get(v, 0.0) + p
+    F, T = False, True
+    assert post[(F, F, F)] == pytest.approx(0.8296918550634872, rel=1e-12)
+    assert post[(T, F, F)] == pytest.approx(0.09218798389594302, rel=1e-12)
+    assert post[(T, T, T)] == pytest.approx(0.0026556209352740765, rel=1e-12)

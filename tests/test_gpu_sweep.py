@@ -1,0 +1,271 @@
+"""GPU parity of the full SMC sweep / PMCMC / MH against the CPU oracle on the same Philox stream
+(bit-exact for the discrete model), and against Enumerate / forward algorithm / Kalman closed forms."""
+import numpy as np
+import pytest
+
+from gpu_util import cfg2_tables, cfg3_tables, cfg4_data, cfg5_bnet, need_gpu
+
+pytestmark = pytest.mark.gpu
+
+MODES = {"systematic": 0, "multinomial": 1, "literal": 2}
+
+
+def sb_mod():
+    need_gpu()
+    import stochy_jl_b200 as sb
+    return sb
+
+
+@pytest.mark.parametrize("resample", ["systematic", "multinomial", "literal"])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("N", [100, 2048, 5000])
+def test_hmm_sweep_bitexact(oracle, resample, precision, N):
+    sb = sb_mod()
+    A, logF, pi = cfg2_tables()
+    T = logF.shape[0]
+    with sb.Engine(precision=precision, resample=resample, seed=11, store_logw=True) as eng:
+        eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+        lz = eng.smc_sweep(N, it=3, history=True)
+        ref = oracle.hmm_sweep(oracle.Hmm(A, logF, pi=pi), oracle.opts(MODES[resample], fp32=(precision == "fp32"), seed=11), N, it=3)
+        for t in range(T):
+            x, a, lw = eng.history(t, N, want_lw=True)
+            assert np.array_equal(x, ref["x"][t, :N]), t
+            assert np.array_equal(a, ref["anc"][t, :N]), t
+            assert np.array_equal(lw, ref["lw"][t, :N]), t
+        # log-evidence: 1e-5 relative is the north-star bar; the grid is far tighter
+        assert lz == pytest.approx(ref["logZ"], rel=1e-9 if resample != "literal" else 1e-6)
+
+
+def test_hmm2_fixed_x0_and_partial_factors(oracle):
+    sb = sb_mod()
+    # examples/hmm2.jl form (fixed initial state) and the examples/hmm.jl form (one terminal hard factor)
+    for model in (sb.hmm2_example(), sb.hmm_example(3)):
+        for resample in ("systematic", "multinomial", "literal"):
+            with sb.Engine(precision="fp64", resample=resample, seed=5) as eng:
+                eng.load(model)
+                N = 3000
+                lz = eng.smc_sweep(N, it=0, history=True)
+                om = oracle.Hmm(model.A, model.logF, x0=model.x0, has_factor=model.has_factor)
+                ref = oracle.hmm_sweep(om, oracle.opts(MODES[resample], seed=5), N)
+                for t in range(model.T):
+                    x, a, _ = eng.history(t, N)
+                    assert np.array_equal(x, ref["x"][t, :N])
+                    assert np.array_equal(a, ref["anc"][t, :N])
+                assert lz == pytest.approx(ref["logZ"], rel=1e-6, abs=1e-9)
+
+
+@pytest.mark.parametrize("resample", ["systematic", "multinomial", "literal"])
+@pytest.mark.parametrize("N", [100, 2048])
+def test_pmcmc_counts_bitexact(oracle, resample, N):
+    """Conditional SMC with the retained particle appended as pool entry N+1 (src/pmcmc.jl:59-66),
+    retained = particle 1 (src/pmcmc.jl:89), ALL N values counted (src/pmcmc.jl:90-92)."""
+    sb = sb_mod()
+    A, logF, pi = cfg2_tables()
+    iters = 20
+    with sb.Engine(precision="fp64", resample=resample, seed=3) as eng:
+        eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+        marg, joint = eng.pmcmc_counts(iters, N)
+        xs = eng.retained()
+    ref = oracle.hmm_pmcmc(oracle.Hmm(A, logF, pi=pi), oracle.opts(MODES[resample], seed=3), iters, N)
+    assert marg.sum() == iters * N * logF.shape[0]
+    assert np.array_equal(marg, ref["marg"])
+    assert np.array_equal(joint, ref["joint"])
+    assert xs.min() >= 0 and xs.max() < 3
+
+
+def test_cfg2_pmcmc_vs_enumerate(enumref):
+    """BASELINE config 2: T=10, K=3 PMCMC 100 particles x 1000 iterations in the reference's own
+    numerics vs Stochy's exhaustive Enumerate.  Stated bound: TV <= 0.02 on per-time
+    marginals; joint TV over 59049 outcomes reported (bound 0.15: 1e5 samples on ~6e4 cells)."""
+    sb = sb_mod()
+    A, logF, pi = cfg2_tables()
+    Z, joint_exact = enumref.hmm_enumerate_joint(A, logF, pi=pi)
+    _, post = enumref.hmm_forward(A, logF, pi=pi)
+    with sb.Engine(precision="fp64", resample="literal", seed=1) as eng:
+        eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+        marg, joint = eng.pmcmc_counts(1000, 100)
+    pm = marg / marg.sum(axis=1, keepdims=True)
+    tv_t = 0.5 * np.abs(pm - post).sum(axis=1)
+    assert tv_t.max() <= 0.02, tv_t
+    tv_joint = 0.5 * np.abs(joint / joint.sum() - joint_exact).sum()
+    assert tv_joint <= 0.15, tv_joint
+
+
+def test_hmm2_api_vs_enumerate(enumref):
+    """examples/hmm2.jl through the reference-shaped API: smc(100) / pmcmc(1000,100) vs enum()."""
+    sb = sb_mod()
+    m = sb.hmm2_example()
+    Z, joint_exact = enumref.hmm_enumerate_joint(m.A, m.logF, x0=0)
+    exact = {}
+    for code, p in enumerate(joint_exact):
+        exact[m.value(tuple((code >> t) & 1 for t in range(4)))] = p
+    d = sb.pmcmc(m, 1000, 100, seed=2)
+    est = {k: d.prob(k) for k in d.support()}
+    assert enumref.total_variation(est, exact) <= 0.02
+    d1 = sb.smc(m, 100, seed=2)
+    assert set(d1.support()) <= set(exact)
+    # test/inferencetests.jl:36-44 smoke: flip + soft factor, support == {true,false}
+    flipm = sb.DiscreteHMM([[0.5, 0.5], [0.5, 0.5]], [[-1.0, 0.0]], x0=0, value=lambda xs: bool(xs[0]))
+    d2 = sb.pmcmc(flipm, 5, 5)
+    assert set(d2.support()) <= {True, False}
+    d3 = sb.pmcmc(flipm, 50, 50)
+    assert set(d3.support()) == {True, False}
+    assert d3.prob(True) == pytest.approx(1 / (1 + np.exp(-1.0)), abs=0.05)
+
+
+def test_zero_mass_and_hard_factor():
+    sb = sb_mod()
+    # test/memtests.jl:52-68 spirit: -Inf factors with a surviving particle must work ...
+    A = [[0.5, 0.5], [0.5, 0.5]]
+    ok = sb.DiscreteHMM(A, [[0.0, -np.inf], [0.0, 0.0]], x0=0)
+    with sb.Engine(precision="fp64", seed=1) as eng:
+        eng.load(ok)
+        eng.smc_sweep(1000, history=True)
+        x0, _, _ = eng.history(0, 1000)
+        x1, a0, _ = eng.history(1, 1000)
+        assert np.all(x0[a0] == 0)
+    # ... and an all -Inf factor is the reference's zero-mass / NaN error (test/inferencetests.jl:17-20)
+    bad = sb.DiscreteHMM(A, [[-np.inf, -np.inf]], x0=0)
+    for resample in ("systematic", "literal"):
+        with sb.Engine(precision="fp64", resample=resample) as eng:
+            eng.load(bad)
+            with pytest.raises(sb.StochyError):
+                eng.smc_sweep(100)
+
+
+def test_cfg3_logZ_vs_forward(enumref):
+    """BASELINE config 3 model (K=16, sticky) at reduced T: log Z-hat of unconditional sweeps vs the
+    forward algorithm, |mean - exact| within 4 standard errors over 16 seeds."""
+    sb = sb_mod()
+    A, logF, pi = cfg3_tables(T=200)
+    exact, _ = enumref.hmm_forward(A, logF, pi=pi)
+    vals = []
+    for seed in range(16):
+        with sb.Engine(precision="fp32", resample="systematic", seed=100 + seed) as eng:
+            eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+            vals.append(eng.smc_sweep(1 << 16))
+    vals = np.array(vals)
+    se = vals.std(ddof=1) / np.sqrt(len(vals))
+    assert abs(vals.mean() - exact) < 4 * se + 1e-3, (vals.mean(), exact, se)
+    assert vals.std(ddof=1) < 0.1
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_lg_stepwise_parity(oracle, precision):
+    """Linear-Gaussian model: every step's propagate+weight is checked against the oracle given the
+    SAME parents (tolerance: transcendental functions differ in the last ulp between libm and CUDA);
+    ancestors are checked bit-exactly by feeding the GPU's own log-weights to the oracle's grid."""
+    sb = sb_mod()
+    d = cfg4_data(T=12)
+    N = 6000
+    fp32 = precision == "fp32"
+    m = oracle.Lg(d["a"], d["q"], d["c"], d["r"], d["m0"], d["P0"], d["y"])
+    o = oracle.opts(oracle.SYSTEMATIC, fp32=fp32, seed=9)
+    tol = 2e-5 if fp32 else 1e-11
+    for T in range(1, 5):
+        dd = dict(d); dd["y"] = d["y"][:T]
+        with sb.Engine(precision=precision, seed=9, store_logw=True) as eng:
+            eng.load(sb.LinearGaussian(**dd))
+            eng.smc_sweep(N, it=2)
+            x_gpu = eng.particles(N)
+            lw_gpu = eng.logw_row(T - 1, N)
+            lw_prev = eng.logw_row(T - 2, N) if T > 1 else None
+        if T == 1:
+            x_ref, lw_ref = oracle.lg_step(m, o, N, 0, 2, None)
+        else:
+            # parents as the GPU saw them: previous-step particles come from a (T-1)-step run
+            dd2 = dict(d); dd2["y"] = d["y"][:T - 1]
+            with sb.Engine(precision=precision, seed=9, store_logw=True) as e2:
+                e2.load(sb.LinearGaussian(**dd2))
+                e2.smc_sweep(N, it=2)
+                x_prev = e2.particles(N)
+            u = oracle.uniform53(9, 0, T - 2, 2, 1, 0)
+            anc = oracle.resample_systematic(lw_prev.astype(np.float32) if fp32 else lw_prev, u, N, kind=2 if fp32 else 1)
+            x_ref, lw_ref = oracle.lg_step(m, o, N, T - 1, 2, x_prev[anc])
+        assert np.allclose(x_gpu, x_ref, rtol=tol, atol=tol)
+        assert np.allclose(lw_gpu, lw_ref, rtol=1e-5 if not fp32 else 2e-4, atol=tol * 10)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_lg_logZ_vs_kalman(enumref, precision):
+    """BASELINE config 4 model at reduced size: |log Z-hat - log Z_Kalman| within 4 sigma over 16 seeds."""
+    sb = sb_mod()
+    d = cfg4_data(T=100)
+    exact, _ = enumref.kalman_loglik(d["a"], d["q"], d["c"], d["r"], d["m0"], d["P0"], d["y"])
+    vals = []
+    for seed in range(16):
+        with sb.Engine(precision=precision, seed=500 + seed) as eng:
+            eng.load(sb.LinearGaussian(**d))
+            vals.append(eng.smc_sweep(1 << 17))
+    vals = np.array(vals)
+    se = vals.std(ddof=1) / np.sqrt(len(vals))
+    assert abs(vals.mean() - exact) < 4 * se + (2e-3 if precision == "fp32" else 1e-4), (vals.mean(), exact, se)
+    assert vals.std(ddof=1) < 0.05
+
+
+def test_mh_bitexact_and_posterior(oracle, enumref):
+    """BASELINE config 5 model: batched MH counts equal the oracle's chain for chain; pooled estimate
+    of P(R | W) matches the Enumerate posterior 0.7079."""
+    sb = sb_mod()
+    sites, factors, query = cfg5_bnet()
+    net = sb.BayesNet(sites, factors, query)
+    ob = oracle.Bnet([m for m, _ in sites], [c for _, c in sites], [m for m, _ in factors], [t for _, t in factors], net.query_mask)
+    with sb.Engine(precision="fp64", seed=21) as eng:
+        eng.load(net)
+        got = eng.mh_counts(4096, 200, chain0=5)
+        acc = eng.stats().accepts
+    ref, racc = oracle.bnet_mh(ob, 21, 4096, 200, chain0=5)
+    assert np.array_equal(got, ref)
+    assert acc == racc
+
+    def model(c):
+        C_ = c.flip(0.5)
+        S = c.flip(0.1 if C_ else 0.5)
+        R = c.flip(0.8 if C_ else 0.2)
+        pw = {(False, False): 0.0, (True, False): 0.9, (False, True): 0.9, (True, True): 0.99}[(S, R)]
+        c.observe(enumref.Bernoulli(pw), 1)
+        return R
+    exact = enumref.enum(model).prob(True)
+    assert exact == pytest.approx(0.7079, abs=5e-4)
+    with sb.Engine(precision="fp64", seed=22) as eng:
+        eng.load(net)
+        cnt = eng.mh_counts(65536, 2000)
+    assert cnt[1] / cnt.sum() == pytest.approx(exact, abs=3e-3)
+    d = sb.mh(net, 500, chains=2048, seed=4)                       # reference-shaped API
+    assert set(d.support()) == {True, False}
+    assert d.prob(True) == pytest.approx(exact, abs=0.02)
+
+
+def test_erp_vocabulary():
+    """flip / randominteger / Normal / Beta / Gamma / Dirichlet (src/erp.jl:1-30): moments of the
+    samplers, log-densities against scipy.stats."""
+    sb = sb_mod()
+    from scipy import stats
+    n = 400000
+    with sb.Engine(precision="fp64") as eng:
+        nat = sb._native
+        f = eng.erp_sample(nat.ERP_FLIP, [0.3], n, seed=1)
+        assert set(np.unique(f)) == {0.0, 1.0} and f.mean() == pytest.approx(0.3, abs=4e-3)
+        r = eng.erp_sample(nat.ERP_RANDOMINTEGER, [7], n, seed=2)
+        assert r.min() == 1 and r.max() == 7                                   # 1-based, src/erp.jl:28-30
+        assert np.bincount(r.astype(int))[1:] / n == pytest.approx(np.full(7, 1 / 7), abs=4e-3)
+        z = eng.erp_sample(nat.ERP_NORMAL, [1.5, 2.0], n, seed=3)
+        assert stats.kstest(z, "norm", args=(1.5, 2.0)).pvalue > 1e-3
+        b = eng.erp_sample(nat.ERP_BETA, [2.0, 5.0], n, seed=4)
+        assert stats.kstest(b, "beta", args=(2.0, 5.0)).pvalue > 1e-3
+        b2 = eng.erp_sample(nat.ERP_BETA, [0.5, 0.5], n, seed=5)
+        assert stats.kstest(b2, "beta", args=(0.5, 0.5)).pvalue > 1e-3
+        g = eng.erp_sample(nat.ERP_GAMMA, [3.0, 2.0], n, seed=6)
+        assert stats.kstest(g, "gamma", args=(3.0, 0, 2.0)).pvalue > 1e-3
+        alpha = np.array([0.7, 2.0, 3.5])
+        dsamp = eng.dirichlet_sample(alpha, n, seed=7)
+        assert np.allclose(dsamp.sum(axis=1), 1.0)
+        assert dsamp.mean(axis=0) == pytest.approx(alpha / alpha.sum(), abs=3e-3)
+        x = np.linspace(0.01, 0.99, 99)
+        assert np.allclose(eng.erp_logpdf(nat.ERP_BETA, [2.0, 5.0], x), stats.beta.logpdf(x, 2.0, 5.0), rtol=1e-12, atol=1e-12)
+        assert np.allclose(eng.erp_logpdf(nat.ERP_NORMAL, [1.5, 2.0], x), stats.norm.logpdf(x, 1.5, 2.0), rtol=1e-12)
+        assert np.allclose(eng.erp_logpdf(nat.ERP_GAMMA, [3.0, 2.0], x), stats.gamma.logpdf(x, 3.0, scale=2.0), rtol=1e-12, atol=1e-12)
+        assert np.allclose(eng.erp_logpdf(nat.ERP_FLIP, [0.5], np.array([0.0, 1.0])), np.log(0.5))
+        assert np.allclose(eng.erp_logpdf(nat.ERP_FLIP, [0.7], np.array([0.0, 1.0])), [np.log1p(-0.7), np.log(0.7)])
+        xs = dsamp[:1000]
+        assert np.allclose(eng.dirichlet_logpdf(alpha, xs), [stats.dirichlet.logpdf(v / v.sum(), alpha) for v in xs], rtol=1e-9, atol=1e-9)
