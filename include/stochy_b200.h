@@ -94,6 +94,10 @@ int32_t     sb_create(const sb_options* o, sb_handle** out);
 void        sb_destroy(sb_handle* h);
 const char* sb_last_error(const sb_handle* h);   /* valid until the next call on h; h may be NULL */
 int32_t     sb_get_stats(const sb_handle* h, sb_stats* out);
+/* every > 0: bracket every `every`-th launch of the fused step kernel (t >= 1, at most 128 per run
+ * call) with a CUDA-event pair on the handle's stream; sb_stats.step_kernel_ms is then the AVERAGE
+ * duration of one launch in the last run call.  0 switches it off. */
+int32_t     sb_set_profile(sb_handle* h, int32_t every);
 
 /* ---- models (tables are copied; fixed per-step structure only) ---- */
 

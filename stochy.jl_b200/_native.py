@@ -24,7 +24,7 @@ ERP_FLIP, ERP_RANDOMINTEGER, ERP_NORMAL, ERP_BETA, ERP_GAMMA, ERP_UNIFORM = rang
 TILE = 2048
 
 EXPORTS = [
-    "sb_version", "sb_options_default", "sb_create", "sb_destroy", "sb_last_error", "sb_get_stats",
+    "sb_version", "sb_options_default", "sb_create", "sb_destroy", "sb_last_error", "sb_get_stats", "sb_set_profile",
     "sb_model_discrete_hmm", "sb_model_linear_gaussian", "sb_model_bayesnet",
     "sb_smc_sweep", "sb_pmcmc_run", "sb_mh_run",
     "sb_resample_systematic", "sb_resample_multinomial", "sb_resample_literal", "sb_logsumexp", "sb_gather",
@@ -88,6 +88,7 @@ def lib():
         "sb_destroy": (None, [vp]),
         "sb_last_error": (C.c_char_p, [vp]),
         "sb_get_stats": (i32, [vp, C.POINTER(Stats)]),
+        "sb_set_profile": (i32, [vp, i32]),
         "sb_model_discrete_hmm": (i32, [vp, i32, i32, i32, vp, vp, vp, vp]),
         "sb_model_linear_gaussian": (i32, [vp, i32, dbl, dbl, dbl, dbl, dbl, dbl, vp]),
         "sb_model_bayesnet": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, u32]),

@@ -224,6 +224,17 @@ class Engine:
         self._chk(nat.lib().sb_get_stats(self.h, C.byref(s)))
         return s
 
+    def timer_start(self):
+        self._chk(nat.lib().sb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        self._chk(nat.lib().sb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def set_profile(self, every):
+        self._chk(nat.lib().sb_set_profile(self.h, every))
+
     def load(self, model):
         if not hasattr(model, "load"):
             raise StochyError(nat.EUNSUPPORTED,

@@ -72,6 +72,11 @@ struct sb_handle {
     int sw_cond = 0;
     int xstar_cur = 0;
     bool have_retained = false;
+
+    // optional per-launch timing of the fused step kernel (sb_set_profile)
+    int profile = 0;
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_used = 0;
 };
 
 namespace {
@@ -178,8 +183,23 @@ int launch_literal(sb_handle* h, const double* d_w, int64_t n, int64_t m, const 
 
 inline size_t kind_bytes(int kind) { return kind == SB_W_LOG_F32 ? 4 : 8; }
 
+// bracket one launch of the step kernel with an event pair (at most prof_ev.size()/2 per run call)
+struct ProfScope {
+    sb_handle* h; bool on;
+    ProfScope(sb_handle* h_, int t) : h(h_), on(false) {
+        if (h->profile && (t % h->profile) == 0 && h->prof_used + 2 <= (int)h->prof_ev.size()) {
+            on = true;
+            cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+        }
+    }
+    ~ProfScope() {
+        if (on) { cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream); h->prof_used += 2; }
+    }
+};
+
 int begin_timed(sb_handle* h) {
     h->launches = 0;
+    h->prof_used = 0;
     CK(cudaEventRecord(h->ev0, h->stream));
     return SB_OK;
 }
@@ -190,6 +210,16 @@ int end_timed(sb_handle* h) {
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->stats.device_ms = ms;
     h->stats.kernel_launches = h->launches;
+    h->stats.step_kernel_ms = 0.0;
+    if (h->prof_used) {
+        double acc = 0.0;
+        for (int i = 0; i + 1 < h->prof_used; i += 2) {
+            float f = 0.f;
+            CK(cudaEventElapsedTime(&f, h->prof_ev[i], h->prof_ev[i + 1]));
+            acc += f;
+        }
+        h->stats.step_kernel_ms = acc / (h->prof_used / 2);      // average per launch
+    }
     return SB_OK;
 }
 
@@ -259,6 +289,7 @@ extern "C" void sb_destroy(sb_handle* h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evt0) cudaEventDestroy(h->evt0);
     if (h->evt1) cudaEventDestroy(h->evt1);
+    for (auto& e : h->prof_ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -268,6 +299,16 @@ extern "C" const char* sb_last_error(const sb_handle* h) { return h ? h->err.c_s
 extern "C" int32_t sb_get_stats(const sb_handle* h, sb_stats* out) {
     if (!h || !out) return SB_EINVAL;
     *out = h->stats;
+    return SB_OK;
+}
+
+extern "C" int32_t sb_set_profile(sb_handle* h, int32_t every) {
+    if (!h || every < 0) return SB_EINVAL;
+    h->profile = every;
+    if (every && h->prof_ev.empty()) {
+        h->prof_ev.resize(256);
+        for (auto& e : h->prof_ev) CK(cudaEventCreate(&e));
+    }
     return SB_OK;
 }
 
@@ -470,7 +511,10 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.expF_t = h->hmm_expF.as<double>() + (size_t)t * K;
         a.xstar = conditional ? h->xstar[h->xstar_cur].as<int>() : nullptr;
         a.N = N; a.n_out = n_out; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.err = h->d_err;
-        rc = fp32 ? launch_step_hmm<true>(h, anc_mode, a, grid) : launch_step_hmm<false>(h, anc_mode, a, grid);
+        {
+            ProfScope ps(h, t ? t : -1);                               // t = 0 has no resample/gather: not sampled
+            rc = fp32 ? launch_step_hmm<true>(h, anc_mode, a, grid) : launch_step_hmm<false>(h, anc_mode, a, grid);
+        }
         if (rc != SB_OK) return rc;
         if (h->has_factor[t]) {
             // literal mode still runs the tile scan: it supplies the log-evidence term
@@ -536,7 +580,10 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         a.a = h->lg_a; a.sq = sqrt(h->lg_q); a.sp = sqrt(h->lg_P0); a.c = h->lg_c; a.r = h->lg_r; a.m0 = h->lg_m0;
         a.y = h->lg_y[t]; a.lc = -0.5 * log(SB_TWO_PI * h->lg_r);
         a.err = h->d_err;
-        rc = fp32 ? launch_step_lg<true>(h, anc_mode, a, grid) : launch_step_lg<false>(h, anc_mode, a, grid);
+        {
+            ProfScope ps(h, t ? t : -1);
+            rc = fp32 ? launch_step_lg<true>(h, anc_mode, a, grid) : launch_step_lg<false>(h, anc_mode, a, grid);
+        }
         if (rc != SB_OK) return rc;
         if ((rc = launch_tilescan(h, cur, N, N, (unsigned)t, iter, -1.0, h->d_info.as<SbStepInfo>() + t,
                                   h->d_logZ.as<double>(), h->d_logZ.as<double>() + 1)) != SB_OK) return rc;
