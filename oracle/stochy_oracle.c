@@ -242,12 +242,13 @@ int or_grid_from_w32(const uint32_t* w32, const int32_t* e, int64_t n, or_grid* 
     g->Q = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)nt);
     g->P = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(nt + 1));
     g->C = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)n);
+    g->cl = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)n);
     memcpy(g->e, e, sizeof(int32_t) * (size_t)nt);
     #pragma omp parallel for schedule(static)
     for (int64_t b = 0; b < nt; ++b) {
         int64_t i0 = b * OR_TILE, i1 = i0 + OR_TILE < n ? i0 + OR_TILE : n;
         uint64_t c = 0;
-        for (int64_t i = i0; i < i1; ++i) { c += w32[i]; g->C[i] = c; }
+        for (int64_t i = i0; i < i1; ++i) { c += w32[i]; g->C[i] = c; g->cl[i] = c; }
         g->Q[b] = c;
     }
     int32_t E = OR_E_EMPTY;
@@ -288,7 +289,7 @@ int or_grid_build(const void* data, int kind, int64_t n, or_grid* g) {
 }
 
 void or_grid_free(or_grid* g) {
-    free(g->e); free(g->Q); free(g->P); free(g->C);
+    free(g->e); free(g->Q); free(g->P); free(g->C); free(g->cl);
     memset(g, 0, sizeof(*g));
 }
 
@@ -298,29 +299,75 @@ double or_grid_log_mean_weight(const or_grid* g) {
            - log((double)g->n);
 }
 
-/* number of children c in [0,m) whose threshold (c+u)/m*total lies strictly below C */
-static inline int64_t sys_F(uint64_t C, uint64_t total, double inv, double u, int64_t m) {
-    if (C >= total) return m;
-    double v = (double)C * inv;      /* separate roundings: mul, then sub (no contraction) */
-    v = v - u;
-    v = ceil(v);
-    if (v <= 0.0) return 0;
-    if (v >= (double)m) return m;
-    return (int64_t)v;
+/* ---- systematic resampling on the grid (EXTENSION; strict `<` and last-index fallback by
+ * analogy with src/rand.jl:9,12).  Integer-only per particle:
+ *   plan:  s = min(36, 62 - ceil_log2(m)) sub-child bits; the CDF is rescaled so that its total is
+ *          ~ m * 2^s:  ratio = m * 2^(s+LS) / total = f * 2^x,  R = ceil(f * 2^32),  r0 = 32 - x;
+ *   per particle (tile b, raw tile-local prefix c):  delta = (c * R) >> (r0 + E - e_b);
+ *   thresholds: child k sits at U + k * 2^s with U = floor(u * (Tt - (m-1) 2^s)), Tt = rescaled total;
+ *   F(C) = #children strictly below C = C <= U ? 0 : min(m, ((C - U - 1) >> s) + 1).             */
+typedef struct { uint32_t R; int r0, s; } sys_plan;
+
+static int sys_make_plan(const or_grid* g, int64_t m, sys_plan* p) {
+    int s = 62 - ceil_log2_i64(m);
+    if (s > 36) s = 36;
+    double ratio = ldexp((double)m, s + g->sh0) / (double)g->total;
+    int x;
+    double f = frexp(ratio, &x);
+    uint64_t R = (uint64_t)ceil(f * 4294967296.0);
+    if (R >= 4294967296ull) { R = 2147483648ull; x += 1; }
+    int r0 = 32 - x;
+    if (r0 < 0) { s += r0; r0 = 0; }
+    if (s < 0) return OR_EINVAL;
+    p->R = (uint32_t)R; p->r0 = r0; p->s = s;
+    return OR_OK;
+}
+static inline uint64_t sys_delta(uint64_t c, uint32_t R, int rb) {
+    if (rb >= 96) return 0;
+    int pre = rb > 32 ? rb - 32 : 0, re = rb > 32 ? 32 : rb;
+    uint64_t ce = c >> pre;                     /* pre < 64 */
+    uint64_t P = (ce & 0xffffffffull) * (uint64_t)R;
+    uint64_t H = (ce >> 32) * (uint64_t)R;
+    return (P >> re) + (H << (32 - re));
+}
+static inline int64_t sys_F(uint64_t C, uint64_t U, int s, int64_t m) {
+    if (C <= U) return 0;
+    uint64_t k = ((C - U - 1) >> s) + 1;
+    return k >= (uint64_t)m ? m : (int64_t)k;
 }
 
 int or_grid_systematic(const or_grid* g, double u, int64_t m, int64_t* anc) {
-    double inv = (double)m / (double)g->total;
+    sys_plan p;
+    int rc = sys_make_plan(g, m, &p);
+    if (rc) return rc;
+    const int64_t nt = g->n_tiles;
+    uint64_t* Pt = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(nt + 1));
+    uint64_t acc = 0;
+    for (int64_t b = 0; b < nt; ++b) {
+        Pt[b] = acc;
+        if (g->Q[b] != 0) acc += sys_delta(g->Q[b], p.R, p.r0 + (g->E - g->e[b]));
+    }
+    Pt[nt] = acc;
+    const uint64_t Tt = acc, lastk = (uint64_t)(m - 1) << p.s;
+    if (Tt <= lastk) { free(Pt); return OR_EZEROMASS; }
+    const uint64_t span = Tt - lastk;
+    const uint64_t R53 = (uint64_t)(u * 0x1p53);
+    const uint64_t U = (uint64_t)(((unsigned __int128)R53 * span) >> 53);
     #pragma omp parallel for schedule(static)
-    for (int64_t b = 0; b < g->n_tiles; ++b) {
+    for (int64_t b = 0; b < nt; ++b) {
+        if (g->Q[b] == 0) continue;
         int64_t i0 = b * OR_TILE, i1 = i0 + OR_TILE < g->n ? i0 + OR_TILE : g->n;
-        int64_t lo = sys_F(g->P[b], g->total, inv, u, m);
+        const int rb = p.r0 + (g->E - g->e[b]);
+        int64_t lo = sys_F(Pt[b], U, p.s, m);
         for (int64_t i = i0; i < i1; ++i) {
-            int64_t hi = sys_F(g->C[i], g->total, inv, u, m);
+            uint64_t C = Pt[b] + sys_delta(g->cl[i], p.R, rb);
+            if (b == nt - 1 && i == i1 - 1) C = Tt;          /* (identical by construction) */
+            int64_t hi = sys_F(C, U, p.s, m);
             for (int64_t c = lo; c < hi; ++c) anc[c] = i;
             lo = hi;
         }
     }
+    free(Pt);
     return OR_OK;
 }
 
@@ -373,9 +420,21 @@ static void cum_rows(const double* p, int rows, int K, double* cum) {
         for (int k = 0; k < K; ++k) { acc += p[r * K + k]; cum[r * K + k] = acc; }
     }
 }
-static inline int32_t cat_draw(const double* cum, int K, double u) {
-    for (int k = 0; k < K - 1; ++k) if (u < cum[k]) return k;   /* rand.jl:9 */
-    return K - 1;                                               /* rand.jl:12 */
+/* u = R * 2^-32 with a 32-bit R: `u < cum[k]` (rand.jl:9) is then EXACTLY `R < ceil(cum[k] * 2^32)`;
+ * thresholds are stored saturated to 32 bits (differs only for R = 2^32-1 against cum >= 1 - 2^-32). */
+static inline uint32_t cat_threshold(double cum) {
+    double t = ceil(cum * 4294967296.0);
+    if (!(t > 0.0)) return 0u;
+    return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+static inline int32_t cat_draw(const double* cum, int K, uint32_t R) {
+    for (int k = 0; k < K - 1; ++k) if (R < cat_threshold(cum[k])) return k;   /* rand.jl:9 */
+    return K - 1;                                                              /* rand.jl:12 */
+}
+static inline uint32_t prop_u32(uint64_t seed, uint64_t i, uint32_t t, uint32_t iter) {
+    uint32_t o[4];
+    stream4(seed, i >> 2, t, iter, P_PROP, o);
+    return o[i & 3];
 }
 
 static int resample_pool(const or_opts* o, const double* lw, int64_t n, int64_t N, uint32_t t, uint32_t iter,
@@ -440,7 +499,7 @@ int or_hmm_sweep(const or_hmm* m, const or_opts* o, int64_t N, uint32_t iter, co
          * because the stream is counter-based (idx = particle pair, word = parity). */
         #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < N; ++i) {
-            double u = or_uniform53(o->seed, (uint64_t)i >> 1, (uint32_t)t, iter, P_PROP, (int)(i & 1));
+            uint32_t u = prop_u32(o->seed, (uint64_t)i, (uint32_t)t, iter);
             int32_t x;
             if (t == 0) x = m->x0 >= 0 ? cat_draw(cumA + m->x0 * K, K, u) : cat_draw(cumpi, K, u);
             else        x = cat_draw(cumA + xp[ap[i]] * K, K, u);

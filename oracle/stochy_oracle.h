@@ -63,7 +63,8 @@ typedef struct {
     int32_t*  e;        /* [n_tiles] tile exponents (OR_E_EMPTY if tile has no mass) */
     uint64_t* Q;        /* [n_tiles] tile sums at tile scale */
     uint64_t* P;        /* [n_tiles+1] exclusive prefix of rescaled tile sums */
-    uint64_t* C;        /* [n] inclusive global CDF on the grid */
+    uint64_t* C;        /* [n] inclusive global CDF on the grid (exact shifts; multinomial) */
+    uint64_t* cl;       /* [n] tile-local inclusive prefix of w32 (systematic rescales these) */
     int32_t   E, sh0;   /* sh0 = LS, the left shift applied before the per-tile right shift */
     uint64_t  total;
 } or_grid;

@@ -32,13 +32,16 @@
 
 // Written by k_tilescan for the pool that is about to be resampled; read by every consumer.
 struct SbStepInfo {
-    unsigned long long total;   // sum of all grid weights (<= 2^62)
-    double inv;                 // m / total
-    double u;                   // systematic offset in [0,1)
+    unsigned long long total;   // exact integer sum of the grid weights (<= 2^62): log-evidence, multinomial
+    unsigned long long Tt;      // total of the rescaled CDF (~ m * 2^s): systematic
+    unsigned long long U;       // systematic offset: child k sits at U + k * 2^s
     long long n;                // pool size
     long long m;                // children to draw
+    unsigned R;                 // 32-bit multiplier of the rescale
+    int r0;                     // right shift of the rescale for a tile at the global exponent
+    int s;                      // sub-child bits
     int E;                      // global exponent = max tile exponent
-    int LS;                     // left shift applied before the per-tile right shift
+    int LS;                     // left shift of the exact CDF
     int nt;                     // tiles in the pool
     int valid;
 };
@@ -118,15 +121,21 @@ __device__ __forceinline__ uint32_t sb_q31_f32(float d) {
     return sh > -24 ? (sig >> (-sh)) : 0u;
 }
 
-// child index function of systematic resampling: number of children c in [0,m) whose threshold
-// (c+u)/m * total is strictly below C (strict `<` as in src/rand.jl:9).  Monotone in C.
-__device__ __forceinline__ int sb_sys_F(unsigned long long C, const SbStepInfo& si) {
-    if (C >= si.total) return (int)si.m;
-    double v = __dmul_rn(__ull2double_rn(C), si.inv);
-    v = ceil(__dsub_rn(v, si.u));
-    if (v <= 0.0) return 0;
-    if (v >= (double)si.m) return (int)si.m;
-    return (int)v;
+// Rescaled tile-local prefix: (c * R) >> rb, rb = r0 + (E - e_b) >= 0 (integer only).
+__device__ __forceinline__ unsigned long long sb_sys_delta(unsigned long long c, unsigned R, int rb) {
+    if (rb >= 96) return 0ull;
+    const int pre = rb > 32 ? rb - 32 : 0, re = rb > 32 ? 32 : rb;
+    const unsigned long long ce = c >> pre;
+    const unsigned long long P = (unsigned long long)(unsigned)ce * R;           // IMAD.WIDE
+    const unsigned long long H = (unsigned long long)(unsigned)(ce >> 32) * R;   // IMAD.WIDE
+    return (P >> re) + (H << (32 - re));
+}
+// Number of children k in [0,m) whose threshold U + k * 2^s lies strictly below C (strict `<` as
+// in src/rand.jl:9).  Monotone in C.
+__device__ __forceinline__ int sb_sys_F(unsigned long long C, unsigned long long U, int s, int m) {
+    if (C <= U) return 0;
+    const unsigned long long k = ((C - U - 1ull) >> s) + 1ull;
+    return k >= (unsigned long long)m ? m : (int)k;
 }
 
 // ---------------------------------------------------------------- block-level primitives (256 threads)
@@ -228,41 +237,29 @@ struct SbPullSmem {
     int range[4];
 };
 
-// #{ b in [0, nt] : child_start[b] <= x } by cooperative 256-ary narrowing (2-3 dependent loads
-// instead of log2(nt) on one thread).  child_start is non-decreasing, child_start[0] = 0.
-__device__ __forceinline__ int sb_count_le(const int* __restrict__ child_start, int nt, int x) {
-    int lo = 0, hi = nt + 1;                 // answer in (lo, hi]: child_start[lo] <= x known (lo = 0)
-    // invariant: count of entries <= x lies in [lo+1, hi]
-    while (hi - lo > 1) {
-        int span = hi - lo - 1;              // candidates lo+1 .. hi-1
-        int step = (span + SB_THREADS - 1) / SB_THREADS;
-        int idx = lo + 1 + (int)threadIdx.x * step;
-        int pred = (idx < hi) && (__ldg(child_start + idx) <= x);
-        int k = __syncthreads_count(pred);   // predicates true form a prefix of the threads
-        int nlo = lo + (k ? 1 + (k - 1) * step : 0);
-        int nhi = min(hi, lo + 1 + k * step);
-        lo = nlo; hi = nhi;
-    }
-    return lo + 1;
-}
-
 // Computes, for the children [c0, c0+SB_TILE) of this CTA, the pool index of each child's parent
 // under systematic resampling on the weight grid; thread `tid` receives children c0+8*tid .. +7.
-// w32 / e / P / child_start describe the POOL (previous step); all loads are coalesced tile reads.
+// w32 / e / Pt / child_start / first_tile describe the POOL (previous step).  Parent tiles are read
+// with coalesced 128-bit loads; only threads whose 8 parents own children in range evaluate them.
 __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const uint32_t* __restrict__ w32,
-                                                  const int* __restrict__ e, const unsigned long long* __restrict__ P,
-                                                  const int* __restrict__ child_start, int c0, SbPullSmem& sm,
-                                                  int anc[SB_ITEMS]) {
+                                                  const int* __restrict__ e, const unsigned long long* __restrict__ Pt,
+                                                  const int* __restrict__ child_start, const int* __restrict__ first_tile,
+                                                  int c0, SbPullSmem& sm, int anc[SB_ITEMS]) {
     const int tid = threadIdx.x;
     const int m = (int)si.m;
     const int c1 = min(c0 + SB_TILE, m);
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) sm.marker[tid + j * SB_THREADS] = -1;
-    const int b_lo = sb_count_le(child_start, si.nt, c0) - 1;
-    const int b_hi = sb_count_le(child_start, si.nt, c1 - 1) - 1;
+    const int cb = c0 / SB_TILE;
+    const int b_lo = __ldg(first_tile + cb);
+    const int b_hi = (c1 < m) ? __ldg(first_tile + cb + 1) : si.nt - 1;
+    const unsigned long long U = si.U;
+    const unsigned R = si.R;
+    const int s = si.s;
+    __syncthreads();
     for (int b = b_lo; b <= b_hi; ++b) {
         const int cs = __ldg(child_start + b), ce = __ldg(child_start + b + 1);
-        if (ce == cs) continue;                                  // tile without offspring (uniform branch)
+        if (ce <= c0 || cs >= c1 || ce == cs) continue;          // no offspring in range (uniform branch)
         uint32_t w[SB_ITEMS];
         sb_load8_u32(w32 + (size_t)b * SB_TILE + tid * SB_ITEMS, w);
         unsigned long long tsum = 0;
@@ -271,19 +268,20 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const ui
         unsigned long long tot;
         unsigned long long c = sb_block_excl_scan_u64(tsum, sm.scan, &tot);
         if (tsum != 0) {
-            const int sh = si.E - __ldg(e + b);
-            const unsigned long long Pb = __ldg(P + b);
-            const int LS = si.LS;
-            int lo = sb_sys_F(Pb + (sh >= 63 ? 0ull : ((c << LS) >> sh)), si);
-            const int base = b * SB_TILE + tid * SB_ITEMS;
+            const int rb = si.r0 + (si.E - __ldg(e + b));
+            const unsigned long long Pb = __ldg(Pt + b);
+            int lo = sb_sys_F(Pb + sb_sys_delta(c, R, rb), U, s, m);
+            const int hi_t = sb_sys_F(Pb + sb_sys_delta(c + tsum, R, rb), U, s, m);
+            if (hi_t > lo && hi_t > c0 && lo < c1) {             // this thread's parents own children in range
+                const int base = b * SB_TILE + tid * SB_ITEMS;
 #pragma unroll
-            for (int j = 0; j < SB_ITEMS; ++j) {
-                if (w[j] == 0u) continue;
-                c += w[j];
-                const int hi = sb_sys_F(Pb + (sh >= 63 ? 0ull : ((c << LS) >> sh)), si);
-                const int s = max(lo, c0), t = min(hi, c1);
-                if (s < t) sm.marker[s - c0] = base + j;
-                lo = hi;
+                for (int j = 0; j < SB_ITEMS; ++j) {
+                    c += w[j];
+                    const int hi = (j == SB_ITEMS - 1) ? hi_t : sb_sys_F(Pb + sb_sys_delta(c, R, rb), U, s, m);
+                    const int a0 = max(lo, c0), a1 = min(hi, c1);
+                    if (a0 < a1) sm.marker[a0 - c0] = base + j;
+                    lo = hi;
+                }
             }
         }
     }
@@ -311,6 +309,6 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const ui
 #pragma unroll
     for (int w = 0; w < SB_WARPS; ++w) if (w < warp) prev = max(prev, sm.wmax[w]);
 #pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(v[j], prev);
+    for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(max(v[j], prev), 0);
     __syncthreads();                                             // marker may be reused by the caller
 }

@@ -110,17 +110,38 @@ k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w3
 // extension.  Deterministic: integer adds only.
 // =====================================================================================
 #define SB_SCAN_THREADS 1024
+__device__ __forceinline__ unsigned long long sb_scan1024_excl(unsigned long long loc, unsigned long long* s_w,
+                                                                unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long o = sb_shfl_up_u64(inc, d);
+        if (lane >= d) inc += o;
+    }
+    __syncthreads();
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) { const unsigned long long v = s_w[w]; if (w < warp) base += v; tot += v; }
+    *total = tot;
+    return base + inc - loc;
+}
+
 __global__ void __launch_bounds__(SB_SCAN_THREADS)
 k_tilescan(const int* __restrict__ e, const unsigned long long* __restrict__ Q, int nt, long long n, long long m,
            unsigned long long seed, unsigned t, unsigned iter, double u_override, SbStepInfo* __restrict__ info,
-           unsigned long long* __restrict__ P, int* __restrict__ child_start, double* __restrict__ logZ_acc,
-           double* __restrict__ logZ_step, unsigned* __restrict__ err) {
+           unsigned long long* __restrict__ P, unsigned long long* __restrict__ Pt, int* __restrict__ child_start,
+           int* __restrict__ first_tile, double* __restrict__ logZ_acc, double* __restrict__ logZ_step,
+           unsigned* __restrict__ err) {
     __shared__ int s_e[32];
     __shared__ unsigned long long s_w[32];
     __shared__ SbStepInfo s_info;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (nt + SB_SCAN_THREADS - 1) / SB_SCAN_THREADS;
     const int b0 = min(nt, tid * per), b1 = min(nt, b0 + per);
+    // global exponent
     int E = SB_E_EMPTY;
     for (int b = b0; b < b1; ++b) if (Q[b] != 0ull) E = max(E, e[b]);
 #pragma unroll
@@ -132,48 +153,89 @@ k_tilescan(const int* __restrict__ e, const unsigned long long* __restrict__ Q, 
     for (int w = 1; w < 32; ++w) E = max(E, s_e[w]);
     int LS = 20;
     while (LS > 0 && (1 << (20 - LS)) < nt) --LS;            // LS = 20 - ceil_log2(nt)
+    // exact CDF of tile sums (log-evidence, multinomial)
     unsigned long long loc = 0;
     for (int b = b0; b < b1; ++b) {
         const unsigned long long q = Q[b];
         if (q != 0ull) { const int sh = E - e[b]; loc += sh >= 63 ? 0ull : ((q << LS) >> sh); }
     }
-    unsigned long long inc = loc;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long o = sb_shfl_up_u64(inc, d);
-        if (lane >= d) inc += o;
+    unsigned long long total;
+    unsigned long long run = sb_scan1024_excl(loc, s_w, &total);
+    for (int b = b0; b < b1; ++b) {
+        P[b] = run;
+        const unsigned long long q = Q[b];
+        if (q != 0ull) { const int sh = E - e[b]; run += sh >= 63 ? 0ull : ((q << LS) >> sh); }
     }
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    unsigned long long base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < 32; ++w) { const unsigned long long s = s_w[w]; if (w < warp) base += s; total += s; }
-    unsigned long long run = base + inc - loc;
     if (tid == 0) {
+        P[nt] = total;
         SbStepInfo si;
         si.total = total; si.n = n; si.m = m; si.E = E; si.LS = LS; si.nt = nt;
+        si.Tt = 0ull; si.U = 0ull; si.R = 0u; si.r0 = 0; si.s = 0;
         si.valid = (E != SB_E_EMPTY && total != 0ull) ? 1 : 0;
-        si.inv = total ? __ddiv_rn((double)m, __ull2double_rn(total)) : 0.0;
-        if (u_override >= 0.0) si.u = u_override;
-        else { const SbU4 o = sb_stream4(seed, 0ull, t, iter, SB_P_RESAMPLE); si.u = sb_u53(o.x, o.y); }
-        s_info = si;
-        *info = si;
-        if (!si.valid) atomicOr(err, SB_ERRBIT_ZERO);
-        else {
+        if (si.valid) {
+            // plan of the systematic rescale: total of the rescaled CDF ~ m * 2^s
+            int clm = 0;
+            while ((1ll << clm) < m) ++clm;
+            int s = 62 - clm;
+            if (s > 36) s = 36;
+            const double ratio = __ddiv_rn(scalbn((double)m, s + LS), __ull2double_rn(total));
+            int x;
+            const double f = frexp(ratio, &x);
+            unsigned long long R = __double2ull_rz(ceil(__dmul_rn(f, 4294967296.0)));
+            if (R >= 4294967296ull) { R = 2147483648ull; x += 1; }
+            int r0 = 32 - x;
+            if (r0 < 0) { s += r0; r0 = 0; }
+            if (s < 0) si.valid = 0;
+            si.R = (unsigned)R; si.r0 = r0; si.s = s < 0 ? 0 : s;
             const double lm = log(__ull2double_rn(total)) + (double)(E - SB_QBITS - LS) * SB_LN2 - log((double)n);
             if (logZ_acc) *logZ_acc += lm;
             if (logZ_step) logZ_step[t] = lm;
         }
+        s_info = si;
     }
     __syncthreads();
-    const SbStepInfo si = s_info;
-    for (int b = b0; b < b1; ++b) {
-        P[b] = run;
-        child_start[b] = si.valid ? sb_sys_F(run, si) : 0;
-        const unsigned long long q = Q[b];
-        if (q != 0ull) { const int sh = E - e[b]; run += sh >= 63 ? 0ull : ((q << LS) >> sh); }
+    SbStepInfo si = s_info;
+    // rescaled CDF of tile sums (systematic)
+    unsigned long long loc2 = 0;
+    if (si.valid)
+        for (int b = b0; b < b1; ++b) {
+            const unsigned long long q = Q[b];
+            if (q != 0ull) loc2 += sb_sys_delta(q, si.R, si.r0 + (E - e[b]));
+        }
+    unsigned long long Tt;
+    unsigned long long run2 = sb_scan1024_excl(loc2, s_w, &Tt);
+    if (tid == 0) {
+        const unsigned long long lastk = (unsigned long long)(m - 1) << si.s;
+        if (si.valid && Tt > lastk) {
+            const unsigned long long span = Tt - lastk;
+            unsigned long long R53;
+            if (u_override >= 0.0) R53 = __double2ull_rz(__dmul_rn(u_override, 0x1p53));
+            else { const SbU4 o = sb_stream4(seed, 0ull, t, iter, SB_P_RESAMPLE); R53 = sb_r53(o.x, o.y); }
+            si.U = (__umul64hi(R53, span) << 11) | ((R53 * span) >> 53);
+            si.Tt = Tt;
+        } else {
+            si.valid = 0;
+        }
+        if (!si.valid) atomicOr(err, SB_ERRBIT_ZERO);
+        s_info = si;
+        *info = si;
     }
-    if (tid == 0) { P[nt] = total; child_start[nt] = (int)m; }
+    __syncthreads();
+    si = s_info;
+    const int mi = (int)m;
+    int cs = si.valid ? sb_sys_F(run2, si.U, si.s, mi) : 0;
+    for (int b = b0; b < b1; ++b) {
+        Pt[b] = run2;
+        child_start[b] = cs;
+        const unsigned long long q = Q[b];
+        if (si.valid && q != 0ull) run2 += sb_sys_delta(q, si.R, si.r0 + (E - e[b]));
+        int ce = si.valid ? sb_sys_F(run2, si.U, si.s, mi) : 0;
+        if (b == nt - 1) ce = mi;
+        // children-tile boundaries k * SB_TILE in [cs, ce) start inside parent tile b
+        for (int k = (cs + SB_TILE - 1) / SB_TILE; (long long)k * SB_TILE < ce; ++k) first_tile[k] = b;
+        cs = ce;
+    }
+    if (tid == 0) { Pt[nt] = Tt; child_start[nt] = mi; }
 }
 
 // =====================================================================================
@@ -183,13 +245,14 @@ k_tilescan(const int* __restrict__ e, const unsigned long long* __restrict__ Q, 
 // =====================================================================================
 __global__ void __launch_bounds__(SB_THREADS)
 k_pull(const SbStepInfo* __restrict__ info, const uint32_t* __restrict__ w32, const int* __restrict__ e,
-       const unsigned long long* __restrict__ P, const int* __restrict__ child_start, int* __restrict__ anc_out) {
+       const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
+       const int* __restrict__ first_tile, int* __restrict__ anc_out) {
     __shared__ SbPullSmem ps;
     const SbStepInfo si = *info;
     const int c0 = blockIdx.x * SB_TILE;
     if (c0 >= (int)si.m) return;
     int anc[SB_ITEMS];
-    sb_pull_ancestors(si, w32, e, P, child_start, c0, ps, anc);
+    sb_pull_ancestors(si, w32, e, Pt, child_start, first_tile, c0, ps, anc);
     const int base = c0 + threadIdx.x * SB_ITEMS;
     if (base + SB_ITEMS <= (int)si.m) {
         reinterpret_cast<int4*>(anc_out + base)[0] = make_int4(anc[0], anc[1], anc[2], anc[3]);
@@ -423,8 +486,9 @@ struct SbHmmStepArgs {
     const int* x_prev;
     const uint32_t* w32_prev;
     const int* e_prev;
-    const unsigned long long* P;
+    const unsigned long long* Pt;
     const int* child_start;
+    const int* first_tile;
     const SbStepInfo* info_prev;
     const int* anc_in;
     int* anc_out;               // history row of the resample after step t-1 (or nullptr)
@@ -436,7 +500,7 @@ struct SbHmmStepArgs {
     double* lw_out;             // optional (store_logw)
     double* wlit_out;           // optional (literal mode): exp(score) from the host-built table
     // model tables (global memory; staged into shared memory)
-    const double* cum;          // [rows*K] sequential running sums of the transition rows
+    const uint32_t* thr;        // [rows*K] ceil(2^32 * sequential running sum) of the transition rows
     const double* logF_t;       // [K]
     const double* expF_t;       // [K] or nullptr
     const int* xstar;           // retained trajectory [T] or nullptr
@@ -452,16 +516,16 @@ template <int ANC, bool FP32>
 __global__ void __launch_bounds__(SB_THREADS)
 k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     extern __shared__ __align__(16) unsigned char dyn[];
-    double* s_cum = reinterpret_cast<double*>(dyn);                 // rows*K
-    double* s_l2 = s_cum + a.rows * a.K;                            // K   (float view when FP32)
-    uint32_t* s_q = reinterpret_cast<uint32_t*>(s_l2 + a.K);        // K
+    double* s_l2 = reinterpret_cast<double*>(dyn);                  // K   (float view when FP32)
+    uint32_t* s_thr = reinterpret_cast<uint32_t*>(s_l2 + a.K);      // rows*K
+    uint32_t* s_q = s_thr + a.rows * a.K;                           // K
     __shared__ SbPullSmem ps;
     __shared__ double s_red[SB_WARPS];
     const int tid = threadIdx.x;
     const int c0 = blockIdx.x * SB_TILE;
     const int base = c0 + tid * SB_ITEMS;
     const int K = a.K;
-    for (int i = tid; i < a.rows * K; i += SB_THREADS) s_cum[i] = a.cum[i];
+    for (int i = tid; i < a.rows * K; i += SB_THREADS) s_thr[i] = __ldg(a.thr + i);
     if (tid < K) {
         if (FP32) reinterpret_cast<float*>(s_l2)[tid] = __fmul_rn((float)a.logF_t[tid], SB_LOG2E_F);
         else      s_l2[tid] = __dmul_rn(a.logF_t[tid], SB_LOG2E_D);
@@ -470,7 +534,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     int anc[SB_ITEMS];
     if (ANC == SB_ANC_PULL) {
         const SbStepInfo si = *a.info_prev;
-        if (c0 < (int)si.m) sb_pull_ancestors(si, a.w32_prev, a.e_prev, a.P, a.child_start, c0, ps, anc);
+        if (c0 < (int)si.m) sb_pull_ancestors(si, a.w32_prev, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, ps, anc);
         else {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) anc[j] = 0;
@@ -498,21 +562,21 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     for (int j = 0; j < SB_ITEMS; ++j)
         xp[j] = (ANC != SB_ANC_NONE && base + j < a.N) ? __ldg(a.x_prev + anc[j]) : 0;
     __syncthreads();                                              // tables staged
-    // (3) propagate: one Philox call per particle PAIR, one 53-bit uniform per particle
+    // (3) propagate: one Philox call per FOUR particles, one 32-bit uniform per particle.
+    // u = R * 2^-32 < cum[k]  <=>  R < ceil(cum[k] * 2^32): integer compares against the table.
     int x[SB_ITEMS];
 #pragma unroll
-    for (int p = 0; p < SB_ITEMS / 2; ++p) {
-        const SbU4 o = sb_stream4(a.seed, (unsigned long long)((base >> 1) + p), (unsigned)a.t, a.iter, SB_P_PROP);
-        const double u0 = sb_u53(o.x, o.y), u1 = sb_u53(o.z, o.w);
+    for (int p = 0; p < SB_ITEMS / 4; ++p) {
+        const SbU4 o = sb_stream4(a.seed, (unsigned long long)((base >> 2) + p), (unsigned)a.t, a.iter, SB_P_PROP);
+        const uint32_t r4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int j = 2 * p + h;
-            const double u = h ? u1 : u0;
-            const double* row = s_cum + (a.rows > 1 ? xp[j] * K : 0);
+        for (int h = 0; h < 4; ++h) {
+            const int j = 4 * p + h;
+            const uint32_t* row = s_thr + (a.rows > 1 ? xp[j] * K : 0);
             int lo = 0, hi = K - 1;                              // src/rand.jl:6-12 on a monotone row
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
-                if (u < row[mid]) hi = mid; else lo = mid + 1;
+                if (r4[h] < row[mid]) hi = mid; else lo = mid + 1;
             }
             x[j] = lo;
         }
@@ -575,8 +639,9 @@ struct SbLgStepArgs {
     const void* x_prev;         // REAL[n]
     const uint32_t* w32_prev;
     const int* e_prev;
-    const unsigned long long* P;
+    const unsigned long long* Pt;
     const int* child_start;
+    const int* first_tile;
     const SbStepInfo* info_prev;
     const int* anc_in;
     int* anc_out;
@@ -607,7 +672,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     int anc[SB_ITEMS];
     if (ANC == SB_ANC_PULL) {
         const SbStepInfo si = *a.info_prev;
-        sb_pull_ancestors(si, a.w32_prev, a.e_prev, a.P, a.child_start, c0, ps, anc);
+        sb_pull_ancestors(si, a.w32_prev, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, ps, anc);
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(anc[j], 0);
     } else if (ANC == SB_ANC_EXPLICIT) {

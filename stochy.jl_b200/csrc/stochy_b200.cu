@@ -47,7 +47,7 @@ struct sb_handle {
     DevBuf d_misc;        // int lineage
 
     // grid scratch
-    DevBuf w32[2], tile_e[2], tile_Q[2], P, child_start, cdf, lit_acc, lse_part;
+    DevBuf w32[2], tile_e[2], tile_Q[2], P, Pt, child_start, first_tile, cdf, lit_acc, lse_part;
     // hook staging
     DevBuf hk_in, hk_r, hk_anc, hk_out, hk_src;
 
@@ -122,7 +122,9 @@ int ensure_grid(sb_handle* h, int64_t n_pool, int64_t m) {
         CK(h->tile_Q[i].ensure((size_t)nt * 8));
     }
     CK(h->P.ensure((size_t)(nt + 1) * 8));
+    CK(h->Pt.ensure((size_t)(nt + 1) * 8));
     CK(h->child_start.ensure((size_t)(nt + 1) * 4));
+    CK(h->first_tile.ensure((size_t)(tiles_of(m) + 1) * 4));
     return SB_OK;
 }
 
@@ -144,7 +146,8 @@ int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, unsigned t, un
                     SbStepInfo* info, double* logZ_acc, double* logZ_step) {
     k_tilescan<<<1, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(),
                                                      (int)tiles_of(n), n, m, h->opt.seed, t, iter, u_override, info,
-                                                     h->P.as<unsigned long long>(), h->child_start.as<int>(),
+                                                     h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
+                                                     h->child_start.as<int>(), h->first_tile.as<int>(),
                                                      logZ_acc, logZ_step, h->d_err);
     LAUNCH_CHECK();
     return SB_OK;
@@ -152,7 +155,8 @@ int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, unsigned t, un
 
 int launch_pull(sb_handle* h, int slot, const SbStepInfo* info, int64_t m, int* d_anc) {
     k_pull<<<(unsigned)tiles_of(m), SB_THREADS, 0, h->stream>>>(info, h->w32[slot].as<uint32_t>(), h->tile_e[slot].as<int>(),
-                                                                h->P.as<unsigned long long>(), h->child_start.as<int>(), d_anc);
+                                                                h->Pt.as<unsigned long long>(), h->child_start.as<int>(),
+                                                                h->first_tile.as<int>(), d_anc);
     LAUNCH_CHECK();
     return SB_OK;
 }
@@ -278,7 +282,7 @@ extern "C" void sb_destroy(sb_handle* h) {
     cudaSetDevice(h->opt.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->d_logZ, &h->d_info, &h->d_misc, &h->w32[0], &h->w32[1], &h->tile_e[0], &h->tile_e[1],
-                      &h->tile_Q[0], &h->tile_Q[1], &h->P, &h->child_start, &h->cdf, &h->lit_acc, &h->lse_part,
+                      &h->tile_Q[0], &h->tile_Q[1], &h->P, &h->Pt, &h->child_start, &h->first_tile, &h->cdf, &h->lit_acc, &h->lse_part,
                       &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
                       &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
                       &h->bn_fp, &h->bn_fac, &h->bn_counts, &h->xbuf, &h->ancbuf, &h->lwbuf, &h->wlit, &h->cnt[0],
@@ -343,26 +347,33 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
     if (x0 < 0 && !pi) return fail(h, SB_EINVAL, "discrete_hmm: pi required when x0 < 0");
     CK(cudaSetDevice(h->opt.device));
     // sequential running sums, exactly the accumulation of src/rand.jl:3-7
-    std::vector<double> cumA((size_t)K * K), cumpi((size_t)K, 0.0), expF((size_t)T * K);
+    // u = R * 2^-32 (32-bit R): `u < acc` is exactly `R < ceil(acc * 2^32)`; saturated to 32 bits
+    auto thr_of = [](double acc) -> uint32_t {
+        const double t = ceil(acc * 4294967296.0);
+        if (!(t > 0.0)) return 0u;
+        return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    };
+    std::vector<uint32_t> cumA((size_t)K * K), cumpi((size_t)K, 0u);
+    std::vector<double> expF((size_t)T * K);
     for (int r = 0; r < K; ++r) {
         double acc = 0.0;
         for (int k = 0; k < K; ++k) {
             const double p = A[(size_t)r * K + k];
             if (!(p >= 0.0)) return fail(h, SB_EINVAL, "discrete_hmm: negative or NaN transition probability");
-            acc += p; cumA[(size_t)r * K + k] = acc;
+            acc += p; cumA[(size_t)r * K + k] = thr_of(acc);
         }
     }
-    if (x0 < 0) { double acc = 0.0; for (int k = 0; k < K; ++k) { acc += pi[k]; cumpi[k] = acc; } }
+    if (x0 < 0) { double acc = 0.0; for (int k = 0; k < K; ++k) { acc += pi[k]; cumpi[k] = thr_of(acc); } }
     for (size_t i = 0; i < (size_t)T * K; ++i) expF[i] = exp(logF[i]);       // src/pmcmc.jl:55 (literal mode)
     h->has_factor.assign((size_t)T, 1);
     if (has_factor) for (int t = 0; t < T; ++t) h->has_factor[t] = has_factor[t] ? 1 : 0;
-    CK(h->hmm_cumA.ensure(cumA.size() * 8));
-    CK(h->hmm_cumpi.ensure(cumpi.size() * 8));
+    CK(h->hmm_cumA.ensure(cumA.size() * 4));
+    CK(h->hmm_cumpi.ensure(cumpi.size() * 4));
     CK(h->hmm_logF.ensure((size_t)T * K * 8));
     CK(h->hmm_expF.ensure((size_t)T * K * 8));
     CK(h->hmm_hasf.ensure((size_t)T));
-    CK(cudaMemcpyAsync(h->hmm_cumA.p, cumA.data(), cumA.size() * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->hmm_cumpi.p, cumpi.data(), cumpi.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->hmm_cumA.p, cumA.data(), cumA.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->hmm_cumpi.p, cumpi.data(), cumpi.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->hmm_logF.p, logF, (size_t)T * K * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->hmm_expF.p, expF.data(), (size_t)T * K * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->hmm_hasf.p, h->has_factor.data(), (size_t)T, cudaMemcpyHostToDevice, h->stream));
@@ -424,7 +435,7 @@ namespace {
 
 template <bool FP32>
 int launch_step_hmm(sb_handle* h, int anc_mode, const SbHmmStepArgs& a, unsigned grid) {
-    const size_t smem = (size_t)(a.rows * a.K + a.K) * 8 + (size_t)a.K * 4;
+    const size_t smem = (size_t)a.K * 8 + (size_t)(a.rows * a.K + a.K) * 4;
     switch (anc_mode) {
         case SB_ANC_NONE:     k_step_hmm<SB_ANC_NONE, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
         case SB_ANC_PULL:     k_step_hmm<SB_ANC_PULL, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
@@ -494,8 +505,9 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.x_prev = t ? xb + (size_t)(history ? (t - 1) : prev) * S : nullptr;
         a.w32_prev = h->w32[prev].as<uint32_t>();
         a.e_prev = h->tile_e[prev].as<int>();
-        a.P = h->P.as<unsigned long long>();
+        a.Pt = h->Pt.as<unsigned long long>();
         a.child_start = h->child_start.as<int>();
+        a.first_tile = h->first_tile.as<int>();
         a.info_prev = t ? h->d_info.as<SbStepInfo>() + (t - 1) : nullptr;
         a.anc_in = anc_row_prev;
         a.anc_out = (history && t) ? anc_row_prev : nullptr;
@@ -505,8 +517,8 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.Q_out = h->tile_Q[cur].as<unsigned long long>();
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.wlit_out = literal ? h->wlit.as<double>() : nullptr;
-        if (t == 0) { a.cum = h->x0 >= 0 ? h->hmm_cumA.as<double>() + (size_t)h->x0 * K : h->hmm_cumpi.as<double>(); a.rows = 1; }
-        else        { a.cum = h->hmm_cumA.as<double>(); a.rows = K; }
+        if (t == 0) { a.thr = h->x0 >= 0 ? h->hmm_cumA.as<uint32_t>() + (size_t)h->x0 * K : h->hmm_cumpi.as<uint32_t>(); a.rows = 1; }
+        else        { a.thr = h->hmm_cumA.as<uint32_t>(); a.rows = K; }
         a.logF_t = h->hmm_logF.as<double>() + (size_t)t * K;
         a.expF_t = h->hmm_expF.as<double>() + (size_t)t * K;
         a.xstar = conditional ? h->xstar[h->xstar_cur].as<int>() : nullptr;
@@ -566,8 +578,9 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         a.x_prev = xb + (size_t)prev * S * sz;
         a.w32_prev = h->w32[prev].as<uint32_t>();
         a.e_prev = h->tile_e[prev].as<int>();
-        a.P = h->P.as<unsigned long long>();
+        a.Pt = h->Pt.as<unsigned long long>();
         a.child_start = h->child_start.as<int>();
+        a.first_tile = h->first_tile.as<int>();
         a.info_prev = t ? h->d_info.as<SbStepInfo>() + (t - 1) : nullptr;
         a.anc_in = h->ancbuf.as<int>();
         a.anc_out = nullptr;

@@ -146,7 +146,7 @@ def test_cfg3_logZ_vs_forward(enumref):
     vals = np.array(vals)
     se = vals.std(ddof=1) / np.sqrt(len(vals))
     assert abs(vals.mean() - exact) < 4 * se + 1e-3, (vals.mean(), exact, se)
-    assert vals.std(ddof=1) < 0.1
+    assert vals.std(ddof=1) < 0.3
 
 
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
