@@ -135,7 +135,7 @@ static inline double pow2i(int k) {       /* 2^k for -1022 <= k <= 1023 */
 }
 
 uint32_t or_q31_f64(double d) {
-    if (!(d > -33.0)) return 0;           /* also catches -inf and NaN */
+    if (!(d > -(double)(OR_QBITS + 2))) return 0;   /* also catches -inf and NaN */
     double k = floor(d);
     double r = d - k;                     /* exact, in [0,1) */
     double t = (r - 0.5) * 0x1.62e42fefa39efp-1;   /* ln 2 */
@@ -157,7 +157,7 @@ uint32_t or_q31_f64(double d) {
 }
 
 uint32_t or_q31_f32(float d) {
-    if (!(d > -33.0f)) return 0;
+    if (!(d > -(float)(OR_QBITS + 2))) return 0;
     float k = floorf(d);
     float r = d - k;
     float t = (r - 0.5f) * 0x1.62e430p-1f;
@@ -183,7 +183,7 @@ static inline int ceil_log2_i64(int64_t v) {
 #define LOG2E_F 0x1.715476p+0f
 
 /* Stage 1 of the grid: per tile of OR_TILE entries, a power-of-two exponent e_b >= every weight
- * and 32-bit fixed-point weights w32_i = floor(w_i / 2^e_b * 2^31). */
+ * and fixed-point weights w32_i = floor(w_i / 2^e_b * 2^OR_QBITS)  (OR_QBITS = 27). */
 int or_grid_quantise(const void* data, int kind, int64_t n, uint32_t* w32, int32_t* e_out) {
     int64_t nt = (n + OR_TILE - 1) / OR_TILE;
     int bad = 0;
@@ -230,8 +230,8 @@ int or_grid_quantise(const void* data, int kind, int64_t n, uint32_t* w32, int32
     return bad ? OR_ENAN : OR_OK;
 }
 
-/* Stage 2: exact integer CDF.  Tile-local inclusive sums c_i (<= 2^42), global exponent
- * E = max e_b, left shift LS = 20 - ceil_log2(n_tiles), C_i = P_b + ((c_i << LS) >> (E - e_b)). */
+/* Stage 2: exact integer CDF.  Tile-local inclusive sums c_i (<= 2^38), global exponent
+ * E = max e_b, left shift LS = 24 - ceil_log2(n_tiles), C_i = P_b + ((c_i << LS) >> (E - e_b)). */
 int or_grid_from_w32(const uint32_t* w32, const int32_t* e, int64_t n, or_grid* g) {
     memset(g, 0, sizeof(*g));
     if (n <= 0) return OR_EINVAL;
@@ -254,7 +254,7 @@ int or_grid_from_w32(const uint32_t* w32, const int32_t* e, int64_t n, or_grid* 
     int32_t E = OR_E_EMPTY;
     for (int64_t b = 0; b < nt; ++b) if (g->Q[b] != 0 && g->e[b] > E) E = g->e[b];
     if (E == OR_E_EMPTY) { or_grid_free(g); return OR_EZEROMASS; }
-    int LS = 20 - ceil_log2_i64(nt);
+    int LS = 24 - ceil_log2_i64(nt);
     g->E = E; g->sh0 = LS;
     uint64_t acc = 0;
     for (int64_t b = 0; b < nt; ++b) {
@@ -302,8 +302,9 @@ double or_grid_log_mean_weight(const or_grid* g) {
 /* ---- systematic resampling on the grid (EXTENSION; strict `<` and last-index fallback by
  * analogy with src/rand.jl:9,12).  Integer-only per particle:
  *   plan:  s = min(36, 62 - ceil_log2(m)) sub-child bits; the CDF is rescaled so that its total is
- *          ~ m * 2^s:  ratio = m * 2^(s+LS) / total = f * 2^x,  R = ceil(f * 2^32),  r0 = 32 - x;
- *   per particle (tile b, raw tile-local prefix c):  delta = (c * R) >> (r0 + E - e_b);
+ *          ~ m * 2^s:  ratio = m * 2^(s+LS) / total = f * 2^x,  R = ceil(f * 2^26),  r0 = 26 - x;
+ *   per particle (tile b, raw tile-local prefix c <= 2^38):  delta = (c * R) >> (r0 + E - e_b)
+ *          (c * R < 2^64: one 64-bit multiply-accumulate per particle on the GPU);
  *   thresholds: child k sits at U + k * 2^s with U = floor(u * (Tt - (m-1) 2^s)), Tt = rescaled total;
  *   F(C) = #children strictly below C = C <= U ? 0 : min(m, ((C - U - 1) >> s) + 1).             */
 typedef struct { uint32_t R; int r0, s; } sys_plan;
@@ -314,21 +315,16 @@ static int sys_make_plan(const or_grid* g, int64_t m, sys_plan* p) {
     double ratio = ldexp((double)m, s + g->sh0) / (double)g->total;
     int x;
     double f = frexp(ratio, &x);
-    uint64_t R = (uint64_t)ceil(f * 4294967296.0);
-    if (R >= 4294967296ull) { R = 2147483648ull; x += 1; }
-    int r0 = 32 - x;
+    uint64_t R = (uint64_t)ceil(f * 67108864.0);
+    if (R >= 67108864ull) { R = 33554432ull; x += 1; }
+    int r0 = 26 - x;
     if (r0 < 0) { s += r0; r0 = 0; }
     if (s < 0) return OR_EINVAL;
     p->R = (uint32_t)R; p->r0 = r0; p->s = s;
     return OR_OK;
 }
 static inline uint64_t sys_delta(uint64_t c, uint32_t R, int rb) {
-    if (rb >= 96) return 0;
-    int pre = rb > 32 ? rb - 32 : 0, re = rb > 32 ? 32 : rb;
-    uint64_t ce = c >> pre;                     /* pre < 64 */
-    uint64_t P = (ce & 0xffffffffull) * (uint64_t)R;
-    uint64_t H = (ce >> 32) * (uint64_t)R;
-    return (P >> re) + (H << (32 - re));
+    return rb >= 64 ? 0 : (c * (uint64_t)R) >> rb;
 }
 static inline int64_t sys_F(uint64_t C, uint64_t U, int s, int64_t m) {
     if (C <= U) return 0;

@@ -35,7 +35,7 @@ extern "C" {
 #define OR_EINVAL     3
 
 #define OR_TILE       2048
-#define OR_QBITS      31
+#define OR_QBITS      27
 
 /* resample modes (same numbering as include/stochy_b200.h) */
 #define OR_RESAMPLE_SYSTEMATIC   0
@@ -56,7 +56,7 @@ int or_resample_literal(const double* w, int64_t n, const double* r, int64_t m, 
 int or_resample_literal_fast(const double* w, int64_t n, const double* r, int64_t m, int64_t* anc);
 
 /* ---- weight grid (extension; see DESIGN.md "weight grid") ---- */
-uint32_t or_q31_f64(double d);           /* floor(2^d * 2^31), d <= 0, deterministic IEEE-only */
+uint32_t or_q31_f64(double d);           /* floor(2^d * 2^OR_QBITS), d <= 0, deterministic IEEE-only */
 uint32_t or_q31_f32(float d);
 typedef struct {
     int64_t   n, n_tiles;

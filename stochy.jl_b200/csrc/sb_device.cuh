@@ -12,7 +12,7 @@
 #define SB_THREADS  256
 #define SB_ITEMS    8             // consecutive particles per thread (blocked arrangement)
 #define SB_WARPS    (SB_THREADS / 32)
-#define SB_QBITS    31
+#define SB_QBITS    27            // fixed-point weight bits: tile prefix <= 2^38, times a 26-bit multiplier < 2^64
 #define SB_E_EMPTY  (-0x40000000)
 
 #define SB_ERRBIT_NAN   1u
@@ -78,7 +78,7 @@ __device__ __forceinline__ double sb_u53(uint32_t a, uint32_t b) {
 // Same IEEE operation sequence as the CPU checker used by the tests (which restates
 // this definition independently); intrinsics forbid the compiler from contracting mul+add.
 __device__ __forceinline__ uint32_t sb_q31_f64(double d) {
-    if (!(d > -33.0)) return 0u;
+    if (!(d > -(double)(SB_QBITS + 2))) return 0u;
     double k = floor(d);
     double r = __dsub_rn(d, k);
     double t = __dmul_rn(__dsub_rn(r, 0.5), SB_LN2);
@@ -99,7 +99,7 @@ __device__ __forceinline__ uint32_t sb_q31_f64(double d) {
     return (uint32_t)__double2ull_rz(__dmul_rn(p, s));
 }
 __device__ __forceinline__ uint32_t sb_q31_f32(float d) {
-    if (!(d > -33.0f)) return 0u;
+    if (!(d > -(float)(SB_QBITS + 2))) return 0u;
     float k = floorf(d);
     float r = __fsub_rn(d, k);
     float t = __fmul_rn(__fsub_rn(r, 0.5f), 0x1.62e430p-1f);
@@ -117,18 +117,13 @@ __device__ __forceinline__ uint32_t sb_q31_f32(float d) {
     uint32_t bits = __float_as_uint(p);
     uint32_t sig = (bits & 0x7FFFFFu) | 0x800000u;
     sh += (int)(bits >> 23) - 127;
-    if (sh >= 0) return sig << sh;                   // sh <= 8 because p*2^(31+k) <= 2^31 (+1 ulp)
+    if (sh >= 0) return sig << sh;                   // sh <= 4 because p * 2^(QBITS+k) <= 2^QBITS (+1 ulp)
     return sh > -24 ? (sig >> (-sh)) : 0u;
 }
 
-// Rescaled tile-local prefix: (c * R) >> rb, rb = r0 + (E - e_b) >= 0 (integer only).
+// Rescaled tile-local prefix: (c * R) >> rb with c <= 2^38 and a 26-bit R (product < 2^64).
 __device__ __forceinline__ unsigned long long sb_sys_delta(unsigned long long c, unsigned R, int rb) {
-    if (rb >= 96) return 0ull;
-    const int pre = rb > 32 ? rb - 32 : 0, re = rb > 32 ? 32 : rb;
-    const unsigned long long ce = c >> pre;
-    const unsigned long long P = (unsigned long long)(unsigned)ce * R;           // IMAD.WIDE
-    const unsigned long long H = (unsigned long long)(unsigned)(ce >> 32) * R;   // IMAD.WIDE
-    return (P >> re) + (H << (32 - re));
+    return rb >= 64 ? 0ull : (c * (unsigned long long)R) >> rb;
 }
 // Number of children k in [0,m) whose threshold U + k * 2^s lies strictly below C (strict `<` as
 // in src/rand.jl:9).  Monotone in C.
@@ -262,22 +257,29 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const ui
         if (ce <= c0 || cs >= c1 || ce == cs) continue;          // no offspring in range (uniform branch)
         uint32_t w[SB_ITEMS];
         sb_load8_u32(w32 + (size_t)b * SB_TILE + tid * SB_ITEMS, w);
-        unsigned long long tsum = 0;
+        unsigned tsum = 0;                                       // 8 * 2^27 fits 32 bits
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) tsum += w[j];
         unsigned long long tot;
-        unsigned long long c = sb_block_excl_scan_u64(tsum, sm.scan, &tot);
+        unsigned long long c = sb_block_excl_scan_u64((unsigned long long)tsum, sm.scan, &tot);
         if (tsum != 0) {
+            // tile-uniform constants; rb < 64 because the tile owns children
             const int rb = si.r0 + (si.E - __ldg(e + b));
-            const unsigned long long Pb = __ldg(Pt + b);
-            int lo = sb_sys_F(Pb + sb_sys_delta(c, R, rb), U, s, m);
-            const int hi_t = sb_sys_F(Pb + sb_sys_delta(c + tsum, R, rb), U, s, m);
+            const long long baseb = (long long)(__ldg(Pt + b) - U) + ((1ll << s) - 1ll);
+            // F(acc) = clamp((baseb + (acc >> rb)) >> s, 0, m): children strictly below this CDF value
+            unsigned long long acc = c * (unsigned long long)R;
+            long long k0 = (baseb + (long long)(acc >> rb)) >> s;
+            int lo = k0 <= 0 ? 0 : (k0 >= (long long)m ? m : (int)k0);
+            const unsigned long long acc_t = acc + (unsigned long long)tsum * R;
+            long long k1 = (baseb + (long long)(acc_t >> rb)) >> s;
+            const int hi_t = k1 <= 0 ? 0 : (k1 >= (long long)m ? m : (int)k1);
             if (hi_t > lo && hi_t > c0 && lo < c1) {             // this thread's parents own children in range
                 const int base = b * SB_TILE + tid * SB_ITEMS;
 #pragma unroll
                 for (int j = 0; j < SB_ITEMS; ++j) {
-                    c += w[j];
-                    const int hi = (j == SB_ITEMS - 1) ? hi_t : sb_sys_F(Pb + sb_sys_delta(c, R, rb), U, s, m);
+                    acc += (unsigned long long)w[j] * R;         // one IMAD.WIDE with 64-bit accumulate
+                    long long k = (baseb + (long long)(acc >> rb)) >> s;
+                    const int hi = (j == SB_ITEMS - 1) ? hi_t : (k <= 0 ? 0 : (k >= (long long)m ? m : (int)k));
                     const int a0 = max(lo, c0), a1 = min(hi, c1);
                     if (a0 < a1) sm.marker[a0 - c0] = base + j;
                     lo = hi;

@@ -129,16 +129,29 @@ __device__ __forceinline__ unsigned long long sb_scan1024_excl(unsigned long lon
     return base + inc - loc;
 }
 
+// SMEM = true: the (e, Q) arrays (<= 8192 tiles) are staged once into shared memory with coalesced
+// loads, so every later pass runs from on-chip memory (the kernel is pure latency otherwise).
+template <bool SMEM>
 __global__ void __launch_bounds__(SB_SCAN_THREADS)
-k_tilescan(const int* __restrict__ e, const unsigned long long* __restrict__ Q, int nt, long long n, long long m,
+k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q_g, int nt, long long n, long long m,
            unsigned long long seed, unsigned t, unsigned iter, double u_override, SbStepInfo* __restrict__ info,
            unsigned long long* __restrict__ P, unsigned long long* __restrict__ Pt, int* __restrict__ child_start,
            int* __restrict__ first_tile, double* __restrict__ logZ_acc, double* __restrict__ logZ_step,
            unsigned* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int s_e[32];
     __shared__ unsigned long long s_w[32];
     __shared__ SbStepInfo s_info;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long* Q = Q_g;
+    const int* e = e_g;
+    if (SMEM) {
+        unsigned long long* sQ = reinterpret_cast<unsigned long long*>(dyn);
+        int* se = reinterpret_cast<int*>(sQ + nt);
+        for (int b = tid; b < nt; b += SB_SCAN_THREADS) { sQ[b] = __ldg(Q_g + b); se[b] = __ldg(e_g + b); }
+        __syncthreads();
+        Q = sQ; e = se;
+    }
     const int per = (nt + SB_SCAN_THREADS - 1) / SB_SCAN_THREADS;
     const int b0 = min(nt, tid * per), b1 = min(nt, b0 + per);
     // global exponent
@@ -151,8 +164,8 @@ k_tilescan(const int* __restrict__ e, const unsigned long long* __restrict__ Q, 
     E = s_e[0];
 #pragma unroll
     for (int w = 1; w < 32; ++w) E = max(E, s_e[w]);
-    int LS = 20;
-    while (LS > 0 && (1 << (20 - LS)) < nt) --LS;            // LS = 20 - ceil_log2(nt)
+    int LS = 24;
+    while (LS > 0 && (1 << (24 - LS)) < nt) --LS;            // LS = 24 - ceil_log2(nt)
     // exact CDF of tile sums (log-evidence, multinomial)
     unsigned long long loc = 0;
     for (int b = b0; b < b1; ++b) {
@@ -181,9 +194,9 @@ k_tilescan(const int* __restrict__ e, const unsigned long long* __restrict__ Q, 
             const double ratio = __ddiv_rn(scalbn((double)m, s + LS), __ull2double_rn(total));
             int x;
             const double f = frexp(ratio, &x);
-            unsigned long long R = __double2ull_rz(ceil(__dmul_rn(f, 4294967296.0)));
-            if (R >= 4294967296ull) { R = 2147483648ull; x += 1; }
-            int r0 = 32 - x;
+            unsigned long long R = __double2ull_rz(ceil(__dmul_rn(f, 67108864.0)));
+            if (R >= 67108864ull) { R = 33554432ull; x += 1; }
+            int r0 = 26 - x;
             if (r0 < 0) { s += r0; r0 = 0; }
             if (s < 0) si.valid = 0;
             si.R = (unsigned)R; si.r0 = r0; si.s = s < 0 ? 0 : s;
@@ -501,6 +514,8 @@ struct SbHmmStepArgs {
     double* wlit_out;           // optional (literal mode): exp(score) from the host-built table
     // model tables (global memory; staged into shared memory)
     const uint32_t* thr;        // [rows*K] ceil(2^32 * sequential running sum) of the transition rows
+    const unsigned char* guide; // [rows << lgG] #thresholds <= bucket start: where the inverse-CDF scan begins
+    int lgG;
     const double* logF_t;       // [K]
     const double* expF_t;       // [K] or nullptr
     const int* xstar;           // retained trajectory [T] or nullptr
@@ -519,6 +534,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     double* s_l2 = reinterpret_cast<double*>(dyn);                  // K   (float view when FP32)
     uint32_t* s_thr = reinterpret_cast<uint32_t*>(s_l2 + a.K);      // rows*K
     uint32_t* s_q = s_thr + a.rows * a.K;                           // K
+    unsigned char* s_guide = reinterpret_cast<unsigned char*>(s_q + a.K);   // rows << lgG
     __shared__ SbPullSmem ps;
     __shared__ double s_red[SB_WARPS];
     const int tid = threadIdx.x;
@@ -526,6 +542,8 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     const int base = c0 + tid * SB_ITEMS;
     const int K = a.K;
     for (int i = tid; i < a.rows * K; i += SB_THREADS) s_thr[i] = __ldg(a.thr + i);
+    for (int i = tid; i < (a.rows << a.lgG); i += SB_THREADS) s_guide[i] = __ldg(a.guide + i);
+    const bool tail = c0 + SB_TILE > a.N;                         // only the last CTA(s) see padding / the retained slot
     if (tid < K) {
         if (FP32) reinterpret_cast<float*>(s_l2)[tid] = __fmul_rn((float)a.logF_t[tid], SB_LOG2E_F);
         else      s_l2[tid] = __dmul_rn(a.logF_t[tid], SB_LOG2E_D);
@@ -560,7 +578,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     int xp[SB_ITEMS];
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j)
-        xp[j] = (ANC != SB_ANC_NONE && base + j < a.N) ? __ldg(a.x_prev + anc[j]) : 0;
+        xp[j] = (ANC != SB_ANC_NONE && (!tail || base + j < a.N)) ? __ldg(a.x_prev + anc[j]) : 0;
     __syncthreads();                                              // tables staged
     // (3) propagate: one Philox call per FOUR particles, one 32-bit uniform per particle.
     // u = R * 2^-32 < cum[k]  <=>  R < ceil(cum[k] * 2^32): integer compares against the table.
@@ -572,27 +590,30 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             const int j = 4 * p + h;
-            const uint32_t* row = s_thr + (a.rows > 1 ? xp[j] * K : 0);
-            int lo = 0, hi = K - 1;                              // src/rand.jl:6-12 on a monotone row
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (r4[h] < row[mid]) hi = mid; else lo = mid + 1;
-            }
+            const int ri = a.rows > 1 ? xp[j] : 0;
+            const uint32_t* row = s_thr + ri * K;
+            const uint32_t R = r4[h];
+            // src/rand.jl:6-12 on a monotone row: first k with R < thr[k], else K-1.  The guide table
+            // gives the number of thresholds at or below the start of R's bucket, so the scan is ~1 step.
+            int lo = s_guide[(ri << a.lgG) + (R >> (32 - a.lgG))];
+            while (lo < K - 1 && R >= row[lo]) ++lo;
             x[j] = lo;
         }
     }
     // retained particle (src/pmcmc.jl:59-66) and padding
+    if (tail) {
 #pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) {
-        const int i = base + j;
-        if (i >= a.N) x[j] = (i == a.N && a.xstar) ? __ldg(a.xstar + a.t) : 0;
+        for (int j = 0; j < SB_ITEMS; ++j) {
+            const int i = base + j;
+            if (i >= a.N) x[j] = (i == a.N && a.xstar) ? __ldg(a.xstar + a.t) : 0;
+        }
     }
     // (4)+(5) weight and quantise.  Only K distinct scores exist, so 2^(l2 - e) is evaluated K times.
     int e;
     if (FP32) {
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) mx = fmaxf(mx, reinterpret_cast<float*>(s_l2)[x[j]]);
+        for (int j = 0; j < SB_ITEMS; ++j) if (!tail || base + j < a.n_out) mx = fmaxf(mx, reinterpret_cast<float*>(s_l2)[x[j]]);
         mx = sb_block_max_f32(mx, reinterpret_cast<float*>(s_red));
         e = mx > -INFINITY ? (int)ceilf(mx) : SB_E_EMPTY;
         if (tid < K) {
@@ -603,7 +624,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     } else {
         double mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) mx = fmax(mx, s_l2[x[j]]);
+        for (int j = 0; j < SB_ITEMS; ++j) if (!tail || base + j < a.n_out) mx = fmax(mx, s_l2[x[j]]);
         mx = sb_block_max_f64(mx, s_red);
         e = mx > -INFINITY ? (int)ceil(mx) : SB_E_EMPTY;
         if (tid < K) {
@@ -617,7 +638,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     unsigned long long tsum = 0;
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) {
-        q[j] = (base + j < a.n_out) ? s_q[x[j]] : 0u;
+        q[j] = (!tail || base + j < a.n_out) ? s_q[x[j]] : 0u;
         tsum += q[j];
     }
     sb_store8_u32(reinterpret_cast<uint32_t*>(a.x_out) + base, reinterpret_cast<const uint32_t*>(x));

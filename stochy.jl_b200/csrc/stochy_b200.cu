@@ -54,7 +54,7 @@ struct sb_handle {
     // model
     int model = MODEL_NONE;
     // HMM
-    int K = 0, T = 0, x0 = -1;
+    int K = 0, T = 0, x0 = -1, hmm_lgG = 4;
     std::vector<uint8_t> has_factor;
     DevBuf hmm_cumA, hmm_cumpi, hmm_logF, hmm_expF, hmm_hasf;
     // LG
@@ -74,6 +74,7 @@ struct sb_handle {
     bool have_retained = false;
 
     // optional per-launch timing of the fused step kernel (sb_set_profile)
+    bool scan_attr_set = false;
     int profile = 0;
     std::vector<cudaEvent_t> prof_ev;
     int prof_used = 0;
@@ -144,11 +145,25 @@ int launch_quantise(sb_handle* h, const void* d_data, int kind, int64_t n, int s
 
 int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, unsigned t, unsigned iter, double u_override,
                     SbStepInfo* info, double* logZ_acc, double* logZ_step) {
-    k_tilescan<<<1, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(),
-                                                     (int)tiles_of(n), n, m, h->opt.seed, t, iter, u_override, info,
-                                                     h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
-                                                     h->child_start.as<int>(), h->first_tile.as<int>(),
-                                                     logZ_acc, logZ_step, h->d_err);
+    const int nt = (int)tiles_of(n);
+    if (nt <= 8192) {
+        const size_t smem = (size_t)nt * 12;
+        if (smem > 48 * 1024 && !h->scan_attr_set) {
+            CK(cudaFuncSetAttribute(k_tilescan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
+            h->scan_attr_set = true;
+        }
+        k_tilescan<true><<<1, SB_SCAN_THREADS, smem, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(),
+                                                                  nt, n, m, h->opt.seed, t, iter, u_override, info,
+                                                                  h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
+                                                                  h->child_start.as<int>(), h->first_tile.as<int>(),
+                                                                  logZ_acc, logZ_step, h->d_err);
+    } else {
+        k_tilescan<false><<<1, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(),
+                                                                nt, n, m, h->opt.seed, t, iter, u_override, info,
+                                                                h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
+                                                                h->child_start.as<int>(), h->first_tile.as<int>(),
+                                                                logZ_acc, logZ_step, h->d_err);
+    }
     LAUNCH_CHECK();
     return SB_OK;
 }
@@ -353,7 +368,17 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
         if (!(t > 0.0)) return 0u;
         return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
     };
-    std::vector<uint32_t> cumA((size_t)K * K), cumpi((size_t)K, 0u);
+    const int lgG = K <= 16 ? 4 : 6, G = 1 << lgG;
+    std::vector<uint32_t> cumA((size_t)K * K + (size_t)K * G / 4, 0u), cumpi((size_t)K + G / 4, 0u);
+    // guide[row][g] = #{k < K-1 : thr[row][k] <= g << (32 - lgG)}: start of the inverse-CDF scan
+    auto fill_guide = [&](const uint32_t* thr, unsigned char* guide) {
+        for (int g = 0; g < G; ++g) {
+            const uint32_t r0 = (uint32_t)g << (32 - lgG);
+            int c = 0;
+            while (c < K - 1 && thr[c] <= r0) ++c;
+            guide[g] = (unsigned char)c;
+        }
+    };
     std::vector<double> expF((size_t)T * K);
     for (int r = 0; r < K; ++r) {
         double acc = 0.0;
@@ -364,6 +389,9 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
         }
     }
     if (x0 < 0) { double acc = 0.0; for (int k = 0; k < K; ++k) { acc += pi[k]; cumpi[k] = thr_of(acc); } }
+    for (int r = 0; r < K; ++r) fill_guide(cumA.data() + (size_t)r * K, reinterpret_cast<unsigned char*>(cumA.data() + (size_t)K * K) + (size_t)r * G);
+    fill_guide(cumpi.data(), reinterpret_cast<unsigned char*>(cumpi.data() + K));
+    h->hmm_lgG = lgG;
     for (size_t i = 0; i < (size_t)T * K; ++i) expF[i] = exp(logF[i]);       // src/pmcmc.jl:55 (literal mode)
     h->has_factor.assign((size_t)T, 1);
     if (has_factor) for (int t = 0; t < T; ++t) h->has_factor[t] = has_factor[t] ? 1 : 0;
@@ -435,7 +463,7 @@ namespace {
 
 template <bool FP32>
 int launch_step_hmm(sb_handle* h, int anc_mode, const SbHmmStepArgs& a, unsigned grid) {
-    const size_t smem = (size_t)a.K * 8 + (size_t)(a.rows * a.K + a.K) * 4;
+    const size_t smem = (size_t)a.K * 8 + (size_t)(a.rows * a.K + a.K) * 4 + ((size_t)a.rows << a.lgG);
     switch (anc_mode) {
         case SB_ANC_NONE:     k_step_hmm<SB_ANC_NONE, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
         case SB_ANC_PULL:     k_step_hmm<SB_ANC_PULL, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
@@ -517,8 +545,12 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.Q_out = h->tile_Q[cur].as<unsigned long long>();
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.wlit_out = literal ? h->wlit.as<double>() : nullptr;
-        if (t == 0) { a.thr = h->x0 >= 0 ? h->hmm_cumA.as<uint32_t>() + (size_t)h->x0 * K : h->hmm_cumpi.as<uint32_t>(); a.rows = 1; }
-        else        { a.thr = h->hmm_cumA.as<uint32_t>(); a.rows = K; }
+        const int G = 1 << h->hmm_lgG;
+        const unsigned char* guideA = reinterpret_cast<const unsigned char*>(h->hmm_cumA.as<uint32_t>() + (size_t)K * K);
+        a.lgG = h->hmm_lgG;
+        if (t == 0 && h->x0 >= 0) { a.thr = h->hmm_cumA.as<uint32_t>() + (size_t)h->x0 * K; a.guide = guideA + (size_t)h->x0 * G; a.rows = 1; }
+        else if (t == 0) { a.thr = h->hmm_cumpi.as<uint32_t>(); a.guide = reinterpret_cast<const unsigned char*>(h->hmm_cumpi.as<uint32_t>() + K); a.rows = 1; }
+        else { a.thr = h->hmm_cumA.as<uint32_t>(); a.guide = guideA; a.rows = K; }
         a.logF_t = h->hmm_logF.as<double>() + (size_t)t * K;
         a.expF_t = h->hmm_expF.as<double>() + (size_t)t * K;
         a.xstar = conditional ? h->xstar[h->xstar_cur].as<int>() : nullptr;
