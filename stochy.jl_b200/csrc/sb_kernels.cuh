@@ -129,34 +129,48 @@ __device__ __forceinline__ unsigned long long sb_scan1024_excl(unsigned long lon
     return base + inc - loc;
 }
 
-// SMEM = true: the (e, Q) arrays (<= 8192 tiles) are staged once into shared memory with coalesced
-// loads, so every later pass runs from on-chip memory (the kernel is pure latency otherwise).
-template <bool SMEM>
+// PER > 0: every thread keeps its PER consecutive tiles in registers (nt <= 1024 * PER), all loads
+// issued up front and every pass fully unrolled, so the single CTA runs on ILP instead of on
+// serialised memory latency.  PER == 0: generic looping version for pools above 2^24 particles.
+template <int PER>
 __global__ void __launch_bounds__(SB_SCAN_THREADS)
 k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q_g, int nt, long long n, long long m,
            unsigned long long seed, unsigned t, unsigned iter, double u_override, SbStepInfo* __restrict__ info,
            unsigned long long* __restrict__ P, unsigned long long* __restrict__ Pt, int* __restrict__ child_start,
            int* __restrict__ first_tile, double* __restrict__ logZ_acc, double* __restrict__ logZ_step,
            unsigned* __restrict__ err) {
-    extern __shared__ __align__(16) unsigned char dyn[];
+    constexpr int NR = PER > 0 ? PER : 1;
     __shared__ int s_e[32];
     __shared__ unsigned long long s_w[32];
     __shared__ SbStepInfo s_info;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned long long* Q = Q_g;
-    const int* e = e_g;
-    if (SMEM) {
-        unsigned long long* sQ = reinterpret_cast<unsigned long long*>(dyn);
-        int* se = reinterpret_cast<int*>(sQ + nt);
-        for (int b = tid; b < nt; b += SB_SCAN_THREADS) { sQ[b] = __ldg(Q_g + b); se[b] = __ldg(e_g + b); }
-        __syncthreads();
-        Q = sQ; e = se;
-    }
-    const int per = (nt + SB_SCAN_THREADS - 1) / SB_SCAN_THREADS;
+    const int per = PER > 0 ? PER : (nt + SB_SCAN_THREADS - 1) / SB_SCAN_THREADS;
     const int b0 = min(nt, tid * per), b1 = min(nt, b0 + per);
+    unsigned long long q[NR];
+    int ex[NR];
+    if (PER > 0) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const bool in = b0 + i < b1;
+            q[i] = in ? __ldg(Q_g + b0 + i) : 0ull;
+            ex[i] = in ? __ldg(e_g + b0 + i) : SB_E_EMPTY;
+        }
+    }
+#define SB_TS_FOR(body)                                                                   \
+    if (PER > 0) {                                                                        \
+        _Pragma("unroll") for (int i = 0; i < NR; ++i) {                                  \
+            const int b = b0 + i; const unsigned long long qv = q[i]; const int ev = ex[i]; \
+            if (b < b1) { body }                                                          \
+        }                                                                                 \
+    } else {                                                                              \
+        for (int b = b0; b < b1; ++b) {                                                   \
+            const unsigned long long qv = Q_g[b]; const int ev = e_g[b];                  \
+            { body }                                                                      \
+        }                                                                                 \
+    }
     // global exponent
     int E = SB_E_EMPTY;
-    for (int b = b0; b < b1; ++b) if (Q[b] != 0ull) E = max(E, e[b]);
+    SB_TS_FOR(if (qv != 0ull) E = max(E, ev);)
 #pragma unroll
     for (int d = 16; d; d >>= 1) E = max(E, __shfl_xor_sync(0xffffffffu, E, d));
     if (lane == 0) s_e[warp] = E;
@@ -168,17 +182,10 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     while (LS > 0 && (1 << (24 - LS)) < nt) --LS;            // LS = 24 - ceil_log2(nt)
     // exact CDF of tile sums (log-evidence, multinomial)
     unsigned long long loc = 0;
-    for (int b = b0; b < b1; ++b) {
-        const unsigned long long q = Q[b];
-        if (q != 0ull) { const int sh = E - e[b]; loc += sh >= 63 ? 0ull : ((q << LS) >> sh); }
-    }
+    SB_TS_FOR(if (qv != 0ull) { const int sh = E - ev; loc += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
     unsigned long long total;
     unsigned long long run = sb_scan1024_excl(loc, s_w, &total);
-    for (int b = b0; b < b1; ++b) {
-        P[b] = run;
-        const unsigned long long q = Q[b];
-        if (q != 0ull) { const int sh = E - e[b]; run += sh >= 63 ? 0ull : ((q << LS) >> sh); }
-    }
+    SB_TS_FOR(P[b] = run; if (qv != 0ull) { const int sh = E - ev; run += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
     if (tid == 0) {
         P[nt] = total;
         SbStepInfo si;
@@ -200,9 +207,6 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
             if (r0 < 0) { s += r0; r0 = 0; }
             if (s < 0) si.valid = 0;
             si.R = (unsigned)R; si.r0 = r0; si.s = s < 0 ? 0 : s;
-            const double lm = log(__ull2double_rn(total)) + (double)(E - SB_QBITS - LS) * SB_LN2 - log((double)n);
-            if (logZ_acc) *logZ_acc += lm;
-            if (logZ_step) logZ_step[t] = lm;
         }
         s_info = si;
     }
@@ -210,11 +214,7 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     SbStepInfo si = s_info;
     // rescaled CDF of tile sums (systematic)
     unsigned long long loc2 = 0;
-    if (si.valid)
-        for (int b = b0; b < b1; ++b) {
-            const unsigned long long q = Q[b];
-            if (q != 0ull) loc2 += sb_sys_delta(q, si.R, si.r0 + (E - e[b]));
-        }
+    if (si.valid) { SB_TS_FOR(if (qv != 0ull) loc2 += sb_sys_delta(qv, si.R, si.r0 + (E - ev));) }
     unsigned long long Tt;
     unsigned long long run2 = sb_scan1024_excl(loc2, s_w, &Tt);
     if (tid == 0) {
@@ -237,18 +237,25 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     si = s_info;
     const int mi = (int)m;
     int cs = si.valid ? sb_sys_F(run2, si.U, si.s, mi) : 0;
-    for (int b = b0; b < b1; ++b) {
+    SB_TS_FOR(
         Pt[b] = run2;
         child_start[b] = cs;
-        const unsigned long long q = Q[b];
-        if (si.valid && q != 0ull) run2 += sb_sys_delta(q, si.R, si.r0 + (E - e[b]));
+        if (si.valid && qv != 0ull) run2 += sb_sys_delta(qv, si.R, si.r0 + (E - ev));
         int ce = si.valid ? sb_sys_F(run2, si.U, si.s, mi) : 0;
         if (b == nt - 1) ce = mi;
-        // children-tile boundaries k * SB_TILE in [cs, ce) start inside parent tile b
+        /* children-tile boundaries k * SB_TILE in [cs, ce) start inside parent tile b */
         for (int k = (cs + SB_TILE - 1) / SB_TILE; (long long)k * SB_TILE < ce; ++k) first_tile[k] = b;
         cs = ce;
+    )
+    if (tid == 0) {
+        Pt[nt] = Tt; child_start[nt] = mi;
+        if (si.valid) {      // log(mean weight) of the pool: the log-evidence increment (off the critical path)
+            const double lm = log(__ull2double_rn(total)) + (double)(E - SB_QBITS - LS) * SB_LN2 - log((double)n);
+            if (logZ_acc) *logZ_acc += lm;
+            if (logZ_step) logZ_step[t] = lm;
+        }
     }
-    if (tid == 0) { Pt[nt] = Tt; child_start[nt] = mi; }
+#undef SB_TS_FOR
 }
 
 // =====================================================================================
@@ -542,7 +549,8 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     const int base = c0 + tid * SB_ITEMS;
     const int K = a.K;
     for (int i = tid; i < a.rows * K; i += SB_THREADS) s_thr[i] = __ldg(a.thr + i);
-    for (int i = tid; i < (a.rows << a.lgG); i += SB_THREADS) s_guide[i] = __ldg(a.guide + i);
+    for (int i = tid; i < ((a.rows << a.lgG) >> 2); i += SB_THREADS)
+        reinterpret_cast<uint32_t*>(s_guide)[i] = __ldg(reinterpret_cast<const uint32_t*>(a.guide) + i);
     const bool tail = c0 + SB_TILE > a.N;                         // only the last CTA(s) see padding / the retained slot
     if (tid < K) {
         if (FP32) reinterpret_cast<float*>(s_l2)[tid] = __fmul_rn((float)a.logF_t[tid], SB_LOG2E_F);
@@ -596,6 +604,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
             // src/rand.jl:6-12 on a monotone row: first k with R < thr[k], else K-1.  The guide table
             // gives the number of thresholds at or below the start of R's bucket, so the scan is ~1 step.
             int lo = s_guide[(ri << a.lgG) + (R >> (32 - a.lgG))];
+            lo += (lo < K - 1 && R >= row[lo]) ? 1 : 0;          // common case: at most one threshold per bucket
             while (lo < K - 1 && R >= row[lo]) ++lo;
             x[j] = lo;
         }

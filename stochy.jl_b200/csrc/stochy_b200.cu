@@ -54,7 +54,7 @@ struct sb_handle {
     // model
     int model = MODEL_NONE;
     // HMM
-    int K = 0, T = 0, x0 = -1, hmm_lgG = 4;
+    int K = 0, T = 0, x0 = -1, hmm_lgG = 8;
     std::vector<uint8_t> has_factor;
     DevBuf hmm_cumA, hmm_cumpi, hmm_logF, hmm_expF, hmm_hasf;
     // LG
@@ -74,7 +74,6 @@ struct sb_handle {
     bool have_retained = false;
 
     // optional per-launch timing of the fused step kernel (sb_set_profile)
-    bool scan_attr_set = false;
     int profile = 0;
     std::vector<cudaEvent_t> prof_ev;
     int prof_used = 0;
@@ -146,24 +145,18 @@ int launch_quantise(sb_handle* h, const void* d_data, int kind, int64_t n, int s
 int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, unsigned t, unsigned iter, double u_override,
                     SbStepInfo* info, double* logZ_acc, double* logZ_step) {
     const int nt = (int)tiles_of(n);
-    if (nt <= 8192) {
-        const size_t smem = (size_t)nt * 12;
-        if (smem > 48 * 1024 && !h->scan_attr_set) {
-            CK(cudaFuncSetAttribute(k_tilescan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
-            h->scan_attr_set = true;
-        }
-        k_tilescan<true><<<1, SB_SCAN_THREADS, smem, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(),
-                                                                  nt, n, m, h->opt.seed, t, iter, u_override, info,
-                                                                  h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
-                                                                  h->child_start.as<int>(), h->first_tile.as<int>(),
-                                                                  logZ_acc, logZ_step, h->d_err);
-    } else {
-        k_tilescan<false><<<1, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(),
-                                                                nt, n, m, h->opt.seed, t, iter, u_override, info,
-                                                                h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
-                                                                h->child_start.as<int>(), h->first_tile.as<int>(),
-                                                                logZ_acc, logZ_step, h->d_err);
-    }
+#define SB_TS_LAUNCH(PER)                                                                                           \
+    k_tilescan<PER><<<1, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(), \
+                                                          nt, n, m, h->opt.seed, t, iter, u_override, info,           \
+                                                          h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(), \
+                                                          h->child_start.as<int>(), h->first_tile.as<int>(),          \
+                                                          logZ_acc, logZ_step, h->d_err)
+    if (nt <= 1024) SB_TS_LAUNCH(1);
+    else if (nt <= 2048) SB_TS_LAUNCH(2);
+    else if (nt <= 4096) SB_TS_LAUNCH(4);
+    else if (nt <= 8192) SB_TS_LAUNCH(8);
+    else SB_TS_LAUNCH(0);
+#undef SB_TS_LAUNCH
     LAUNCH_CHECK();
     return SB_OK;
 }
@@ -368,7 +361,7 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
         if (!(t > 0.0)) return 0u;
         return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
     };
-    const int lgG = K <= 16 ? 4 : 6, G = 1 << lgG;
+    const int lgG = 8, G = 1 << lgG;              // 256 buckets per row (K * 256 bytes of shared memory)
     std::vector<uint32_t> cumA((size_t)K * K + (size_t)K * G / 4, 0u), cumpi((size_t)K + G / 4, 0u);
     // guide[row][g] = #{k < K-1 : thr[row][k] <= g << (32 - lgG)}: start of the inverse-CDF scan
     auto fill_guide = [&](const uint32_t* thr, unsigned char* guide) {
