@@ -135,11 +135,12 @@ __device__ __forceinline__ unsigned long long sb_scan1024_excl(unsigned long lon
 template <int PER>
 __global__ void __launch_bounds__(SB_SCAN_THREADS)
 k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q_g, int nt, long long n, long long m,
-           unsigned long long seed, unsigned t, unsigned iter, double u_override, SbStepInfo* __restrict__ info,
+           const unsigned long long* __restrict__ r53_ptr, SbStepInfo* __restrict__ info,
            unsigned long long* __restrict__ P, unsigned long long* __restrict__ Pt, int* __restrict__ child_start,
-           int* __restrict__ first_tile, double* __restrict__ logZ_acc, double* __restrict__ logZ_step,
-           unsigned* __restrict__ err) {
+           int* __restrict__ first_tile, unsigned* __restrict__ err) {
     constexpr int NR = PER > 0 ? PER : 1;
+    // the systematic offset (53-bit uniform, host-drawn from the Philox stream) is fetched up front
+    const unsigned long long R53 = threadIdx.x == 0 ? __ldg(r53_ptr) : 0ull;
     __shared__ int s_e[32];
     __shared__ unsigned long long s_w[32];
     __shared__ SbStepInfo s_info;
@@ -178,8 +179,7 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     E = s_e[0];
 #pragma unroll
     for (int w = 1; w < 32; ++w) E = max(E, s_e[w]);
-    int LS = 24;
-    while (LS > 0 && (1 << (24 - LS)) < nt) --LS;            // LS = 24 - ceil_log2(nt)
+    const int LS = 24 - (nt <= 1 ? 0 : 32 - __clz(nt - 1));  // LS = 24 - ceil_log2(nt)
     // exact CDF of tile sums (log-evidence, multinomial)
     unsigned long long loc = 0;
     SB_TS_FOR(if (qv != 0ull) { const int sh = E - ev; loc += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
@@ -193,15 +193,17 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
         si.Tt = 0ull; si.U = 0ull; si.R = 0u; si.r0 = 0; si.s = 0;
         si.valid = (E != SB_E_EMPTY && total != 0ull) ? 1 : 0;
         if (si.valid) {
-            // plan of the systematic rescale: total of the rescaled CDF ~ m * 2^s
-            int clm = 0;
-            while ((1ll << clm) < m) ++clm;
+            // plan of the systematic rescale: total of the rescaled CDF ~ m * 2^s.  This section is
+            // serial (one thread), so it is kept to a few dozen instructions: clz instead of loops,
+            // bit extraction instead of frexp/ceil.
+            const int clm = m <= 1 ? 0 : 64 - __clzll(m - 1);
             int s = 62 - clm;
             if (s > 36) s = 36;
             const double ratio = __ddiv_rn(scalbn((double)m, s + LS), __ull2double_rn(total));
-            int x;
-            const double f = frexp(ratio, &x);
-            unsigned long long R = __double2ull_rz(ceil(__dmul_rn(f, 67108864.0)));
+            const unsigned long long rb_ = (unsigned long long)__double_as_longlong(ratio);
+            int x = (int)((rb_ >> 52) & 0x7ffull) - 1022;                      // ratio = f * 2^x, f in [0.5, 1)
+            const unsigned long long mant = (rb_ & 0xfffffffffffffull) | (1ull << 52);   // f * 2^53
+            unsigned long long R = (mant >> 27) + ((mant & ((1ull << 27) - 1ull)) ? 1ull : 0ull);   // ceil(f * 2^26)
             if (R >= 67108864ull) { R = 33554432ull; x += 1; }
             int r0 = 26 - x;
             if (r0 < 0) { s += r0; r0 = 0; }
@@ -221,9 +223,6 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
         const unsigned long long lastk = (unsigned long long)(m - 1) << si.s;
         if (si.valid && Tt > lastk) {
             const unsigned long long span = Tt - lastk;
-            unsigned long long R53;
-            if (u_override >= 0.0) R53 = __double2ull_rz(__dmul_rn(u_override, 0x1p53));
-            else { const SbU4 o = sb_stream4(seed, 0ull, t, iter, SB_P_RESAMPLE); R53 = sb_r53(o.x, o.y); }
             si.U = (__umul64hi(R53, span) << 11) | ((R53 * span) >> 53);
             si.Tt = Tt;
         } else {
@@ -247,14 +246,7 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
         for (int k = (cs + SB_TILE - 1) / SB_TILE; (long long)k * SB_TILE < ce; ++k) first_tile[k] = b;
         cs = ce;
     )
-    if (tid == 0) {
-        Pt[nt] = Tt; child_start[nt] = mi;
-        if (si.valid) {      // log(mean weight) of the pool: the log-evidence increment (off the critical path)
-            const double lm = log(__ull2double_rn(total)) + (double)(E - SB_QBITS - LS) * SB_LN2 - log((double)n);
-            if (logZ_acc) *logZ_acc += lm;
-            if (logZ_step) logZ_step[t] = lm;
-        }
-    }
+    if (tid == 0) { Pt[nt] = Tt; child_start[nt] = mi; }
 #undef SB_TS_FOR
 }
 

@@ -42,7 +42,9 @@ struct sb_handle {
 
     // error word, logZ accumulators, lineage index, step infos
     unsigned* d_err = nullptr;
-    DevBuf d_logZ;        // [0] accumulator, [1..T] per step
+    DevBuf d_r53;         // per-step systematic offsets (53-bit uniforms drawn on the host)
+    std::vector<unsigned long long> r53_host;
+    std::vector<SbStepInfo> info_host;
     DevBuf d_info;        // SbStepInfo[max(T,1)]
     DevBuf d_misc;        // int lineage
 
@@ -101,6 +103,28 @@ int fail(sb_handle* h, int code, const std::string& msg) {
 
 inline int64_t tiles_of(int64_t n) { return (n + SB_TILE - 1) / SB_TILE; }
 
+// host copy of the Philox4x32-10 stream (the per-step systematic offsets are drawn on the host so the
+// single-CTA tile scan does not spend its serial section on ten dependent rounds)
+void philox_host(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+uint64_t host_r53(uint64_t seed, uint64_t idx, uint32_t t, uint32_t iter, uint32_t purpose) {
+    uint32_t o[4];
+    philox_host((uint32_t)idx, (uint32_t)(idx >> 32), t, (iter << 4) | purpose, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+    return ((uint64_t)o[0] << 21) | (uint64_t)(o[1] >> 11);
+}
+
+// log(mean weight) of a pool from its tile-scan record: the log-evidence increment (SURVEY D3 extension)
+double log_mean_weight(const SbStepInfo& si) {
+    return log((double)si.total) + (double)(si.E - SB_QBITS - si.LS) * SB_LN2 - log((double)si.n);
+}
+
 int check_err_word(sb_handle* h) {
     unsigned w = 0;
     CK(cudaMemcpyAsync(&w, h->d_err, sizeof(w), cudaMemcpyDeviceToHost, h->stream));
@@ -142,15 +166,13 @@ int launch_quantise(sb_handle* h, const void* d_data, int kind, int64_t n, int s
     return SB_OK;
 }
 
-int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, unsigned t, unsigned iter, double u_override,
-                    SbStepInfo* info, double* logZ_acc, double* logZ_step) {
+int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, const unsigned long long* d_r53, SbStepInfo* info) {
     const int nt = (int)tiles_of(n);
 #define SB_TS_LAUNCH(PER)                                                                                           \
     k_tilescan<PER><<<1, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(), \
-                                                          nt, n, m, h->opt.seed, t, iter, u_override, info,           \
+                                                          nt, n, m, d_r53, info,                                      \
                                                           h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(), \
-                                                          h->child_start.as<int>(), h->first_tile.as<int>(),          \
-                                                          logZ_acc, logZ_step, h->d_err)
+                                                          h->child_start.as<int>(), h->first_tile.as<int>(), h->d_err)
     if (nt <= 1024) SB_TS_LAUNCH(1);
     else if (nt <= 2048) SB_TS_LAUNCH(2);
     else if (nt <= 4096) SB_TS_LAUNCH(4);
@@ -289,7 +311,7 @@ extern "C" void sb_destroy(sb_handle* h) {
     if (!h) return;
     cudaSetDevice(h->opt.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->d_logZ, &h->d_info, &h->d_misc, &h->w32[0], &h->w32[1], &h->tile_e[0], &h->tile_e[1],
+    DevBuf* bufs[] = {&h->d_r53, &h->d_info, &h->d_misc, &h->w32[0], &h->w32[1], &h->tile_e[0], &h->tile_e[1],
                       &h->tile_Q[0], &h->tile_Q[1], &h->P, &h->Pt, &h->child_start, &h->first_tile, &h->cdf, &h->lit_acc, &h->lse_part,
                       &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
                       &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
@@ -485,6 +507,19 @@ int explicit_resample(sb_handle* h, int slot, int t, unsigned iter, int64_t n_po
     return launch_literal(h, h->wlit.as<double>(), n_pool, N, nullptr, (unsigned)t, iter, d_anc);
 }
 
+// systematic offsets of every step of this sweep (Philox stream, purpose RESAMPLE, counter (0, t, iter));
+// also clears the per-step records so steps without a factor statement read as invalid
+int upload_offsets(sb_handle* h, unsigned iter) {
+    const int T = h->T;
+    CK(h->d_r53.ensure(sizeof(unsigned long long) * (size_t)T));
+    CK(h->d_info.ensure(sizeof(SbStepInfo) * (size_t)T));
+    h->r53_host.resize((size_t)T);
+    for (int t = 0; t < T; ++t) h->r53_host[t] = host_r53(h->opt.seed, 0, (uint32_t)t, iter, SB_P_RESAMPLE);
+    CK(cudaMemcpyAsync(h->d_r53.p, h->r53_host.data(), sizeof(unsigned long long) * (size_t)T, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemsetAsync(h->d_info.p, 0, sizeof(SbStepInfo) * (size_t)T, h->stream));
+    return SB_OK;
+}
+
 // One sweep of the discrete model.  conditional: pool of N+1 with the retained particle appended.
 int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool history, bool final_anc) {
     const int T = h->T, K = h->K;
@@ -500,10 +535,9 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
     CK(h->xbuf.ensure((size_t)xrows * S * 4));
     CK(h->ancbuf.ensure((size_t)arows * S * 4));
     CK(h->d_info.ensure(sizeof(SbStepInfo) * (size_t)T));
-    CK(h->d_logZ.ensure(sizeof(double) * (size_t)(T + 1)));
     if (h->opt.store_logw) CK(h->lwbuf.ensure((size_t)T * S * 8));
     if (literal) CK(h->wlit.ensure((size_t)S * 8));
-    CK(cudaMemsetAsync(h->d_logZ.p, 0, sizeof(double) * (size_t)(T + 1), h->stream));
+    if ((rc = upload_offsets(h, iter)) != SB_OK) return rc;
     h->sw_N = N; h->sw_S = S; h->sw_hist = history ? 1 : 0; h->sw_cond = conditional ? 1 : 0;
     int* xb = h->xbuf.as<int>();
     int* ab = h->ancbuf.as<int>();
@@ -555,8 +589,8 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         if (rc != SB_OK) return rc;
         if (h->has_factor[t]) {
             // literal mode still runs the tile scan: it supplies the log-evidence term
-            if ((rc = launch_tilescan(h, cur, n_out, N, (unsigned)t, iter, -1.0, h->d_info.as<SbStepInfo>() + t,
-                                      h->d_logZ.as<double>(), h->d_logZ.as<double>() + 1)) != SB_OK) return rc;
+            if ((rc = launch_tilescan(h, cur, n_out, N, h->d_r53.as<unsigned long long>() + t,
+                                      h->d_info.as<SbStepInfo>() + t)) != SB_OK) return rc;
         }
     }
     if (final_anc) {
@@ -587,9 +621,8 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
     CK(h->xbuf.ensure((size_t)2 * S * sz));
     CK(h->ancbuf.ensure((size_t)S * 4));
     CK(h->d_info.ensure(sizeof(SbStepInfo) * (size_t)T));
-    CK(h->d_logZ.ensure(sizeof(double) * (size_t)(T + 1)));
     if (h->opt.store_logw) CK(h->lwbuf.ensure((size_t)T * S * 8));
-    CK(cudaMemsetAsync(h->d_logZ.p, 0, sizeof(double) * (size_t)(T + 1), h->stream));
+    if ((rc = upload_offsets(h, iter)) != SB_OK) return rc;
     h->sw_N = N; h->sw_S = S; h->sw_hist = 0; h->sw_cond = 0;
     char* xb = h->xbuf.as<char>();
     const unsigned grid = (unsigned)tiles_of(N);
@@ -623,16 +656,22 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
             rc = fp32 ? launch_step_lg<true>(h, anc_mode, a, grid) : launch_step_lg<false>(h, anc_mode, a, grid);
         }
         if (rc != SB_OK) return rc;
-        if ((rc = launch_tilescan(h, cur, N, N, (unsigned)t, iter, -1.0, h->d_info.as<SbStepInfo>() + t,
-                                  h->d_logZ.as<double>(), h->d_logZ.as<double>() + 1)) != SB_OK) return rc;
+        if ((rc = launch_tilescan(h, cur, N, N, h->d_r53.as<unsigned long long>() + t,
+                                  h->d_info.as<SbStepInfo>() + t)) != SB_OK) return rc;
     }
     return SB_OK;
 }
 
+// log-evidence of the last sweep: sum over its factor steps of log(mean weight), accumulated on the
+// host in step order from the tile-scan records (integers), so it is reproducible bit for bit
 int fetch_logZ(sb_handle* h, double* out) {
-    double v = 0.0;
-    CK(cudaMemcpyAsync(&v, h->d_logZ.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    const int T = h->T;
+    h->info_host.resize((size_t)T);
+    CK(cudaMemcpyAsync(h->info_host.data(), h->d_info.p, sizeof(SbStepInfo) * (size_t)T, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    double v = 0.0;
+    for (int t = 0; t < T; ++t)
+        if (h->info_host[t].valid) v += log_mean_weight(h->info_host[t]);
     *out = v;
     return SB_OK;
 }
@@ -772,6 +811,16 @@ extern "C" int32_t sb_mh_run(sb_handle* h, int64_t chains, int64_t steps, int64_
 
 // ======================================================================= hooks
 namespace {
+// one caller-supplied systematic offset u in [0,1) -> 53-bit integer in d_r53[0]
+int stage_offset(sb_handle* h, double u) {
+    const size_t need = sizeof(unsigned long long) * (size_t)(h->T > 1 ? h->T : 1);
+    CK(h->d_r53.ensure(need));
+    CK(h->d_info.ensure(sizeof(SbStepInfo) * (size_t)(h->T > 1 ? h->T : 1)));
+    h->r53_host.resize(1);
+    h->r53_host[0] = (unsigned long long)(u * 0x1p53);
+    CK(cudaMemcpyAsync(h->d_r53.p, h->r53_host.data(), sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream));
+    return SB_OK;
+}
 int stage_in(sb_handle* h, DevBuf& b, const void* src, size_t bytes) {
     CK(b.ensure(bytes));
     CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
@@ -785,9 +834,9 @@ extern "C" int32_t sb_dev_resample_systematic(sb_handle* h, const void* d_weight
     if (!d_weights || !d_anc || n < 1 || m < 1 || !(u >= 0.0 && u < 1.0)) return fail(h, SB_EINVAL, "resample_systematic: bad arguments");
     int rc;
     if ((rc = ensure_grid(h, n, m)) != SB_OK) return rc;
-    CK(h->d_info.ensure(sizeof(SbStepInfo)));
+    if ((rc = stage_offset(h, u)) != SB_OK) return rc;
     if ((rc = launch_quantise(h, d_weights, kind, n, 0)) != SB_OK) return rc;
-    if ((rc = launch_tilescan(h, 0, n, m, 0, 0, u, h->d_info.as<SbStepInfo>(), nullptr, nullptr)) != SB_OK) return rc;
+    if ((rc = launch_tilescan(h, 0, n, m, h->d_r53.as<unsigned long long>(), h->d_info.as<SbStepInfo>())) != SB_OK) return rc;
     return launch_pull(h, 0, h->d_info.as<SbStepInfo>(), m, d_anc);
 }
 
@@ -819,10 +868,10 @@ extern "C" int32_t sb_resample_multinomial(sb_handle* h, const void* weights, in
     if ((rc = stage_in(h, h->hk_r, r, (size_t)m * 8)) != SB_OK) return rc;
     CK(h->hk_anc.ensure((size_t)m * 4));
     if ((rc = ensure_grid(h, n, m)) != SB_OK) return rc;
-    CK(h->d_info.ensure(sizeof(SbStepInfo)));
+    if ((rc = stage_offset(h, 0.0)) != SB_OK) return rc;
     if ((rc = begin_timed(h)) != SB_OK) return rc;
     if ((rc = launch_quantise(h, h->hk_in.p, kind, n, 0)) != SB_OK) return rc;
-    if ((rc = launch_tilescan(h, 0, n, m, 0, 0, 0.0, h->d_info.as<SbStepInfo>(), nullptr, nullptr)) != SB_OK) return rc;
+    if ((rc = launch_tilescan(h, 0, n, m, h->d_r53.as<unsigned long long>(), h->d_info.as<SbStepInfo>())) != SB_OK) return rc;
     if ((rc = launch_grid_multinomial(h, 0, h->d_info.as<SbStepInfo>(), n, m, h->hk_r.as<double>(), 0, 0, h->hk_anc.as<int>())) != SB_OK) return rc;
     if ((rc = end_timed(h)) != SB_OK) return rc;
     if ((rc = check_err_word(h)) != SB_OK) return rc;
