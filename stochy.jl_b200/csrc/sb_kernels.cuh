@@ -5,6 +5,8 @@
 #include <cfloat>
 #include <cmath>
 #include <type_traits>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 // =====================================================================================
 // k_quantise: host/device supplied weights -> (w32, tile exponent, tile sum).
@@ -110,8 +112,47 @@ k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w3
 // extension.  Deterministic: integer adds only.
 // =====================================================================================
 #define SB_SCAN_THREADS 1024
-__device__ __forceinline__ unsigned long long sb_scan1024_excl(unsigned long long loc, unsigned long long* s_w,
-                                                                unsigned long long* total) {
+#define SB_SCAN_CTAS    8      // one thread-block cluster: 8 SMs x 1024 threads = one tile per thread at 2^24 particles
+
+// The scan runs as ONE thread-block cluster: block-local warp-shuffle scans, then the 8 block totals
+// are exchanged through distributed shared memory (cluster.sync is ~0.2 us, a second kernel launch
+// or a single-SM scan of 8192 tiles is 10-30 us).  All arithmetic is integer: any association
+// order gives the same bits.
+struct SbScanSmem {
+    unsigned long long warp_tot[32];
+    unsigned long long blk_tot;      // read by the other CTAs of the cluster
+    int blk_max;                     // idem
+    int warp_max[32];
+    unsigned long long base, total;  // broadcast inside the CTA
+    int gmax;
+};
+
+__device__ __forceinline__ int sb_cluster_max(int v, SbScanSmem& sm, cg::cluster_group& cl) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if (lane == 0) sm.warp_max[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int w = sm.warp_max[lane];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, d));
+        if (lane == 0) sm.blk_max = w;
+    }
+    cl.sync();
+    if (threadIdx.x < SB_SCAN_CTAS) {
+        int r = *cl.map_shared_rank(&sm.blk_max, threadIdx.x);
+#pragma unroll
+        for (int d = 4; d; d >>= 1) r = max(r, __shfl_xor_sync(0xffu, r, d));
+        if (threadIdx.x == 0) sm.gmax = r;
+    }
+    __syncthreads();
+    return sm.gmax;
+}
+
+// exclusive prefix of `loc` over all threads of the cluster (thread order = rank * 1024 + tid)
+__device__ __forceinline__ unsigned long long sb_cluster_excl_scan(unsigned long long loc, SbScanSmem& sm,
+                                                                    cg::cluster_group& cl, unsigned long long* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long inc = loc;
 #pragma unroll
@@ -119,121 +160,110 @@ __device__ __forceinline__ unsigned long long sb_scan1024_excl(unsigned long lon
         unsigned long long o = sb_shfl_up_u64(inc, d);
         if (lane >= d) inc += o;
     }
+    cl.sync();                                   // previous readers of blk_tot / base are done
+    if (lane == 31) sm.warp_tot[warp] = inc;
     __syncthreads();
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    unsigned long long base = 0, tot = 0;
+    if (warp == 0) {
+        const unsigned long long wt = sm.warp_tot[lane];
+        unsigned long long wi = wt;
 #pragma unroll
-    for (int w = 0; w < 32; ++w) { const unsigned long long v = s_w[w]; if (w < warp) base += v; tot += v; }
-    *total = tot;
-    return base + inc - loc;
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long o = sb_shfl_up_u64(wi, d);
+            if (lane >= d) wi += o;
+        }
+        sm.warp_tot[lane] = wi - wt;             // exclusive prefix of the warp totals
+        if (lane == 31) sm.blk_tot = wi;
+    }
+    cl.sync();
+    if (threadIdx.x < 32) {
+        const unsigned rank = cl.block_rank();
+        unsigned long long bt = lane < SB_SCAN_CTAS ? *cl.map_shared_rank(&sm.blk_tot, lane) : 0ull;
+        unsigned long long base = lane < (int)rank ? bt : 0ull, tot = bt;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            const uint32_t blo = __shfl_xor_sync(0xffffffffu, (uint32_t)base, d), bhi = __shfl_xor_sync(0xffffffffu, (uint32_t)(base >> 32), d);
+            const uint32_t tlo = __shfl_xor_sync(0xffffffffu, (uint32_t)tot, d), thi = __shfl_xor_sync(0xffffffffu, (uint32_t)(tot >> 32), d);
+            base += ((unsigned long long)bhi << 32) | blo;
+            tot += ((unsigned long long)thi << 32) | tlo;
+        }
+        if (lane == 0) { sm.base = base; sm.total = tot; }
+    }
+    __syncthreads();
+    *total = sm.total;
+    return sm.base + sm.warp_tot[warp] + inc - loc;
 }
 
-// PER > 0: every thread keeps its PER consecutive tiles in registers (nt <= 1024 * PER), all loads
-// issued up front and every pass fully unrolled, so the single CTA runs on ILP instead of on
-// serialised memory latency.  PER == 0: generic looping version for pools above 2^24 particles.
-template <int PER>
-__global__ void __launch_bounds__(SB_SCAN_THREADS)
+__global__ void __cluster_dims__(SB_SCAN_CTAS, 1, 1) __launch_bounds__(SB_SCAN_THREADS)
 k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q_g, int nt, long long n, long long m,
            const unsigned long long* __restrict__ r53_ptr, SbStepInfo* __restrict__ info,
            unsigned long long* __restrict__ P, unsigned long long* __restrict__ Pt, int* __restrict__ child_start,
-           int* __restrict__ first_tile, unsigned* __restrict__ err) {
-    constexpr int NR = PER > 0 ? PER : 1;
-    // the systematic offset (53-bit uniform, host-drawn from the Philox stream) is fetched up front
-    const unsigned long long R53 = threadIdx.x == 0 ? __ldg(r53_ptr) : 0ull;
-    __shared__ int s_e[32];
-    __shared__ unsigned long long s_w[32];
-    __shared__ SbStepInfo s_info;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = PER > 0 ? PER : (nt + SB_SCAN_THREADS - 1) / SB_SCAN_THREADS;
-    const int b0 = min(nt, tid * per), b1 = min(nt, b0 + per);
-    unsigned long long q[NR];
-    int ex[NR];
-    if (PER > 0) {
-#pragma unroll
-        for (int i = 0; i < NR; ++i) {
-            const bool in = b0 + i < b1;
-            q[i] = in ? __ldg(Q_g + b0 + i) : 0ull;
-            ex[i] = in ? __ldg(e_g + b0 + i) : SB_E_EMPTY;
-        }
-    }
-#define SB_TS_FOR(body)                                                                   \
-    if (PER > 0) {                                                                        \
-        _Pragma("unroll") for (int i = 0; i < NR; ++i) {                                  \
-            const int b = b0 + i; const unsigned long long qv = q[i]; const int ev = ex[i]; \
-            if (b < b1) { body }                                                          \
-        }                                                                                 \
-    } else {                                                                              \
-        for (int b = b0; b < b1; ++b) {                                                   \
-            const unsigned long long qv = Q_g[b]; const int ev = e_g[b];                  \
-            { body }                                                                      \
-        }                                                                                 \
-    }
+           int* __restrict__ first_tile, int want_exact, unsigned* __restrict__ err) {
+    cg::cluster_group cl = cg::this_cluster();
+    __shared__ SbScanSmem sm;
+    const unsigned rank = cl.block_rank();
+    const int gtid = (int)rank * SB_SCAN_THREADS + threadIdx.x;
+    const unsigned long long R53 = __ldg(r53_ptr);            // host-drawn systematic offset (53-bit uniform)
+    const int per = (nt + SB_SCAN_THREADS * SB_SCAN_CTAS - 1) / (SB_SCAN_THREADS * SB_SCAN_CTAS);
+    const int b0 = min(nt, gtid * per), b1 = min(nt, b0 + per);
+    // fast path: one tile per thread, kept in registers
+    const bool one = per == 1;
+    unsigned long long q1 = 0ull;
+    int e1 = SB_E_EMPTY;
+    if (one && b0 < b1) { q1 = __ldg(Q_g + b0); e1 = __ldg(e_g + b0); }
+#define SB_TS_FOR(body)                                                                        \
+    if (one) { if (b0 < b1) { const int b = b0; (void)b; const unsigned long long qv = q1; const int ev = e1; body } } \
+    else for (int b = b0; b < b1; ++b) { (void)b; const unsigned long long qv = __ldg(Q_g + b); const int ev = __ldg(e_g + b); body }
     // global exponent
     int E = SB_E_EMPTY;
     SB_TS_FOR(if (qv != 0ull) E = max(E, ev);)
-#pragma unroll
-    for (int d = 16; d; d >>= 1) E = max(E, __shfl_xor_sync(0xffffffffu, E, d));
-    if (lane == 0) s_e[warp] = E;
-    __syncthreads();
-    E = s_e[0];
-#pragma unroll
-    for (int w = 1; w < 32; ++w) E = max(E, s_e[w]);
+    E = sb_cluster_max(E, sm, cl);
     const int LS = 24 - (nt <= 1 ? 0 : 32 - __clz(nt - 1));  // LS = 24 - ceil_log2(nt)
-    // exact CDF of tile sums (log-evidence, multinomial)
+    // exact CDF of tile sums (log-evidence; multinomial resampling)
     unsigned long long loc = 0;
     SB_TS_FOR(if (qv != 0ull) { const int sh = E - ev; loc += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
     unsigned long long total;
-    unsigned long long run = sb_scan1024_excl(loc, s_w, &total);
-    SB_TS_FOR(P[b] = run; if (qv != 0ull) { const int sh = E - ev; run += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
-    if (tid == 0) {
-        P[nt] = total;
-        SbStepInfo si;
-        si.total = total; si.n = n; si.m = m; si.E = E; si.LS = LS; si.nt = nt;
-        si.Tt = 0ull; si.U = 0ull; si.R = 0u; si.r0 = 0; si.s = 0;
-        si.valid = (E != SB_E_EMPTY && total != 0ull) ? 1 : 0;
-        if (si.valid) {
-            // plan of the systematic rescale: total of the rescaled CDF ~ m * 2^s.  This section is
-            // serial (one thread), so it is kept to a few dozen instructions: clz instead of loops,
-            // bit extraction instead of frexp/ceil.
-            const int clm = m <= 1 ? 0 : 64 - __clzll(m - 1);
-            int s = 62 - clm;
-            if (s > 36) s = 36;
-            const double ratio = __ddiv_rn(scalbn((double)m, s + LS), __ull2double_rn(total));
-            const unsigned long long rb_ = (unsigned long long)__double_as_longlong(ratio);
-            int x = (int)((rb_ >> 52) & 0x7ffull) - 1022;                      // ratio = f * 2^x, f in [0.5, 1)
-            const unsigned long long mant = (rb_ & 0xfffffffffffffull) | (1ull << 52);   // f * 2^53
-            unsigned long long R = (mant >> 27) + ((mant & ((1ull << 27) - 1ull)) ? 1ull : 0ull);   // ceil(f * 2^26)
-            if (R >= 67108864ull) { R = 33554432ull; x += 1; }
-            int r0 = 26 - x;
-            if (r0 < 0) { s += r0; r0 = 0; }
-            if (s < 0) si.valid = 0;
-            si.R = (unsigned)R; si.r0 = r0; si.s = s < 0 ? 0 : s;
-        }
-        s_info = si;
+    unsigned long long run = sb_cluster_excl_scan(loc, sm, cl, &total);
+    if (want_exact) {
+        SB_TS_FOR(P[b] = run; if (qv != 0ull) { const int sh = E - ev; run += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
+        if (gtid == 0) P[nt] = total;
     }
-    __syncthreads();
-    SbStepInfo si = s_info;
+    // plan of the systematic rescale (every thread computes the same few integers)
+    SbStepInfo si;
+    si.total = total; si.n = n; si.m = m; si.E = E; si.LS = LS; si.nt = nt;
+    si.Tt = 0ull; si.U = 0ull; si.R = 0u; si.r0 = 0; si.s = 0;
+    si.valid = (E != SB_E_EMPTY && total != 0ull) ? 1 : 0;
+    if (si.valid) {
+        const int clm = m <= 1 ? 0 : 64 - __clzll(m - 1);
+        int s = 62 - clm;
+        if (s > 36) s = 36;
+        const double ratio = __ddiv_rn(scalbn((double)m, s + LS), __ull2double_rn(total));
+        const unsigned long long rb_ = (unsigned long long)__double_as_longlong(ratio);
+        int x = (int)((rb_ >> 52) & 0x7ffull) - 1022;                      // ratio = f * 2^x, f in [0.5, 1)
+        const unsigned long long mant = (rb_ & 0xfffffffffffffull) | (1ull << 52);   // f * 2^53
+        unsigned long long R = (mant >> 27) + ((mant & ((1ull << 27) - 1ull)) ? 1ull : 0ull);   // ceil(f * 2^26)
+        if (R >= 67108864ull) { R = 33554432ull; x += 1; }
+        int r0 = 26 - x;
+        if (r0 < 0) { s += r0; r0 = 0; }
+        if (s < 0) si.valid = 0;
+        si.R = (unsigned)R; si.r0 = r0; si.s = s < 0 ? 0 : s;
+    }
     // rescaled CDF of tile sums (systematic)
     unsigned long long loc2 = 0;
     if (si.valid) { SB_TS_FOR(if (qv != 0ull) loc2 += sb_sys_delta(qv, si.R, si.r0 + (E - ev));) }
     unsigned long long Tt;
-    unsigned long long run2 = sb_scan1024_excl(loc2, s_w, &Tt);
-    if (tid == 0) {
-        const unsigned long long lastk = (unsigned long long)(m - 1) << si.s;
-        if (si.valid && Tt > lastk) {
-            const unsigned long long span = Tt - lastk;
-            si.U = (__umul64hi(R53, span) << 11) | ((R53 * span) >> 53);
-            si.Tt = Tt;
-        } else {
-            si.valid = 0;
-        }
+    unsigned long long run2 = sb_cluster_excl_scan(loc2, sm, cl, &Tt);
+    const unsigned long long lastk = (unsigned long long)(m - 1) << si.s;
+    if (si.valid && Tt > lastk) {
+        const unsigned long long span = Tt - lastk;
+        si.U = (__umul64hi(R53, span) << 11) | ((R53 * span) >> 53);
+        si.Tt = Tt;
+    } else {
+        si.valid = 0;
+    }
+    if (gtid == 0) {
         if (!si.valid) atomicOr(err, SB_ERRBIT_ZERO);
-        s_info = si;
         *info = si;
     }
-    __syncthreads();
-    si = s_info;
     const int mi = (int)m;
     int cs = si.valid ? sb_sys_F(run2, si.U, si.s, mi) : 0;
     SB_TS_FOR(
@@ -246,7 +276,8 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
         for (int k = (cs + SB_TILE - 1) / SB_TILE; (long long)k * SB_TILE < ce; ++k) first_tile[k] = b;
         cs = ce;
     )
-    if (tid == 0) { Pt[nt] = Tt; child_start[nt] = mi; }
+    if (gtid == 0) { Pt[nt] = Tt; child_start[nt] = mi; }
+    cl.sync();                                   // no CTA may exit while its shared memory can still be read
 #undef SB_TS_FOR
 }
 

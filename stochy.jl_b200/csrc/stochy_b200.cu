@@ -76,6 +76,7 @@ struct sb_handle {
     bool have_retained = false;
 
     // optional per-launch timing of the fused step kernel (sb_set_profile)
+    int hook_exact = 0;     // the multinomial hook needs the exact CDF whatever the handle's mode
     int profile = 0;
     std::vector<cudaEvent_t> prof_ev;
     int prof_used = 0;
@@ -168,17 +169,11 @@ int launch_quantise(sb_handle* h, const void* d_data, int kind, int64_t n, int s
 
 int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, const unsigned long long* d_r53, SbStepInfo* info) {
     const int nt = (int)tiles_of(n);
-#define SB_TS_LAUNCH(PER)                                                                                           \
-    k_tilescan<PER><<<1, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(), \
-                                                          nt, n, m, d_r53, info,                                      \
-                                                          h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(), \
-                                                          h->child_start.as<int>(), h->first_tile.as<int>(), h->d_err)
-    if (nt <= 1024) SB_TS_LAUNCH(1);
-    else if (nt <= 2048) SB_TS_LAUNCH(2);
-    else if (nt <= 4096) SB_TS_LAUNCH(4);
-    else if (nt <= 8192) SB_TS_LAUNCH(8);
-    else SB_TS_LAUNCH(0);
-#undef SB_TS_LAUNCH
+    k_tilescan<<<SB_SCAN_CTAS, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(),
+                                                                nt, n, m, d_r53, info, h->P.as<unsigned long long>(),
+                                                                h->Pt.as<unsigned long long>(), h->child_start.as<int>(),
+                                                                h->first_tile.as<int>(),
+                                                                h->opt.resample_mode == SB_RESAMPLE_MULTINOMIAL || h->hook_exact, h->d_err);
     LAUNCH_CHECK();
     return SB_OK;
 }
@@ -871,7 +866,10 @@ extern "C" int32_t sb_resample_multinomial(sb_handle* h, const void* weights, in
     if ((rc = stage_offset(h, 0.0)) != SB_OK) return rc;
     if ((rc = begin_timed(h)) != SB_OK) return rc;
     if ((rc = launch_quantise(h, h->hk_in.p, kind, n, 0)) != SB_OK) return rc;
-    if ((rc = launch_tilescan(h, 0, n, m, h->d_r53.as<unsigned long long>(), h->d_info.as<SbStepInfo>())) != SB_OK) return rc;
+    h->hook_exact = 1;
+    rc = launch_tilescan(h, 0, n, m, h->d_r53.as<unsigned long long>(), h->d_info.as<SbStepInfo>());
+    h->hook_exact = 0;
+    if (rc != SB_OK) return rc;
     if ((rc = launch_grid_multinomial(h, 0, h->d_info.as<SbStepInfo>(), n, m, h->hk_r.as<double>(), 0, 0, h->hk_anc.as<int>())) != SB_OK) return rc;
     if ((rc = end_timed(h)) != SB_OK) return rc;
     if ((rc = check_err_word(h)) != SB_OK) return rc;
