@@ -232,10 +232,49 @@ struct SbPullSmem {
     int range[4];
 };
 
+// One parent tile's contribution to the children [c0, c1): block scan of its weights, then every
+// parent that owns children in range writes its index at its first child's slot ("head marker").
+__device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const uint32_t w[SB_ITEMS], int eb,
+                                             unsigned long long Ptb, int c0, int c1, SbPullSmem& sm) {
+    const int tid = threadIdx.x;
+    const int m = (int)si.m, s = si.s;
+    const unsigned R = si.R;
+    unsigned tsum = 0;                                           // 8 * 2^27 fits 32 bits
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) tsum += w[j];
+    unsigned long long tot;
+    unsigned long long c = sb_block_excl_scan_u64((unsigned long long)tsum, sm.scan, &tot);
+    if (tsum != 0) {
+        // tile-uniform constants; rb < 64 because the tile owns children
+        const int rb = si.r0 + (si.E - eb);
+        const long long baseb = (long long)(Ptb - si.U) + ((1ll << s) - 1ll);
+        // F(acc) = clamp((baseb + (acc >> rb)) >> s, 0, m): children strictly below this CDF value
+        unsigned long long acc = c * (unsigned long long)R;
+        long long k0 = (baseb + (long long)(acc >> rb)) >> s;
+        int lo = k0 <= 0 ? 0 : (k0 >= (long long)m ? m : (int)k0);
+        const unsigned long long acc_t = acc + (unsigned long long)tsum * R;
+        long long k1 = (baseb + (long long)(acc_t >> rb)) >> s;
+        const int hi_t = k1 <= 0 ? 0 : (k1 >= (long long)m ? m : (int)k1);
+        if (hi_t > lo && hi_t > c0 && lo < c1) {                 // this thread's parents own children in range
+            const int base = b * SB_TILE + tid * SB_ITEMS;
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) {
+                acc += (unsigned long long)w[j] * R;             // one IMAD.WIDE with 64-bit accumulate
+                long long k = (baseb + (long long)(acc >> rb)) >> s;
+                const int hi = (j == SB_ITEMS - 1) ? hi_t : (k <= 0 ? 0 : (k >= (long long)m ? m : (int)k));
+                const int a0 = max(lo, c0), a1 = min(hi, c1);
+                if (a0 < a1) sm.marker[a0 - c0] = base + j;
+                lo = hi;
+            }
+        }
+    }
+}
+
 // Computes, for the children [c0, c0+SB_TILE) of this CTA, the pool index of each child's parent
 // under systematic resampling on the weight grid; thread `tid` receives children c0+8*tid .. +7.
 // w32 / e / Pt / child_start / first_tile describe the POOL (previous step).  Parent tiles are read
-// with coalesced 128-bit loads; only threads whose 8 parents own children in range evaluate them.
+// with coalesced 128-bit loads.  The first two candidate tiles (almost always all there are) and
+// their metadata are requested together, so the CTA pays one memory latency instead of a chain.
 __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const uint32_t* __restrict__ w32,
                                                   const int* __restrict__ e, const unsigned long long* __restrict__ Pt,
                                                   const int* __restrict__ child_start, const int* __restrict__ first_tile,
@@ -243,49 +282,28 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const ui
     const int tid = threadIdx.x;
     const int m = (int)si.m;
     const int c1 = min(c0 + SB_TILE, m);
-#pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) sm.marker[tid + j * SB_THREADS] = -1;
     const int cb = c0 / SB_TILE;
     const int b_lo = __ldg(first_tile + cb);
     const int b_hi = (c1 < m) ? __ldg(first_tile + cb + 1) : si.nt - 1;
-    const unsigned long long U = si.U;
-    const unsigned R = si.R;
-    const int s = si.s;
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) sm.marker[tid + j * SB_THREADS] = -1;
+    const int bA = b_lo, bB = min(b_lo + 1, si.nt - 1);
+    uint32_t wA[SB_ITEMS], wB[SB_ITEMS];
+    sb_load8_u32(w32 + (size_t)bA * SB_TILE + tid * SB_ITEMS, wA);
+    sb_load8_u32(w32 + (size_t)bB * SB_TILE + tid * SB_ITEMS, wB);
+    const int csA = __ldg(child_start + bA), ceA = __ldg(child_start + bA + 1);
+    const int csB = __ldg(child_start + bB), ceB = __ldg(child_start + bB + 1);
+    const int eA = __ldg(e + bA), eB = __ldg(e + bB);
+    const unsigned long long PtA = __ldg(Pt + bA), PtB = __ldg(Pt + bB);
     __syncthreads();
-    for (int b = b_lo; b <= b_hi; ++b) {
+    if (!(ceA <= c0 || csA >= c1 || ceA == csA)) sb_pull_tile(si, bA, wA, eA, PtA, c0, c1, sm);
+    if (bB != bA && bB <= b_hi && !(ceB <= c0 || csB >= c1 || ceB == csB)) sb_pull_tile(si, bB, wB, eB, PtB, c0, c1, sm);
+    for (int b = b_lo + 2; b <= b_hi; ++b) {
         const int cs = __ldg(child_start + b), ce = __ldg(child_start + b + 1);
         if (ce <= c0 || cs >= c1 || ce == cs) continue;          // no offspring in range (uniform branch)
         uint32_t w[SB_ITEMS];
         sb_load8_u32(w32 + (size_t)b * SB_TILE + tid * SB_ITEMS, w);
-        unsigned tsum = 0;                                       // 8 * 2^27 fits 32 bits
-#pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) tsum += w[j];
-        unsigned long long tot;
-        unsigned long long c = sb_block_excl_scan_u64((unsigned long long)tsum, sm.scan, &tot);
-        if (tsum != 0) {
-            // tile-uniform constants; rb < 64 because the tile owns children
-            const int rb = si.r0 + (si.E - __ldg(e + b));
-            const long long baseb = (long long)(__ldg(Pt + b) - U) + ((1ll << s) - 1ll);
-            // F(acc) = clamp((baseb + (acc >> rb)) >> s, 0, m): children strictly below this CDF value
-            unsigned long long acc = c * (unsigned long long)R;
-            long long k0 = (baseb + (long long)(acc >> rb)) >> s;
-            int lo = k0 <= 0 ? 0 : (k0 >= (long long)m ? m : (int)k0);
-            const unsigned long long acc_t = acc + (unsigned long long)tsum * R;
-            long long k1 = (baseb + (long long)(acc_t >> rb)) >> s;
-            const int hi_t = k1 <= 0 ? 0 : (k1 >= (long long)m ? m : (int)k1);
-            if (hi_t > lo && hi_t > c0 && lo < c1) {             // this thread's parents own children in range
-                const int base = b * SB_TILE + tid * SB_ITEMS;
-#pragma unroll
-                for (int j = 0; j < SB_ITEMS; ++j) {
-                    acc += (unsigned long long)w[j] * R;         // one IMAD.WIDE with 64-bit accumulate
-                    long long k = (baseb + (long long)(acc >> rb)) >> s;
-                    const int hi = (j == SB_ITEMS - 1) ? hi_t : (k <= 0 ? 0 : (k >= (long long)m ? m : (int)k));
-                    const int a0 = max(lo, c0), a1 = min(hi, c1);
-                    if (a0 < a1) sm.marker[a0 - c0] = base + j;
-                    lo = hi;
-                }
-            }
-        }
+        sb_pull_tile(si, b, w, __ldg(e + b), __ldg(Pt + b), c0, c1, sm);
     }
     __syncthreads();
     // inclusive max-scan of the head markers fills every child slot with its parent
