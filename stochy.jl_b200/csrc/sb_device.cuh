@@ -46,6 +46,27 @@ struct SbStepInfo {
     int valid;
 };
 
+// Where the POOL lives.  One GPU: w32[0] / x[0] with log2n = 31 (owner is always 0).  Particles
+// sharded over G GPUs (each a power-of-two 2^log2n of them): pool index i lives on GPU i >> log2n
+// at local index i & (2^log2n - 1); the pointers are peer mappings (CUDA IPC) read over NVLink by
+// the same loads that read local HBM -- the migration of resampled particles IS the gather.
+#define SB_MAX_PEERS 8
+struct SbPeers {
+    const void* w32[SB_MAX_PEERS];
+    const void* x[SB_MAX_PEERS];
+    int log2n;          // particles per GPU = 2^log2n  (31 on a single GPU)
+    int c_off;          // global index of this GPU's first child
+    int tile_off;       // global index of this GPU's first tile
+};
+__device__ __forceinline__ const uint32_t* sb_peer_tile(const SbPeers& p, int b) {
+    const int ts = p.log2n - 11;                                 // log2(SB_TILE) = 11
+    return reinterpret_cast<const uint32_t*>(p.w32[b >> ts]) + (size_t)(b & ((1 << ts) - 1)) * SB_TILE;
+}
+template <typename T>
+__device__ __forceinline__ T sb_peer_x(const SbPeers& p, int i) {
+    return __ldg(reinterpret_cast<const T*>(p.x[i >> p.log2n]) + (i & (int)((1u << p.log2n) - 1u)));
+}
+
 // ---------------------------------------------------------------- Philox4x32-10
 struct SbU4 { uint32_t x, y, z, w; };
 
@@ -275,22 +296,22 @@ __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const 
 // w32 / e / Pt / child_start / first_tile describe the POOL (previous step).  Parent tiles are read
 // with coalesced 128-bit loads.  The first two candidate tiles (almost always all there are) and
 // their metadata are requested together, so the CTA pays one memory latency instead of a chain.
-__device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const uint32_t* __restrict__ w32,
+__device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const SbPeers& peers,
                                                   const int* __restrict__ e, const unsigned long long* __restrict__ Pt,
                                                   const int* __restrict__ child_start, const int* __restrict__ first_tile,
                                                   int c0, SbPullSmem& sm, int anc[SB_ITEMS]) {
     const int tid = threadIdx.x;
     const int m = (int)si.m;
     const int c1 = min(c0 + SB_TILE, m);
-    const int cb = c0 / SB_TILE;
+    const int cb = c0 / SB_TILE;                                 // global children tile
     const int b_lo = __ldg(first_tile + cb);
     const int b_hi = (c1 < m) ? __ldg(first_tile + cb + 1) : si.nt - 1;
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) sm.marker[tid + j * SB_THREADS] = -1;
     const int bA = b_lo, bB = min(b_lo + 1, si.nt - 1);
     uint32_t wA[SB_ITEMS], wB[SB_ITEMS];
-    sb_load8_u32(w32 + (size_t)bA * SB_TILE + tid * SB_ITEMS, wA);
-    sb_load8_u32(w32 + (size_t)bB * SB_TILE + tid * SB_ITEMS, wB);
+    sb_load8_u32(sb_peer_tile(peers, bA) + tid * SB_ITEMS, wA);
+    sb_load8_u32(sb_peer_tile(peers, bB) + tid * SB_ITEMS, wB);
     const int csA = __ldg(child_start + bA), ceA = __ldg(child_start + bA + 1);
     const int csB = __ldg(child_start + bB), ceB = __ldg(child_start + bB + 1);
     const int eA = __ldg(e + bA), eB = __ldg(e + bB);
@@ -302,7 +323,7 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const ui
         const int cs = __ldg(child_start + b), ce = __ldg(child_start + b + 1);
         if (ce <= c0 || cs >= c1 || ce == cs) continue;          // no offspring in range (uniform branch)
         uint32_t w[SB_ITEMS];
-        sb_load8_u32(w32 + (size_t)b * SB_TILE + tid * SB_ITEMS, w);
+        sb_load8_u32(sb_peer_tile(peers, b) + tid * SB_ITEMS, w);
         sb_pull_tile(si, b, w, __ldg(e + b), __ldg(Pt + b), c0, c1, sm);
     }
     __syncthreads();

@@ -287,7 +287,7 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
 // sorted child thresholds with the integer CDF.  Bytes per child: read 4 (w32), write 4 (anc).
 // =====================================================================================
 __global__ void __launch_bounds__(SB_THREADS)
-k_pull(const SbStepInfo* __restrict__ info, const uint32_t* __restrict__ w32, const int* __restrict__ e,
+k_pull(const SbStepInfo* __restrict__ info, const __grid_constant__ SbPeers peers, const int* __restrict__ e,
        const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
        const int* __restrict__ first_tile, int* __restrict__ anc_out) {
     __shared__ SbPullSmem ps;
@@ -295,7 +295,7 @@ k_pull(const SbStepInfo* __restrict__ info, const uint32_t* __restrict__ w32, co
     const int c0 = blockIdx.x * SB_TILE;
     if (c0 >= (int)si.m) return;
     int anc[SB_ITEMS];
-    sb_pull_ancestors(si, w32, e, Pt, child_start, first_tile, c0, ps, anc);
+    sb_pull_ancestors(si, peers, e, Pt, child_start, first_tile, c0, ps, anc);
     const int base = c0 + threadIdx.x * SB_ITEMS;
     if (base + SB_ITEMS <= (int)si.m) {
         reinterpret_cast<int4*>(anc_out + base)[0] = make_int4(anc[0], anc[1], anc[2], anc[3]);
@@ -526,8 +526,7 @@ k_lse_final(const SbLse* __restrict__ partial, int np, double* __restrict__ out)
 
 struct SbHmmStepArgs {
     // previous pool
-    const int* x_prev;
-    const uint32_t* w32_prev;
+    SbPeers peers;
     const int* e_prev;
     const unsigned long long* Pt;
     const int* child_start;
@@ -568,8 +567,9 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     __shared__ SbPullSmem ps;
     __shared__ double s_red[SB_WARPS];
     const int tid = threadIdx.x;
-    const int c0 = blockIdx.x * SB_TILE;
+    const int c0 = a.peers.c_off + blockIdx.x * SB_TILE;          // global child index of this tile
     const int base = c0 + tid * SB_ITEMS;
+    const int lbase = blockIdx.x * SB_TILE + tid * SB_ITEMS;      // where this GPU stores it
     const int K = a.K;
     for (int i = tid; i < a.rows * K; i += SB_THREADS) s_thr[i] = __ldg(a.thr + i);
     for (int i = tid; i < ((a.rows << a.lgG) >> 2); i += SB_THREADS)
@@ -583,7 +583,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     int anc[SB_ITEMS];
     if (ANC == SB_ANC_PULL) {
         const SbStepInfo si = *a.info_prev;
-        if (c0 < (int)si.m) sb_pull_ancestors(si, a.w32_prev, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, ps, anc);
+        if (c0 < (int)si.m) sb_pull_ancestors(si, a.peers, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, ps, anc);
         else {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) anc[j] = 0;
@@ -609,7 +609,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     int xp[SB_ITEMS];
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j)
-        xp[j] = (ANC != SB_ANC_NONE && (!tail || base + j < a.N)) ? __ldg(a.x_prev + anc[j]) : 0;
+        xp[j] = (ANC != SB_ANC_NONE && (!tail || base + j < a.N)) ? sb_peer_x<int>(a.peers, anc[j]) : 0;
     __syncthreads();                                              // tables staged
     // (3) propagate: one Philox call per FOUR particles, one 32-bit uniform per particle.
     // u = R * 2^-32 < cum[k]  <=>  R < ceil(cum[k] * 2^32): integer compares against the table.
@@ -673,8 +673,8 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         q[j] = (!tail || base + j < a.n_out) ? s_q[x[j]] : 0u;
         tsum += q[j];
     }
-    sb_store8_u32(reinterpret_cast<uint32_t*>(a.x_out) + base, reinterpret_cast<const uint32_t*>(x));
-    sb_store8_u32(a.w32_out + base, q);
+    sb_store8_u32(reinterpret_cast<uint32_t*>(a.x_out) + lbase, reinterpret_cast<const uint32_t*>(x));
+    sb_store8_u32(a.w32_out + lbase, q);
     if (a.lw_out) {
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.lw_out[base + j] = a.logF_t[x[j]];
@@ -684,13 +684,12 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.wlit_out[base + j] = a.expF_t[x[j]];
     }
     const unsigned long long tot = sb_block_sum_u64(tsum, ps.scan);
-    if (tid == 0) { a.e_out[blockIdx.x] = e; a.Q_out[blockIdx.x] = tot; }
+    if (tid == 0) { a.e_out[a.peers.tile_off + blockIdx.x] = e; a.Q_out[a.peers.tile_off + blockIdx.x] = tot; }
 }
 
 // ---------------------------------------------------------------- linear-Gaussian step
 struct SbLgStepArgs {
-    const void* x_prev;         // REAL[n]
-    const uint32_t* w32_prev;
+    SbPeers peers;              // previous pool (x is REAL)
     const int* e_prev;
     const unsigned long long* Pt;
     const int* child_start;
@@ -720,12 +719,13 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     __shared__ SbPullSmem ps;
     __shared__ double s_red[SB_WARPS];
     const int tid = threadIdx.x;
-    const int c0 = blockIdx.x * SB_TILE;
+    const int c0 = a.peers.c_off + blockIdx.x * SB_TILE;          // global child index of this tile
     const int base = c0 + tid * SB_ITEMS;
+    const int lbase = blockIdx.x * SB_TILE + tid * SB_ITEMS;      // where this GPU stores it
     int anc[SB_ITEMS];
     if (ANC == SB_ANC_PULL) {
         const SbStepInfo si = *a.info_prev;
-        sb_pull_ancestors(si, a.w32_prev, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, ps, anc);
+        sb_pull_ancestors(si, a.peers, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, ps, anc);
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(anc[j], 0);
     } else if (ANC == SB_ANC_EXPLICIT) {
@@ -743,7 +743,6 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     REAL l2[SB_ITEMS];
     REAL mx = -INFINITY;
     bool bad = false;
-    const REAL* xprev = reinterpret_cast<const REAL*>(a.x_prev);
     if (FP32) {
         const float fa = (float)a.a, fsq = (float)a.sq, fsp = (float)a.sp, fc = (float)a.c, fy = (float)a.y;
         const float hr = -0.5f / (float)a.r, flc = (float)a.lc, fm0 = (float)a.m0;
@@ -758,7 +757,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                 const float z = sqrtf(-2.0f * logf(1.0f - u1)) * cosf((float)SB_TWO_PI * u2);
                 float xv;
                 if (ANC == SB_ANC_NONE) xv = fm0 + fsp * z;
-                else xv = fa * ((base + j < a.N) ? (float)__ldg(xprev + anc[j]) : 0.0f) + fsq * z;
+                else xv = fa * ((base + j < a.N) ? sb_peer_x<float>(a.peers, anc[j]) : 0.0f) + fsq * z;
                 const float d = fy - fc * xv;
                 const float lw = hr * d * d + flc;
                 const bool live = base + j < a.N;
@@ -766,7 +765,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                 if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
                 x[j] = (REAL)xv; l2[j] = (REAL)v;
                 mx = (REAL)fmaxf((float)mx, v);
-                if (a.lw_out && live) a.lw_out[base + j] = (double)lw;
+                if (a.lw_out && live) a.lw_out[lbase + j] = (double)lw;
             }
         }
     } else {
@@ -777,7 +776,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(SB_TWO_PI * u2);
             double xv;
             if (ANC == SB_ANC_NONE) xv = a.m0 + a.sp * z;
-            else xv = a.a * ((base + j < a.N) ? (double)__ldg(xprev + anc[j]) : 0.0) + a.sq * z;
+            else xv = a.a * ((base + j < a.N) ? sb_peer_x<double>(a.peers, anc[j]) : 0.0) + a.sq * z;
             const double d = a.y - a.c * xv;
             const double lw = -0.5 * d * d / a.r + a.lc;
             const bool live = base + j < a.N;
@@ -785,7 +784,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
             x[j] = (REAL)xv; l2[j] = (REAL)v;
             mx = (REAL)fmax((double)mx, v);
-            if (a.lw_out && live) a.lw_out[base + j] = lw;
+            if (a.lw_out && live) a.lw_out[lbase + j] = lw;
         }
     }
     int e;
@@ -799,7 +798,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         if (e != SB_E_EMPTY) v = FP32 ? sb_q31_f32(__fsub_rn((float)l2[j], (float)e)) : sb_q31_f64(__dsub_rn((double)l2[j], (double)e));
         q[j] = v; tsum += v;
     }
-    REAL* xo = reinterpret_cast<REAL*>(a.x_out) + base;
+    REAL* xo = reinterpret_cast<REAL*>(a.x_out) + lbase;
     if (FP32) {
         reinterpret_cast<float4*>(xo)[0] = make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
         reinterpret_cast<float4*>(xo)[1] = make_float4((float)x[4], (float)x[5], (float)x[6], (float)x[7]);
@@ -807,9 +806,9 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; j += 2) reinterpret_cast<double2*>(xo)[j / 2] = make_double2((double)x[j], (double)x[j + 1]);
     }
-    sb_store8_u32(a.w32_out + base, q);
+    sb_store8_u32(a.w32_out + lbase, q);
     const unsigned long long tot = sb_block_sum_u64(tsum, ps.scan);
-    if (tid == 0) { a.e_out[blockIdx.x] = e; a.Q_out[blockIdx.x] = tot; }
+    if (tid == 0) { a.e_out[a.peers.tile_off + blockIdx.x] = e; a.Q_out[a.peers.tile_off + blockIdx.x] = tot; }
     if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
 }
 

@@ -104,6 +104,14 @@ int fail(sb_handle* h, int code, const std::string& msg) {
 
 inline int64_t tiles_of(int64_t n) { return (n + SB_TILE - 1) / SB_TILE; }
 
+// the whole pool on this GPU
+inline SbPeers local_peers(const void* w32, const void* x) {
+    SbPeers p;
+    memset(&p, 0, sizeof(p));
+    p.w32[0] = w32; p.x[0] = x; p.log2n = 31; p.c_off = 0; p.tile_off = 0;
+    return p;
+}
+
 // host copy of the Philox4x32-10 stream (the per-step systematic offsets are drawn on the host so the
 // single-CTA tile scan does not spend its serial section on ten dependent rounds)
 void philox_host(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
@@ -179,7 +187,7 @@ int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, const unsigned
 }
 
 int launch_pull(sb_handle* h, int slot, const SbStepInfo* info, int64_t m, int* d_anc) {
-    k_pull<<<(unsigned)tiles_of(m), SB_THREADS, 0, h->stream>>>(info, h->w32[slot].as<uint32_t>(), h->tile_e[slot].as<int>(),
+    k_pull<<<(unsigned)tiles_of(m), SB_THREADS, 0, h->stream>>>(info, local_peers(h->w32[slot].p, nullptr), h->tile_e[slot].as<int>(),
                                                                 h->Pt.as<unsigned long long>(), h->child_start.as<int>(),
                                                                 h->first_tile.as<int>(), d_anc);
     LAUNCH_CHECK();
@@ -552,8 +560,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         }
         SbHmmStepArgs a;
         memset(&a, 0, sizeof(a));
-        a.x_prev = t ? xb + (size_t)(history ? (t - 1) : prev) * S : nullptr;
-        a.w32_prev = h->w32[prev].as<uint32_t>();
+        a.peers = local_peers(h->w32[prev].p, t ? xb + (size_t)(history ? (t - 1) : prev) * S : nullptr);
         a.e_prev = h->tile_e[prev].as<int>();
         a.Pt = h->Pt.as<unsigned long long>();
         a.child_start = h->child_start.as<int>();
@@ -628,8 +635,7 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
             if ((rc = explicit_resample(h, prev, t - 1, iter, N, N, h->ancbuf.as<int>())) != SB_OK) return rc;
         SbLgStepArgs a;
         memset(&a, 0, sizeof(a));
-        a.x_prev = xb + (size_t)prev * S * sz;
-        a.w32_prev = h->w32[prev].as<uint32_t>();
+        a.peers = local_peers(h->w32[prev].p, xb + (size_t)prev * S * sz);
         a.e_prev = h->tile_e[prev].as<int>();
         a.Pt = h->Pt.as<unsigned long long>();
         a.child_start = h->child_start.as<int>();
