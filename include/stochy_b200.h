@@ -41,7 +41,7 @@ extern "C" {
 #define SB_EINVAL       3
 #define SB_EUNSUPPORTED 4   /* model is not of fixed per-step structure; there is NO CPU fallback */
 #define SB_ECUDA        5
-#define SB_ENCCL        6
+#define SB_EPEER        6   /* multi-GPU: a peer GPU never signalled (flag barrier timed out) */
 #define SB_ENOMEM       7
 
 /* precision of log-weights and of the linear-Gaussian state */
@@ -177,12 +177,18 @@ int32_t sb_get_retained(sb_handle* h, int32_t* xstar_out /* [T] */);
 /* final particle states of the last sweep (LG: double[N]; discrete: int32[N]) */
 int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out);
 
-/* ---- multi-GPU (one process per GPU; ids travel over the host's own plumbing) ---- */
-int32_t sb_dist_unique_id(uint8_t out_id[128]);
-int32_t sb_dist_init(sb_handle* h, int32_t rank, int32_t world, const uint8_t id[128]);
-/* local IPC export of this rank's particle buffers, and import of every peer's (world * 64 bytes) */
-int32_t sb_dist_ipc_export(sb_handle* h, int64_t N_local, uint8_t out_handles[64 * 4]);
-int32_t sb_dist_ipc_import(sb_handle* h, const uint8_t* all_handles /* [world][64*4] */);
+/* ---- multi-GPU: ONE particle pool sharded over `world` GPUs, one process per GPU ----
+ * sb_dist_init, then sb_dist_ipc_export (allocates this rank's share of the pool, N_local particles, a
+ * power of two, and returns its 64-byte CUDA-IPC handle), exchange the handles over the host's own
+ * plumbing, sb_dist_ipc_import with all of them in rank order.  Afterwards sb_smc_sweep(h, N_local, ...)
+ * runs a GLOBAL sweep over world x N_local particles on every rank (same seed on every rank): parent
+ * weights / states on other GPUs are read over NVLink by the fused step kernel itself, tile records
+ * are exchanged through peer memory behind a flag barrier.  out_logZ is identical on every rank.
+ * All ranks must make the same sequence of sweep calls, and must not destroy their handle before every
+ * rank has finished (barrier first). */
+int32_t sb_dist_init(sb_handle* h, int32_t rank, int32_t world);
+int32_t sb_dist_ipc_export(sb_handle* h, int64_t N_local, uint8_t out_handle[64]);
+int32_t sb_dist_ipc_import(sb_handle* h, const uint8_t* all_handles /* [world][64] */);
 
 #ifdef __cplusplus
 }

@@ -13,10 +13,10 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libstochy_b200.so")
-SOURCES = ["stochy_b200.cu", "sb_dist.cu"]
-HEADERS = ["sb_device.cuh", "sb_kernels.cuh", "sb_internal.h"]
+SOURCES = ["stochy_b200.cu"]
+HEADERS = ["sb_device.cuh", "sb_kernels.cuh"]
 
-OK, ENAN, EZEROMASS, EINVAL, EUNSUPPORTED, ECUDA, ENCCL, ENOMEM = range(8)
+OK, ENAN, EZEROMASS, EINVAL, EUNSUPPORTED, ECUDA, EPEER, ENOMEM = range(8)
 FP32, FP64 = 0, 1
 SYSTEMATIC, MULTINOMIAL, LITERAL = 0, 1, 2
 W_LINEAR_F64, W_LOG_F64, W_LOG_F32 = 0, 1, 2
@@ -31,7 +31,7 @@ EXPORTS = [
     "sb_dev_resample_systematic", "sb_dev_gather", "sb_sync", "sb_timer_start", "sb_timer_stop",
     "sb_erp_sample", "sb_erp_logpdf", "sb_erp_sample_dirichlet", "sb_erp_logpdf_dirichlet",
     "sb_get_history", "sb_get_retained", "sb_get_particles",
-    "sb_dist_unique_id", "sb_dist_init", "sb_dist_ipc_export", "sb_dist_ipc_import",
+    "sb_dist_init", "sb_dist_ipc_export", "sb_dist_ipc_import",
 ]
 
 
@@ -112,8 +112,7 @@ def lib():
         "sb_get_history": (i32, [vp, i32, i64, vp, vp, vp]),
         "sb_get_retained": (i32, [vp, vp]),
         "sb_get_particles": (i32, [vp, i64, vp]),
-        "sb_dist_unique_id": (i32, [vp]),
-        "sb_dist_init": (i32, [vp, i32, i32, vp]),
+        "sb_dist_init": (i32, [vp, i32, i32]),
         "sb_dist_ipc_export": (i32, [vp, i64, vp]),
         "sb_dist_ipc_import": (i32, [vp, vp]),
     }

@@ -17,6 +17,7 @@
 
 #define SB_ERRBIT_NAN   1u
 #define SB_ERRBIT_ZERO  2u
+#define SB_ERRBIT_PEER  4u          // a peer GPU never signalled (multi-GPU flag barrier timed out)
 
 #define SB_P_PROP     0u
 #define SB_P_RESAMPLE 1u
@@ -46,25 +47,40 @@ struct SbStepInfo {
     int valid;
 };
 
-// Where the POOL lives.  One GPU: w32[0] / x[0] with log2n = 31 (owner is always 0).  Particles
-// sharded over G GPUs (each a power-of-two 2^log2n of them): pool index i lives on GPU i >> log2n
-// at local index i & (2^log2n - 1); the pointers are peer mappings (CUDA IPC) read over NVLink by
-// the same loads that read local HBM -- the migration of resampled particles IS the gather.
+// Where a POOL (the particle set of one step) lives.
+// PEERS == false (one GPU): the local pointers w32 / x / wp.
+// PEERS == true  (particles sharded over G GPUs, each a power-of-two 2^log2n of them): pool index i
+// lives on GPU i >> log2n at local index i & (2^log2n - 1).  Every GPU keeps its share in one
+// arena with the same layout; base[g] is GPU g's arena (a CUDA-IPC peer mapping for g != self),
+// read over NVLink by the same loads that read local HBM -- the migration of resampled particles
+// IS the gather, there is no pack / send / unpack.
 #define SB_MAX_PEERS 8
-struct SbPeers {
-    const void* w32[SB_MAX_PEERS];
-    const void* x[SB_MAX_PEERS];
-    int log2n;          // particles per GPU = 2^log2n  (31 on a single GPU)
-    int c_off;          // global index of this GPU's first child
-    int tile_off;       // global index of this GPU's first tile
+struct SbPool {
+    const uint32_t* w32;                // [tiles * SB_TILE] fixed-point weights
+    const void* x;                      // [tiles * SB_TILE] particle states
+    const unsigned long long* wp;       // [tiles * SB_WARPS] exclusive prefix of the warp sums inside each tile
+    const char* base[SB_MAX_PEERS];
+    unsigned long long off_w32, off_x, off_wp;
+    int log2n;                          // particles per GPU = 2^log2n
+    int c_off;                          // global index of this GPU's first child
+    int tile_off;                       // global index of this GPU's first tile
 };
-__device__ __forceinline__ const uint32_t* sb_peer_tile(const SbPeers& p, int b) {
+template <bool PEERS>
+__device__ __forceinline__ const uint32_t* sb_pool_tile(const SbPool& p, int b) {
+    if (!PEERS) return p.w32 + (size_t)b * SB_TILE;
     const int ts = p.log2n - 11;                                 // log2(SB_TILE) = 11
-    return reinterpret_cast<const uint32_t*>(p.w32[b >> ts]) + (size_t)(b & ((1 << ts) - 1)) * SB_TILE;
+    return reinterpret_cast<const uint32_t*>(p.base[b >> ts] + p.off_w32) + (size_t)(b & ((1 << ts) - 1)) * SB_TILE;
 }
-template <typename T>
-__device__ __forceinline__ T sb_peer_x(const SbPeers& p, int i) {
-    return __ldg(reinterpret_cast<const T*>(p.x[i >> p.log2n]) + (i & (int)((1u << p.log2n) - 1u)));
+template <bool PEERS>
+__device__ __forceinline__ unsigned long long sb_pool_wp(const SbPool& p, int b, int warp) {
+    if (!PEERS) return __ldg(p.wp + (size_t)b * SB_WARPS + warp);
+    const int ts = p.log2n - 11;
+    return __ldg(reinterpret_cast<const unsigned long long*>(p.base[b >> ts] + p.off_wp) + (size_t)(b & ((1 << ts) - 1)) * SB_WARPS + warp);
+}
+template <typename T, bool PEERS>
+__device__ __forceinline__ T sb_pool_x(const SbPool& p, int i) {
+    if (!PEERS) return __ldg(reinterpret_cast<const T*>(p.x) + i);
+    return __ldg(reinterpret_cast<const T*>(p.base[i >> p.log2n] + p.off_x) + (i & (int)((1u << p.log2n) - 1u)));
 }
 
 // ---------------------------------------------------------------- Philox4x32-10
@@ -250,41 +266,56 @@ struct SbPullSmem {
     int marker[SB_TILE];
     unsigned long long scan[SB_WARPS + 1];
     int wmax[SB_WARPS];
-    int range[4];
 };
 
-// One parent tile's contribution to the children [c0, c1): block scan of its weights, then every
-// parent that owns children in range writes its index at its first child's slot ("head marker").
+// children (relative to c0, clamped to [0, cw]) whose threshold lies strictly below the CDF value
+// Ptb + (acc >> rb);  D = baseb + (acc >> rb) with baseb = Ptb - U + 2^s - 1 - (c0 << s).
+// S32: s >= 32, so D >> s is the arithmetic shift of D's high word alone.
+template <bool S32>
+__device__ __forceinline__ int sb_pull_k(long long baseb, unsigned long long acc, int rb, int s, int cw) {
+    const long long D = baseb + (long long)(acc >> rb);
+    if (S32) {
+        const int k = (int)(D >> 32) >> (s - 32);
+        return min(max(k, 0), cw);
+    }
+    const long long k = D >> s;
+    return k <= 0 ? 0 : (k >= (long long)cw ? cw : (int)k);
+}
+
+// One parent tile's contribution to the children [c0, c0 + cw): warp scan of its weights on top of
+// the warp prefix the producer left, then every parent that owns children in range writes its
+// index at its first child's slot ("head marker").  No block-level synchronisation.
+template <bool S32>
 __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const uint32_t w[SB_ITEMS], int eb,
-                                             unsigned long long Ptb, int c0, int c1, SbPullSmem& sm) {
-    const int tid = threadIdx.x;
-    const int m = (int)si.m, s = si.s;
+                                             unsigned long long Ptb, unsigned long long wbase, int c0, int cw,
+                                             int* __restrict__ marker) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int s = si.s;
     const unsigned R = si.R;
     unsigned tsum = 0;                                           // 8 * 2^27 fits 32 bits
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) tsum += w[j];
-    unsigned long long tot;
-    unsigned long long c = sb_block_excl_scan_u64((unsigned long long)tsum, sm.scan, &tot);
+    unsigned long long inc = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = sb_shfl_up_u64(inc, d);
+        if (lane >= d) inc += o;
+    }
     if (tsum != 0) {
+        const unsigned long long c = wbase + inc - tsum;        // tile-local exclusive prefix of this thread
         // tile-uniform constants; rb < 64 because the tile owns children
         const int rb = si.r0 + (si.E - eb);
-        const long long baseb = (long long)(Ptb - si.U) + ((1ll << s) - 1ll);
-        // F(acc) = clamp((baseb + (acc >> rb)) >> s, 0, m): children strictly below this CDF value
+        const long long baseb = (long long)(Ptb - si.U) + ((1ll << s) - 1ll) - ((long long)c0 << s);
         unsigned long long acc = c * (unsigned long long)R;
-        long long k0 = (baseb + (long long)(acc >> rb)) >> s;
-        int lo = k0 <= 0 ? 0 : (k0 >= (long long)m ? m : (int)k0);
-        const unsigned long long acc_t = acc + (unsigned long long)tsum * R;
-        long long k1 = (baseb + (long long)(acc_t >> rb)) >> s;
-        const int hi_t = k1 <= 0 ? 0 : (k1 >= (long long)m ? m : (int)k1);
-        if (hi_t > lo && hi_t > c0 && lo < c1) {                 // this thread's parents own children in range
+        int lo = sb_pull_k<S32>(baseb, acc, rb, s, cw);
+        const int hi_t = sb_pull_k<S32>(baseb, acc + (unsigned long long)tsum * R, rb, s, cw);
+        if (hi_t > lo) {                                         // this thread's parents own children in range
             const int base = b * SB_TILE + tid * SB_ITEMS;
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) {
                 acc += (unsigned long long)w[j] * R;             // one IMAD.WIDE with 64-bit accumulate
-                long long k = (baseb + (long long)(acc >> rb)) >> s;
-                const int hi = (j == SB_ITEMS - 1) ? hi_t : (k <= 0 ? 0 : (k >= (long long)m ? m : (int)k));
-                const int a0 = max(lo, c0), a1 = min(hi, c1);
-                if (a0 < a1) sm.marker[a0 - c0] = base + j;
+                const int hi = (j == SB_ITEMS - 1) ? hi_t : sb_pull_k<S32>(baseb, acc, rb, s, cw);
+                if (lo < hi) marker[lo] = base + j;
                 lo = hi;
             }
         }
@@ -293,38 +324,44 @@ __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const 
 
 // Computes, for the children [c0, c0+SB_TILE) of this CTA, the pool index of each child's parent
 // under systematic resampling on the weight grid; thread `tid` receives children c0+8*tid .. +7.
-// w32 / e / Pt / child_start / first_tile describe the POOL (previous step).  Parent tiles are read
+// pool / e / Pt / child_start / first_tile describe the POOL (previous step).  Parent tiles are read
 // with coalesced 128-bit loads.  The first two candidate tiles (almost always all there are) and
 // their metadata are requested together, so the CTA pays one memory latency instead of a chain.
-__device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const SbPeers& peers,
+template <bool PEERS, bool S32>
+__device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const SbPool& pool,
                                                   const int* __restrict__ e, const unsigned long long* __restrict__ Pt,
                                                   const int* __restrict__ child_start, const int* __restrict__ first_tile,
                                                   int c0, SbPullSmem& sm, int anc[SB_ITEMS]) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int m = (int)si.m;
     const int c1 = min(c0 + SB_TILE, m);
+    const int cw = c1 - c0;
     const int cb = c0 / SB_TILE;                                 // global children tile
     const int b_lo = __ldg(first_tile + cb);
     const int b_hi = (c1 < m) ? __ldg(first_tile + cb + 1) : si.nt - 1;
-#pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) sm.marker[tid + j * SB_THREADS] = -1;
     const int bA = b_lo, bB = min(b_lo + 1, si.nt - 1);
     uint32_t wA[SB_ITEMS], wB[SB_ITEMS];
-    sb_load8_u32(sb_peer_tile(peers, bA) + tid * SB_ITEMS, wA);
-    sb_load8_u32(sb_peer_tile(peers, bB) + tid * SB_ITEMS, wB);
+    sb_load8_u32(sb_pool_tile<PEERS>(pool, bA) + tid * SB_ITEMS, wA);
+    sb_load8_u32(sb_pool_tile<PEERS>(pool, bB) + tid * SB_ITEMS, wB);
+    const unsigned long long wbA = sb_pool_wp<PEERS>(pool, bA, warp), wbB = sb_pool_wp<PEERS>(pool, bB, warp);
     const int csA = __ldg(child_start + bA), ceA = __ldg(child_start + bA + 1);
     const int csB = __ldg(child_start + bB), ceB = __ldg(child_start + bB + 1);
     const int eA = __ldg(e + bA), eB = __ldg(e + bB);
     const unsigned long long PtA = __ldg(Pt + bA), PtB = __ldg(Pt + bB);
+    {
+        const int4 neg = make_int4(-1, -1, -1, -1);
+        reinterpret_cast<int4*>(sm.marker)[tid * 2] = neg;
+        reinterpret_cast<int4*>(sm.marker)[tid * 2 + 1] = neg;
+    }
     __syncthreads();
-    if (!(ceA <= c0 || csA >= c1 || ceA == csA)) sb_pull_tile(si, bA, wA, eA, PtA, c0, c1, sm);
-    if (bB != bA && bB <= b_hi && !(ceB <= c0 || csB >= c1 || ceB == csB)) sb_pull_tile(si, bB, wB, eB, PtB, c0, c1, sm);
+    if (!(ceA <= c0 || csA >= c1 || ceA == csA)) sb_pull_tile<S32>(si, bA, wA, eA, PtA, wbA, c0, cw, sm.marker);
+    if (bB != bA && bB <= b_hi && !(ceB <= c0 || csB >= c1 || ceB == csB)) sb_pull_tile<S32>(si, bB, wB, eB, PtB, wbB, c0, cw, sm.marker);
     for (int b = b_lo + 2; b <= b_hi; ++b) {
         const int cs = __ldg(child_start + b), ce = __ldg(child_start + b + 1);
         if (ce <= c0 || cs >= c1 || ce == cs) continue;          // no offspring in range (uniform branch)
         uint32_t w[SB_ITEMS];
-        sb_load8_u32(sb_peer_tile(peers, b) + tid * SB_ITEMS, w);
-        sb_pull_tile(si, b, w, __ldg(e + b), __ldg(Pt + b), c0, c1, sm);
+        sb_load8_u32(sb_pool_tile<PEERS>(pool, b) + tid * SB_ITEMS, w);
+        sb_pull_tile<S32>(si, b, w, __ldg(e + b), __ldg(Pt + b), sb_pool_wp<PEERS>(pool, b, warp), c0, cw, sm.marker);
     }
     __syncthreads();
     // inclusive max-scan of the head markers fills every child slot with its parent
@@ -337,7 +374,7 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
 #pragma unroll
     for (int j = 1; j < SB_ITEMS; ++j) v[j] = max(v[j], v[j - 1]);
     int inc = v[SB_ITEMS - 1];
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         int o = __shfl_up_sync(0xffffffffu, inc, d);
@@ -349,7 +386,32 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < SB_WARPS; ++w) if (w < warp) prev = max(prev, sm.wmax[w]);
+    prev = max(prev, 0);
 #pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(max(v[j], prev), 0);
-    __syncthreads();                                             // marker may be reused by the caller
+    for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(v[j], prev);
+}
+
+// Tile sum of the weights a CTA just produced, and the exclusive prefix of its warp sums (what the
+// pull of the NEXT step starts its warp scans from).  smem: SB_WARPS u64.  Returns the tile sum.
+__device__ __forceinline__ unsigned long long sb_block_sum_wp(unsigned tsum, unsigned long long* sm,
+                                                              unsigned long long* __restrict__ wp_tile) {
+    unsigned long long v = tsum;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, d);
+        uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+        v += ((unsigned long long)hi << 32) | lo;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long r = 0, pre = 0;
+#pragma unroll
+    for (int w = 0; w < SB_WARPS; ++w) {
+        const unsigned long long t = sm[w];
+        if (w < (int)threadIdx.x) pre += t;
+        r += t;
+    }
+    if (threadIdx.x < SB_WARPS) wp_tile[threadIdx.x] = pre;
+    return r;
 }

@@ -16,7 +16,7 @@ namespace cg = cooperative_groups;
 template <int KIND>
 __global__ void __launch_bounds__(SB_THREADS)
 k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w32, int* __restrict__ e_out,
-           unsigned long long* __restrict__ Q_out, unsigned* __restrict__ err) {
+           unsigned long long* __restrict__ Q_out, unsigned long long* __restrict__ wp_out, unsigned* __restrict__ err) {
     __shared__ unsigned long long s_u64[SB_WARPS + 1];
     __shared__ double s_f64[SB_WARPS];
     __shared__ int s_i32[SB_WARPS];
@@ -87,7 +87,7 @@ k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w3
         }
     }
     uint32_t q[SB_ITEMS];
-    unsigned long long tsum = 0;
+    unsigned tsum = 0;
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) {
         uint32_t v = 0;
@@ -100,7 +100,7 @@ k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w3
         tsum += v;
     }
     sb_store8_u32(w32 + base, q);                 // w32 is padded to whole tiles
-    unsigned long long tot = sb_block_sum_u64(tsum, s_u64);
+    unsigned long long tot = sb_block_sum_wp(tsum, s_u64, wp_out + (size_t)blockIdx.x * SB_WARPS);
     if (tid == 0) { e_out[blockIdx.x] = e; Q_out[blockIdx.x] = tot; }
     if (bad) atomicOr(err, SB_ERRBIT_NAN);
 }
@@ -193,34 +193,78 @@ __device__ __forceinline__ unsigned long long sb_cluster_excl_scan(unsigned long
     return sm.base + sm.warp_tot[warp] + inc - loc;
 }
 
+// Per-GPU tile records of a sharded pool: GPU g keeps (e, Q) of its own tiles in its arena; the scan
+// of every GPU reads all of them (local HBM or NVLink peer loads) after a flag barrier.
+struct SbScanPeers {
+    const char* base[SB_MAX_PEERS];
+    unsigned long long off_e, off_Q;    // this pool slot's arrays inside every arena
+    unsigned long long off_flags;       // unsigned[SB_MAX_PEERS]: flags[g] = last epoch GPU g has finished
+    int log2t;                          // tiles per GPU = 2^log2t
+    int world, self;
+    unsigned epoch;                     // wait until every flags[g] >= epoch
+    int* e_all;                         // [global tiles] local copy for the pull
+};
+#define SB_SCAN_MAXPER 8
+
+// PER > 0: every thread keeps its PER consecutive tiles in registers (PER = 1: 2^24 particles, PER = 8:
+// 2^27); PER == 0: any size, tile records re-read from global memory in every pass.
+template <int PER, bool PEERS>
 __global__ void __cluster_dims__(SB_SCAN_CTAS, 1, 1) __launch_bounds__(SB_SCAN_THREADS)
 k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q_g, int nt, long long n, long long m,
            const unsigned long long* __restrict__ r53_ptr, SbStepInfo* __restrict__ info,
            unsigned long long* __restrict__ P, unsigned long long* __restrict__ Pt, int* __restrict__ child_start,
-           int* __restrict__ first_tile, int want_exact, unsigned* __restrict__ err) {
+           int* __restrict__ first_tile, int want_exact, unsigned* __restrict__ err, const __grid_constant__ SbScanPeers sp) {
     cg::cluster_group cl = cg::this_cluster();
     __shared__ SbScanSmem sm;
     const unsigned rank = cl.block_rank();
     const int gtid = (int)rank * SB_SCAN_THREADS + threadIdx.x;
     const unsigned long long R53 = __ldg(r53_ptr);            // host-drawn systematic offset (53-bit uniform)
-    const int per = (nt + SB_SCAN_THREADS * SB_SCAN_CTAS - 1) / (SB_SCAN_THREADS * SB_SCAN_CTAS);
+    const int per = PER > 0 ? PER : (nt + SB_SCAN_THREADS * SB_SCAN_CTAS - 1) / (SB_SCAN_THREADS * SB_SCAN_CTAS);
     const int b0 = min(nt, gtid * per), b1 = min(nt, b0 + per);
-    // fast path: one tile per thread, kept in registers
-    const bool one = per == 1;
-    unsigned long long q1 = 0ull;
-    int e1 = SB_E_EMPTY;
-    if (one && b0 < b1) { q1 = __ldg(Q_g + b0); e1 = __ldg(e_g + b0); }
+    if (PEERS) {
+        // every peer has finished the step kernel that produced this pool (and therefore also every
+        // read of the pool before it): flags are written by k_signal over NVLink
+        if (threadIdx.x < sp.world) {
+            const volatile unsigned* f = reinterpret_cast<const volatile unsigned*>(sp.base[sp.self] + sp.off_flags) + threadIdx.x;
+            const long long t0 = clock64();
+            while ((int)(*f - sp.epoch) < 0) {
+                if (clock64() - t0 > 8000000000ll) { atomicOr(err, SB_ERRBIT_PEER); break; }   // ~4 s: a peer died
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+    }
+    unsigned long long qr[PER > 0 ? PER : 1];
+    int er[PER > 0 ? PER : 1];
+    if (PER > 0) {
+#pragma unroll
+        for (int i = 0; i < (PER > 0 ? PER : 1); ++i) {
+            const int b = b0 + i;
+            qr[i] = 0ull; er[i] = SB_E_EMPTY;
+            if (b < b1) {
+                if (PEERS) {
+                    const int g = b >> sp.log2t, bl = b & ((1 << sp.log2t) - 1);
+                    qr[i] = __ldcv(reinterpret_cast<const unsigned long long*>(sp.base[g] + sp.off_Q) + bl);
+                    er[i] = __ldcv(reinterpret_cast<const int*>(sp.base[g] + sp.off_e) + bl);
+                } else { qr[i] = __ldg(Q_g + b); er[i] = __ldg(e_g + b); }
+            }
+        }
+        if (PEERS) {
+#pragma unroll
+            for (int i = 0; i < (PER > 0 ? PER : 1); ++i) if (b0 + i < b1) sp.e_all[b0 + i] = er[i];
+        }
+    }
 #define SB_TS_FOR(body)                                                                        \
-    if (one) { if (b0 < b1) { const int b = b0; (void)b; const unsigned long long qv = q1; const int ev = e1; body } } \
-    else for (int b = b0; b < b1; ++b) { (void)b; const unsigned long long qv = __ldg(Q_g + b); const int ev = __ldg(e_g + b); body }
+    if (PER > 0) { _Pragma("unroll") for (int i_ = 0; i_ < (PER > 0 ? PER : 1); ++i_) { const int b = b0 + i_; if (b < b1) { const unsigned long long qv = qr[i_]; const int ev = er[i_]; body } } } \
+    else for (int b = b0; b < b1; ++b) { const unsigned long long qv = __ldg(Q_g + b); const int ev = __ldg(e_g + b); body }
     // global exponent
     int E = SB_E_EMPTY;
-    SB_TS_FOR(if (qv != 0ull) E = max(E, ev);)
+    SB_TS_FOR((void)b; if (qv != 0ull) E = max(E, ev);)
     E = sb_cluster_max(E, sm, cl);
     const int LS = 24 - (nt <= 1 ? 0 : 32 - __clz(nt - 1));  // LS = 24 - ceil_log2(nt)
     // exact CDF of tile sums (log-evidence; multinomial resampling)
     unsigned long long loc = 0;
-    SB_TS_FOR(if (qv != 0ull) { const int sh = E - ev; loc += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
+    SB_TS_FOR((void)b; if (qv != 0ull) { const int sh = E - ev; loc += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
     unsigned long long total;
     unsigned long long run = sb_cluster_excl_scan(loc, sm, cl, &total);
     if (want_exact) {
@@ -249,7 +293,7 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     }
     // rescaled CDF of tile sums (systematic)
     unsigned long long loc2 = 0;
-    if (si.valid) { SB_TS_FOR(if (qv != 0ull) loc2 += sb_sys_delta(qv, si.R, si.r0 + (E - ev));) }
+    if (si.valid) { SB_TS_FOR((void)b; if (qv != 0ull) loc2 += sb_sys_delta(qv, si.R, si.r0 + (E - ev));) }
     unsigned long long Tt;
     unsigned long long run2 = sb_cluster_excl_scan(loc2, sm, cl, &Tt);
     const unsigned long long lastk = (unsigned long long)(m - 1) << si.s;
@@ -281,28 +325,42 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
 #undef SB_TS_FOR
 }
 
+// Tells every peer that this GPU has finished epoch `epoch` (stream-ordered after the step kernel that
+// produced the pool): one 4-byte store per peer over NVLink into flags[self] of the peer's arena.
+__global__ void k_signal(const __grid_constant__ SbScanPeers sp) {
+    if ((int)threadIdx.x < sp.world) {
+        __threadfence_system();
+        volatile unsigned* f = reinterpret_cast<volatile unsigned*>(const_cast<char*>(sp.base[threadIdx.x]) + sp.off_flags) + sp.self;
+        *f = sp.epoch;
+        __threadfence_system();
+    }
+}
+
 // =====================================================================================
 // k_pull: ancestors only (hooks, and the final resample of a sweep).
 // Replaces the N calls of rand(ps) (src/rand.jl:2-13 via src/pmcmc.jl:51) by ONE merge of the
 // sorted child thresholds with the integer CDF.  Bytes per child: read 4 (w32), write 4 (anc).
 // =====================================================================================
+template <bool PEERS>
 __global__ void __launch_bounds__(SB_THREADS)
-k_pull(const SbStepInfo* __restrict__ info, const __grid_constant__ SbPeers peers, const int* __restrict__ e,
+k_pull(const SbStepInfo* __restrict__ info, const __grid_constant__ SbPool pool, const int* __restrict__ e,
        const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
        const int* __restrict__ first_tile, int* __restrict__ anc_out) {
     __shared__ SbPullSmem ps;
     const SbStepInfo si = *info;
-    const int c0 = blockIdx.x * SB_TILE;
+    const int c0 = pool.c_off + blockIdx.x * SB_TILE;             // global child index
     if (c0 >= (int)si.m) return;
     int anc[SB_ITEMS];
-    sb_pull_ancestors(si, peers, e, Pt, child_start, first_tile, c0, ps, anc);
+    if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, pool, e, Pt, child_start, first_tile, c0, ps, anc);
+    else            sb_pull_ancestors<PEERS, false>(si, pool, e, Pt, child_start, first_tile, c0, ps, anc);
     const int base = c0 + threadIdx.x * SB_ITEMS;
+    int* out = anc_out + (size_t)blockIdx.x * SB_TILE + threadIdx.x * SB_ITEMS;      // local children row
     if (base + SB_ITEMS <= (int)si.m) {
-        reinterpret_cast<int4*>(anc_out + base)[0] = make_int4(anc[0], anc[1], anc[2], anc[3]);
-        reinterpret_cast<int4*>(anc_out + base)[1] = make_int4(anc[4], anc[5], anc[6], anc[7]);
+        reinterpret_cast<int4*>(out)[0] = make_int4(anc[0], anc[1], anc[2], anc[3]);
+        reinterpret_cast<int4*>(out)[1] = make_int4(anc[4], anc[5], anc[6], anc[7]);
     } else {
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < (int)si.m) anc_out[base + j] = anc[j];
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < (int)si.m) out[j] = anc[j];
     }
 }
 
@@ -508,12 +566,13 @@ k_lse_final(const SbLse* __restrict__ partial, int np, double* __restrict__ out)
 }
 
 // =====================================================================================
-// The fused step kernels.  One CTA = one tile of 2048 children:
+// The fused step kernels.  One CTA works through tiles of 2048 children (persistent grid, model
+// tables staged into shared memory once per CTA).  Per tile:
 //   (1) resample: pull this tile's ancestors from the previous pool (or explicit / identity),
 //   (2) gather the parents' states,
 //   (3) propagate through the model's ERP draw with a counter-based Philox stream,
 //   (4) weight with the step's factor / observe score,
-//   (5) quantise the weights onto the grid and emit the tile exponent and tile sum.
+//   (5) quantise the weights onto the grid and emit the tile exponent, tile sum and warp prefixes.
 // Replaces, per particle-step: sample -> rand(e) (src/pmcmc.jl:32-34), the model body,
 // factor's Step push (src/pmcmc.jl:37), and resample + deepcopy (src/pmcmc.jl:42,48-66).
 // Algorithmic bytes per particle-step: read w32 (4) + read parent state (S) + write state (S)
@@ -524,95 +583,101 @@ k_lse_final(const SbLse* __restrict__ partial, int np, double* __restrict__ out)
 #define SB_ANC_EXPLICIT 2   // ancestors already materialised (multinomial / literal)
 #define SB_ANC_IDENTITY 3   // previous step had no factor statement
 
+#define SB_LG_BUCKETS 8     // inverse-CDF lookup: 256 buckets per transition row
+
 struct SbHmmStepArgs {
     // previous pool
-    SbPeers peers;
-    const int* e_prev;
+    SbPool pool;
+    const int* e_prev;          // [global tiles]
     const unsigned long long* Pt;
     const int* child_start;
     const int* first_tile;
     const SbStepInfo* info_prev;
-    const int* anc_in;
+    const int* anc_in;          // local children row
     int* anc_out;               // history row of the resample after step t-1 (or nullptr)
-    // this step's outputs
+    // this step's outputs (local indices)
     int* x_out;
     uint32_t* w32_out;
     int* e_out;
     unsigned long long* Q_out;
+    unsigned long long* wp_out;
     double* lw_out;             // optional (store_logw)
     double* wlit_out;           // optional (literal mode): exp(score) from the host-built table
     // model tables (global memory; staged into shared memory)
-    const uint32_t* thr;        // [rows*K] ceil(2^32 * sequential running sum) of the transition rows
-    const unsigned char* guide; // [rows << lgG] #thresholds <= bucket start: where the inverse-CDF scan begins
-    int lgG;
+    const uint32_t* tab;        // [rows * 256] inverse-CDF lookup words (see sb_model_discrete_hmm)
+    const uint32_t* thr;        // [rows * K] ceil(2^32 * sequential running sum) of the transition rows
     const double* logF_t;       // [K]
     const double* expF_t;       // [K] or nullptr
     const int* xstar;           // retained trajectory [T] or nullptr
-    long long N;
+    long long N;                // global particle count
     int n_out;                  // N (+1 with a retained particle)
+    int ntiles;                 // local tiles to produce
     int K, rows, t;
     unsigned iter;
     unsigned long long seed;
     unsigned* err;
 };
 
-template <int ANC, bool FP32>
-__global__ void __launch_bounds__(SB_THREADS)
-k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
-    extern __shared__ __align__(16) unsigned char dyn[];
-    double* s_l2 = reinterpret_cast<double*>(dyn);                  // K   (float view when FP32)
-    uint32_t* s_thr = reinterpret_cast<uint32_t*>(s_l2 + a.K);      // rows*K
-    uint32_t* s_q = s_thr + a.rows * a.K;                           // K
-    unsigned char* s_guide = reinterpret_cast<unsigned char*>(s_q + a.K);   // rows << lgG
-    __shared__ SbPullSmem ps;
-    __shared__ double s_red[SB_WARPS];
+struct SbHmmSmem {
+    SbPullSmem ps;
+    double red[SB_WARPS];
+};
+
+template <int ANC, bool FP32, bool PEERS, bool MULTI, bool TAIL>
+__device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStepInfo& si, int tile, SbHmmSmem& sm,
+                                            const void* s_l2v, const uint32_t* s_thr, uint32_t* s_q, const uint32_t* s_tab) {
     const int tid = threadIdx.x;
-    const int c0 = a.peers.c_off + blockIdx.x * SB_TILE;          // global child index of this tile
+    const int c0 = a.pool.c_off + tile * SB_TILE;                 // global child index of this tile
     const int base = c0 + tid * SB_ITEMS;
-    const int lbase = blockIdx.x * SB_TILE + tid * SB_ITEMS;      // where this GPU stores it
+    const int lbase = tile * SB_TILE + tid * SB_ITEMS;            // where this GPU stores it
     const int K = a.K;
-    for (int i = tid; i < a.rows * K; i += SB_THREADS) s_thr[i] = __ldg(a.thr + i);
-    for (int i = tid; i < ((a.rows << a.lgG) >> 2); i += SB_THREADS)
-        reinterpret_cast<uint32_t*>(s_guide)[i] = __ldg(reinterpret_cast<const uint32_t*>(a.guide) + i);
-    const bool tail = c0 + SB_TILE > a.N;                         // only the last CTA(s) see padding / the retained slot
-    if (tid < K) {
-        if (FP32) reinterpret_cast<float*>(s_l2)[tid] = __fmul_rn((float)a.logF_t[tid], SB_LOG2E_F);
-        else      s_l2[tid] = __dmul_rn(a.logF_t[tid], SB_LOG2E_D);
-    }
+    const int N = (int)a.N;
     // (1) ancestors
     int anc[SB_ITEMS];
     if (ANC == SB_ANC_PULL) {
-        const SbStepInfo si = *a.info_prev;
-        if (c0 < (int)si.m) sb_pull_ancestors(si, a.peers, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, ps, anc);
-        else {
+        if (c0 < (int)si.m) {
+            if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, sm.ps, anc);
+            else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, sm.ps, anc);
+        } else {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) anc[j] = 0;
         }
-#pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(anc[j], 0);
     } else if (ANC == SB_ANC_EXPLICIT) {
+        if (!TAIL) {
+            const int4 u = __ldg(reinterpret_cast<const int4*>(a.anc_in + lbase));
+            const int4 v = __ldg(reinterpret_cast<const int4*>(a.anc_in + lbase) + 1);
+            anc[0] = u.x; anc[1] = u.y; anc[2] = u.z; anc[3] = u.w; anc[4] = v.x; anc[5] = v.y; anc[6] = v.z; anc[7] = v.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < a.N) ? __ldg(a.anc_in + base + j) : 0;
+            for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < N) ? __ldg(a.anc_in + lbase + j) : 0;
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;
     }
     if (ANC != SB_ANC_NONE && ANC != SB_ANC_EXPLICIT && a.anc_out) {
+        if (!TAIL) {
+            reinterpret_cast<int4*>(a.anc_out + lbase)[0] = make_int4(anc[0], anc[1], anc[2], anc[3]);
+            reinterpret_cast<int4*>(a.anc_out + lbase)[1] = make_int4(anc[4], anc[5], anc[6], anc[7]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) {
-            const int i = base + j;
-            if (i < a.N) a.anc_out[i] = anc[j];
-            else if (i == a.N) a.anc_out[i] = (int)a.N;      // the retained slot descends from itself
+            for (int j = 0; j < SB_ITEMS; ++j) {
+                const int i = base + j;
+                if (i < N) a.anc_out[lbase + j] = anc[j];
+                else if (i == N) a.anc_out[lbase + j] = N;       // the retained slot descends from itself
+            }
         }
     }
     // (2) gather parents
     int xp[SB_ITEMS];
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j)
-        xp[j] = (ANC != SB_ANC_NONE && (!tail || base + j < a.N)) ? sb_peer_x<int>(a.peers, anc[j]) : 0;
-    __syncthreads();                                              // tables staged
+        xp[j] = (ANC != SB_ANC_NONE && (!TAIL || base + j < N)) ? sb_pool_x<int, PEERS>(a.pool, anc[j]) : 0;
     // (3) propagate: one Philox call per FOUR particles, one 32-bit uniform per particle.
     // u = R * 2^-32 < cum[k]  <=>  R < ceil(cum[k] * 2^32): integer compares against the table.
+    // src/rand.jl:6-12 on a monotone row: first k with R < thr[k], else K-1.  The lookup word of R's
+    // bucket holds the number of thresholds at or below the bucket start and the (only) threshold
+    // inside the bucket, so the draw is one shared-memory load and one compare.
     int x[SB_ITEMS];
 #pragma unroll
     for (int p = 0; p < SB_ITEMS / 4; ++p) {
@@ -622,87 +687,119 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         for (int h = 0; h < 4; ++h) {
             const int j = 4 * p + h;
             const int ri = a.rows > 1 ? xp[j] : 0;
-            const uint32_t* row = s_thr + ri * K;
             const uint32_t R = r4[h];
-            // src/rand.jl:6-12 on a monotone row: first k with R < thr[k], else K-1.  The guide table
-            // gives the number of thresholds at or below the start of R's bucket, so the scan is ~1 step.
-            int lo = s_guide[(ri << a.lgG) + (R >> (32 - a.lgG))];
-            lo += (lo < K - 1 && R >= row[lo]) ? 1 : 0;          // common case: at most one threshold per bucket
-            while (lo < K - 1 && R >= row[lo]) ++lo;
+            const uint32_t g = s_tab[(ri << SB_LG_BUCKETS) + (R >> (32 - SB_LG_BUCKETS))];
+            int lo = (int)(g & 63u) + (((R & 0xFFFFFFu) >= ((g >> 6) & 0x1FFFFFFu)) ? 1 : 0);
+            if (MULTI && (g >> 31)) {                            // several thresholds inside one bucket: scan
+                const uint32_t* row = s_thr + ri * K;
+                lo = (int)(g & 63u);
+                while (lo < K - 1 && R >= row[lo]) ++lo;
+            }
             x[j] = lo;
         }
     }
     // retained particle (src/pmcmc.jl:59-66) and padding
-    if (tail) {
+    if (TAIL) {
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) {
             const int i = base + j;
-            if (i >= a.N) x[j] = (i == a.N && a.xstar) ? __ldg(a.xstar + a.t) : 0;
+            if (i >= N) x[j] = (i == N && a.xstar) ? __ldg(a.xstar + a.t) : 0;
         }
     }
     // (4)+(5) weight and quantise.  Only K distinct scores exist, so 2^(l2 - e) is evaluated K times.
     int e;
     if (FP32) {
+        const float* s_l2 = reinterpret_cast<const float*>(s_l2v);
         float mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (!tail || base + j < a.n_out) mx = fmaxf(mx, reinterpret_cast<float*>(s_l2)[x[j]]);
-        mx = sb_block_max_f32(mx, reinterpret_cast<float*>(s_red));
+        for (int j = 0; j < SB_ITEMS; ++j) if (!TAIL || base + j < a.n_out) mx = fmaxf(mx, s_l2[x[j]]);
+        mx = sb_block_max_f32(mx, reinterpret_cast<float*>(sm.red));
         e = mx > -INFINITY ? (int)ceilf(mx) : SB_E_EMPTY;
-        if (tid < K) {
-            const float l2 = reinterpret_cast<float*>(s_l2)[tid];
-            if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
-            s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f32(__fsub_rn(l2, (float)e));
-        }
+        if (tid < K) s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f32(__fsub_rn(s_l2[tid], (float)e));
     } else {
+        const double* s_l2 = reinterpret_cast<const double*>(s_l2v);
         double mx = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (!tail || base + j < a.n_out) mx = fmax(mx, s_l2[x[j]]);
-        mx = sb_block_max_f64(mx, s_red);
+        for (int j = 0; j < SB_ITEMS; ++j) if (!TAIL || base + j < a.n_out) mx = fmax(mx, s_l2[x[j]]);
+        mx = sb_block_max_f64(mx, sm.red);
         e = mx > -INFINITY ? (int)ceil(mx) : SB_E_EMPTY;
-        if (tid < K) {
-            const double l2 = s_l2[tid];
-            if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
-            s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f64(__dsub_rn(l2, (double)e));
-        }
+        if (tid < K) s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f64(__dsub_rn(s_l2[tid], (double)e));
     }
     __syncthreads();
     uint32_t q[SB_ITEMS];
-    unsigned long long tsum = 0;
+    unsigned tsum = 0;
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) {
-        q[j] = (!tail || base + j < a.n_out) ? s_q[x[j]] : 0u;
+        q[j] = (!TAIL || base + j < a.n_out) ? s_q[x[j]] : 0u;
         tsum += q[j];
     }
     sb_store8_u32(reinterpret_cast<uint32_t*>(a.x_out) + lbase, reinterpret_cast<const uint32_t*>(x));
     sb_store8_u32(a.w32_out + lbase, q);
     if (a.lw_out) {
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.lw_out[base + j] = a.logF_t[x[j]];
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.lw_out[lbase + j] = a.logF_t[x[j]];
     }
     if (a.wlit_out) {
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.wlit_out[base + j] = a.expF_t[x[j]];
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.wlit_out[lbase + j] = a.expF_t[x[j]];
     }
-    const unsigned long long tot = sb_block_sum_u64(tsum, ps.scan);
-    if (tid == 0) { a.e_out[a.peers.tile_off + blockIdx.x] = e; a.Q_out[a.peers.tile_off + blockIdx.x] = tot; }
+    const unsigned long long tot = sb_block_sum_wp(tsum, sm.ps.scan, a.wp_out + (size_t)tile * SB_WARPS);
+    if (tid == 0) { a.e_out[tile] = e; a.Q_out[tile] = tot; }
+    __syncthreads();                                              // shared scratch is reused by the next tile
+}
+
+template <int ANC, bool FP32, bool PEERS, bool MULTI>
+__global__ void __launch_bounds__(SB_THREADS)
+k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(dyn);             // rows * 256 (16-byte aligned: staged as uint4)
+    double* s_l2 = reinterpret_cast<double*>(s_tab + (a.rows << SB_LG_BUCKETS));   // K   (float view when FP32)
+    uint32_t* s_thr = reinterpret_cast<uint32_t*>(s_l2 + a.K);      // rows*K
+    uint32_t* s_q = s_thr + a.rows * a.K;                           // K
+    __shared__ SbHmmSmem sm;
+    const int tid = threadIdx.x;
+    const int K = a.K;
+    if (MULTI) for (int i = tid; i < a.rows * K; i += SB_THREADS) s_thr[i] = __ldg(a.thr + i);
+    for (int i = tid; i < ((a.rows << SB_LG_BUCKETS) >> 2); i += SB_THREADS)
+        reinterpret_cast<uint4*>(s_tab)[i] = __ldg(reinterpret_cast<const uint4*>(a.tab) + i);
+    if (tid < K) {
+        if (FP32) {
+            const float l2 = __fmul_rn((float)a.logF_t[tid], SB_LOG2E_F);
+            if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
+            reinterpret_cast<float*>(s_l2)[tid] = l2;
+        } else {
+            const double l2 = __dmul_rn(a.logF_t[tid], SB_LOG2E_D);
+            if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
+            s_l2[tid] = l2;
+        }
+    }
+    SbStepInfo si;
+    if (ANC == SB_ANC_PULL) si = *a.info_prev;
+    __syncthreads();                                              // tables staged
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const bool tail = a.pool.c_off + (tile + 1) * SB_TILE > a.N;   // only the last tile(s) see padding / the retained slot
+        if (!tail) sb_hmm_tile<ANC, FP32, PEERS, MULTI, false>(a, si, tile, sm, s_l2, s_thr, s_q, s_tab);
+        else       sb_hmm_tile<ANC, FP32, PEERS, MULTI, true>(a, si, tile, sm, s_l2, s_thr, s_q, s_tab);
+    }
 }
 
 // ---------------------------------------------------------------- linear-Gaussian step
 struct SbLgStepArgs {
-    SbPeers peers;              // previous pool (x is REAL)
+    SbPool pool;                // previous pool (x is REAL)
     const int* e_prev;
     const unsigned long long* Pt;
     const int* child_start;
     const int* first_tile;
     const SbStepInfo* info_prev;
     const int* anc_in;
-    int* anc_out;
     void* x_out;
     uint32_t* w32_out;
     int* e_out;
     unsigned long long* Q_out;
+    unsigned long long* wp_out;
     double* lw_out;
-    long long N;
+    long long N;                // global particle count
+    int ntiles;                 // local tiles to produce
     int t;
     unsigned iter;
     unsigned long long seed;
@@ -712,104 +809,107 @@ struct SbLgStepArgs {
 
 #define SB_TWO_PI 6.283185307179586476925286766559
 
-template <int ANC, bool FP32>
+template <int ANC, bool FP32, bool PEERS>
 __global__ void __launch_bounds__(SB_THREADS)
 k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     typedef typename std::conditional<FP32, float, double>::type REAL;
-    __shared__ SbPullSmem ps;
-    __shared__ double s_red[SB_WARPS];
+    __shared__ SbHmmSmem sm;
     const int tid = threadIdx.x;
-    const int c0 = a.peers.c_off + blockIdx.x * SB_TILE;          // global child index of this tile
-    const int base = c0 + tid * SB_ITEMS;
-    const int lbase = blockIdx.x * SB_TILE + tid * SB_ITEMS;      // where this GPU stores it
-    int anc[SB_ITEMS];
-    if (ANC == SB_ANC_PULL) {
-        const SbStepInfo si = *a.info_prev;
-        sb_pull_ancestors(si, a.peers, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, ps, anc);
+    const int N = (int)a.N;
+    SbStepInfo si;
+    if (ANC == SB_ANC_PULL) si = *a.info_prev;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int c0 = a.pool.c_off + tile * SB_TILE;             // global child index of this tile
+        const int base = c0 + tid * SB_ITEMS;
+        const int lbase = tile * SB_TILE + tid * SB_ITEMS;        // where this GPU stores it
+        int anc[SB_ITEMS];
+        if (ANC == SB_ANC_PULL) {
+            if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, sm.ps, anc);
+            else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, sm.ps, anc);
+        } else if (ANC == SB_ANC_EXPLICIT) {
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(anc[j], 0);
-    } else if (ANC == SB_ANC_EXPLICIT) {
+            for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < N) ? __ldg(a.anc_in + lbase + j) : 0;
+        } else {
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < a.N) ? __ldg(a.anc_in + base + j) : 0;
-    } else {
+            for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;
+        }
+        REAL xpar[SB_ITEMS];
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;
-    }
-    if (ANC == SB_ANC_PULL && a.anc_out) {
+        for (int j = 0; j < SB_ITEMS; ++j)
+            xpar[j] = (ANC != SB_ANC_NONE && base + j < N) ? sb_pool_x<REAL, PEERS>(a.pool, anc[j]) : (REAL)0;
+        REAL x[SB_ITEMS];
+        REAL l2[SB_ITEMS];
+        REAL mx = -INFINITY;
+        bool bad = false;
+        if (FP32) {
+            const float fa = (float)a.a, fsq = (float)a.sq, fsp = (float)a.sp, fc = (float)a.c, fy = (float)a.y;
+            const float hr = -0.5f / (float)a.r, flc = (float)a.lc, fm0 = (float)a.m0;
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.N) a.anc_out[base + j] = anc[j];
-    }
-    REAL x[SB_ITEMS];
-    REAL l2[SB_ITEMS];
-    REAL mx = -INFINITY;
-    bool bad = false;
-    if (FP32) {
-        const float fa = (float)a.a, fsq = (float)a.sq, fsp = (float)a.sp, fc = (float)a.c, fy = (float)a.y;
-        const float hr = -0.5f / (float)a.r, flc = (float)a.lc, fm0 = (float)a.m0;
+            for (int p = 0; p < SB_ITEMS / 2; ++p) {
+                const SbU4 o = sb_stream4(a.seed, (unsigned long long)((base >> 1) + p), (unsigned)a.t, a.iter, SB_P_PROP);
 #pragma unroll
-        for (int p = 0; p < SB_ITEMS / 2; ++p) {
-            const SbU4 o = sb_stream4(a.seed, (unsigned long long)((base >> 1) + p), (unsigned)a.t, a.iter, SB_P_PROP);
+                for (int h = 0; h < 2; ++h) {
+                    const int j = 2 * p + h;
+                    const float u1 = (float)((h ? o.z : o.x) >> 8) * 0x1p-24f;
+                    const float u2 = (float)((h ? o.w : o.y) >> 8) * 0x1p-24f;
+                    const float z = sqrtf(-2.0f * logf(1.0f - u1)) * cosf((float)SB_TWO_PI * u2);
+                    float xv;
+                    if (ANC == SB_ANC_NONE) xv = fm0 + fsp * z;
+                    else xv = fa * (float)xpar[j] + fsq * z;
+                    const float d = fy - fc * xv;
+                    const float lw = hr * d * d + flc;
+                    const bool live = base + j < N;
+                    float v = live ? __fmul_rn(lw, SB_LOG2E_F) : -INFINITY;
+                    if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
+                    x[j] = (REAL)xv; l2[j] = (REAL)v;
+                    mx = (REAL)fmaxf((float)mx, v);
+                    if (a.lw_out && live) a.lw_out[lbase + j] = (double)lw;
+                }
+            }
+        } else {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = 2 * p + h;
-                const float u1 = (float)((h ? o.z : o.x) >> 8) * 0x1p-24f;
-                const float u2 = (float)((h ? o.w : o.y) >> 8) * 0x1p-24f;
-                const float z = sqrtf(-2.0f * logf(1.0f - u1)) * cosf((float)SB_TWO_PI * u2);
-                float xv;
-                if (ANC == SB_ANC_NONE) xv = fm0 + fsp * z;
-                else xv = fa * ((base + j < a.N) ? sb_peer_x<float>(a.peers, anc[j]) : 0.0f) + fsq * z;
-                const float d = fy - fc * xv;
-                const float lw = hr * d * d + flc;
-                const bool live = base + j < a.N;
-                float v = live ? __fmul_rn(lw, SB_LOG2E_F) : -INFINITY;
+            for (int j = 0; j < SB_ITEMS; ++j) {
+                const SbU4 o = sb_stream4(a.seed, (unsigned long long)(base + j), (unsigned)a.t, a.iter, SB_P_PROP);
+                const double u1 = sb_u53(o.x, o.y), u2 = sb_u53(o.z, o.w);
+                const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(SB_TWO_PI * u2);
+                double xv;
+                if (ANC == SB_ANC_NONE) xv = a.m0 + a.sp * z;
+                else xv = a.a * (double)xpar[j] + a.sq * z;
+                const double d = a.y - a.c * xv;
+                const double lw = -0.5 * d * d / a.r + a.lc;
+                const bool live = base + j < N;
+                double v = live ? __dmul_rn(lw, SB_LOG2E_D) : -INFINITY;
                 if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
                 x[j] = (REAL)xv; l2[j] = (REAL)v;
-                mx = (REAL)fmaxf((float)mx, v);
-                if (a.lw_out && live) a.lw_out[lbase + j] = (double)lw;
+                mx = (REAL)fmax((double)mx, v);
+                if (a.lw_out && live) a.lw_out[lbase + j] = lw;
             }
         }
-    } else {
+        int e;
+        if (FP32) { const float m2 = sb_block_max_f32((float)mx, reinterpret_cast<float*>(sm.red)); e = m2 > -INFINITY ? (int)ceilf(m2) : SB_E_EMPTY; }
+        else      { const double m2 = sb_block_max_f64((double)mx, sm.red); e = m2 > -INFINITY ? (int)ceil(m2) : SB_E_EMPTY; }
+        uint32_t q[SB_ITEMS];
+        unsigned tsum = 0;
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) {
-            const SbU4 o = sb_stream4(a.seed, (unsigned long long)(base + j), (unsigned)a.t, a.iter, SB_P_PROP);
-            const double u1 = sb_u53(o.x, o.y), u2 = sb_u53(o.z, o.w);
-            const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(SB_TWO_PI * u2);
-            double xv;
-            if (ANC == SB_ANC_NONE) xv = a.m0 + a.sp * z;
-            else xv = a.a * ((base + j < a.N) ? sb_peer_x<double>(a.peers, anc[j]) : 0.0) + a.sq * z;
-            const double d = a.y - a.c * xv;
-            const double lw = -0.5 * d * d / a.r + a.lc;
-            const bool live = base + j < a.N;
-            double v = live ? __dmul_rn(lw, SB_LOG2E_D) : -INFINITY;
-            if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
-            x[j] = (REAL)xv; l2[j] = (REAL)v;
-            mx = (REAL)fmax((double)mx, v);
-            if (a.lw_out && live) a.lw_out[lbase + j] = lw;
+            uint32_t v = 0;
+            if (e != SB_E_EMPTY) v = FP32 ? sb_q31_f32(__fsub_rn((float)l2[j], (float)e)) : sb_q31_f64(__dsub_rn((double)l2[j], (double)e));
+            q[j] = v; tsum += v;
         }
-    }
-    int e;
-    if (FP32) { const float m2 = sb_block_max_f32((float)mx, reinterpret_cast<float*>(s_red)); e = m2 > -INFINITY ? (int)ceilf(m2) : SB_E_EMPTY; }
-    else      { const double m2 = sb_block_max_f64((double)mx, s_red); e = m2 > -INFINITY ? (int)ceil(m2) : SB_E_EMPTY; }
-    uint32_t q[SB_ITEMS];
-    unsigned long long tsum = 0;
+        REAL* xo = reinterpret_cast<REAL*>(a.x_out) + lbase;
+        if (FP32) {
+            reinterpret_cast<float4*>(xo)[0] = make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
+            reinterpret_cast<float4*>(xo)[1] = make_float4((float)x[4], (float)x[5], (float)x[6], (float)x[7]);
+        } else {
 #pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) {
-        uint32_t v = 0;
-        if (e != SB_E_EMPTY) v = FP32 ? sb_q31_f32(__fsub_rn((float)l2[j], (float)e)) : sb_q31_f64(__dsub_rn((double)l2[j], (double)e));
-        q[j] = v; tsum += v;
+            for (int j = 0; j < SB_ITEMS; j += 2) reinterpret_cast<double2*>(xo)[j / 2] = make_double2((double)x[j], (double)x[j + 1]);
+        }
+        sb_store8_u32(a.w32_out + lbase, q);
+        const unsigned long long tot = sb_block_sum_wp(tsum, sm.ps.scan, a.wp_out + (size_t)tile * SB_WARPS);
+        if (tid == 0) { a.e_out[tile] = e; a.Q_out[tile] = tot; }
+        if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
+        __syncthreads();                                          // shared scratch is reused by the next tile
     }
-    REAL* xo = reinterpret_cast<REAL*>(a.x_out) + lbase;
-    if (FP32) {
-        reinterpret_cast<float4*>(xo)[0] = make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
-        reinterpret_cast<float4*>(xo)[1] = make_float4((float)x[4], (float)x[5], (float)x[6], (float)x[7]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < SB_ITEMS; j += 2) reinterpret_cast<double2*>(xo)[j / 2] = make_double2((double)x[j], (double)x[j + 1]);
-    }
-    sb_store8_u32(a.w32_out + lbase, q);
-    const unsigned long long tot = sb_block_sum_u64(tsum, ps.scan);
-    if (tid == 0) { a.e_out[a.peers.tile_off + blockIdx.x] = e; a.Q_out[a.peers.tile_off + blockIdx.x] = tot; }
-    if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
 }
 
 // =====================================================================================

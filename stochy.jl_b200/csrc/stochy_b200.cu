@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -48,17 +49,32 @@ struct sb_handle {
     DevBuf d_info;        // SbStepInfo[max(T,1)]
     DevBuf d_misc;        // int lineage
 
-    // grid scratch
-    DevBuf w32[2], tile_e[2], tile_Q[2], P, Pt, child_start, first_tile, cdf, lit_acc, lse_part;
+    // grid scratch (one GPU: plain buffers; sharded: the same arrays live inside `arena`)
+    DevBuf w32[2], tile_e[2], tile_Q[2], tile_wp[2], P, Pt, child_start, first_tile, cdf, lit_acc, lse_part;
+    int num_sms = 148;
+    std::map<std::pair<const void*, size_t>, int> occ;     // resident CTAs per kernel (persistent grids)
+
+    // sharded pool (multi-GPU, one process per GPU): see DESIGN.md "Multi-GPU"
+    int rank = 0, world = 1;
+    bool dist_ready = false;
+    int64_t NL = 0;                   // particles per GPU (power of two)
+    int dist_sz = 0;                  // bytes per particle state in the arena
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t off_w32[2] = {0, 0}, off_x[2] = {0, 0}, off_wp[2] = {0, 0}, off_e[2] = {0, 0}, off_Q[2] = {0, 0}, off_flags = 0;
+    char* peer_base[SB_MAX_PEERS] = {nullptr};
+    unsigned epoch = 0;
+    DevBuf e_all;
     // hook staging
     DevBuf hk_in, hk_r, hk_anc, hk_out, hk_src;
 
     // model
     int model = MODEL_NONE;
     // HMM
-    int K = 0, T = 0, x0 = -1, hmm_lgG = 8;
+    int K = 0, T = 0, x0 = -1;
+    bool hmm_multi = false;           // some lookup bucket holds several thresholds (slow scan needed)
     std::vector<uint8_t> has_factor;
-    DevBuf hmm_cumA, hmm_cumpi, hmm_logF, hmm_expF, hmm_hasf;
+    DevBuf hmm_cumA, hmm_cumpi, hmm_tabA, hmm_tabpi, hmm_logF, hmm_expF, hmm_hasf;
     // LG
     double lg_a = 0, lg_q = 0, lg_c = 0, lg_r = 0, lg_m0 = 0, lg_P0 = 0;
     std::vector<double> lg_y;
@@ -104,11 +120,36 @@ int fail(sb_handle* h, int code, const std::string& msg) {
 
 inline int64_t tiles_of(int64_t n) { return (n + SB_TILE - 1) / SB_TILE; }
 
-// the whole pool on this GPU
-inline SbPeers local_peers(const void* w32, const void* x) {
-    SbPeers p;
+// ---- where the grid arrays of pool slot `slot` live (plain buffers, or the shared arena when sharded)
+inline uint32_t* W32(sb_handle* h, int slot) {
+    return h->dist_ready ? reinterpret_cast<uint32_t*>((char*)h->arena + h->off_w32[slot]) : h->w32[slot].as<uint32_t>();
+}
+inline int* TE(sb_handle* h, int slot) {
+    return h->dist_ready ? reinterpret_cast<int*>((char*)h->arena + h->off_e[slot]) : h->tile_e[slot].as<int>();
+}
+inline unsigned long long* TQ(sb_handle* h, int slot) {
+    return h->dist_ready ? reinterpret_cast<unsigned long long*>((char*)h->arena + h->off_Q[slot]) : h->tile_Q[slot].as<unsigned long long>();
+}
+inline unsigned long long* WP(sb_handle* h, int slot) {
+    return h->dist_ready ? reinterpret_cast<unsigned long long*>((char*)h->arena + h->off_wp[slot]) : h->tile_wp[slot].as<unsigned long long>();
+}
+// tile exponents as the pull reads them (indexed by GLOBAL tile)
+inline const int* TE_pull(sb_handle* h, int slot) { return h->dist_ready ? h->e_all.as<int>() : TE(h, slot); }
+
+// the pool held in slot `slot` whose particle states are at `x` (single GPU) / in the arena (sharded)
+inline SbPool make_pool(sb_handle* h, int slot, const void* x) {
+    SbPool p;
     memset(&p, 0, sizeof(p));
-    p.w32[0] = w32; p.x[0] = x; p.log2n = 31; p.c_off = 0; p.tile_off = 0;
+    p.w32 = W32(h, slot); p.x = x; p.wp = WP(h, slot);
+    p.log2n = 31;
+    if (h->dist_ready) {
+        for (int g = 0; g < h->world; ++g) p.base[g] = h->peer_base[g];
+        p.off_w32 = h->off_w32[slot]; p.off_x = h->off_x[slot]; p.off_wp = h->off_wp[slot];
+        p.log2n = 0; while ((1ll << p.log2n) < h->NL) ++p.log2n;
+        p.c_off = (int)(h->rank * h->NL);
+        p.tile_off = (int)(h->rank * (h->NL / SB_TILE));
+        p.x = (char*)h->arena + h->off_x[slot];
+    }
     return p;
 }
 
@@ -140,19 +181,28 @@ int check_err_word(sb_handle* h) {
     CK(cudaStreamSynchronize(h->stream));
     if (w) {
         cudaMemsetAsync(h->d_err, 0, sizeof(unsigned), h->stream);
+        if (w & SB_ERRBIT_PEER) return fail(h, SB_EPEER, "multi-GPU barrier timed out: a peer GPU never signalled");
         if (w & SB_ERRBIT_NAN) return fail(h, SB_ENAN, "unexpected nan in rand");
         return fail(h, SB_EZEROMASS, "Distribution has zero probability mass.");
     }
     return SB_OK;
 }
 
+// scratch of the resampling grid for a pool of n_pool entries (GLOBAL count when sharded) and m children
 int ensure_grid(sb_handle* h, int64_t n_pool, int64_t m) {
     const int64_t nt = tiles_of(n_pool);
     if (nt > (1 << 20) || m > 0x7fffffffLL - SB_TILE) return fail(h, SB_EINVAL, "pool too large (max 2^31 particles)");
-    for (int i = 0; i < 2; ++i) {
-        CK(h->w32[i].ensure((size_t)nt * SB_TILE * 4));
-        CK(h->tile_e[i].ensure((size_t)nt * 4));
-        CK(h->tile_Q[i].ensure((size_t)nt * 8));
+    if (h->dist_ready) {
+        if (n_pool != h->NL * h->world || m != n_pool)
+            return fail(h, SB_EINVAL, "sharded handle: the pool is fixed at world x N_local particles");
+        CK(h->e_all.ensure((size_t)nt * 4));
+    } else {
+        for (int i = 0; i < 2; ++i) {
+            CK(h->w32[i].ensure((size_t)nt * SB_TILE * 4));
+            CK(h->tile_e[i].ensure((size_t)nt * 4));
+            CK(h->tile_Q[i].ensure((size_t)nt * 8));
+            CK(h->tile_wp[i].ensure((size_t)nt * SB_WARPS * 8));
+        }
     }
     CK(h->P.ensure((size_t)(nt + 1) * 8));
     CK(h->Pt.ensure((size_t)(nt + 1) * 8));
@@ -161,35 +211,83 @@ int ensure_grid(sb_handle* h, int64_t n_pool, int64_t m) {
     return SB_OK;
 }
 
+// resident CTAs of a persistent kernel (cached per kernel and shared-memory size)
+template <typename Kern>
+int resident_ctas(sb_handle* h, Kern kern, size_t smem, int* out) {
+    const std::pair<const void*, size_t> key((const void*)kern, smem);
+    auto it = h->occ.find(key);
+    if (it == h->occ.end()) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SB_THREADS, smem));
+        if (nb < 1) return fail(h, SB_ECUDA, "step kernel does not fit on an SM");
+        it = h->occ.emplace(key, nb * h->num_sms).first;
+    }
+    *out = it->second;
+    return SB_OK;
+}
+
 // quantise (device data) into grid buffer `slot`
 int launch_quantise(sb_handle* h, const void* d_data, int kind, int64_t n, int slot) {
     const int nt = (int)tiles_of(n);
-    uint32_t* w32 = h->w32[slot].as<uint32_t>();
-    int* e = h->tile_e[slot].as<int>();
-    unsigned long long* Q = h->tile_Q[slot].as<unsigned long long>();
-    if (kind == SB_W_LINEAR_F64) k_quantise<0><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, h->d_err);
-    else if (kind == SB_W_LOG_F64) k_quantise<1><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, h->d_err);
-    else if (kind == SB_W_LOG_F32) k_quantise<2><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, h->d_err);
+    uint32_t* w32 = W32(h, slot);
+    int* e = TE(h, slot);
+    unsigned long long* Q = TQ(h, slot);
+    unsigned long long* wp = WP(h, slot);
+    if (kind == SB_W_LINEAR_F64) k_quantise<0><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, wp, h->d_err);
+    else if (kind == SB_W_LOG_F64) k_quantise<1><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, wp, h->d_err);
+    else if (kind == SB_W_LOG_F32) k_quantise<2><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, wp, h->d_err);
     else return fail(h, SB_EINVAL, "unknown weight kind");
     LAUNCH_CHECK();
     return SB_OK;
 }
 
-int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, const unsigned long long* d_r53, SbStepInfo* info) {
-    const int nt = (int)tiles_of(n);
-    k_tilescan<<<SB_SCAN_CTAS, SB_SCAN_THREADS, 0, h->stream>>>(h->tile_e[slot].as<int>(), h->tile_Q[slot].as<unsigned long long>(),
-                                                                nt, n, m, d_r53, info, h->P.as<unsigned long long>(),
-                                                                h->Pt.as<unsigned long long>(), h->child_start.as<int>(),
-                                                                h->first_tile.as<int>(),
-                                                                h->opt.resample_mode == SB_RESAMPLE_MULTINOMIAL || h->hook_exact, h->d_err);
+template <bool PEERS>
+int launch_tilescan_t(sb_handle* h, int per, const int* e, const unsigned long long* Q, int nt, int64_t n, int64_t m,
+                      const unsigned long long* d_r53, SbStepInfo* info, int want_exact, const SbScanPeers& sp) {
+    unsigned long long* P = h->P.as<unsigned long long>();
+    unsigned long long* Pt = h->Pt.as<unsigned long long>();
+    int* cs = h->child_start.as<int>();
+    int* ft = h->first_tile.as<int>();
+#define SB_TS_LAUNCH(PER) k_tilescan<PER, PEERS><<<SB_SCAN_CTAS, SB_SCAN_THREADS, 0, h->stream>>>(e, Q, nt, n, m, d_r53, info, P, Pt, cs, ft, want_exact, h->d_err, sp)
+    if (per <= 1) SB_TS_LAUNCH(1);
+    else if (per <= 2) SB_TS_LAUNCH(2);
+    else if (per <= 4) SB_TS_LAUNCH(4);
+    else if (per <= 8) SB_TS_LAUNCH(8);
+    else if (!PEERS) SB_TS_LAUNCH(0);
+    else return fail(h, SB_EINVAL, "sharded pool too large (max 2^27 particles over all GPUs)");
+#undef SB_TS_LAUNCH
     LAUNCH_CHECK();
     return SB_OK;
 }
 
-int launch_pull(sb_handle* h, int slot, const SbStepInfo* info, int64_t m, int* d_anc) {
-    k_pull<<<(unsigned)tiles_of(m), SB_THREADS, 0, h->stream>>>(info, local_peers(h->w32[slot].p, nullptr), h->tile_e[slot].as<int>(),
-                                                                h->Pt.as<unsigned long long>(), h->child_start.as<int>(),
-                                                                h->first_tile.as<int>(), d_anc);
+// scan of pool `slot` (n entries, m children).  Sharded: first tell the peers that this GPU's share of
+// the pool is complete, then scan all GPUs' tile records behind the flag barrier.
+int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, const unsigned long long* d_r53, SbStepInfo* info) {
+    const int nt = (int)tiles_of(n);
+    const int per = (nt + SB_SCAN_THREADS * SB_SCAN_CTAS - 1) / (SB_SCAN_THREADS * SB_SCAN_CTAS);
+    const int want_exact = h->opt.resample_mode == SB_RESAMPLE_MULTINOMIAL || h->hook_exact;
+    SbScanPeers sp;
+    memset(&sp, 0, sizeof(sp));
+    if (!h->dist_ready)
+        return launch_tilescan_t<false>(h, per, TE(h, slot), TQ(h, slot), nt, n, m, d_r53, info, want_exact, sp);
+    for (int g = 0; g < h->world; ++g) sp.base[g] = h->peer_base[g];
+    sp.off_e = h->off_e[slot]; sp.off_Q = h->off_Q[slot]; sp.off_flags = h->off_flags;
+    sp.log2t = 0; while ((1ll << sp.log2t) < h->NL / SB_TILE) ++sp.log2t;
+    sp.world = h->world; sp.self = h->rank; sp.epoch = ++h->epoch; sp.e_all = h->e_all.as<int>();
+    k_signal<<<1, 32, 0, h->stream>>>(sp);
+    LAUNCH_CHECK();
+    return launch_tilescan_t<true>(h, per, nullptr, nullptr, nt, n, m, d_r53, info, want_exact, sp);
+}
+
+int launch_pull(sb_handle* h, int slot, const SbStepInfo* info, int64_t m_local, int* d_anc) {
+    const SbPool pool = make_pool(h, slot, nullptr);
+    if (h->dist_ready)
+        k_pull<true><<<(unsigned)tiles_of(m_local), SB_THREADS, 0, h->stream>>>(info, pool, TE_pull(h, slot), h->Pt.as<unsigned long long>(),
+                                                                              h->child_start.as<int>(), h->first_tile.as<int>(), d_anc);
+    else
+        k_pull<false><<<(unsigned)tiles_of(m_local), SB_THREADS, 0, h->stream>>>(info, pool, TE_pull(h, slot), h->Pt.as<unsigned long long>(),
+                                                                               h->child_start.as<int>(), h->first_tile.as<int>(), d_anc);
     LAUNCH_CHECK();
     return SB_OK;
 }
@@ -197,8 +295,9 @@ int launch_pull(sb_handle* h, int slot, const SbStepInfo* info, int64_t m, int* 
 // grid multinomial on pool `slot`: CDF + search.  d_r may be nullptr (Philox stream)
 int launch_grid_multinomial(sb_handle* h, int slot, const SbStepInfo* info, int64_t n, int64_t m, const double* d_r,
                             unsigned t, unsigned iter, int* d_anc) {
+    if (h->dist_ready) return fail(h, SB_EUNSUPPORTED, "sharded pools resample systematically");
     CK(h->cdf.ensure((size_t)n * 8));
-    k_cdf<<<(unsigned)tiles_of(n), SB_THREADS, 0, h->stream>>>(info, h->w32[slot].as<uint32_t>(), h->tile_e[slot].as<int>(),
+    k_cdf<<<(unsigned)tiles_of(n), SB_THREADS, 0, h->stream>>>(info, W32(h, slot), TE(h, slot),
                                                                h->P.as<unsigned long long>(), h->cdf.as<unsigned long long>());
     LAUNCH_CHECK();
     k_multinomial_search<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(info, h->cdf.as<unsigned long long>(), d_r,
@@ -306,6 +405,8 @@ extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
         sb_destroy(h);
         return SB_ECUDA;
     }
+    if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, opt.device) != cudaSuccess || h->num_sms < 1)
+        h->num_sms = 148;
     *out = h;
     return SB_OK;
 }
@@ -315,12 +416,15 @@ extern "C" void sb_destroy(sb_handle* h) {
     cudaSetDevice(h->opt.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->d_r53, &h->d_info, &h->d_misc, &h->w32[0], &h->w32[1], &h->tile_e[0], &h->tile_e[1],
-                      &h->tile_Q[0], &h->tile_Q[1], &h->P, &h->Pt, &h->child_start, &h->first_tile, &h->cdf, &h->lit_acc, &h->lse_part,
+                      &h->tile_Q[0], &h->tile_Q[1], &h->tile_wp[0], &h->tile_wp[1], &h->e_all, &h->hmm_tabA, &h->hmm_tabpi, &h->P, &h->Pt, &h->child_start, &h->first_tile, &h->cdf, &h->lit_acc, &h->lse_part,
                       &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
                       &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
                       &h->bn_fp, &h->bn_fac, &h->bn_counts, &h->xbuf, &h->ancbuf, &h->lwbuf, &h->wlit, &h->cnt[0],
                       &h->cnt[1], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint};
     for (DevBuf* b : bufs) b->release();
+    for (int g = 0; g < SB_MAX_PEERS; ++g)
+        if (h->peer_base[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_base[g]);
+    if (h->arena) cudaFree(h->arena);
     if (h->d_err) cudaFree(h->d_err);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -386,15 +490,24 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
         if (!(t > 0.0)) return 0u;
         return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
     };
-    const int lgG = 8, G = 1 << lgG;              // 256 buckets per row (K * 256 bytes of shared memory)
-    std::vector<uint32_t> cumA((size_t)K * K + (size_t)K * G / 4, 0u), cumpi((size_t)K + G / 4, 0u);
-    // guide[row][g] = #{k < K-1 : thr[row][k] <= g << (32 - lgG)}: start of the inverse-CDF scan
-    auto fill_guide = [&](const uint32_t* thr, unsigned char* guide) {
+    // inverse-CDF lookup words, 256 buckets per row (bucket g = draws R with R >> 24 == g):
+    //   bits 0..5   lo  = #{k < K-1 : thr[k] <= g << 24}        (where the scan of src/rand.jl:6-12 stands at the bucket start)
+    //   bits 6..30  t24 = low 24 bits of the first threshold inside the bucket, or 2^24 if there is none
+    //   bit  31     several thresholds fall inside the bucket (the kernel scans the thresholds from lo)
+    // so that  x = lo + ((R & 0xFFFFFF) >= t24)  whenever bit 31 is clear.
+    const int G = 1 << SB_LG_BUCKETS;
+    std::vector<uint32_t> cumA((size_t)K * K, 0u), cumpi((size_t)K, 0u), tabA((size_t)K * G, 0u), tabpi((size_t)G, 0u);
+    bool multi = false;
+    auto fill_tab = [&](const uint32_t* thr, uint32_t* tab) {
         for (int g = 0; g < G; ++g) {
-            const uint32_t r0 = (uint32_t)g << (32 - lgG);
-            int c = 0;
-            while (c < K - 1 && thr[c] <= r0) ++c;
-            guide[g] = (unsigned char)c;
+            const uint32_t r0 = (uint32_t)g << (32 - SB_LG_BUCKETS), r1 = r0 + ((1u << (32 - SB_LG_BUCKETS)) - 1u);
+            int lo = 0;
+            while (lo < K - 1 && thr[lo] <= r0) ++lo;
+            int cnt = 0;
+            while (lo + cnt < K - 1 && thr[lo + cnt] <= r1) ++cnt;
+            const uint32_t t24 = cnt ? (thr[lo] & 0xFFFFFFu) : (1u << 24);
+            tab[g] = (uint32_t)lo | (t24 << 6) | (cnt > 1 ? 0x80000000u : 0u);
+            if (cnt > 1) multi = true;
         }
     };
     std::vector<double> expF((size_t)T * K);
@@ -407,14 +520,18 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
         }
     }
     if (x0 < 0) { double acc = 0.0; for (int k = 0; k < K; ++k) { acc += pi[k]; cumpi[k] = thr_of(acc); } }
-    for (int r = 0; r < K; ++r) fill_guide(cumA.data() + (size_t)r * K, reinterpret_cast<unsigned char*>(cumA.data() + (size_t)K * K) + (size_t)r * G);
-    fill_guide(cumpi.data(), reinterpret_cast<unsigned char*>(cumpi.data() + K));
-    h->hmm_lgG = lgG;
+    for (int r = 0; r < K; ++r) fill_tab(cumA.data() + (size_t)r * K, tabA.data() + (size_t)r * G);
+    fill_tab(cumpi.data(), tabpi.data());
+    h->hmm_multi = multi;
     for (size_t i = 0; i < (size_t)T * K; ++i) expF[i] = exp(logF[i]);       // src/pmcmc.jl:55 (literal mode)
     h->has_factor.assign((size_t)T, 1);
     if (has_factor) for (int t = 0; t < T; ++t) h->has_factor[t] = has_factor[t] ? 1 : 0;
     CK(h->hmm_cumA.ensure(cumA.size() * 4));
     CK(h->hmm_cumpi.ensure(cumpi.size() * 4));
+    CK(h->hmm_tabA.ensure(tabA.size() * 4));
+    CK(h->hmm_tabpi.ensure(tabpi.size() * 4));
+    CK(cudaMemcpyAsync(h->hmm_tabA.p, tabA.data(), tabA.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->hmm_tabpi.p, tabpi.data(), tabpi.size() * 4, cudaMemcpyHostToDevice, h->stream));
     CK(h->hmm_logF.ensure((size_t)T * K * 8));
     CK(h->hmm_expF.ensure((size_t)T * K * 8));
     CK(h->hmm_hasf.ensure((size_t)T));
@@ -479,25 +596,59 @@ extern "C" int32_t sb_model_bayesnet(sb_handle* h, int32_t D, int32_t F, const u
 // ======================================================================= sweeps
 namespace {
 
-template <bool FP32>
-int launch_step_hmm(sb_handle* h, int anc_mode, const SbHmmStepArgs& a, unsigned grid) {
-    const size_t smem = (size_t)a.K * 8 + (size_t)(a.rows * a.K + a.K) * 4 + ((size_t)a.rows << a.lgG);
-    switch (anc_mode) {
-        case SB_ANC_NONE:     k_step_hmm<SB_ANC_NONE, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
-        case SB_ANC_PULL:     k_step_hmm<SB_ANC_PULL, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
-        case SB_ANC_EXPLICIT: k_step_hmm<SB_ANC_EXPLICIT, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
-        default:              k_step_hmm<SB_ANC_IDENTITY, FP32><<<grid, SB_THREADS, smem, h->stream>>>(a); break;
+template <bool FP32, bool MULTI>
+int launch_step_hmm_m(sb_handle* h, int anc_mode, const SbHmmStepArgs& a) {
+    const size_t smem = ((size_t)a.rows << SB_LG_BUCKETS) * 4 + (size_t)a.K * 8 + (size_t)(a.rows * a.K + a.K) * 4;
+    int cap = 0, rc;
+#define SB_HMM_LAUNCH(ANC, PEERS)                                                              \
+    do {                                                                                       \
+        auto kern = k_step_hmm<ANC, FP32, PEERS, MULTI>;                                       \
+        if ((rc = resident_ctas(h, kern, smem, &cap)) != SB_OK) return rc;                     \
+        kern<<<(unsigned)(a.ntiles < cap ? a.ntiles : cap), SB_THREADS, smem, h->stream>>>(a); \
+    } while (0)
+    if (h->dist_ready) {
+        if (anc_mode == SB_ANC_NONE) SB_HMM_LAUNCH(SB_ANC_NONE, false);
+        else if (anc_mode == SB_ANC_PULL) SB_HMM_LAUNCH(SB_ANC_PULL, true);
+        else return fail(h, SB_EUNSUPPORTED, "sharded pools resample systematically at every step");
+    } else {
+        switch (anc_mode) {
+            case SB_ANC_NONE:     SB_HMM_LAUNCH(SB_ANC_NONE, false); break;
+            case SB_ANC_PULL:     SB_HMM_LAUNCH(SB_ANC_PULL, false); break;
+            case SB_ANC_EXPLICIT: SB_HMM_LAUNCH(SB_ANC_EXPLICIT, false); break;
+            default:              SB_HMM_LAUNCH(SB_ANC_IDENTITY, false); break;
+        }
     }
+#undef SB_HMM_LAUNCH
     LAUNCH_CHECK();
     return SB_OK;
 }
+int launch_step_hmm(sb_handle* h, int anc_mode, const SbHmmStepArgs& a) {
+    const bool fp32 = h->opt.precision == SB_FP32;
+    if (h->hmm_multi) return fp32 ? launch_step_hmm_m<true, true>(h, anc_mode, a) : launch_step_hmm_m<false, true>(h, anc_mode, a);
+    return fp32 ? launch_step_hmm_m<true, false>(h, anc_mode, a) : launch_step_hmm_m<false, false>(h, anc_mode, a);
+}
+
 template <bool FP32>
-int launch_step_lg(sb_handle* h, int anc_mode, const SbLgStepArgs& a, unsigned grid) {
-    switch (anc_mode) {
-        case SB_ANC_NONE:     k_step_lg<SB_ANC_NONE, FP32><<<grid, SB_THREADS, 0, h->stream>>>(a); break;
-        case SB_ANC_PULL:     k_step_lg<SB_ANC_PULL, FP32><<<grid, SB_THREADS, 0, h->stream>>>(a); break;
-        default:              k_step_lg<SB_ANC_EXPLICIT, FP32><<<grid, SB_THREADS, 0, h->stream>>>(a); break;
+int launch_step_lg(sb_handle* h, int anc_mode, const SbLgStepArgs& a) {
+    int cap = 0, rc;
+#define SB_LG_LAUNCH(ANC, PEERS)                                                               \
+    do {                                                                                       \
+        auto kern = k_step_lg<ANC, FP32, PEERS>;                                               \
+        if ((rc = resident_ctas(h, kern, 0, &cap)) != SB_OK) return rc;                        \
+        kern<<<(unsigned)(a.ntiles < cap ? a.ntiles : cap), SB_THREADS, 0, h->stream>>>(a);    \
+    } while (0)
+    if (h->dist_ready) {
+        if (anc_mode == SB_ANC_NONE) SB_LG_LAUNCH(SB_ANC_NONE, false);
+        else if (anc_mode == SB_ANC_PULL) SB_LG_LAUNCH(SB_ANC_PULL, true);
+        else return fail(h, SB_EUNSUPPORTED, "sharded pools resample systematically at every step");
+    } else {
+        switch (anc_mode) {
+            case SB_ANC_NONE:     SB_LG_LAUNCH(SB_ANC_NONE, false); break;
+            case SB_ANC_PULL:     SB_LG_LAUNCH(SB_ANC_PULL, false); break;
+            default:              SB_LG_LAUNCH(SB_ANC_EXPLICIT, false); break;
+        }
     }
+#undef SB_LG_LAUNCH
     LAUNCH_CHECK();
     return SB_OK;
 }
@@ -524,31 +675,40 @@ int upload_offsets(sb_handle* h, unsigned iter) {
 }
 
 // One sweep of the discrete model.  conditional: pool of N+1 with the retained particle appended.
+// Sharded handle: N is the GLOBAL particle count (world x N_local); this GPU produces its own share.
 int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool history, bool final_anc) {
     const int T = h->T, K = h->K;
-    const int64_t S = tiles_of(N + 1) * SB_TILE;                       // row stride (slot N = retained)
+    const bool dist = h->dist_ready;
+    if (dist && (conditional || history || final_anc || h->opt.store_logw || h->opt.resample_mode != SB_RESAMPLE_SYSTEMATIC))
+        return fail(h, SB_EUNSUPPORTED, "sharded pools run plain SMC sweeps with systematic resampling and no history");
+    const int64_t S = dist ? h->NL : tiles_of(N + 1) * SB_TILE;        // row stride (slot N = retained)
     const int n_out = (int)(N + (conditional ? 1 : 0));
-    const bool fp32 = h->opt.precision == SB_FP32;
     const int mode = h->opt.resample_mode;
     const bool literal = mode == SB_RESAMPLE_LITERAL;
     int rc;
-    if ((rc = ensure_grid(h, N + 1, N)) != SB_OK) return rc;
+    if ((rc = ensure_grid(h, dist ? N : N + 1, N)) != SB_OK) return rc;
     const int xrows = history ? T : 2;
     const int arows = history ? T : 1;
-    CK(h->xbuf.ensure((size_t)xrows * S * 4));
-    CK(h->ancbuf.ensure((size_t)arows * S * 4));
+    if (!dist) {
+        CK(h->xbuf.ensure((size_t)xrows * S * 4));
+        CK(h->ancbuf.ensure((size_t)arows * S * 4));
+    }
     CK(h->d_info.ensure(sizeof(SbStepInfo) * (size_t)T));
     if (h->opt.store_logw) CK(h->lwbuf.ensure((size_t)T * S * 8));
     if (literal) CK(h->wlit.ensure((size_t)S * 8));
     if ((rc = upload_offsets(h, iter)) != SB_OK) return rc;
-    h->sw_N = N; h->sw_S = S; h->sw_hist = history ? 1 : 0; h->sw_cond = conditional ? 1 : 0;
+    h->sw_N = dist ? h->NL : N; h->sw_S = S; h->sw_hist = history ? 1 : 0; h->sw_cond = conditional ? 1 : 0;
     int* xb = h->xbuf.as<int>();
     int* ab = h->ancbuf.as<int>();
-    const unsigned grid = (unsigned)tiles_of(n_out);
+    auto xrow = [&](int t) -> int* {
+        if (dist) return reinterpret_cast<int*>((char*)h->arena + h->off_x[t & 1]);
+        return xb + (size_t)(history ? t : (t & 1)) * S;
+    };
+    const int ntiles = dist ? (int)(h->NL / SB_TILE) : (int)tiles_of(n_out);
     for (int t = 0; t < T; ++t) {
         const int cur = t & 1, prev = cur ^ 1;
         int anc_mode = SB_ANC_NONE;
-        int* anc_row_prev = t ? ab + (size_t)(history ? (t - 1) : 0) * S : nullptr;
+        int* anc_row_prev = (t && !dist) ? ab + (size_t)(history ? (t - 1) : 0) * S : nullptr;
         if (t > 0) {
             if (!h->has_factor[t - 1]) anc_mode = SB_ANC_IDENTITY;
             else if (mode == SB_RESAMPLE_SYSTEMATIC) anc_mode = SB_ANC_PULL;
@@ -558,35 +718,36 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
                 if ((rc = explicit_resample(h, prev, t - 1, iter, n_pool, N, anc_row_prev)) != SB_OK) return rc;
             }
         }
+        if (dist && anc_mode == SB_ANC_IDENTITY)
+            return fail(h, SB_EUNSUPPORTED, "sharded pools need a factor statement at every step");
         SbHmmStepArgs a;
         memset(&a, 0, sizeof(a));
-        a.peers = local_peers(h->w32[prev].p, t ? xb + (size_t)(history ? (t - 1) : prev) * S : nullptr);
-        a.e_prev = h->tile_e[prev].as<int>();
+        a.pool = make_pool(h, prev, t ? xrow(t - 1) : nullptr);
+        a.e_prev = TE_pull(h, prev);
         a.Pt = h->Pt.as<unsigned long long>();
         a.child_start = h->child_start.as<int>();
         a.first_tile = h->first_tile.as<int>();
         a.info_prev = t ? h->d_info.as<SbStepInfo>() + (t - 1) : nullptr;
         a.anc_in = anc_row_prev;
         a.anc_out = (history && t) ? anc_row_prev : nullptr;
-        a.x_out = xb + (size_t)(history ? t : cur) * S;
-        a.w32_out = h->w32[cur].as<uint32_t>();
-        a.e_out = h->tile_e[cur].as<int>();
-        a.Q_out = h->tile_Q[cur].as<unsigned long long>();
+        a.x_out = xrow(t);
+        a.w32_out = W32(h, cur);
+        a.e_out = TE(h, cur);
+        a.Q_out = TQ(h, cur);
+        a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.wlit_out = literal ? h->wlit.as<double>() : nullptr;
-        const int G = 1 << h->hmm_lgG;
-        const unsigned char* guideA = reinterpret_cast<const unsigned char*>(h->hmm_cumA.as<uint32_t>() + (size_t)K * K);
-        a.lgG = h->hmm_lgG;
-        if (t == 0 && h->x0 >= 0) { a.thr = h->hmm_cumA.as<uint32_t>() + (size_t)h->x0 * K; a.guide = guideA + (size_t)h->x0 * G; a.rows = 1; }
-        else if (t == 0) { a.thr = h->hmm_cumpi.as<uint32_t>(); a.guide = reinterpret_cast<const unsigned char*>(h->hmm_cumpi.as<uint32_t>() + K); a.rows = 1; }
-        else { a.thr = h->hmm_cumA.as<uint32_t>(); a.guide = guideA; a.rows = K; }
+        const int G = 1 << SB_LG_BUCKETS;
+        if (t == 0 && h->x0 >= 0) { a.thr = h->hmm_cumA.as<uint32_t>() + (size_t)h->x0 * K; a.tab = h->hmm_tabA.as<uint32_t>() + (size_t)h->x0 * G; a.rows = 1; }
+        else if (t == 0) { a.thr = h->hmm_cumpi.as<uint32_t>(); a.tab = h->hmm_tabpi.as<uint32_t>(); a.rows = 1; }
+        else { a.thr = h->hmm_cumA.as<uint32_t>(); a.tab = h->hmm_tabA.as<uint32_t>(); a.rows = K; }
         a.logF_t = h->hmm_logF.as<double>() + (size_t)t * K;
         a.expF_t = h->hmm_expF.as<double>() + (size_t)t * K;
         a.xstar = conditional ? h->xstar[h->xstar_cur].as<int>() : nullptr;
-        a.N = N; a.n_out = n_out; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.err = h->d_err;
+        a.N = N; a.n_out = n_out; a.ntiles = ntiles; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.err = h->d_err;
         {
             ProfScope ps(h, t ? t : -1);                               // t = 0 has no resample/gather: not sampled
-            rc = fp32 ? launch_step_hmm<true>(h, anc_mode, a, grid) : launch_step_hmm<false>(h, anc_mode, a, grid);
+            rc = launch_step_hmm(h, anc_mode, a);
         }
         if (rc != SB_OK) return rc;
         if (h->has_factor[t]) {
@@ -610,24 +771,31 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
     return SB_OK;
 }
 
+// Sharded handle: N is the GLOBAL particle count.
 int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
     const int T = h->T;
     const bool fp32 = h->opt.precision == SB_FP32;
+    const bool dist = h->dist_ready;
     const size_t sz = fp32 ? 4 : 8;
-    const int64_t S = tiles_of(N) * SB_TILE;
+    const int64_t S = dist ? h->NL : tiles_of(N) * SB_TILE;
     const int mode = h->opt.resample_mode;
     if (mode == SB_RESAMPLE_LITERAL)
         return fail(h, SB_EUNSUPPORTED, "literal resampling is a parity mode of the discrete model only");
+    if (dist && (mode != SB_RESAMPLE_SYSTEMATIC || h->opt.store_logw || (int)sz != h->dist_sz))
+        return fail(h, SB_EUNSUPPORTED, "sharded pools run systematic resampling at the precision given to sb_dist_ipc_export");
     int rc;
     if ((rc = ensure_grid(h, N, N)) != SB_OK) return rc;
-    CK(h->xbuf.ensure((size_t)2 * S * sz));
-    CK(h->ancbuf.ensure((size_t)S * 4));
+    if (!dist) {
+        CK(h->xbuf.ensure((size_t)2 * S * sz));
+        CK(h->ancbuf.ensure((size_t)S * 4));
+    }
     CK(h->d_info.ensure(sizeof(SbStepInfo) * (size_t)T));
     if (h->opt.store_logw) CK(h->lwbuf.ensure((size_t)T * S * 8));
     if ((rc = upload_offsets(h, iter)) != SB_OK) return rc;
-    h->sw_N = N; h->sw_S = S; h->sw_hist = 0; h->sw_cond = 0;
+    h->sw_N = dist ? h->NL : N; h->sw_S = S; h->sw_hist = 0; h->sw_cond = 0;
     char* xb = h->xbuf.as<char>();
-    const unsigned grid = (unsigned)tiles_of(N);
+    auto xrow = [&](int slot) -> char* { return dist ? (char*)h->arena + h->off_x[slot] : xb + (size_t)slot * S * sz; };
+    const int ntiles = (int)(S / SB_TILE);
     for (int t = 0; t < T; ++t) {
         const int cur = t & 1, prev = cur ^ 1;
         int anc_mode = t ? (mode == SB_RESAMPLE_SYSTEMATIC ? SB_ANC_PULL : SB_ANC_EXPLICIT) : SB_ANC_NONE;
@@ -635,26 +803,26 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
             if ((rc = explicit_resample(h, prev, t - 1, iter, N, N, h->ancbuf.as<int>())) != SB_OK) return rc;
         SbLgStepArgs a;
         memset(&a, 0, sizeof(a));
-        a.peers = local_peers(h->w32[prev].p, xb + (size_t)prev * S * sz);
-        a.e_prev = h->tile_e[prev].as<int>();
+        a.pool = make_pool(h, prev, xrow(prev));
+        a.e_prev = TE_pull(h, prev);
         a.Pt = h->Pt.as<unsigned long long>();
         a.child_start = h->child_start.as<int>();
         a.first_tile = h->first_tile.as<int>();
         a.info_prev = t ? h->d_info.as<SbStepInfo>() + (t - 1) : nullptr;
         a.anc_in = h->ancbuf.as<int>();
-        a.anc_out = nullptr;
-        a.x_out = xb + (size_t)cur * S * sz;
-        a.w32_out = h->w32[cur].as<uint32_t>();
-        a.e_out = h->tile_e[cur].as<int>();
-        a.Q_out = h->tile_Q[cur].as<unsigned long long>();
+        a.x_out = xrow(cur);
+        a.w32_out = W32(h, cur);
+        a.e_out = TE(h, cur);
+        a.Q_out = TQ(h, cur);
+        a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
-        a.N = N; a.t = t; a.iter = iter; a.seed = h->opt.seed;
+        a.N = N; a.ntiles = ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed;
         a.a = h->lg_a; a.sq = sqrt(h->lg_q); a.sp = sqrt(h->lg_P0); a.c = h->lg_c; a.r = h->lg_r; a.m0 = h->lg_m0;
         a.y = h->lg_y[t]; a.lc = -0.5 * log(SB_TWO_PI * h->lg_r);
         a.err = h->d_err;
         {
             ProfScope ps(h, t ? t : -1);
-            rc = fp32 ? launch_step_lg<true>(h, anc_mode, a, grid) : launch_step_lg<false>(h, anc_mode, a, grid);
+            rc = fp32 ? launch_step_lg<true>(h, anc_mode, a) : launch_step_lg<false>(h, anc_mode, a);
         }
         if (rc != SB_OK) return rc;
         if ((rc = launch_tilescan(h, cur, N, N, h->d_r53.as<unsigned long long>() + t,
@@ -687,8 +855,10 @@ extern "C" int32_t sb_smc_sweep(sb_handle* h, int64_t N, uint32_t iter, int32_t 
     CK(cudaSetDevice(h->opt.device));
     int rc;
     if ((rc = begin_timed(h)) != SB_OK) return rc;
-    if (h->model == MODEL_HMM) rc = sweep_hmm(h, N, iter, false, store_history != 0, store_history != 0);
-    else rc = sweep_lg(h, N, iter);
+    if (h->dist_ready && N != h->NL) return fail(h, SB_EINVAL, "smc: a sharded handle sweeps exactly N_local particles per GPU");
+    const int64_t Ng = h->dist_ready ? N * h->world : N;            // the sweep is global over all GPUs
+    if (h->model == MODEL_HMM) rc = sweep_hmm(h, Ng, iter, false, store_history != 0, store_history != 0);
+    else rc = sweep_lg(h, Ng, iter);
     if (rc != SB_OK) return rc;
     if ((rc = end_timed(h)) != SB_OK) return rc;
     h->stats.particle_steps = N * (int64_t)h->T;
@@ -704,6 +874,7 @@ extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t*
     if (h->model != MODEL_HMM)
         return fail(h, SB_EUNSUPPORTED, "pmcmc: only the fixed-structure discrete model is supported (no CPU fallback)");
     if (iters < 1 || N < 1) return fail(h, SB_EINVAL, "pmcmc: numiterations and numparticles must be >= 1");
+    if (h->dist_ready) return fail(h, SB_EUNSUPPORTED, "pmcmc: independent chains run one handle per GPU, not on a sharded handle");
     CK(cudaSetDevice(h->opt.device));
     const int T = h->T, K = h->K;
     int64_t njoint = 0;
@@ -1061,8 +1232,65 @@ extern "C" int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out) {
     return SB_OK;
 }
 
-// ======================================================================= multi-GPU (see sb_dist.cu)
-extern "C" int32_t sb_dist_unique_id(uint8_t out_id[128]) { (void)out_id; return SB_EUNSUPPORTED; }
-extern "C" int32_t sb_dist_init(sb_handle* h, int32_t, int32_t, const uint8_t*) { return fail(h, SB_EUNSUPPORTED, "multi-GPU path not built yet"); }
-extern "C" int32_t sb_dist_ipc_export(sb_handle* h, int64_t, uint8_t*) { return fail(h, SB_EUNSUPPORTED, "multi-GPU path not built yet"); }
-extern "C" int32_t sb_dist_ipc_import(sb_handle* h, const uint8_t*) { return fail(h, SB_EUNSUPPORTED, "multi-GPU path not built yet"); }
+// ======================================================================= multi-GPU
+// One process per GPU.  Every rank keeps its share of the particle pool (both double-buffer slots:
+// weights, states, warp prefixes, tile records) and a flag word per peer in ONE device allocation,
+// the arena, exported over CUDA IPC.  After the import every rank holds a mapping of every arena:
+// the fused step kernel reads parent weights and states of any GPU with ordinary loads over
+// NVLink, the tile scan reads every GPU's tile records behind a flag barrier (k_signal).  No NCCL
+// call sits on the data path; the 64-byte handles travel over the host's own plumbing
+// (torch.distributed.all_gather in the Python mirror).
+extern "C" int32_t sb_dist_init(sb_handle* h, int32_t rank, int32_t world) {
+    if (!h) return SB_EINVAL;
+    if (world < 1 || world > SB_MAX_PEERS || (world & (world - 1)) || rank < 0 || rank >= world)
+        return fail(h, SB_EINVAL, "dist_init: world must be 1, 2, 4 or 8 and 0 <= rank < world");
+    if (h->arena) return fail(h, SB_EINVAL, "dist_init: handle is already sharded");
+    h->rank = rank; h->world = world;
+    return SB_OK;
+}
+
+extern "C" int32_t sb_dist_ipc_export(sb_handle* h, int64_t N_local, uint8_t out_handle[64]) {
+    if (!h || !out_handle) return SB_EINVAL;
+    if (h->arena) return fail(h, SB_EINVAL, "dist_ipc_export: arena already allocated");
+    if (N_local < SB_TILE || (N_local & (N_local - 1)) || N_local * h->world > (1ll << 27))
+        return fail(h, SB_EINVAL, "dist_ipc_export: N_local must be a power of two >= 2048 with world x N_local <= 2^27");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    CK(cudaSetDevice(h->opt.device));
+    const size_t ntl = (size_t)(N_local / SB_TILE);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    for (int sl = 0; sl < 2; ++sl) {
+        h->off_w32[sl] = take((size_t)N_local * 4);
+        h->off_x[sl] = take((size_t)N_local * 8);              // room for fp64 states
+        h->off_wp[sl] = take(ntl * SB_WARPS * 8);
+        h->off_e[sl] = take(ntl * 4);
+        h->off_Q[sl] = take(ntl * 8);
+    }
+    h->off_flags = take(SB_MAX_PEERS * sizeof(unsigned));
+    CK(cudaMalloc(&h->arena, off));
+    h->arena_bytes = off;
+    CK(cudaMemset(h->arena, 0, off));
+    CK(cudaDeviceSynchronize());
+    h->NL = N_local;
+    cudaIpcMemHandle_t ipc;
+    CK(cudaIpcGetMemHandle(&ipc, h->arena));
+    memcpy(out_handle, &ipc, 64);
+    return SB_OK;
+}
+
+extern "C" int32_t sb_dist_ipc_import(sb_handle* h, const uint8_t* all_handles) {
+    if (!h || !all_handles) return SB_EINVAL;
+    if (!h->arena) return fail(h, SB_EINVAL, "dist_ipc_import: call sb_dist_ipc_export first");
+    CK(cudaSetDevice(h->opt.device));
+    for (int g = 0; g < h->world; ++g) {
+        if (g == h->rank) { h->peer_base[g] = (char*)h->arena; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, all_handles + (size_t)g * 64, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_base[g] = (char*)p;
+    }
+    h->epoch = 0;
+    h->dist_ready = true;
+    return SB_OK;
+}
