@@ -72,10 +72,10 @@ __device__ __forceinline__ const uint32_t* sb_pool_tile(const SbPool& p, int b) 
     return reinterpret_cast<const uint32_t*>(p.base[b >> ts] + p.off_w32) + (size_t)(b & ((1 << ts) - 1)) * SB_TILE;
 }
 template <bool PEERS>
-__device__ __forceinline__ unsigned long long sb_pool_wp(const SbPool& p, int b, int warp) {
-    if (!PEERS) return __ldg(p.wp + (size_t)b * SB_WARPS + warp);
+__device__ __forceinline__ const unsigned long long* sb_pool_wp_ptr(const SbPool& p, int b) {
+    if (!PEERS) return p.wp + (size_t)b * SB_WARPS;
     const int ts = p.log2n - 11;
-    return __ldg(reinterpret_cast<const unsigned long long*>(p.base[b >> ts] + p.off_wp) + (size_t)(b & ((1 << ts) - 1)) * SB_WARPS + warp);
+    return reinterpret_cast<const unsigned long long*>(p.base[b >> ts] + p.off_wp) + (size_t)(b & ((1 << ts) - 1)) * SB_WARPS;
 }
 template <typename T, bool PEERS>
 __device__ __forceinline__ T sb_pool_x(const SbPool& p, int i) {
@@ -261,11 +261,57 @@ __device__ __forceinline__ void sb_store8_u32(uint32_t* p, const uint32_t v[8]) 
     reinterpret_cast<uint4*>(p)[1] = make_uint4(v[4], v[5], v[6], v[7]);
 }
 
+// ---------------------------------------------------------------- asynchronous copies (TMA bulk, cp.async) and mbarrier
+__device__ __forceinline__ uint32_t sb_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sb_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sb_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void sb_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sb_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SB_DONE;\n"
+        "bra SB_WAIT;\n"
+        "SB_DONE:\n"
+        "}\n" ::"r"(sb_smem_addr(bar)), "r"(parity) : "memory");
+}
+// one thread: `bytes` (multiple of 16, 16-byte aligned both sides) from global memory -- local HBM or a
+// peer GPU's arena over NVLink -- into shared memory; completion is counted on the mbarrier
+__device__ __forceinline__ void sb_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sb_smem_addr(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(sb_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void sb_cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sb_smem_addr(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+__device__ __forceinline__ void sb_cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sb_smem_addr(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+__device__ __forceinline__ void sb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void sb_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- the pull: ancestors of one children tile
-struct SbPullSmem {
-    int marker[SB_TILE];
+#define SB_FT_CHUNK 64
+struct __align__(16) SbPullMeta {           // records of the two candidate parent tiles A, B of a children tile
+    unsigned long long wp[2][SB_WARPS];
+    unsigned long long Pt[2];
+    int cs[2], ce[2], e[2], pad[2];
+};
+struct __align__(16) SbPullSmem {
+    int marker[SB_TILE];                     // head markers, then the children's parents
+    uint32_t w[2][SB_TILE];                  // weights of parent tiles A and B (TMA bulk copies, one tile ahead)
+    SbPullMeta meta[2];                      // double-buffered (cp.async, one tile ahead)
+    unsigned long long bar;                  // mbarrier: the bytes of w have landed
     unsigned long long scan[SB_WARPS + 1];
     int wmax[SB_WARPS];
+    int2 ft[SB_FT_CHUNK + 1];                // (first, last) candidate parent tile of this CTA's next children tiles
 };
 
 // children (relative to c0, clamped to [0, cw]) whose threshold lies strictly below the CDF value
@@ -288,7 +334,7 @@ __device__ __forceinline__ int sb_pull_k(long long baseb, unsigned long long acc
 template <bool S32>
 __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const uint32_t w[SB_ITEMS], int eb,
                                              unsigned long long Ptb, unsigned long long wbase, int c0, int cw,
-                                             int* __restrict__ marker) {
+                                             SbPullSmem& sm) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int s = si.s;
     const unsigned R = si.R;
@@ -315,55 +361,96 @@ __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const 
             for (int j = 0; j < SB_ITEMS; ++j) {
                 acc += (unsigned long long)w[j] * R;             // one IMAD.WIDE with 64-bit accumulate
                 const int hi = (j == SB_ITEMS - 1) ? hi_t : sb_pull_k<S32>(baseb, acc, rb, s, cw);
-                if (lo < hi) marker[lo] = base + j;
+                if (lo < hi) sm.marker[lo] = base + j;
                 lo = hi;
             }
         }
     }
 }
 
+// (first, last) candidate parent tile of the children tile that starts at global child c0
+__device__ __forceinline__ int2 sb_pull_range(const SbStepInfo& si, const int* __restrict__ first_tile, int c0) {
+    const int m = (int)si.m;
+    if (c0 >= m) return make_int2(0, -1);                        // no children here: nothing is pulled
+    const int cb = c0 / SB_TILE;
+    return make_int2(__ldg(first_tile + cb), (c0 + SB_TILE < m) ? __ldg(first_tile + cb + 1) : si.nt - 1);
+}
+
+// Warp 0 (all 32 lanes): start the copies of the two candidate parent tiles b_lo, b_lo+1 of an upcoming
+// children tile -- weights by TMA bulk copy (one lane), tile records by 4/8-byte cp.async -- into
+// sm.w / sm.meta[slot].  The pool may live on a peer GPU: the copies then run over NVLink.
+template <bool PEERS>
+__device__ __forceinline__ void sb_pull_prefetch(const SbStepInfo& si, const SbPool& pool, const int* __restrict__ e,
+                                                 const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
+                                                 int b_lo, int slot, SbPullSmem& sm) {
+    const int lane = threadIdx.x & 31;
+    const int bA = b_lo, bB = min(b_lo + 1, si.nt - 1);
+    if (lane == 0) {
+        sb_mbar_expect_tx(&sm.bar, 2u * SB_TILE * 4u);
+        sb_bulk_g2s(sm.w[0], sb_pool_tile<PEERS>(pool, bA), SB_TILE * 4u, &sm.bar);
+        sb_bulk_g2s(sm.w[1], sb_pool_tile<PEERS>(pool, bB), SB_TILE * 4u, &sm.bar);
+    }
+    SbPullMeta& mt = sm.meta[slot];
+    const int which = (lane >> 3) & 1 ? 1 : 0;                   // lanes 0-7: A, 8-15: B (warp prefixes)
+    if (lane < 16) sb_cp_async8(&mt.wp[which][lane & 7], sb_pool_wp_ptr<PEERS>(pool, which ? bB : bA) + (lane & 7));
+    else if (lane < 18) sb_cp_async8(&mt.Pt[lane - 16], Pt + (lane == 16 ? bA : bB));
+    else if (lane < 20) sb_cp_async4(&mt.cs[lane - 18], child_start + (lane == 18 ? bA : bB));
+    else if (lane < 22) sb_cp_async4(&mt.ce[lane - 20], child_start + (lane == 20 ? bA : bB) + 1);
+    else if (lane < 24) sb_cp_async4(&mt.e[lane - 22], e + (lane == 22 ? bA : bB));
+    sb_cp_async_commit();
+}
+
 // Computes, for the children [c0, c0+SB_TILE) of this CTA, the pool index of each child's parent
 // under systematic resampling on the weight grid; thread `tid` receives children c0+8*tid .. +7.
-// pool / e / Pt / child_start / first_tile describe the POOL (previous step).  Parent tiles are read
-// with coalesced 128-bit loads.  The first two candidate tiles (almost always all there are) and
-// their metadata are requested together, so the CTA pays one memory latency instead of a chain.
+// The weights and records of the candidate parent tiles [rng.x, rng.x+1] were requested one tile ahead
+// (sb_pull_prefetch, slot/parity of this tile); further candidates -- rare: a children tile that spans
+// more than two parent tiles -- are read directly.  When `more`, the copies for the next children
+// tile (first candidate next_b_lo) are started as soon as this tile's staging buffers are free.
 template <bool PEERS, bool S32>
 __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const SbPool& pool,
                                                   const int* __restrict__ e, const unsigned long long* __restrict__ Pt,
-                                                  const int* __restrict__ child_start, const int* __restrict__ first_tile,
-                                                  int c0, SbPullSmem& sm, int anc[SB_ITEMS]) {
+                                                  const int* __restrict__ child_start, int c0, int2 rng, int slot,
+                                                  uint32_t parity, bool more, int next_b_lo, SbPullSmem& sm,
+                                                  int anc[SB_ITEMS]) {
     const int tid = threadIdx.x, warp = tid >> 5;
     const int m = (int)si.m;
     const int c1 = min(c0 + SB_TILE, m);
-    const int cw = c1 - c0;
-    const int cb = c0 / SB_TILE;                                 // global children tile
-    const int b_lo = __ldg(first_tile + cb);
-    const int b_hi = (c1 < m) ? __ldg(first_tile + cb + 1) : si.nt - 1;
+    const int cw = max(c1 - c0, 0);
+    const int b_lo = rng.x, b_hi = rng.y;
     const int bA = b_lo, bB = min(b_lo + 1, si.nt - 1);
-    uint32_t wA[SB_ITEMS], wB[SB_ITEMS];
-    sb_load8_u32(sb_pool_tile<PEERS>(pool, bA) + tid * SB_ITEMS, wA);
-    sb_load8_u32(sb_pool_tile<PEERS>(pool, bB) + tid * SB_ITEMS, wB);
-    const unsigned long long wbA = sb_pool_wp<PEERS>(pool, bA, warp), wbB = sb_pool_wp<PEERS>(pool, bB, warp);
-    const int csA = __ldg(child_start + bA), ceA = __ldg(child_start + bA + 1);
-    const int csB = __ldg(child_start + bB), ceB = __ldg(child_start + bB + 1);
-    const int eA = __ldg(e + bA), eB = __ldg(e + bB);
-    const unsigned long long PtA = __ldg(Pt + bA), PtB = __ldg(Pt + bB);
     {
         const int4 neg = make_int4(-1, -1, -1, -1);
         reinterpret_cast<int4*>(sm.marker)[tid * 2] = neg;
         reinterpret_cast<int4*>(sm.marker)[tid * 2 + 1] = neg;
     }
+    if (warp == 0) sb_cp_async_wait_all();
+    sb_mbar_wait(&sm.bar, parity);
     __syncthreads();
-    if (!(ceA <= c0 || csA >= c1 || ceA == csA)) sb_pull_tile<S32>(si, bA, wA, eA, PtA, wbA, c0, cw, sm.marker);
-    if (bB != bA && bB <= b_hi && !(ceB <= c0 || csB >= c1 || ceB == csB)) sb_pull_tile<S32>(si, bB, wB, eB, PtB, wbB, c0, cw, sm.marker);
+    const SbPullMeta& mt = sm.meta[slot];
+    const int csA = mt.cs[0], ceA = mt.ce[0], csB = mt.cs[1], ceB = mt.ce[1];
+    const bool useA = !(ceA <= c0 || csA >= c1 || ceA == csA);
+    const bool useB = bB != bA && bB <= b_hi && !(ceB <= c0 || csB >= c1 || ceB == csB);
+    if (useA) {
+        uint32_t w[SB_ITEMS];
+        const uint4 u = reinterpret_cast<const uint4*>(sm.w[0])[tid * 2], v = reinterpret_cast<const uint4*>(sm.w[0])[tid * 2 + 1];
+        w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w; w[4] = v.x; w[5] = v.y; w[6] = v.z; w[7] = v.w;
+        sb_pull_tile<S32>(si, bA, w, mt.e[0], mt.Pt[0], mt.wp[0][warp], c0, cw, sm);
+    }
+    if (useB) {
+        uint32_t w[SB_ITEMS];
+        const uint4 u = reinterpret_cast<const uint4*>(sm.w[1])[tid * 2], v = reinterpret_cast<const uint4*>(sm.w[1])[tid * 2 + 1];
+        w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w; w[4] = v.x; w[5] = v.y; w[6] = v.z; w[7] = v.w;
+        sb_pull_tile<S32>(si, bB, w, mt.e[1], mt.Pt[1], mt.wp[1][warp], c0, cw, sm);
+    }
     for (int b = b_lo + 2; b <= b_hi; ++b) {
         const int cs = __ldg(child_start + b), ce = __ldg(child_start + b + 1);
         if (ce <= c0 || cs >= c1 || ce == cs) continue;          // no offspring in range (uniform branch)
         uint32_t w[SB_ITEMS];
         sb_load8_u32(sb_pool_tile<PEERS>(pool, b) + tid * SB_ITEMS, w);
-        sb_pull_tile<S32>(si, b, w, __ldg(e + b), __ldg(Pt + b), sb_pool_wp<PEERS>(pool, b, warp), c0, cw, sm.marker);
+        sb_pull_tile<S32>(si, b, w, __ldg(e + b), __ldg(Pt + b), __ldg(sb_pool_wp_ptr<PEERS>(pool, b) + warp), c0, cw, sm);
     }
-    __syncthreads();
+    __syncthreads();                                             // markers complete; sm.w and sm.meta[slot] are free
+    if (more && warp == 0) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, next_b_lo, slot ^ 1, sm);
     // inclusive max-scan of the head markers fills every child slot with its parent
     int v[SB_ITEMS];
     {
@@ -384,17 +471,57 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
     int prev = __shfl_up_sync(0xffffffffu, inc, 1);
     if (lane == 0) prev = -1;
     __syncthreads();
+    {
+        const int4 a = reinterpret_cast<const int4*>(sm.wmax)[0], b = reinterpret_cast<const int4*>(sm.wmax)[1];
+        const int wm[SB_WARPS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int w = 0; w < SB_WARPS; ++w) if (w < warp) prev = max(prev, sm.wmax[w]);
+        for (int w = 0; w < SB_WARPS; ++w) if (w < warp) prev = max(prev, wm[w]);
+    }
     prev = max(prev, 0);
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(v[j], prev);
 }
 
+// Candidate parent tiles of this CTA's next SB_FT_CHUNK + 1 children tiles (tile, tile + grid, ...), looked
+// up once per chunk; on the CTA's first tile also starts the copies for that tile.
+template <bool PEERS>
+__device__ __forceinline__ void sb_pull_ranges(const SbStepInfo& si, const SbPool& pool, const int* __restrict__ e,
+                                               const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
+                                               const int* __restrict__ first_tile, int tile, int ntiles, bool first, SbPullSmem& sm) {
+    __syncthreads();                                             // previous chunk no longer read
+    if (threadIdx.x <= SB_FT_CHUNK) {
+        const long long tl = (long long)tile + (long long)threadIdx.x * gridDim.x;
+        sm.ft[threadIdx.x] = tl < ntiles ? sb_pull_range(si, first_tile, pool.c_off + (int)tl * SB_TILE) : make_int2(0, -1);
+    }
+    __syncthreads();
+    if (first && threadIdx.x < 32) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, sm.ft[0].x, 0, sm);
+}
+
+// block maxima with ONE barrier (the caller's later barriers protect the scratch array)
+__device__ __forceinline__ float sb_block_max_f32_1(float v, float* sm) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    const float4 a = reinterpret_cast<const float4*>(sm)[0], b = reinterpret_cast<const float4*>(sm)[1];
+    return fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+}
+__device__ __forceinline__ double sb_block_max_f64_1(double v, double* sm) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = sm[0];
+#pragma unroll
+    for (int w = 1; w < SB_WARPS; ++w) r = fmax(r, sm[w]);
+    return r;
+}
+
 // Tile sum of the weights a CTA just produced, and the exclusive prefix of its warp sums (what the
-// pull of the NEXT step starts its warp scans from).  smem: SB_WARPS u64.  Returns the tile sum.
-__device__ __forceinline__ unsigned long long sb_block_sum_wp(unsigned tsum, unsigned long long* sm,
-                                                              unsigned long long* __restrict__ wp_tile) {
+// pull of the NEXT step starts its warp scans from).  One barrier; the caller's own barriers keep
+// `sm` (SB_WARPS u64) from being rewritten before warp 0 has read it.
+__device__ __forceinline__ void sb_block_sum_wp(unsigned tsum, unsigned long long* sm, unsigned long long* __restrict__ wp_tile,
+                                                unsigned long long* __restrict__ Q_tile) {
     unsigned long long v = tsum;
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -402,16 +529,12 @@ __device__ __forceinline__ unsigned long long sb_block_sum_wp(unsigned tsum, uns
         uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), d);
         v += ((unsigned long long)hi << 32) | lo;
     }
-    __syncthreads();
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
     __syncthreads();
-    unsigned long long r = 0, pre = 0;
+    if (threadIdx.x <= SB_WARPS) {                               // thread w < 8: prefix of warp w; thread 8: the tile sum
+        unsigned long long pre = 0;
 #pragma unroll
-    for (int w = 0; w < SB_WARPS; ++w) {
-        const unsigned long long t = sm[w];
-        if (w < (int)threadIdx.x) pre += t;
-        r += t;
+        for (int w = 0; w < SB_WARPS; ++w) if (w < (int)threadIdx.x) pre += sm[w];
+        if (threadIdx.x < SB_WARPS) wp_tile[threadIdx.x] = pre; else *Q_tile = pre;
     }
-    if (threadIdx.x < SB_WARPS) wp_tile[threadIdx.x] = pre;
-    return r;
 }

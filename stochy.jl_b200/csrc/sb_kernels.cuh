@@ -100,8 +100,8 @@ k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w3
         tsum += v;
     }
     sb_store8_u32(w32 + base, q);                 // w32 is padded to whole tiles
-    unsigned long long tot = sb_block_sum_wp(tsum, s_u64, wp_out + (size_t)blockIdx.x * SB_WARPS);
-    if (tid == 0) { e_out[blockIdx.x] = e; Q_out[blockIdx.x] = tot; }
+    sb_block_sum_wp(tsum, s_u64, wp_out + (size_t)blockIdx.x * SB_WARPS, Q_out + blockIdx.x);
+    if (tid == 0) e_out[blockIdx.x] = e;
     if (bad) atomicOr(err, SB_ERRBIT_NAN);
 }
 
@@ -350,9 +350,13 @@ k_pull(const SbStepInfo* __restrict__ info, const __grid_constant__ SbPool pool,
     const SbStepInfo si = *info;
     const int c0 = pool.c_off + blockIdx.x * SB_TILE;             // global child index
     if (c0 >= (int)si.m) return;
+    if (threadIdx.x == 0) sb_mbar_init(&ps.bar, 1);
+    const int2 rng = sb_pull_range(si, first_tile, c0);
+    __syncthreads();
+    if (threadIdx.x < 32) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, rng.x, 0, ps);
     int anc[SB_ITEMS];
-    if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, pool, e, Pt, child_start, first_tile, c0, ps, anc);
-    else            sb_pull_ancestors<PEERS, false>(si, pool, e, Pt, child_start, first_tile, c0, ps, anc);
+    if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, pool, e, Pt, child_start, c0, rng, 0, 0u, false, 0, ps, anc);
+    else            sb_pull_ancestors<PEERS, false>(si, pool, e, Pt, child_start, c0, rng, 0, 0u, false, 0, ps, anc);
     const int base = c0 + threadIdx.x * SB_ITEMS;
     int* out = anc_out + (size_t)blockIdx.x * SB_TILE + threadIdx.x * SB_ITEMS;      // local children row
     if (base + SB_ITEMS <= (int)si.m) {
@@ -623,8 +627,9 @@ struct SbHmmSmem {
     double red[SB_WARPS];
 };
 
+// k: how many tiles this CTA has done before this one (staging slot / mbarrier parity of the pull)
 template <int ANC, bool FP32, bool PEERS, bool MULTI, bool TAIL>
-__device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStepInfo& si, int tile, SbHmmSmem& sm,
+__device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStepInfo& si, int tile, int k, SbHmmSmem& sm,
                                             const void* s_l2v, const uint32_t* s_thr, uint32_t* s_q, const uint32_t* s_tab) {
     const int tid = threadIdx.x;
     const int c0 = a.pool.c_off + tile * SB_TILE;                 // global child index of this tile
@@ -635,13 +640,12 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     // (1) ancestors
     int anc[SB_ITEMS];
     if (ANC == SB_ANC_PULL) {
-        if (c0 < (int)si.m) {
-            if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, sm.ps, anc);
-            else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, sm.ps, anc);
-        } else {
-#pragma unroll
-            for (int j = 0; j < SB_ITEMS; ++j) anc[j] = 0;
-        }
+        const int kk = k % SB_FT_CHUNK;
+        const int2 rng = sm.ps.ft[kk];
+        const bool more = tile + (int)gridDim.x < a.ntiles;
+        const int nb = sm.ps.ft[kk + 1].x;
+        if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
+        else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
     } else if (ANC == SB_ANC_EXPLICIT) {
         if (!TAIL) {
             const int4 u = __ldg(reinterpret_cast<const int4*>(a.anc_in + lbase));
@@ -689,8 +693,8 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
             const int ri = a.rows > 1 ? xp[j] : 0;
             const uint32_t R = r4[h];
             const uint32_t g = s_tab[(ri << SB_LG_BUCKETS) + (R >> (32 - SB_LG_BUCKETS))];
-            int lo = (int)(g & 63u) + (((R & 0xFFFFFFu) >= ((g >> 6) & 0x1FFFFFFu)) ? 1 : 0);
-            if (MULTI && (g >> 31)) {                            // several thresholds inside one bucket: scan
+            int lo = (int)(g & 63u) + (((R << SB_LG_BUCKETS) > g) ? 1 : 0);
+            if (MULTI && (g & 128u)) {                           // several thresholds inside one bucket: scan
                 const uint32_t* row = s_thr + ri * K;
                 lo = (int)(g & 63u);
                 while (lo < K - 1 && R >= row[lo]) ++lo;
@@ -713,7 +717,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) if (!TAIL || base + j < a.n_out) mx = fmaxf(mx, s_l2[x[j]]);
-        mx = sb_block_max_f32(mx, reinterpret_cast<float*>(sm.red));
+        mx = sb_block_max_f32_1(mx, reinterpret_cast<float*>(sm.red));
         e = mx > -INFINITY ? (int)ceilf(mx) : SB_E_EMPTY;
         if (tid < K) s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f32(__fsub_rn(s_l2[tid], (float)e));
     } else {
@@ -721,7 +725,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         double mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) if (!TAIL || base + j < a.n_out) mx = fmax(mx, s_l2[x[j]]);
-        mx = sb_block_max_f64(mx, sm.red);
+        mx = sb_block_max_f64_1(mx, sm.red);
         e = mx > -INFINITY ? (int)ceil(mx) : SB_E_EMPTY;
         if (tid < K) s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f64(__dsub_rn(s_l2[tid], (double)e));
     }
@@ -743,9 +747,9 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.wlit_out[lbase + j] = a.expF_t[x[j]];
     }
-    const unsigned long long tot = sb_block_sum_wp(tsum, sm.ps.scan, a.wp_out + (size_t)tile * SB_WARPS);
-    if (tid == 0) { a.e_out[tile] = e; a.Q_out[tile] = tot; }
-    __syncthreads();                                              // shared scratch is reused by the next tile
+    sb_block_sum_wp(tsum, sm.ps.scan, a.wp_out + (size_t)tile * SB_WARPS, a.Q_out + tile);
+    if (tid == 0) a.e_out[tile] = e;
+    // no barrier here: every shared scratch array is rewritten only after a later barrier of the next tile
 }
 
 template <int ANC, bool FP32, bool PEERS, bool MULTI>
@@ -774,12 +778,18 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         }
     }
     SbStepInfo si;
-    if (ANC == SB_ANC_PULL) si = *a.info_prev;
+    if (ANC == SB_ANC_PULL) {
+        si = *a.info_prev;
+        if (tid == 0) sb_mbar_init(&sm.ps.bar, 1);
+    }
     __syncthreads();                                              // tables staged
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    int k = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
+        if (ANC == SB_ANC_PULL && (k % SB_FT_CHUNK) == 0)
+            sb_pull_ranges<PEERS>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, tile, a.ntiles, k == 0, sm.ps);
         const bool tail = a.pool.c_off + (tile + 1) * SB_TILE > a.N;   // only the last tile(s) see padding / the retained slot
-        if (!tail) sb_hmm_tile<ANC, FP32, PEERS, MULTI, false>(a, si, tile, sm, s_l2, s_thr, s_q, s_tab);
-        else       sb_hmm_tile<ANC, FP32, PEERS, MULTI, true>(a, si, tile, sm, s_l2, s_thr, s_q, s_tab);
+        if (!tail) sb_hmm_tile<ANC, FP32, PEERS, MULTI, false>(a, si, tile, k, sm, s_l2, s_thr, s_q, s_tab);
+        else       sb_hmm_tile<ANC, FP32, PEERS, MULTI, true>(a, si, tile, k, sm, s_l2, s_thr, s_q, s_tab);
     }
 }
 
@@ -817,15 +827,26 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     const int tid = threadIdx.x;
     const int N = (int)a.N;
     SbStepInfo si;
-    if (ANC == SB_ANC_PULL) si = *a.info_prev;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    if (ANC == SB_ANC_PULL) {
+        si = *a.info_prev;
+        if (tid == 0) sb_mbar_init(&sm.ps.bar, 1);
+        __syncthreads();
+    }
+    int k = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
+        if (ANC == SB_ANC_PULL && (k % SB_FT_CHUNK) == 0)
+            sb_pull_ranges<PEERS>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, tile, a.ntiles, k == 0, sm.ps);
         const int c0 = a.pool.c_off + tile * SB_TILE;             // global child index of this tile
         const int base = c0 + tid * SB_ITEMS;
         const int lbase = tile * SB_TILE + tid * SB_ITEMS;        // where this GPU stores it
         int anc[SB_ITEMS];
         if (ANC == SB_ANC_PULL) {
-            if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, sm.ps, anc);
-            else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, c0, sm.ps, anc);
+            const int kk = k % SB_FT_CHUNK;
+            const int2 rng = sm.ps.ft[kk];
+            const bool more = tile + (int)gridDim.x < a.ntiles;
+            const int nb = sm.ps.ft[kk + 1].x;
+            if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
+            else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
         } else if (ANC == SB_ANC_EXPLICIT) {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < N) ? __ldg(a.anc_in + lbase + j) : 0;
@@ -886,8 +907,8 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             }
         }
         int e;
-        if (FP32) { const float m2 = sb_block_max_f32((float)mx, reinterpret_cast<float*>(sm.red)); e = m2 > -INFINITY ? (int)ceilf(m2) : SB_E_EMPTY; }
-        else      { const double m2 = sb_block_max_f64((double)mx, sm.red); e = m2 > -INFINITY ? (int)ceil(m2) : SB_E_EMPTY; }
+        if (FP32) { const float m2 = sb_block_max_f32_1((float)mx, reinterpret_cast<float*>(sm.red)); e = m2 > -INFINITY ? (int)ceilf(m2) : SB_E_EMPTY; }
+        else      { const double m2 = sb_block_max_f64_1((double)mx, sm.red); e = m2 > -INFINITY ? (int)ceil(m2) : SB_E_EMPTY; }
         uint32_t q[SB_ITEMS];
         unsigned tsum = 0;
 #pragma unroll
@@ -905,10 +926,9 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             for (int j = 0; j < SB_ITEMS; j += 2) reinterpret_cast<double2*>(xo)[j / 2] = make_double2((double)x[j], (double)x[j + 1]);
         }
         sb_store8_u32(a.w32_out + lbase, q);
-        const unsigned long long tot = sb_block_sum_wp(tsum, sm.ps.scan, a.wp_out + (size_t)tile * SB_WARPS);
-        if (tid == 0) { a.e_out[tile] = e; a.Q_out[tile] = tot; }
+        sb_block_sum_wp(tsum, sm.ps.scan, a.wp_out + (size_t)tile * SB_WARPS, a.Q_out + tile);
+        if (tid == 0) a.e_out[tile] = e;
         if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
-        __syncthreads();                                          // shared scratch is reused by the next tile
     }
 }
 

@@ -492,9 +492,9 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
     };
     // inverse-CDF lookup words, 256 buckets per row (bucket g = draws R with R >> 24 == g):
     //   bits 0..5   lo  = #{k < K-1 : thr[k] <= g << 24}        (where the scan of src/rand.jl:6-12 stands at the bucket start)
-    //   bits 6..30  t24 = low 24 bits of the first threshold inside the bucket, or 2^24 if there is none
-    //   bit  31     several thresholds fall inside the bucket (the kernel scans the thresholds from lo)
-    // so that  x = lo + ((R & 0xFFFFFF) >= t24)  whenever bit 31 is clear.
+    //   bit  7      several thresholds fall inside the bucket (the kernel scans the thresholds from lo)
+    //   bits 8..31  t24 - 1, t24 = low 24 bits of the first threshold inside the bucket, or 2^24 if there is none
+    // so that  x = lo + ((R << 8) > word)  whenever bit 7 is clear: one shared-memory load and one compare.
     const int G = 1 << SB_LG_BUCKETS;
     std::vector<uint32_t> cumA((size_t)K * K, 0u), cumpi((size_t)K, 0u), tabA((size_t)K * G, 0u), tabpi((size_t)G, 0u);
     bool multi = false;
@@ -506,7 +506,7 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
             int cnt = 0;
             while (lo + cnt < K - 1 && thr[lo + cnt] <= r1) ++cnt;
             const uint32_t t24 = cnt ? (thr[lo] & 0xFFFFFFu) : (1u << 24);
-            tab[g] = (uint32_t)lo | (t24 << 6) | (cnt > 1 ? 0x80000000u : 0u);
+            tab[g] = (uint32_t)lo | ((t24 - 1u) << 8) | (cnt > 1 ? 128u : 0u);
             if (cnt > 1) multi = true;
         }
     };
