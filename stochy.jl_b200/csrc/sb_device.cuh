@@ -517,6 +517,23 @@ __device__ __forceinline__ double sb_block_max_f64_1(double v, double* sm) {
     return r;
 }
 
+// Deferred form of sb_block_sum_wp for the persistent step kernels: sb_warp_total at the end of a tile,
+// sb_flush_totals after ANY later barrier (the next tile's first one) -- no barrier of its own.
+__device__ __forceinline__ void sb_warp_total(unsigned tsum, unsigned long long* sm) {
+    // tsum <= 2^30: the two 16-bit halves sum to < 2^22 over a warp, so two REDUX.ADD give the exact total
+    const unsigned lo = __reduce_add_sync(0xffffffffu, tsum & 0xFFFFu), hi = __reduce_add_sync(0xffffffffu, tsum >> 16);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = ((unsigned long long)hi << 16) + lo;
+}
+__device__ __forceinline__ void sb_flush_totals(const unsigned long long* sm, unsigned long long* __restrict__ wp_tile,
+                                                unsigned long long* __restrict__ Q_tile) {
+    if (threadIdx.x <= SB_WARPS) {                               // thread w < 8: prefix of warp w; thread 8: the tile sum
+        unsigned long long pre = 0;
+#pragma unroll
+        for (int w = 0; w < SB_WARPS; ++w) if (w < (int)threadIdx.x) pre += sm[w];
+        if (threadIdx.x < SB_WARPS) wp_tile[threadIdx.x] = pre; else *Q_tile = pre;
+    }
+}
+
 // Tile sum of the weights a CTA just produced, and the exclusive prefix of its warp sums (what the
 // pull of the NEXT step starts its warp scans from).  One barrier; the caller's own barriers keep
 // `sm` (SB_WARPS u64) from being rewritten before warp 0 has read it.

@@ -588,6 +588,7 @@ k_lse_final(const SbLse* __restrict__ partial, int np, double* __restrict__ out)
 #define SB_ANC_IDENTITY 3   // previous step had no factor statement
 
 #define SB_LG_BUCKETS 8     // inverse-CDF lookup: 256 buckets per transition row
+#define SB_KEY_BIAS (1 << 24)
 
 struct SbHmmStepArgs {
     // previous pool
@@ -630,7 +631,7 @@ struct SbHmmSmem {
 // k: how many tiles this CTA has done before this one (staging slot / mbarrier parity of the pull)
 template <int ANC, bool FP32, bool PEERS, bool MULTI, bool TAIL>
 __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStepInfo& si, int tile, int k, SbHmmSmem& sm,
-                                            const void* s_l2v, const uint32_t* s_thr, uint32_t* s_q, const uint32_t* s_tab) {
+                                            const uint32_t* s_thr, const uint32_t* s_key, const uint32_t* s_qtab, const uint32_t* s_tab) {
     const int tid = threadIdx.x;
     const int c0 = a.pool.c_off + tile * SB_TILE;                 // global child index of this tile
     const int base = c0 + tid * SB_ITEMS;
@@ -710,31 +711,28 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
             if (i >= N) x[j] = (i == N && a.xstar) ? __ldg(a.xstar + a.t) : 0;
         }
     }
-    // (4)+(5) weight and quantise.  Only K distinct scores exist, so 2^(l2 - e) is evaluated K times.
-    int e;
-    if (FP32) {
-        const float* s_l2 = reinterpret_cast<const float*>(s_l2v);
-        float mx = -INFINITY;
+    // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
+    if (ANC != SB_ANC_PULL) __syncthreads();                     // the pull has its own barriers
+    if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.Q_out + pt); }
+    // (4)+(5) weight and quantise.  Only K distinct scores exist: the tile exponent is the largest
+    // ceil(log2 weight) present (an integer max), and 2^(l2 - e) 2^27 comes from a K x K table.
+    unsigned key = 0u;
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (!TAIL || base + j < a.n_out) mx = fmaxf(mx, s_l2[x[j]]);
-        mx = sb_block_max_f32_1(mx, reinterpret_cast<float*>(sm.red));
-        e = mx > -INFINITY ? (int)ceilf(mx) : SB_E_EMPTY;
-        if (tid < K) s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f32(__fsub_rn(s_l2[tid], (float)e));
-    } else {
-        const double* s_l2 = reinterpret_cast<const double*>(s_l2v);
-        double mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (!TAIL || base + j < a.n_out) mx = fmax(mx, s_l2[x[j]]);
-        mx = sb_block_max_f64_1(mx, sm.red);
-        e = mx > -INFINITY ? (int)ceil(mx) : SB_E_EMPTY;
-        if (tid < K) s_q[tid] = e == SB_E_EMPTY ? 0u : sb_q31_f64(__dsub_rn(s_l2[tid], (double)e));
-    }
+    for (int j = 0; j < SB_ITEMS; ++j) if (!TAIL || base + j < a.n_out) key = max(key, s_key[x[j]]);
+    key = __reduce_max_sync(0xffffffffu, key);
+    if ((tid & 31) == 0) reinterpret_cast<unsigned*>(sm.red)[tid >> 5] = key;
     __syncthreads();
+    {
+        const uint4 u = reinterpret_cast<const uint4*>(sm.red)[0], v = reinterpret_cast<const uint4*>(sm.red)[1];
+        key = max(max(max(u.x, u.y), max(u.z, u.w)), max(max(v.x, v.y), max(v.z, v.w)));
+    }
+    const int e = key ? (int)(key >> 6) - SB_KEY_BIAS : SB_E_EMPTY;
+    const uint32_t* qrow = s_qtab + (key & 63u) * K;
     uint32_t q[SB_ITEMS];
     unsigned tsum = 0;
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) {
-        q[j] = (!TAIL || base + j < a.n_out) ? s_q[x[j]] : 0u;
+        q[j] = (key != 0u && (!TAIL || base + j < a.n_out)) ? qrow[x[j]] : 0u;
         tsum += q[j];
     }
     sb_store8_u32(reinterpret_cast<uint32_t*>(a.x_out) + lbase, reinterpret_cast<const uint32_t*>(x));
@@ -747,7 +745,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.wlit_out[lbase + j] = a.expF_t[x[j]];
     }
-    sb_block_sum_wp(tsum, sm.ps.scan, a.wp_out + (size_t)tile * SB_WARPS, a.Q_out + tile);
+    sb_warp_total(tsum, sm.ps.scan);                              // flushed after the next barrier (next tile / kernel end)
     if (tid == 0) a.e_out[tile] = e;
     // no barrier here: every shared scratch array is rewritten only after a later barrier of the next tile
 }
@@ -759,7 +757,8 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(dyn);             // rows * 256 (16-byte aligned: staged as uint4)
     double* s_l2 = reinterpret_cast<double*>(s_tab + (a.rows << SB_LG_BUCKETS));   // K   (float view when FP32)
     uint32_t* s_thr = reinterpret_cast<uint32_t*>(s_l2 + a.K);      // rows*K
-    uint32_t* s_q = s_thr + a.rows * a.K;                           // K
+    uint32_t* s_key = s_thr + a.rows * a.K;                         // K: (ceil(l2) + bias) << 6 | state, 0 = no mass
+    uint32_t* s_qtab = s_key + a.K;                                 // K*K: row k* = weights on the grid of exponent ceil(l2[k*])
     __shared__ SbHmmSmem sm;
     const int tid = threadIdx.x;
     const int K = a.K;
@@ -767,15 +766,28 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     for (int i = tid; i < ((a.rows << SB_LG_BUCKETS) >> 2); i += SB_THREADS)
         reinterpret_cast<uint4*>(s_tab)[i] = __ldg(reinterpret_cast<const uint4*>(a.tab) + i);
     if (tid < K) {
+        int ce; bool live;
         if (FP32) {
             const float l2 = __fmul_rn((float)a.logF_t[tid], SB_LOG2E_F);
             if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
             reinterpret_cast<float*>(s_l2)[tid] = l2;
+            live = l2 > -INFINITY; ce = (int)ceilf(fminf(fmaxf(l2, -16777215.0f), 16777215.0f));
         } else {
             const double l2 = __dmul_rn(a.logF_t[tid], SB_LOG2E_D);
             if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
             s_l2[tid] = l2;
+            live = l2 > -INFINITY; ce = (int)ceil(fmin(fmax(l2, -16777215.0), 16777215.0));
         }
+        s_key[tid] = live ? (((unsigned)(ce + SB_KEY_BIAS) << 6) | (unsigned)tid) : 0u;
+    }
+    __syncthreads();
+    for (int i = tid; i < K * K; i += SB_THREADS) {
+        const int ks = i / K, kx = i - ks * K;
+        const unsigned key = s_key[ks];
+        const int e = (int)(key >> 6) - SB_KEY_BIAS;
+        uint32_t q = 0u;
+        if (key) q = FP32 ? sb_q31_f32(__fsub_rn(reinterpret_cast<float*>(s_l2)[kx], (float)e)) : sb_q31_f64(__dsub_rn(s_l2[kx], (double)e));
+        s_qtab[i] = q;
     }
     SbStepInfo si;
     if (ANC == SB_ANC_PULL) {
@@ -788,8 +800,13 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         if (ANC == SB_ANC_PULL && (k % SB_FT_CHUNK) == 0)
             sb_pull_ranges<PEERS>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, tile, a.ntiles, k == 0, sm.ps);
         const bool tail = a.pool.c_off + (tile + 1) * SB_TILE > a.N;   // only the last tile(s) see padding / the retained slot
-        if (!tail) sb_hmm_tile<ANC, FP32, PEERS, MULTI, false>(a, si, tile, k, sm, s_l2, s_thr, s_q, s_tab);
-        else       sb_hmm_tile<ANC, FP32, PEERS, MULTI, true>(a, si, tile, k, sm, s_l2, s_thr, s_q, s_tab);
+        if (!tail) sb_hmm_tile<ANC, FP32, PEERS, MULTI, false>(a, si, tile, k, sm, s_thr, s_key, s_qtab, s_tab);
+        else       sb_hmm_tile<ANC, FP32, PEERS, MULTI, true>(a, si, tile, k, sm, s_thr, s_key, s_qtab, s_tab);
+    }
+    if (k > 0) {                                                  // the last tile's totals
+        __syncthreads();
+        const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
+        sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.Q_out + pt);
     }
 }
 
@@ -854,6 +871,9 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;
         }
+        // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
+        if (ANC != SB_ANC_PULL) __syncthreads();                 // the pull has its own barriers
+        if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.Q_out + pt); }
         REAL xpar[SB_ITEMS];
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j)
@@ -926,9 +946,14 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             for (int j = 0; j < SB_ITEMS; j += 2) reinterpret_cast<double2*>(xo)[j / 2] = make_double2((double)x[j], (double)x[j + 1]);
         }
         sb_store8_u32(a.w32_out + lbase, q);
-        sb_block_sum_wp(tsum, sm.ps.scan, a.wp_out + (size_t)tile * SB_WARPS, a.Q_out + tile);
+        sb_warp_total(tsum, sm.ps.scan);                          // flushed after the next barrier (next tile / kernel end)
         if (tid == 0) a.e_out[tile] = e;
         if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
+    }
+    if (k > 0) {
+        __syncthreads();
+        const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
+        sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.Q_out + pt);
     }
 }
 

@@ -598,7 +598,7 @@ namespace {
 
 template <bool FP32, bool MULTI>
 int launch_step_hmm_m(sb_handle* h, int anc_mode, const SbHmmStepArgs& a) {
-    const size_t smem = ((size_t)a.rows << SB_LG_BUCKETS) * 4 + (size_t)a.K * 8 + (size_t)(a.rows * a.K + a.K) * 4;
+    const size_t smem = ((size_t)a.rows << SB_LG_BUCKETS) * 4 + (size_t)a.K * 8 + (size_t)(a.rows * a.K + a.K + a.K * a.K) * 4;
     int cap = 0, rc;
 #define SB_HMM_LAUNCH(ANC, PEERS)                                                              \
     do {                                                                                       \
