@@ -2,7 +2,7 @@
 
 The directory name carries a dot, so import it through the `stochy_jl_b200` shim at the repo root.
 """
-from . import _native
+from . import _native, dist
 from ._native import build, lib
 from .api import (BayesNet, Discrete, DiscreteHMM, Engine, LinearGaussian, StochyError, hellingerdistance,
                   hmm2_example, hmm_example, kl, mh, pmcmc, score, smc, support)

@@ -244,6 +244,24 @@ class Engine:
         self.model = model
         return self
 
+    # ---- multi-GPU: ONE pool sharded over the ranks of a torch.distributed group (one process per GPU)
+    def shard(self, N_local, group=None):
+        """Make this handle rank `dist.get_rank()`'s share of a global pool of world x N_local particles.
+        torch.distributed is only the plumbing (the 64-byte CUDA-IPC handles travel through one
+        all_gather); afterwards smc_sweep(N_local) sweeps the GLOBAL pool, with resampled particles
+        read across GPUs by the step kernel itself (NVLink peer loads)."""
+        from . import dist as sbdist
+        rank, world = sbdist.rank_world(group)
+        self._chk(nat.lib().sb_dist_init(self.h, rank, world))
+        mine = (C.c_uint8 * 64)()
+        self._chk(nat.lib().sb_dist_ipc_export(self.h, N_local, mine))
+        allh = sbdist.exchange_handles(bytes(mine), group)          # rank order
+        buf = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(allh))
+        self._chk(nat.lib().sb_dist_ipc_import(self.h, buf))
+        sbdist.barrier(group)                                       # every arena is mapped everywhere
+        self.rank, self.world, self.N_local = rank, world, N_local
+        return self
+
     # ---- inference
     def smc_sweep(self, N, it=0, history=False):
         lz = C.c_double(0)

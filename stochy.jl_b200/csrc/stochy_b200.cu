@@ -58,7 +58,6 @@ struct sb_handle {
     int rank = 0, world = 1;
     bool dist_ready = false;
     int64_t NL = 0;                   // particles per GPU (power of two)
-    int dist_sz = 0;                  // bytes per particle state in the arena
     void* arena = nullptr;
     size_t arena_bytes = 0;
     size_t off_w32[2] = {0, 0}, off_x[2] = {0, 0}, off_wp[2] = {0, 0}, off_e[2] = {0, 0}, off_Q[2] = {0, 0}, off_flags = 0;
@@ -781,8 +780,8 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
     const int mode = h->opt.resample_mode;
     if (mode == SB_RESAMPLE_LITERAL)
         return fail(h, SB_EUNSUPPORTED, "literal resampling is a parity mode of the discrete model only");
-    if (dist && (mode != SB_RESAMPLE_SYSTEMATIC || h->opt.store_logw || (int)sz != h->dist_sz))
-        return fail(h, SB_EUNSUPPORTED, "sharded pools run systematic resampling at the precision given to sb_dist_ipc_export");
+    if (dist && (mode != SB_RESAMPLE_SYSTEMATIC || h->opt.store_logw))
+        return fail(h, SB_EUNSUPPORTED, "sharded pools run plain SMC sweeps with systematic resampling");
     int rc;
     if ((rc = ensure_grid(h, N, N)) != SB_OK) return rc;
     if (!dist) {
@@ -1220,11 +1219,14 @@ extern "C" int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out) {
     const int t = h->T - 1;
     if (h->model == MODEL_HMM) {
         const int row = h->sw_hist ? t : (t & 1);
-        CK(cudaMemcpy(x_out, h->xbuf.as<int>() + (size_t)row * h->sw_S, (size_t)count * 4, cudaMemcpyDeviceToHost));
+        const int* src = h->dist_ready ? reinterpret_cast<const int*>((char*)h->arena + h->off_x[t & 1])
+                                       : h->xbuf.as<int>() + (size_t)row * h->sw_S;
+        CK(cudaMemcpy(x_out, src, (size_t)count * 4, cudaMemcpyDeviceToHost));
     } else {
         const size_t sz = h->opt.precision == SB_FP32 ? 4 : 8;
         std::vector<char> tmp((size_t)count * sz);
-        CK(cudaMemcpy(tmp.data(), h->xbuf.as<char>() + (size_t)(t & 1) * h->sw_S * sz, tmp.size(), cudaMemcpyDeviceToHost));
+        const char* src = h->dist_ready ? (char*)h->arena + h->off_x[t & 1] : h->xbuf.as<char>() + (size_t)(t & 1) * h->sw_S * sz;
+        CK(cudaMemcpy(tmp.data(), src, tmp.size(), cudaMemcpyDeviceToHost));
         double* o = (double*)x_out;
         if (sz == 4) for (int64_t i = 0; i < count; ++i) o[i] = (double)((float*)tmp.data())[i];
         else memcpy(o, tmp.data(), tmp.size());

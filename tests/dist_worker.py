@@ -1,0 +1,73 @@
+"""Multi-GPU parity worker (run under torchrun, one rank per GPU; not collected by pytest).
+
+Every rank shards one global pool of world x N_local particles, runs the global SMC sweep, and
+rank 0 checks that (a) the log-evidence is identical on every rank and (b) the concatenated final
+particle sets and the log-evidence are BIT-IDENTICAL to a single-GPU sweep of the same global pool
+(same seed): the result must not depend on how many GPUs the pool is spread over."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import stochy_jl_b200 as sb
+    from gpu_util import cfg3_tables, cfg4_data
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 14
+    NL = 1 << log2n
+    fails = []
+    cases = []
+    A, logF, pi = cfg3_tables(T=25)
+    cases.append(("hmm fp32", lambda: sb.DiscreteHMM(A, logF, pi=pi), "fp32", np.int32))
+    cases.append(("hmm fp64", lambda: sb.DiscreteHMM(A, logF, pi=pi), "fp64", np.int32))
+    d = cfg4_data(T=20)
+    cases.append(("lg fp32", lambda: sb.LinearGaussian(**d), "fp32", np.float64))
+    cases.append(("lg fp64", lambda: sb.LinearGaussian(**d), "fp64", np.float64))
+    for name, mk, prec, dt in cases:
+        eng = sb.Engine(device=local, precision=prec, resample="systematic", seed=11)
+        eng.load(mk())
+        eng.shard(NL)
+        lz = [eng.smc_sweep(NL, it=i) for i in range(2)]            # two sweeps: the flag epochs keep counting
+        x = torch.from_numpy(eng.particles(NL).astype(np.float64)).cuda()
+        allx = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(allx, x)
+        lzt = torch.tensor(lz, dtype=torch.float64, device="cuda")
+        alllz = [torch.empty_like(lzt) for _ in range(world)]
+        dist.all_gather(alllz, lzt)
+        dist.barrier()
+        eng.close()
+        if rank == 0:
+            for r in range(world):
+                if not torch.equal(alllz[r], alllz[0]):
+                    fails.append("%s: logZ differs between rank 0 and rank %d" % (name, r))
+            ref = sb.Engine(device=local, precision=prec, resample="systematic", seed=11)
+            ref.load(mk())
+            lz_ref = [ref.smc_sweep(NL * world, it=i) for i in range(2)]
+            x_ref = ref.particles(NL * world).astype(np.float64)
+            ref.close()
+            got = torch.cat(allx).cpu().numpy()
+            if lz_ref != lz:
+                fails.append("%s: logZ %r != single-GPU %r" % (name, lz, lz_ref))
+            if not np.array_equal(got, x_ref):
+                fails.append("%s: %d of %d final particles differ from the single-GPU sweep"
+                             % (name, int((got != x_ref).sum()), got.size))
+            print("[dist] %-9s world=%d N_local=2^%d logZ=%.6f %s" % (name, world, log2n, lz[-1],
+                                                                      "ok" if not fails else "FAIL"), flush=True)
+        dist.barrier()
+    if rank == 0:
+        print("DIST_PARITY_OK" if not fails else "DIST_PARITY_FAIL\n" + "\n".join(fails), flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if fails else 0)
+
+
+if __name__ == "__main__":
+    main()
