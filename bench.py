@@ -157,8 +157,12 @@ def run_ours(args):
     T = args.T
     A, logF, pi = workload_tables(T=T)
     model = sb.DiscreteHMM(A, logF, pi=pi)
-    eng = sb.Engine(device=local, precision="fp32", resample="systematic", seed=1 + rank)
+    # N > 1: ONE global pool of world x 2^24 particles sharded over the GPUs (weak scaling), resampled
+    # globally at every step; every rank uses the same seed (the Philox counters are global particle ids)
+    eng = sb.Engine(device=local, precision="fp32", resample="systematic", seed=1)
     eng.load(model)
+    if world > 1:
+        eng.shard(N)
     eng.set_profile(max(1, T // 100))
 
     def barrier():
@@ -220,7 +224,9 @@ def run_ours(args):
                                        "history off" % (K_STATES, T, args.log2n),
                            "particles_per_gpu": N, "T": T, "K": K_STATES, "resample": "systematic",
                            "l2": "per-step working set 4 x N x 4 B = %d MB > 126 MB L2 (inputs larger than L2)" % (16 * N >> 20),
-                           "parallelism": "1 GPU" if world == 1 else "%d independent particle shards (weak)" % world},
+                           "parallelism": "1 GPU" if world == 1 else
+                           "one global pool of %d x 2^%d particles sharded over %d GPUs, global systematic resampling, "
+                           "parents read across GPUs by peer loads over NVLink (no NCCL on the data path)" % (world, args.log2n, world)},
                 "wall_ms_per_step": wall * 1e3 / args.steps,
                 "gpu_launches": int(launches),
                 "clocks": clocks,
@@ -240,6 +246,7 @@ def run_ours(args):
             except Exception:
                 pass
         print(json.dumps(line))
+    barrier()                                       # no rank unmaps its arena while a peer may still read it
     eng.close()
     if world > 1:
         torch.distributed.destroy_process_group()
