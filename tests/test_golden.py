@@ -128,7 +128,8 @@ def test_gpu_frozen_pmcmc_and_mh():
             eng.load(sb.DiscreteHMM(A, logF, pi=pi))
             marg, _ = eng.pmcmc_counts(g["iters"], g["N"], want_joint=False)
             assert marg.tolist() == g["marg"]
-            assert eng.stats().logZ_first == pytest.approx(g["logZ_first"], rel=1e-9)
+            # literal mode: the oracle sums plain exp weights, the library reads the grid's tile scan
+            assert eng.stats().logZ_first == pytest.approx(g["logZ_first"], rel=1e-9 if name != "literal" else 1e-6)
     sites, factors, query = cfg5_bnet()
     g = VEC["mh_cfg5"]
     with sb.Engine(precision="fp64", seed=g["seed"]) as eng:
