@@ -331,13 +331,29 @@ __device__ __forceinline__ int sb_pull_k(long long baseb, unsigned long long acc
 // One parent tile's contribution to the children [c0, c0 + cw): warp scan of its weights on top of
 // the warp prefix the producer left, then every parent that owns children in range writes its
 // index at its first child's slot ("head marker").  No block-level synchronisation.
+// A warp whose 256 parents own no child in range (known from its prefix and the next warp's) skips
+// everything: a children tile overlaps about one tile's worth of parents out of the two staged.
+// wsrc: the tile's weights (shared-memory stage or global memory), read only by warps that work.
 template <bool S32>
-__device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const uint32_t w[SB_ITEMS], int eb,
-                                             unsigned long long Ptb, unsigned long long wbase, int c0, int cw,
-                                             SbPullSmem& sm) {
+__device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const uint32_t* __restrict__ wsrc, int eb,
+                                             unsigned long long Ptb, unsigned long long wbase, unsigned long long wnext,
+                                             int ce_rel, int c0, int cw, SbPullSmem& sm) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int s = si.s;
     const unsigned R = si.R;
+    // tile-uniform constants; rb < 64 because the tile owns children
+    const int rb = si.r0 + (si.E - eb);
+    const long long baseb = (long long)(Ptb - si.U) + ((1ll << s) - 1ll) - ((long long)c0 << s);
+    {
+        const int k0 = sb_pull_k<S32>(baseb, wbase * (unsigned long long)R, rb, s, cw);
+        const int k1 = (tid >> 5) == SB_WARPS - 1 ? ce_rel : sb_pull_k<S32>(baseb, wnext * (unsigned long long)R, rb, s, cw);
+        if (k1 <= k0) return;                                    // warp-uniform
+    }
+    uint32_t w[SB_ITEMS];
+    {
+        const uint4 u = reinterpret_cast<const uint4*>(wsrc)[tid * 2], v = reinterpret_cast<const uint4*>(wsrc)[tid * 2 + 1];
+        w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w; w[4] = v.x; w[5] = v.y; w[6] = v.z; w[7] = v.w;
+    }
     unsigned tsum = 0;                                           // 8 * 2^27 fits 32 bits
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) tsum += w[j];
@@ -349,9 +365,6 @@ __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const 
     }
     if (tsum != 0) {
         const unsigned long long c = wbase + inc - tsum;        // tile-local exclusive prefix of this thread
-        // tile-uniform constants; rb < 64 because the tile owns children
-        const int rb = si.r0 + (si.E - eb);
-        const long long baseb = (long long)(Ptb - si.U) + ((1ll << s) - 1ll) - ((long long)c0 << s);
         unsigned long long acc = c * (unsigned long long)R;
         int lo = sb_pull_k<S32>(baseb, acc, rb, s, cw);
         const int hi_t = sb_pull_k<S32>(baseb, acc + (unsigned long long)tsum * R, rb, s, cw);
@@ -430,24 +443,15 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
     const int csA = mt.cs[0], ceA = mt.ce[0], csB = mt.cs[1], ceB = mt.ce[1];
     const bool useA = !(ceA <= c0 || csA >= c1 || ceA == csA);
     const bool useB = bB != bA && bB <= b_hi && !(ceB <= c0 || csB >= c1 || ceB == csB);
-    if (useA) {
-        uint32_t w[SB_ITEMS];
-        const uint4 u = reinterpret_cast<const uint4*>(sm.w[0])[tid * 2], v = reinterpret_cast<const uint4*>(sm.w[0])[tid * 2 + 1];
-        w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w; w[4] = v.x; w[5] = v.y; w[6] = v.z; w[7] = v.w;
-        sb_pull_tile<S32>(si, bA, w, mt.e[0], mt.Pt[0], mt.wp[0][warp], c0, cw, sm);
-    }
-    if (useB) {
-        uint32_t w[SB_ITEMS];
-        const uint4 u = reinterpret_cast<const uint4*>(sm.w[1])[tid * 2], v = reinterpret_cast<const uint4*>(sm.w[1])[tid * 2 + 1];
-        w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w; w[4] = v.x; w[5] = v.y; w[6] = v.z; w[7] = v.w;
-        sb_pull_tile<S32>(si, bB, w, mt.e[1], mt.Pt[1], mt.wp[1][warp], c0, cw, sm);
-    }
+    const int wn = min(warp + 1, SB_WARPS - 1);                  // the last warp's end is the tile's own child_start
+    if (useA) sb_pull_tile<S32>(si, bA, sm.w[0], mt.e[0], mt.Pt[0], mt.wp[0][warp], mt.wp[0][wn], min(max(ceA - c0, 0), cw), c0, cw, sm);
+    if (useB) sb_pull_tile<S32>(si, bB, sm.w[1], mt.e[1], mt.Pt[1], mt.wp[1][warp], mt.wp[1][wn], min(max(ceB - c0, 0), cw), c0, cw, sm);
     for (int b = b_lo + 2; b <= b_hi; ++b) {
         const int cs = __ldg(child_start + b), ce = __ldg(child_start + b + 1);
         if (ce <= c0 || cs >= c1 || ce == cs) continue;          // no offspring in range (uniform branch)
-        uint32_t w[SB_ITEMS];
-        sb_load8_u32(sb_pool_tile<PEERS>(pool, b) + tid * SB_ITEMS, w);
-        sb_pull_tile<S32>(si, b, w, __ldg(e + b), __ldg(Pt + b), __ldg(sb_pool_wp_ptr<PEERS>(pool, b) + warp), c0, cw, sm);
+        const unsigned long long* wpb = sb_pool_wp_ptr<PEERS>(pool, b);
+        sb_pull_tile<S32>(si, b, sb_pool_tile<PEERS>(pool, b), __ldg(e + b), __ldg(Pt + b), __ldg(wpb + warp), __ldg(wpb + wn),
+                          min(max(ce - c0, 0), cw), c0, cw, sm);
     }
     __syncthreads();                                             // markers complete; sm.w and sm.meta[slot] are free
     if (more && warp == 0) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, next_b_lo, slot ^ 1, sm);
