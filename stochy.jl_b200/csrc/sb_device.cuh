@@ -521,6 +521,29 @@ __device__ __forceinline__ double sb_block_max_f64_1(double v, double* sm) {
     return r;
 }
 
+// Where the tile records (e, Q) of the pool being PRODUCED go: the local arrays and, when the pool is
+// sharded, the replicated copy in every peer's arena -- fire-and-forget stores over NVLink from inside
+// the step kernel, so that every GPU's tile scan later reads local memory only.
+struct SbRecOut {
+    int* e;                             // local arrays, local tile index
+    unsigned long long* Q;
+    int* emax;                          // single GPU: running max of the tile exponents (read by the tile scan)
+    char* base[SB_MAX_PEERS];
+    unsigned long long off_e, off_Q;    // replicated arrays (GLOBAL tile index) inside every arena
+    int world, self, tile_off;
+};
+__device__ __forceinline__ void sb_put_e(const SbRecOut& r, int tile, int e) {
+    r.e[tile] = e;
+    if (r.world == 1) { if (e != SB_E_EMPTY) atomicMax(r.emax, e); return; }
+    for (int p = 0; p < r.world; ++p)
+        if (p != r.self) reinterpret_cast<int*>(r.base[p] + r.off_e)[r.tile_off + tile] = e;
+}
+__device__ __forceinline__ void sb_put_Q(const SbRecOut& r, int tile, unsigned long long q) {
+    r.Q[tile] = q;
+    for (int p = 0; p < r.world; ++p)
+        if (p != r.self) reinterpret_cast<unsigned long long*>(r.base[p] + r.off_Q)[r.tile_off + tile] = q;
+}
+
 // Deferred form of sb_block_sum_wp for the persistent step kernels: sb_warp_total at the end of a tile,
 // sb_flush_totals after ANY later barrier (the next tile's first one) -- no barrier of its own.
 __device__ __forceinline__ void sb_warp_total(unsigned tsum, unsigned long long* sm) {
@@ -529,12 +552,12 @@ __device__ __forceinline__ void sb_warp_total(unsigned tsum, unsigned long long*
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = ((unsigned long long)hi << 16) + lo;
 }
 __device__ __forceinline__ void sb_flush_totals(const unsigned long long* sm, unsigned long long* __restrict__ wp_tile,
-                                                unsigned long long* __restrict__ Q_tile) {
+                                                const SbRecOut& rec, int tile) {
     if (threadIdx.x <= SB_WARPS) {                               // thread w < 8: prefix of warp w; thread 8: the tile sum
         unsigned long long pre = 0;
 #pragma unroll
         for (int w = 0; w < SB_WARPS; ++w) if (w < (int)threadIdx.x) pre += sm[w];
-        if (threadIdx.x < SB_WARPS) wp_tile[threadIdx.x] = pre; else *Q_tile = pre;
+        if (threadIdx.x < SB_WARPS) wp_tile[threadIdx.x] = pre; else sb_put_Q(rec, tile, pre);
     }
 }
 

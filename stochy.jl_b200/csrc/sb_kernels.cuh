@@ -16,7 +16,8 @@ namespace cg = cooperative_groups;
 template <int KIND>
 __global__ void __launch_bounds__(SB_THREADS)
 k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w32, int* __restrict__ e_out,
-           unsigned long long* __restrict__ Q_out, unsigned long long* __restrict__ wp_out, unsigned* __restrict__ err) {
+           unsigned long long* __restrict__ Q_out, unsigned long long* __restrict__ wp_out, int* __restrict__ emax,
+           unsigned* __restrict__ err) {
     __shared__ unsigned long long s_u64[SB_WARPS + 1];
     __shared__ double s_f64[SB_WARPS];
     __shared__ int s_i32[SB_WARPS];
@@ -101,7 +102,11 @@ k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w3
     }
     sb_store8_u32(w32 + base, q);                 // w32 is padded to whole tiles
     sb_block_sum_wp(tsum, s_u64, wp_out + (size_t)blockIdx.x * SB_WARPS, Q_out + blockIdx.x);
-    if (tid == 0) e_out[blockIdx.x] = e;
+    if (tid == 0) {
+        e_out[blockIdx.x] = e;
+        // e != EMPTY means some weight of the tile is positive: its grid value is at least 2^26, so the tile has mass
+        if (e != SB_E_EMPTY) atomicMax(emax, e);
+    }
     if (bad) atomicOr(err, SB_ERRBIT_NAN);
 }
 
@@ -112,15 +117,17 @@ k_quantise(const void* __restrict__ data, long long n, uint32_t* __restrict__ w3
 // extension.  Deterministic: integer adds only.
 // =====================================================================================
 #define SB_SCAN_THREADS 1024
-#define SB_SCAN_CTAS    8      // one thread-block cluster: 8 SMs x 1024 threads = one tile per thread at 2^24 particles
+#define SB_SCAN_CTAS    8      // portable cluster: 8 SMs x 1024 threads = one tile per thread at 2^24 particles
+#define SB_SCAN_CTAS_MAX 16    // B200 allows 16 (opt-in): used for pools above 2^26 particles
 
-// The scan runs as ONE thread-block cluster: block-local warp-shuffle scans, then the 8 block totals
-// are exchanged through distributed shared memory (cluster.sync is ~0.2 us, a second kernel launch
-// or a single-SM scan of 8192 tiles is 10-30 us).  All arithmetic is integer: any association
-// order gives the same bits.
+// The scan runs as ONE thread-block cluster: block-local warp-shuffle scans, then the block totals
+// are exchanged through distributed shared memory (a cluster barrier is ~0.5 us; a second kernel
+// launch or a single-SM scan of 8192 tiles is 10-30 us).  All arithmetic is integer: any association
+// order gives the same bits.  Every cluster-wide exchange has its own shared-memory slot, so the only
+// cluster barriers are the ones that publish a slot (no guard barriers).
 struct SbScanSmem {
     unsigned long long warp_tot[32];
-    unsigned long long blk_tot;      // read by the other CTAs of the cluster
+    unsigned long long blk_tot[2];   // one slot per scan; read by the other CTAs of the cluster
     int blk_max;                     // idem
     int warp_max[32];
     unsigned long long base, total;  // broadcast inside the CTA
@@ -129,6 +136,7 @@ struct SbScanSmem {
 
 __device__ __forceinline__ int sb_cluster_max(int v, SbScanSmem& sm, cg::cluster_group& cl) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = (int)cl.num_blocks();
 #pragma unroll
     for (int d = 16; d; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
     if (lane == 0) sm.warp_max[warp] = v;
@@ -140,27 +148,29 @@ __device__ __forceinline__ int sb_cluster_max(int v, SbScanSmem& sm, cg::cluster
         if (lane == 0) sm.blk_max = w;
     }
     cl.sync();
-    if (threadIdx.x < SB_SCAN_CTAS) {
-        int r = *cl.map_shared_rank(&sm.blk_max, threadIdx.x);
+    if (threadIdx.x < 32) {
+        int r = lane < nb ? *cl.map_shared_rank(&sm.blk_max, lane) : SB_E_EMPTY;
 #pragma unroll
-        for (int d = 4; d; d >>= 1) r = max(r, __shfl_xor_sync(0xffu, r, d));
-        if (threadIdx.x == 0) sm.gmax = r;
+        for (int d = 16; d; d >>= 1) r = max(r, __shfl_xor_sync(0xffffffffu, r, d));
+        if (lane == 0) sm.gmax = r;
     }
     __syncthreads();
     return sm.gmax;
 }
 
-// exclusive prefix of `loc` over all threads of the cluster (thread order = rank * 1024 + tid)
+// exclusive prefix of `loc` over all threads of the cluster (thread order = rank * 1024 + tid); `which`
+// selects the exchange slot (each slot is used once per kernel)
 __device__ __forceinline__ unsigned long long sb_cluster_excl_scan(unsigned long long loc, SbScanSmem& sm,
-                                                                    cg::cluster_group& cl, unsigned long long* total) {
+                                                                    cg::cluster_group& cl, int which, unsigned long long* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nb = (int)cl.num_blocks();
     unsigned long long inc = loc;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         unsigned long long o = sb_shfl_up_u64(inc, d);
         if (lane >= d) inc += o;
     }
-    cl.sync();                                   // previous readers of blk_tot / base are done
+    __syncthreads();                             // warp_tot / base / total of the previous scan are no longer read
     if (lane == 31) sm.warp_tot[warp] = inc;
     __syncthreads();
     if (warp == 0) {
@@ -172,12 +182,12 @@ __device__ __forceinline__ unsigned long long sb_cluster_excl_scan(unsigned long
             if (lane >= d) wi += o;
         }
         sm.warp_tot[lane] = wi - wt;             // exclusive prefix of the warp totals
-        if (lane == 31) sm.blk_tot = wi;
+        if (lane == 31) sm.blk_tot[which] = wi;
     }
     cl.sync();
     if (threadIdx.x < 32) {
         const unsigned rank = cl.block_rank();
-        unsigned long long bt = lane < SB_SCAN_CTAS ? *cl.map_shared_rank(&sm.blk_tot, lane) : 0ull;
+        unsigned long long bt = lane < nb ? *cl.map_shared_rank(&sm.blk_tot[which], lane) : 0ull;
         unsigned long long base = lane < (int)rank ? bt : 0ull, tot = bt;
 #pragma unroll
         for (int d = 16; d; d >>= 1) {
@@ -193,33 +203,35 @@ __device__ __forceinline__ unsigned long long sb_cluster_excl_scan(unsigned long
     return sm.base + sm.warp_tot[warp] + inc - loc;
 }
 
-// Per-GPU tile records of a sharded pool: GPU g keeps (e, Q) of its own tiles in its arena; the scan
-// of every GPU reads all of them (local HBM or NVLink peer loads) after a flag barrier.
+// Sharded pool: every GPU's step kernel pushed its tile records (e, Q) into the replicated arrays of
+// every arena; the (replicated, deterministic) scan of each GPU reads its local copy behind a flag barrier.
 struct SbScanPeers {
     const char* base[SB_MAX_PEERS];
-    unsigned long long off_e, off_Q;    // this pool slot's arrays inside every arena
     unsigned long long off_flags;       // unsigned[SB_MAX_PEERS]: flags[g] = last epoch GPU g has finished
-    int log2t;                          // tiles per GPU = 2^log2t
     int world, self;
     unsigned epoch;                     // wait until every flags[g] >= epoch
-    int* e_all;                         // [global tiles] local copy for the pull
 };
 #define SB_SCAN_MAXPER 8
 
 // PER > 0: every thread keeps its PER consecutive tiles in registers (PER = 1: 2^24 particles, PER = 8:
 // 2^27); PER == 0: any size, tile records re-read from global memory in every pass.
+// emax (single GPU): the largest tile exponent, accumulated with atomicMax by the kernels that produced the
+// pool; consumed and cleared here (saves one cluster-wide reduction).  Sharded pools reduce e instead.
+// The cluster size is given at launch (8, or 16 for large pools).
 template <int PER, bool PEERS>
-__global__ void __cluster_dims__(SB_SCAN_CTAS, 1, 1) __launch_bounds__(SB_SCAN_THREADS)
+__global__ void __launch_bounds__(SB_SCAN_THREADS)
 k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q_g, int nt, long long n, long long m,
            const unsigned long long* __restrict__ r53_ptr, SbStepInfo* __restrict__ info,
            unsigned long long* __restrict__ P, unsigned long long* __restrict__ Pt, int* __restrict__ child_start,
-           int* __restrict__ first_tile, int want_exact, unsigned* __restrict__ err, const __grid_constant__ SbScanPeers sp) {
+           int* __restrict__ first_tile, int want_exact, unsigned* __restrict__ err, int* __restrict__ emax,
+           const __grid_constant__ SbScanPeers sp) {
     cg::cluster_group cl = cg::this_cluster();
     __shared__ SbScanSmem sm;
     const unsigned rank = cl.block_rank();
+    const int nthreads = SB_SCAN_THREADS * (int)cl.num_blocks();
     const int gtid = (int)rank * SB_SCAN_THREADS + threadIdx.x;
     const unsigned long long R53 = __ldg(r53_ptr);            // host-drawn systematic offset (53-bit uniform)
-    const int per = PER > 0 ? PER : (nt + SB_SCAN_THREADS * SB_SCAN_CTAS - 1) / (SB_SCAN_THREADS * SB_SCAN_CTAS);
+    const int per = PER > 0 ? PER : (nt + nthreads - 1) / nthreads;
     const int b0 = min(nt, gtid * per), b1 = min(nt, b0 + per);
     if (PEERS) {
         // every peer has finished the step kernel that produced this pool (and therefore also every
@@ -242,31 +254,29 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
             const int b = b0 + i;
             qr[i] = 0ull; er[i] = SB_E_EMPTY;
             if (b < b1) {
-                if (PEERS) {
-                    const int g = b >> sp.log2t, bl = b & ((1 << sp.log2t) - 1);
-                    qr[i] = __ldcv(reinterpret_cast<const unsigned long long*>(sp.base[g] + sp.off_Q) + bl);
-                    er[i] = __ldcv(reinterpret_cast<const int*>(sp.base[g] + sp.off_e) + bl);
-                } else { qr[i] = __ldg(Q_g + b); er[i] = __ldg(e_g + b); }
+                if (PEERS) { qr[i] = __ldcg(Q_g + b); er[i] = __ldcg(e_g + b); }      // written by peers over NVLink: L2 is the point of coherence
+                else { qr[i] = __ldg(Q_g + b); er[i] = __ldg(e_g + b); }
             }
-        }
-        if (PEERS) {
-#pragma unroll
-            for (int i = 0; i < (PER > 0 ? PER : 1); ++i) if (b0 + i < b1) sp.e_all[b0 + i] = er[i];
         }
     }
 #define SB_TS_FOR(body)                                                                        \
     if (PER > 0) { _Pragma("unroll") for (int i_ = 0; i_ < (PER > 0 ? PER : 1); ++i_) { const int b = b0 + i_; if (b < b1) { const unsigned long long qv = qr[i_]; const int ev = er[i_]; body } } } \
-    else for (int b = b0; b < b1; ++b) { const unsigned long long qv = __ldg(Q_g + b); const int ev = __ldg(e_g + b); body }
+    else for (int b = b0; b < b1; ++b) { const unsigned long long qv = __ldcg(Q_g + b); const int ev = __ldcg(e_g + b); body }
     // global exponent
     int E = SB_E_EMPTY;
-    SB_TS_FOR((void)b; if (qv != 0ull) E = max(E, ev);)
-    E = sb_cluster_max(E, sm, cl);
+    if (PEERS) {
+        SB_TS_FOR((void)b; if (qv != 0ull) E = max(E, ev);)
+        E = sb_cluster_max(E, sm, cl);
+    } else {
+        E = __ldcg(emax);                        // cleared below, after the first cluster barrier
+    }
     const int LS = 24 - (nt <= 1 ? 0 : 32 - __clz(nt - 1));  // LS = 24 - ceil_log2(nt)
     // exact CDF of tile sums (log-evidence; multinomial resampling)
     unsigned long long loc = 0;
     SB_TS_FOR((void)b; if (qv != 0ull) { const int sh = E - ev; loc += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
     unsigned long long total;
-    unsigned long long run = sb_cluster_excl_scan(loc, sm, cl, &total);
+    unsigned long long run = sb_cluster_excl_scan(loc, sm, cl, 0, &total);
+    if (!PEERS && gtid == 0) *emax = SB_E_EMPTY;              // every thread of the cluster has read it
     if (want_exact) {
         SB_TS_FOR(P[b] = run; if (qv != 0ull) { const int sh = E - ev; run += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
         if (gtid == 0) P[nt] = total;
@@ -295,7 +305,7 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     unsigned long long loc2 = 0;
     if (si.valid) { SB_TS_FOR((void)b; if (qv != 0ull) loc2 += sb_sys_delta(qv, si.R, si.r0 + (E - ev));) }
     unsigned long long Tt;
-    unsigned long long run2 = sb_cluster_excl_scan(loc2, sm, cl, &Tt);
+    unsigned long long run2 = sb_cluster_excl_scan(loc2, sm, cl, 1, &Tt);
     const unsigned long long lastk = (unsigned long long)(m - 1) << si.s;
     if (si.valid && Tt > lastk) {
         const unsigned long long span = Tt - lastk;
@@ -603,8 +613,7 @@ struct SbHmmStepArgs {
     // this step's outputs (local indices)
     int* x_out;
     uint32_t* w32_out;
-    int* e_out;
-    unsigned long long* Q_out;
+    SbRecOut rec;               // tile exponents and sums
     unsigned long long* wp_out;
     double* lw_out;             // optional (store_logw)
     double* wlit_out;           // optional (literal mode): exp(score) from the host-built table
@@ -713,7 +722,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     }
     // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
     if (ANC != SB_ANC_PULL) __syncthreads();                     // the pull has its own barriers
-    if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.Q_out + pt); }
+    if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
     // (4)+(5) weight and quantise.  Only K distinct scores exist: the tile exponent is the largest
     // ceil(log2 weight) present (an integer max), and 2^(l2 - e) 2^27 comes from a K x K table.
     unsigned key = 0u;
@@ -746,7 +755,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.wlit_out[lbase + j] = a.expF_t[x[j]];
     }
     sb_warp_total(tsum, sm.ps.scan);                              // flushed after the next barrier (next tile / kernel end)
-    if (tid == 0) a.e_out[tile] = e;
+    if (tid == 0) sb_put_e(a.rec, tile, e);
     // no barrier here: every shared scratch array is rewritten only after a later barrier of the next tile
 }
 
@@ -806,7 +815,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     if (k > 0) {                                                  // the last tile's totals
         __syncthreads();
         const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
-        sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.Q_out + pt);
+        sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
     }
 }
 
@@ -821,8 +830,7 @@ struct SbLgStepArgs {
     const int* anc_in;
     void* x_out;
     uint32_t* w32_out;
-    int* e_out;
-    unsigned long long* Q_out;
+    SbRecOut rec;               // tile exponents and sums
     unsigned long long* wp_out;
     double* lw_out;
     long long N;                // global particle count
@@ -873,7 +881,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         }
         // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
         if (ANC != SB_ANC_PULL) __syncthreads();                 // the pull has its own barriers
-        if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.Q_out + pt); }
+        if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
         REAL xpar[SB_ITEMS];
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j)
@@ -947,13 +955,13 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         }
         sb_store8_u32(a.w32_out + lbase, q);
         sb_warp_total(tsum, sm.ps.scan);                          // flushed after the next barrier (next tile / kernel end)
-        if (tid == 0) a.e_out[tile] = e;
+        if (tid == 0) sb_put_e(a.rec, tile, e);
         if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
     }
     if (k > 0) {
         __syncthreads();
         const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
-        sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.Q_out + pt);
+        sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
     }
 }
 

@@ -63,6 +63,8 @@ struct sb_handle {
     size_t off_w32[2] = {0, 0}, off_x[2] = {0, 0}, off_wp[2] = {0, 0}, off_e[2] = {0, 0}, off_Q[2] = {0, 0}, off_flags = 0;
     char* peer_base[SB_MAX_PEERS] = {nullptr};
     unsigned epoch = 0;
+    int scan16 = -1;                  // 16-CTA scan cluster: -1 not probed, 0 unavailable, 1 available
+    int* d_emax = nullptr;            // running max of the tile exponents of the pool in production (single GPU)
     DevBuf e_all;
     // hook staging
     DevBuf hk_in, hk_r, hk_anc, hk_out, hk_src;
@@ -123,17 +125,30 @@ inline int64_t tiles_of(int64_t n) { return (n + SB_TILE - 1) / SB_TILE; }
 inline uint32_t* W32(sb_handle* h, int slot) {
     return h->dist_ready ? reinterpret_cast<uint32_t*>((char*)h->arena + h->off_w32[slot]) : h->w32[slot].as<uint32_t>();
 }
+// tile records by GLOBAL tile index (sharded: the replicated arrays every rank's step kernel pushes into)
 inline int* TE(sb_handle* h, int slot) {
     return h->dist_ready ? reinterpret_cast<int*>((char*)h->arena + h->off_e[slot]) : h->tile_e[slot].as<int>();
 }
 inline unsigned long long* TQ(sb_handle* h, int slot) {
     return h->dist_ready ? reinterpret_cast<unsigned long long*>((char*)h->arena + h->off_Q[slot]) : h->tile_Q[slot].as<unsigned long long>();
 }
+// where the step kernels put the records of the tiles they produce
+inline SbRecOut make_rec(sb_handle* h, int slot) {
+    SbRecOut r;
+    memset(&r, 0, sizeof(r));
+    r.world = 1; r.emax = h->d_emax;
+    if (h->dist_ready) {
+        r.tile_off = (int)(h->rank * (h->NL / SB_TILE));
+        r.world = h->world; r.self = h->rank; r.off_e = h->off_e[slot]; r.off_Q = h->off_Q[slot];
+        for (int g = 0; g < h->world; ++g) r.base[g] = h->peer_base[g];
+    }
+    r.e = TE(h, slot) + r.tile_off; r.Q = TQ(h, slot) + r.tile_off;
+    return r;
+}
 inline unsigned long long* WP(sb_handle* h, int slot) {
     return h->dist_ready ? reinterpret_cast<unsigned long long*>((char*)h->arena + h->off_wp[slot]) : h->tile_wp[slot].as<unsigned long long>();
 }
-// tile exponents as the pull reads them (indexed by GLOBAL tile)
-inline const int* TE_pull(sb_handle* h, int slot) { return h->dist_ready ? h->e_all.as<int>() : TE(h, slot); }
+inline const int* TE_pull(sb_handle* h, int slot) { return TE(h, slot); }
 
 // the pool held in slot `slot` whose particle states are at `x` (single GPU) / in the arena (sharded)
 inline SbPool make_pool(sb_handle* h, int slot, const void* x) {
@@ -194,7 +209,6 @@ int ensure_grid(sb_handle* h, int64_t n_pool, int64_t m) {
     if (h->dist_ready) {
         if (n_pool != h->NL * h->world || m != n_pool)
             return fail(h, SB_EINVAL, "sharded handle: the pool is fixed at world x N_local particles");
-        CK(h->e_all.ensure((size_t)nt * 4));
     } else {
         for (int i = 0; i < 2; ++i) {
             CK(h->w32[i].ensure((size_t)nt * SB_TILE * 4));
@@ -233,50 +247,85 @@ int launch_quantise(sb_handle* h, const void* d_data, int kind, int64_t n, int s
     int* e = TE(h, slot);
     unsigned long long* Q = TQ(h, slot);
     unsigned long long* wp = WP(h, slot);
-    if (kind == SB_W_LINEAR_F64) k_quantise<0><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, wp, h->d_err);
-    else if (kind == SB_W_LOG_F64) k_quantise<1><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, wp, h->d_err);
-    else if (kind == SB_W_LOG_F32) k_quantise<2><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, wp, h->d_err);
+    if (kind == SB_W_LINEAR_F64) k_quantise<0><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, wp, h->d_emax, h->d_err);
+    else if (kind == SB_W_LOG_F64) k_quantise<1><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, wp, h->d_emax, h->d_err);
+    else if (kind == SB_W_LOG_F32) k_quantise<2><<<nt, SB_THREADS, 0, h->stream>>>(d_data, n, w32, e, Q, wp, h->d_emax, h->d_err);
     else return fail(h, SB_EINVAL, "unknown weight kind");
     LAUNCH_CHECK();
     return SB_OK;
 }
 
-template <bool PEERS>
-int launch_tilescan_t(sb_handle* h, int per, const int* e, const unsigned long long* Q, int nt, int64_t n, int64_t m,
+template <int PER, bool PEERS>
+int launch_tilescan_k(sb_handle* h, int ctas, const int* e, const unsigned long long* Q, int nt, int64_t n, int64_t m,
                       const unsigned long long* d_r53, SbStepInfo* info, int want_exact, const SbScanPeers& sp) {
-    unsigned long long* P = h->P.as<unsigned long long>();
-    unsigned long long* Pt = h->Pt.as<unsigned long long>();
-    int* cs = h->child_start.as<int>();
-    int* ft = h->first_tile.as<int>();
-#define SB_TS_LAUNCH(PER) k_tilescan<PER, PEERS><<<SB_SCAN_CTAS, SB_SCAN_THREADS, 0, h->stream>>>(e, Q, nt, n, m, d_r53, info, P, Pt, cs, ft, want_exact, h->d_err, sp)
-    if (per <= 1) SB_TS_LAUNCH(1);
-    else if (per <= 2) SB_TS_LAUNCH(2);
-    else if (per <= 4) SB_TS_LAUNCH(4);
-    else if (per <= 8) SB_TS_LAUNCH(8);
-    else if (!PEERS) SB_TS_LAUNCH(0);
-    else return fail(h, SB_EINVAL, "sharded pool too large (max 2^27 particles over all GPUs)");
-#undef SB_TS_LAUNCH
-    LAUNCH_CHECK();
+    auto kern = k_tilescan<PER, PEERS>;
+    if (ctas > SB_SCAN_CTAS) {
+        const std::pair<const void*, size_t> key((const void*)kern, (size_t)1 << 40);     // "non-portable size allowed" set once
+        if (h->occ.find(key) == h->occ.end()) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            h->occ.emplace(key, 1);
+        }
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(SB_SCAN_THREADS); cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    long long nn = n, mm = m;
+    CK(cudaLaunchKernelEx(&cfg, kern, e, Q, nt, nn, mm, d_r53, info, h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
+                          h->child_start.as<int>(), h->first_tile.as<int>(), want_exact, h->d_err, h->d_emax, sp));
+    ++h->launches;
     return SB_OK;
+}
+
+template <bool PEERS>
+int launch_tilescan_t(sb_handle* h, const int* e, const unsigned long long* Q, int nt, int64_t n, int64_t m,
+                      const unsigned long long* d_r53, SbStepInfo* info, int want_exact, const SbScanPeers& sp) {
+    // one cluster: 8 CTAs (portable) up to 4 tiles per thread, 16 CTAs beyond that when the device takes them
+    int ctas = SB_SCAN_CTAS;
+    if (nt > SB_SCAN_CTAS * SB_SCAN_THREADS * 4 && h->scan16 != 0) {
+        if (h->scan16 < 0) {                                         // probe once
+            auto kern = k_tilescan<4, PEERS>;
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(SB_SCAN_CTAS_MAX); cfg.blockDim = dim3(SB_SCAN_THREADS);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = SB_SCAN_CTAS_MAX; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nc = 0;
+            h->scan16 = (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                         cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) == cudaSuccess && nc >= 1) ? 1 : 0;
+            cudaGetLastError();
+        }
+        if (h->scan16 == 1) ctas = SB_SCAN_CTAS_MAX;
+    }
+    const int per = (nt + SB_SCAN_THREADS * ctas - 1) / (SB_SCAN_THREADS * ctas);
+    if (per <= 1) return launch_tilescan_k<1, PEERS>(h, ctas, e, Q, nt, n, m, d_r53, info, want_exact, sp);
+    if (per <= 2) return launch_tilescan_k<2, PEERS>(h, ctas, e, Q, nt, n, m, d_r53, info, want_exact, sp);
+    if (per <= 4) return launch_tilescan_k<4, PEERS>(h, ctas, e, Q, nt, n, m, d_r53, info, want_exact, sp);
+    if (per <= 8) return launch_tilescan_k<8, PEERS>(h, ctas, e, Q, nt, n, m, d_r53, info, want_exact, sp);
+    if (!PEERS) return launch_tilescan_k<0, PEERS>(h, ctas, e, Q, nt, n, m, d_r53, info, want_exact, sp);
+    return fail(h, SB_EINVAL, "sharded pool too large (max 2^27 particles over all GPUs)");
 }
 
 // scan of pool `slot` (n entries, m children).  Sharded: first tell the peers that this GPU's share of
 // the pool is complete, then scan all GPUs' tile records behind the flag barrier.
 int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, const unsigned long long* d_r53, SbStepInfo* info) {
     const int nt = (int)tiles_of(n);
-    const int per = (nt + SB_SCAN_THREADS * SB_SCAN_CTAS - 1) / (SB_SCAN_THREADS * SB_SCAN_CTAS);
     const int want_exact = h->opt.resample_mode == SB_RESAMPLE_MULTINOMIAL || h->hook_exact;
     SbScanPeers sp;
     memset(&sp, 0, sizeof(sp));
     if (!h->dist_ready)
-        return launch_tilescan_t<false>(h, per, TE(h, slot), TQ(h, slot), nt, n, m, d_r53, info, want_exact, sp);
+        return launch_tilescan_t<false>(h, TE(h, slot), TQ(h, slot), nt, n, m, d_r53, info, want_exact, sp);
     for (int g = 0; g < h->world; ++g) sp.base[g] = h->peer_base[g];
-    sp.off_e = h->off_e[slot]; sp.off_Q = h->off_Q[slot]; sp.off_flags = h->off_flags;
-    sp.log2t = 0; while ((1ll << sp.log2t) < h->NL / SB_TILE) ++sp.log2t;
-    sp.world = h->world; sp.self = h->rank; sp.epoch = ++h->epoch; sp.e_all = h->e_all.as<int>();
+    sp.off_flags = h->off_flags;
+    sp.world = h->world; sp.self = h->rank; sp.epoch = ++h->epoch;
     k_signal<<<1, 32, 0, h->stream>>>(sp);
     LAUNCH_CHECK();
-    return launch_tilescan_t<true>(h, per, nullptr, nullptr, nt, n, m, d_r53, info, want_exact, sp);
+    return launch_tilescan_t<true>(h, TE(h, slot), TQ(h, slot), nt, n, m, d_r53, info, want_exact, sp);
 }
 
 int launch_pull(sb_handle* h, int slot, const SbStepInfo* info, int64_t m_local, int* d_anc) {
@@ -335,6 +384,8 @@ struct ProfScope {
 int begin_timed(sb_handle* h) {
     h->launches = 0;
     h->prof_used = 0;
+    static const int empty = SB_E_EMPTY;            // an aborted call may have left a partial maximum behind
+    CK(cudaMemcpyAsync(h->d_emax, &empty, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
     return SB_OK;
 }
@@ -399,10 +450,15 @@ extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
         cudaEventCreate(&h->evt0) != cudaSuccess || cudaEventCreate(&h->evt1) != cudaSuccess ||
         cudaMalloc(&h->d_err, sizeof(unsigned)) != cudaSuccess ||
         cudaMemset(h->d_err, 0, sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&h->d_emax, sizeof(int)) != cudaSuccess ||
         h->d_misc.ensure(64) != cudaSuccess) {
         g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
         sb_destroy(h);
         return SB_ECUDA;
+    }
+    {
+        const int empty = SB_E_EMPTY;
+        cudaMemcpy(h->d_emax, &empty, sizeof(int), cudaMemcpyHostToDevice);
     }
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, opt.device) != cudaSuccess || h->num_sms < 1)
         h->num_sms = 148;
@@ -425,6 +481,7 @@ extern "C" void sb_destroy(sb_handle* h) {
         if (h->peer_base[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_base[g]);
     if (h->arena) cudaFree(h->arena);
     if (h->d_err) cudaFree(h->d_err);
+    if (h->d_emax) cudaFree(h->d_emax);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evt0) cudaEventDestroy(h->evt0);
@@ -731,8 +788,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.anc_out = (history && t) ? anc_row_prev : nullptr;
         a.x_out = xrow(t);
         a.w32_out = W32(h, cur);
-        a.e_out = TE(h, cur);
-        a.Q_out = TQ(h, cur);
+        a.rec = make_rec(h, cur);
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.wlit_out = literal ? h->wlit.as<double>() : nullptr;
@@ -811,8 +867,7 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         a.anc_in = h->ancbuf.as<int>();
         a.x_out = xrow(cur);
         a.w32_out = W32(h, cur);
-        a.e_out = TE(h, cur);
-        a.Q_out = TQ(h, cur);
+        a.rec = make_rec(h, cur);
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.N = N; a.ntiles = ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed;
@@ -1265,8 +1320,8 @@ extern "C" int32_t sb_dist_ipc_export(sb_handle* h, int64_t N_local, uint8_t out
         h->off_w32[sl] = take((size_t)N_local * 4);
         h->off_x[sl] = take((size_t)N_local * 8);              // room for fp64 states
         h->off_wp[sl] = take(ntl * SB_WARPS * 8);
-        h->off_e[sl] = take(ntl * 4);
-        h->off_Q[sl] = take(ntl * 8);
+        h->off_e[sl] = take(ntl * h->world * 4);               // replicated: every rank's records, global tile index
+        h->off_Q[sl] = take(ntl * h->world * 8);
     }
     h->off_flags = take(SB_MAX_PEERS * sizeof(unsigned));
     CK(cudaMalloc(&h->arena, off));
