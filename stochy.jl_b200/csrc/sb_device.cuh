@@ -521,27 +521,44 @@ __device__ __forceinline__ double sb_block_max_f64_1(double v, double* sm) {
     return r;
 }
 
-// Where the tile records (e, Q) of the pool being PRODUCED go: the local arrays and, when the pool is
-// sharded, the replicated copy in every peer's arena -- fire-and-forget stores over NVLink from inside
-// the step kernel, so that every GPU's tile scan later reads local memory only.
+// Where the tile records (e, Q) of the pool being PRODUCED go (local tile index).  Single GPU: the
+// running maximum of the exponents is kept with atomicMax for the tile scan.  Sharded: k_signal copies
+// the records into every peer's replica after the step kernel (no remote stores inside the hot kernel).
 struct SbRecOut {
-    int* e;                             // local arrays, local tile index
+    int* e;
     unsigned long long* Q;
-    int* emax;                          // single GPU: running max of the tile exponents (read by the tile scan)
-    char* base[SB_MAX_PEERS];
-    unsigned long long off_e, off_Q;    // replicated arrays (GLOBAL tile index) inside every arena
-    int world, self, tile_off;
+    int* emax;                          // nullptr when sharded
 };
 __device__ __forceinline__ void sb_put_e(const SbRecOut& r, int tile, int e) {
     r.e[tile] = e;
-    if (r.world == 1) { if (e != SB_E_EMPTY) atomicMax(r.emax, e); return; }
-    for (int p = 0; p < r.world; ++p)
-        if (p != r.self) reinterpret_cast<int*>(r.base[p] + r.off_e)[r.tile_off + tile] = e;
+    if (r.emax && e != SB_E_EMPTY) atomicMax(r.emax, e);
 }
-__device__ __forceinline__ void sb_put_Q(const SbRecOut& r, int tile, unsigned long long q) {
-    r.Q[tile] = q;
-    for (int p = 0; p < r.world; ++p)
-        if (p != r.self) reinterpret_cast<unsigned long long*>(r.base[p] + r.off_Q)[r.tile_off + tile] = q;
+__device__ __forceinline__ void sb_put_Q(const SbRecOut& r, int tile, unsigned long long q) { r.Q[tile] = q; }
+
+// Sharded pool: the LAST CTA of a step kernel to finish tells every peer that this GPU's share of the pool
+// (weights, states, warp prefixes, tile records) is complete: one 4-byte store over NVLink into flags[self]
+// of every arena -- compute and notification in one kernel, no separate launch.  Peers wait for the flags
+// in their tile scan.  world <= 1: nothing to do.
+struct SbSignal {
+    unsigned* counter;                  // CTAs of this launch that have finished
+    char* base[SB_MAX_PEERS];
+    unsigned long long off_flags;
+    int world, self;
+    unsigned epoch;
+};
+__device__ __forceinline__ void sb_signal_done(const SbSignal& sg) {
+    if (sg.world <= 1) return;
+    __syncthreads();                                             // the CTA's writes are ordered before thread 0's fence
+    if (threadIdx.x == 0) {
+        __threadfence_system();                                  // cumulative over the barrier: visible to every GPU
+        const unsigned done = atomicAdd(sg.counter, 1u) + 1u;
+        if (done == gridDim.x) {
+            *sg.counter = 0u;                                    // next launch
+            __threadfence_system();                              // cumulative: every CTA's writes precede the flags
+            for (int p = 0; p < sg.world; ++p)
+                *(reinterpret_cast<volatile unsigned*>(sg.base[p] + sg.off_flags) + sg.self) = sg.epoch;
+        }
+    }
 }
 
 // Deferred form of sb_block_sum_wp for the persistent step kernels: sb_warp_total at the end of a tile,

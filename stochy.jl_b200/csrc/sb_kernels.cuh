@@ -203,12 +203,16 @@ __device__ __forceinline__ unsigned long long sb_cluster_excl_scan(unsigned long
     return sm.base + sm.warp_tot[warp] + inc - loc;
 }
 
-// Sharded pool: every GPU's step kernel pushed its tile records (e, Q) into the replicated arrays of
-// every arena; the (replicated, deterministic) scan of each GPU reads its local copy behind a flag barrier.
+// Sharded pool: GPU g's tile records (e, Q) live in section g of the record arrays of ITS arena (arrays are
+// laid out by GLOBAL tile index in every arena).  The (replicated, deterministic) scan of every GPU reads
+// section g from GPU g -- local HBM or NVLink peer loads, one round trip, all loads in flight together --
+// behind a flag barrier, and fills the foreign sections of its own exponent array for the pull.
 struct SbScanPeers {
     const char* base[SB_MAX_PEERS];
     unsigned long long off_flags;       // unsigned[SB_MAX_PEERS]: flags[g] = last epoch GPU g has finished
+    unsigned long long off_e, off_Q;    // record arrays of the pool slot inside every arena
     int world, self;
+    int log2t;                          // tiles per GPU = 2^log2t
     unsigned epoch;                     // wait until every flags[g] >= epoch
 };
 #define SB_SCAN_MAXPER 8
@@ -254,8 +258,19 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
             const int b = b0 + i;
             qr[i] = 0ull; er[i] = SB_E_EMPTY;
             if (b < b1) {
-                if (PEERS) { qr[i] = __ldcg(Q_g + b); er[i] = __ldcg(e_g + b); }      // written by peers over NVLink: L2 is the point of coherence
-                else { qr[i] = __ldg(Q_g + b); er[i] = __ldg(e_g + b); }
+                if (PEERS) {
+                    const char* owner = sp.base[b >> sp.log2t];
+                    qr[i] = __ldcv(reinterpret_cast<const unsigned long long*>(owner + sp.off_Q) + b);
+                    er[i] = __ldcv(reinterpret_cast<const int*>(owner + sp.off_e) + b);
+                } else { qr[i] = __ldg(Q_g + b); er[i] = __ldg(e_g + b); }
+            }
+        }
+        if (PEERS) {                             // the pull reads exponents of any tile from the local array
+            int* e_mine = reinterpret_cast<int*>(const_cast<char*>(sp.base[sp.self]) + sp.off_e);
+#pragma unroll
+            for (int i = 0; i < (PER > 0 ? PER : 1); ++i) {
+                const int b = b0 + i;
+                if (b < b1 && (b >> sp.log2t) != sp.self) e_mine[b] = er[i];
             }
         }
     }
@@ -333,17 +348,6 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     if (gtid == 0) { Pt[nt] = Tt; child_start[nt] = mi; }
     cl.sync();                                   // no CTA may exit while its shared memory can still be read
 #undef SB_TS_FOR
-}
-
-// Tells every peer that this GPU has finished epoch `epoch` (stream-ordered after the step kernel that
-// produced the pool): one 4-byte store per peer over NVLink into flags[self] of the peer's arena.
-__global__ void k_signal(const __grid_constant__ SbScanPeers sp) {
-    if ((int)threadIdx.x < sp.world) {
-        __threadfence_system();
-        volatile unsigned* f = reinterpret_cast<volatile unsigned*>(const_cast<char*>(sp.base[threadIdx.x]) + sp.off_flags) + sp.self;
-        *f = sp.epoch;
-        __threadfence_system();
-    }
 }
 
 // =====================================================================================
@@ -614,6 +618,7 @@ struct SbHmmStepArgs {
     int* x_out;
     uint32_t* w32_out;
     SbRecOut rec;               // tile exponents and sums
+    SbSignal sig;               // sharded: tell the peers when this GPU's share of the pool is complete
     unsigned long long* wp_out;
     double* lw_out;             // optional (store_logw)
     double* wlit_out;           // optional (literal mode): exp(score) from the host-built table
@@ -817,6 +822,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
         sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
     }
+    sb_signal_done(a.sig);
 }
 
 // ---------------------------------------------------------------- linear-Gaussian step
@@ -831,6 +837,7 @@ struct SbLgStepArgs {
     void* x_out;
     uint32_t* w32_out;
     SbRecOut rec;               // tile exponents and sums
+    SbSignal sig;               // sharded: tell the peers when this GPU's share of the pool is complete
     unsigned long long* wp_out;
     double* lw_out;
     long long N;                // global particle count
@@ -963,6 +970,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
         sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
     }
+    sb_signal_done(a.sig);
 }
 
 // =====================================================================================

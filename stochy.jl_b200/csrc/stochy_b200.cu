@@ -132,17 +132,24 @@ inline int* TE(sb_handle* h, int slot) {
 inline unsigned long long* TQ(sb_handle* h, int slot) {
     return h->dist_ready ? reinterpret_cast<unsigned long long*>((char*)h->arena + h->off_Q[slot]) : h->tile_Q[slot].as<unsigned long long>();
 }
-// where the step kernels put the records of the tiles they produce
+// sharded: the step kernel that produces a pool raises this GPU's flag to a fresh epoch when it is done
+inline SbSignal make_signal(sb_handle* h) {
+    SbSignal sg;
+    memset(&sg, 0, sizeof(sg));
+    sg.world = 1;
+    if (h->dist_ready) {
+        sg.counter = reinterpret_cast<unsigned*>((char*)h->arena + h->off_flags) + SB_MAX_PEERS;
+        for (int g = 0; g < h->world; ++g) sg.base[g] = h->peer_base[g];
+        sg.off_flags = h->off_flags; sg.world = h->world; sg.self = h->rank; sg.epoch = ++h->epoch;
+    }
+    return sg;
+}
+// where the step kernels put the records of the tiles they produce (local tile index)
 inline SbRecOut make_rec(sb_handle* h, int slot) {
     SbRecOut r;
-    memset(&r, 0, sizeof(r));
-    r.world = 1; r.emax = h->d_emax;
-    if (h->dist_ready) {
-        r.tile_off = (int)(h->rank * (h->NL / SB_TILE));
-        r.world = h->world; r.self = h->rank; r.off_e = h->off_e[slot]; r.off_Q = h->off_Q[slot];
-        for (int g = 0; g < h->world; ++g) r.base[g] = h->peer_base[g];
-    }
-    r.e = TE(h, slot) + r.tile_off; r.Q = TQ(h, slot) + r.tile_off;
+    const int tile_off = h->dist_ready ? (int)(h->rank * (h->NL / SB_TILE)) : 0;
+    r.e = TE(h, slot) + tile_off; r.Q = TQ(h, slot) + tile_off;
+    r.emax = h->dist_ready ? nullptr : h->d_emax;
     return r;
 }
 inline unsigned long long* WP(sb_handle* h, int slot) {
@@ -321,10 +328,9 @@ int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, const unsigned
     if (!h->dist_ready)
         return launch_tilescan_t<false>(h, TE(h, slot), TQ(h, slot), nt, n, m, d_r53, info, want_exact, sp);
     for (int g = 0; g < h->world; ++g) sp.base[g] = h->peer_base[g];
-    sp.off_flags = h->off_flags;
-    sp.world = h->world; sp.self = h->rank; sp.epoch = ++h->epoch;
-    k_signal<<<1, 32, 0, h->stream>>>(sp);
-    LAUNCH_CHECK();
+    sp.off_flags = h->off_flags; sp.off_e = h->off_e[slot]; sp.off_Q = h->off_Q[slot];
+    sp.log2t = 0; while ((1ll << sp.log2t) < h->NL / SB_TILE) ++sp.log2t;
+    sp.world = h->world; sp.self = h->rank; sp.epoch = h->epoch;      // the epoch the step kernel just signalled
     return launch_tilescan_t<true>(h, TE(h, slot), TQ(h, slot), nt, n, m, d_r53, info, want_exact, sp);
 }
 
@@ -789,6 +795,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.x_out = xrow(t);
         a.w32_out = W32(h, cur);
         a.rec = make_rec(h, cur);
+        a.sig = make_signal(h);
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.wlit_out = literal ? h->wlit.as<double>() : nullptr;
@@ -868,6 +875,7 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         a.x_out = xrow(cur);
         a.w32_out = W32(h, cur);
         a.rec = make_rec(h, cur);
+        a.sig = make_signal(h);
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.N = N; a.ntiles = ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed;
@@ -1323,7 +1331,7 @@ extern "C" int32_t sb_dist_ipc_export(sb_handle* h, int64_t N_local, uint8_t out
         h->off_e[sl] = take(ntl * h->world * 4);               // replicated: every rank's records, global tile index
         h->off_Q[sl] = take(ntl * h->world * 8);
     }
-    h->off_flags = take(SB_MAX_PEERS * sizeof(unsigned));
+    h->off_flags = take((SB_MAX_PEERS + 1) * sizeof(unsigned));     // flags[8] + the CTA counter of the step kernel
     CK(cudaMalloc(&h->arena, off));
     h->arena_bytes = off;
     CK(cudaMemset(h->arena, 0, off));
