@@ -161,8 +161,8 @@ def run_ours(args):
     # globally at every step; every rank uses the same seed (the Philox counters are global particle ids)
     eng = sb.Engine(device=local, precision="fp32", resample="systematic", seed=1)
     eng.load(model)
-    if world > 1:
-        eng.shard(N)
+    if world > 1 or args.force_shard:
+        eng.shard(N)                                # --force-shard: the sharded code path on one GPU (diagnostics)
     eng.set_profile(max(1, T // 100))
 
     def barrier():
@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2_N)
     ap.add_argument("--T", type=int, default=T_STEPS)
+    ap.add_argument("--force-shard", action="store_true", help="run the sharded (peer-addressed) kernels even on one GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

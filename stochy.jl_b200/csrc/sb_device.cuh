@@ -538,7 +538,7 @@ __device__ __forceinline__ void sb_put_Q(const SbRecOut& r, int tile, unsigned l
 // Sharded pool: the LAST CTA of a step kernel to finish tells every peer that this GPU's share of the pool
 // (weights, states, warp prefixes, tile records) is complete: one 4-byte store over NVLink into flags[self]
 // of every arena -- compute and notification in one kernel, no separate launch.  Peers wait for the flags
-// in their tile scan.  world <= 1: nothing to do.
+// in their tile scan.  counter == nullptr: not sharded, nothing to do.
 struct SbSignal {
     unsigned* counter;                  // CTAs of this launch that have finished
     char* base[SB_MAX_PEERS];
@@ -547,7 +547,7 @@ struct SbSignal {
     unsigned epoch;
 };
 __device__ __forceinline__ void sb_signal_done(const SbSignal& sg) {
-    if (sg.world <= 1) return;
+    if (!sg.counter) return;                                     // not sharded
     __syncthreads();                                             // the CTA's writes are ordered before thread 0's fence
     if (threadIdx.x == 0) {
         __threadfence_system();                                  // cumulative over the barrier: visible to every GPU

@@ -689,9 +689,18 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     }
     // (2) gather parents
     int xp[SB_ITEMS];
+    if (PEERS && !TAIL && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
+        // the pull returns parents in ascending order: first and last on the same GPU means all eight are,
+        // and one base pointer serves them (the usual case; only shard boundaries take the general path)
+        const int g = anc[0] >> a.pool.log2n;
+        const int* xg = reinterpret_cast<const int*>(a.pool.base[g] + a.pool.off_x) - ((size_t)g << a.pool.log2n);
 #pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j)
-        xp[j] = (ANC != SB_ANC_NONE && (!TAIL || base + j < N)) ? sb_pool_x<int, PEERS>(a.pool, anc[j]) : 0;
+        for (int j = 0; j < SB_ITEMS; ++j) xp[j] = __ldg(xg + anc[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j)
+            xp[j] = (ANC != SB_ANC_NONE && (!TAIL || base + j < N)) ? sb_pool_x<int, PEERS>(a.pool, anc[j]) : 0;
+    }
     // (3) propagate: one Philox call per FOUR particles, one 32-bit uniform per particle.
     // u = R * 2^-32 < cum[k]  <=>  R < ceil(cum[k] * 2^32): integer compares against the table.
     // src/rand.jl:6-12 on a monotone row: first k with R < thr[k], else K-1.  The lookup word of R's
@@ -890,9 +899,16 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         if (ANC != SB_ANC_PULL) __syncthreads();                 // the pull has its own barriers
         if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
         REAL xpar[SB_ITEMS];
+        if (PEERS && base + SB_ITEMS <= N && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
+            const int g = anc[0] >> a.pool.log2n;               // ascending parents: all eight on GPU g
+            const REAL* xg = reinterpret_cast<const REAL*>(a.pool.base[g] + a.pool.off_x) - ((size_t)g << a.pool.log2n);
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j)
-            xpar[j] = (ANC != SB_ANC_NONE && base + j < N) ? sb_pool_x<REAL, PEERS>(a.pool, anc[j]) : (REAL)0;
+            for (int j = 0; j < SB_ITEMS; ++j) xpar[j] = __ldg(xg + anc[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j)
+                xpar[j] = (ANC != SB_ANC_NONE && base + j < N) ? sb_pool_x<REAL, PEERS>(a.pool, anc[j]) : (REAL)0;
+        }
         REAL x[SB_ITEMS];
         REAL l2[SB_ITEMS];
         REAL mx = -INFINITY;
