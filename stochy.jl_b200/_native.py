@@ -12,7 +12,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
-LIB_PATH = os.path.join(_PKG, "libstochy_b200.so")
+LIB_PATH = os.environ.get("STOCHY_B200_LIB") or os.path.join(_PKG, "libstochy_b200.so")   # same override as the Julia shim
 SOURCES = ["stochy_b200.cu"]
 HEADERS = ["sb_device.cuh", "sb_kernels.cuh"]
 

@@ -99,6 +99,23 @@ __device__ __forceinline__ SbU4 sb_philox(uint32_t c0, uint32_t c1, uint32_t c2,
     }
     return SbU4{c0, c1, c2, c3};
 }
+// Same function with the ten round keys precomputed on the host (kernel parameters are constant-bank
+// operands: the key schedule costs no instruction in the hot loop).
+struct SbRoundKeys { uint32_t k[20]; };
+__device__ __forceinline__ SbU4 sb_philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const SbRoundKeys& rk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ rk.k[2 * r];
+        uint32_t n2 = h0 ^ c3 ^ rk.k[2 * r + 1];
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    }
+    return SbU4{c0, c1, c2, c3};
+}
+__device__ __forceinline__ SbU4 sb_stream4_rk(const SbRoundKeys& rk, unsigned long long idx, uint32_t t, uint32_t iter, uint32_t purpose) {
+    return sb_philox_rk((uint32_t)idx, (uint32_t)(idx >> 32), t, (iter << 4) | purpose, rk);
+}
 __device__ __forceinline__ SbU4 sb_stream4(unsigned long long seed, unsigned long long idx, uint32_t t,
                                            uint32_t iter, uint32_t purpose) {
     return sb_philox((uint32_t)idx, (uint32_t)(idx >> 32), t, (iter << 4) | purpose,

@@ -603,6 +603,9 @@ k_lse_final(const SbLse* __restrict__ partial, int np, double* __restrict__ out)
 
 #define SB_LG_BUCKETS 8     // inverse-CDF lookup: 256 buckets per transition row
 #define SB_KEY_BIAS (1 << 24)
+#ifndef SB_ABLATE
+#define SB_ABLATE 0            // diagnostics only: 1 = no Philox, 2 = no gather, 3 = no pull (identity ancestors)
+#endif
 
 struct SbHmmStepArgs {
     // previous pool
@@ -634,6 +637,7 @@ struct SbHmmStepArgs {
     int K, rows, t;
     unsigned iter;
     unsigned long long seed;
+    SbRoundKeys rk;             // Philox round keys of `seed`
     unsigned* err;
 };
 
@@ -655,12 +659,18 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     // (1) ancestors
     int anc[SB_ITEMS];
     if (ANC == SB_ANC_PULL) {
+#if SB_ABLATE == 3
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;
+        __syncthreads();
+#else
         const int kk = k % SB_FT_CHUNK;
         const int2 rng = sm.ps.ft[kk];
         const bool more = tile + (int)gridDim.x < a.ntiles;
         const int nb = sm.ps.ft[kk + 1].x;
         if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
         else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
+#endif
     } else if (ANC == SB_ANC_EXPLICIT) {
         if (!TAIL) {
             const int4 u = __ldg(reinterpret_cast<const int4*>(a.anc_in + lbase));
@@ -689,6 +699,12 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     }
     // (2) gather parents
     int xp[SB_ITEMS];
+#if SB_ABLATE == 2
+    if (ANC == SB_ANC_PULL && !TAIL) {
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) xp[j] = anc[j] & 15;
+    } else
+#endif
     if (PEERS && !TAIL && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
         // the pull returns parents in ascending order: first and last on the same GPU means all eight are,
         // and one base pointer serves them (the usual case; only shard boundaries take the general path)
@@ -709,7 +725,12 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     int x[SB_ITEMS];
 #pragma unroll
     for (int p = 0; p < SB_ITEMS / 4; ++p) {
-        const SbU4 o = sb_stream4(a.seed, (unsigned long long)((base >> 2) + p), (unsigned)a.t, a.iter, SB_P_PROP);
+#if SB_ABLATE == 1
+        const uint32_t hh = (uint32_t)((base >> 2) + p) * 2654435761u + a.t;
+        const SbU4 o = SbU4{hh, hh * 3u, hh * 5u, hh * 7u};
+#else
+        const SbU4 o = sb_stream4_rk(a.rk, (unsigned long long)((base >> 2) + p), (unsigned)a.t, a.iter, SB_P_PROP);
+#endif
         const uint32_t r4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -820,7 +841,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     __syncthreads();                                              // tables staged
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
-        if (ANC == SB_ANC_PULL && (k % SB_FT_CHUNK) == 0)
+        if (ANC == SB_ANC_PULL && (k % SB_FT_CHUNK) == 0 && SB_ABLATE != 3)
             sb_pull_ranges<PEERS>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, tile, a.ntiles, k == 0, sm.ps);
         const bool tail = a.pool.c_off + (tile + 1) * SB_TILE > a.N;   // only the last tile(s) see padding / the retained slot
         if (!tail) sb_hmm_tile<ANC, FP32, PEERS, MULTI, false>(a, si, tile, k, sm, s_thr, s_key, s_qtab, s_tab);
@@ -854,6 +875,7 @@ struct SbLgStepArgs {
     int t;
     unsigned iter;
     unsigned long long seed;
+    SbRoundKeys rk;             // Philox round keys of `seed`
     double a, sq, sp, c, r, m0, y, lc;   // sq = sqrt(q), sp = sqrt(P0), lc = -0.5 log(2 pi r)
     unsigned* err;
 };
@@ -918,7 +940,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             const float hr = -0.5f / (float)a.r, flc = (float)a.lc, fm0 = (float)a.m0;
 #pragma unroll
             for (int p = 0; p < SB_ITEMS / 2; ++p) {
-                const SbU4 o = sb_stream4(a.seed, (unsigned long long)((base >> 1) + p), (unsigned)a.t, a.iter, SB_P_PROP);
+                const SbU4 o = sb_stream4_rk(a.rk, (unsigned long long)((base >> 1) + p), (unsigned)a.t, a.iter, SB_P_PROP);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int j = 2 * p + h;
@@ -941,7 +963,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         } else {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) {
-                const SbU4 o = sb_stream4(a.seed, (unsigned long long)(base + j), (unsigned)a.t, a.iter, SB_P_PROP);
+                const SbU4 o = sb_stream4_rk(a.rk, (unsigned long long)(base + j), (unsigned)a.t, a.iter, SB_P_PROP);
                 const double u1 = sb_u53(o.x, o.y), u2 = sb_u53(o.z, o.w);
                 const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(SB_TWO_PI * u2);
                 double xv;

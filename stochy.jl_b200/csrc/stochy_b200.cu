@@ -191,6 +191,13 @@ uint64_t host_r53(uint64_t seed, uint64_t idx, uint32_t t, uint32_t iter, uint32
     return ((uint64_t)o[0] << 21) | (uint64_t)(o[1] >> 11);
 }
 
+SbRoundKeys round_keys(uint64_t seed) {
+    SbRoundKeys rk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk.k[2 * r] = k0; rk.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return rk;
+}
+
 // log(mean weight) of a pool from its tile-scan record: the log-evidence increment (SURVEY D3 extension)
 double log_mean_weight(const SbStepInfo& si) {
     return log((double)si.total) + (double)(si.E - SB_QBITS - si.LS) * SB_LN2 - log((double)si.n);
@@ -241,6 +248,10 @@ int resident_ctas(sb_handle* h, Kern kern, size_t smem, int* out) {
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SB_THREADS, smem));
         if (nb < 1) return fail(h, SB_ECUDA, "step kernel does not fit on an SM");
+        if (const char* ov = getenv("SB_CTAS_PER_SM")) {             // tuning knob: fewer resident CTAs than fit
+            const int want = atoi(ov);
+            if (want >= 1 && want < nb) nb = want;
+        }
         it = h->occ.emplace(key, nb * h->num_sms).first;
     }
     *out = it->second;
@@ -806,7 +817,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.logF_t = h->hmm_logF.as<double>() + (size_t)t * K;
         a.expF_t = h->hmm_expF.as<double>() + (size_t)t * K;
         a.xstar = conditional ? h->xstar[h->xstar_cur].as<int>() : nullptr;
-        a.N = N; a.n_out = n_out; a.ntiles = ntiles; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.err = h->d_err;
+        a.N = N; a.n_out = n_out; a.ntiles = ntiles; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed); a.err = h->d_err;
         {
             ProfScope ps(h, t ? t : -1);                               // t = 0 has no resample/gather: not sampled
             rc = launch_step_hmm(h, anc_mode, a);
@@ -878,7 +889,7 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         a.sig = make_signal(h);
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
-        a.N = N; a.ntiles = ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed;
+        a.N = N; a.ntiles = ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed);
         a.a = h->lg_a; a.sq = sqrt(h->lg_q); a.sp = sqrt(h->lg_P0); a.c = h->lg_c; a.r = h->lg_r; a.m0 = h->lg_m0;
         a.y = h->lg_y[t]; a.lc = -0.5 * log(SB_TWO_PI * h->lg_r);
         a.err = h->d_err;
