@@ -301,8 +301,10 @@ int launch_tilescan_k(sb_handle* h, int ctas, const int* e, const unsigned long 
 template <bool PEERS>
 int launch_tilescan_t(sb_handle* h, const int* e, const unsigned long long* Q, int nt, int64_t n, int64_t m,
                       const unsigned long long* d_r53, SbStepInfo* info, int want_exact, const SbScanPeers& sp) {
-    // one cluster: 8 CTAs (portable) up to 4 tiles per thread, 16 CTAs beyond that when the device takes them
-    int ctas = SB_SCAN_CTAS;
+    // one cluster: as many CTAs as give one tile per thread (1, 2, 4 or 8: small pools skip the cluster barriers'
+    // cross-SM latency), 8 CTAs (portable) up to 4 tiles per thread, 16 CTAs beyond that when the device takes them
+    int ctas = 1;
+    while (ctas < SB_SCAN_CTAS && nt > ctas * SB_SCAN_THREADS) ctas *= 2;
     if (nt > SB_SCAN_CTAS * SB_SCAN_THREADS * 4 && h->scan16 != 0) {
         if (h->scan16 < 0) {                                         // probe once
             auto kern = k_tilescan<4, PEERS>;
