@@ -567,11 +567,14 @@ __device__ __forceinline__ void sb_signal_done(const SbSignal& sg) {
     if (!sg.counter) return;                                     // not sharded
     __syncthreads();                                             // the CTA's writes are ordered before thread 0's fence
     if (threadIdx.x == 0) {
-        __threadfence_system();                                  // cumulative over the barrier: visible to every GPU
+        // device scope is enough here: peers read THIS GPU's memory through this GPU's L2.  The one
+        // system-scope fence is the last CTA's, between everybody's writes (observed through the counter)
+        // and the flag stores that leave the GPU.
+        __threadfence();
         const unsigned done = atomicAdd(sg.counter, 1u) + 1u;
         if (done == gridDim.x) {
             *sg.counter = 0u;                                    // next launch
-            __threadfence_system();                              // cumulative: every CTA's writes precede the flags
+            __threadfence_system();
             for (int p = 0; p < sg.world; ++p)
                 *(reinterpret_cast<volatile unsigned*>(sg.base[p] + sg.off_flags) + sg.self) = sg.epoch;
         }

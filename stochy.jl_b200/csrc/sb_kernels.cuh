@@ -709,9 +709,10 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         // the pull returns parents in ascending order: first and last on the same GPU means all eight are,
         // and one base pointer serves them (the usual case; only shard boundaries take the general path)
         const int g = anc[0] >> a.pool.log2n;
-        const int* xg = reinterpret_cast<const int*>(a.pool.base[g] + a.pool.off_x) - ((size_t)g << a.pool.log2n);
+        const int* xg = reinterpret_cast<const int*>(a.pool.base[g] + a.pool.off_x);
+        const unsigned lmask = (1u << a.pool.log2n) - 1u;
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) xp[j] = __ldg(xg + anc[j]);
+        for (int j = 0; j < SB_ITEMS; ++j) xp[j] = __ldg(xg + ((unsigned)anc[j] & lmask));
     } else {
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j)
@@ -795,7 +796,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
 }
 
 template <int ANC, bool FP32, bool PEERS, bool MULTI>
-__global__ void __launch_bounds__(SB_THREADS)
+__global__ void __launch_bounds__(SB_THREADS, 5)                  // 5 resident CTAs per SM: at most 48 registers
 k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     extern __shared__ __align__(16) unsigned char dyn[];
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(dyn);             // rows * 256 (16-byte aligned: staged as uint4)
@@ -923,9 +924,10 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         REAL xpar[SB_ITEMS];
         if (PEERS && base + SB_ITEMS <= N && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
             const int g = anc[0] >> a.pool.log2n;               // ascending parents: all eight on GPU g
-            const REAL* xg = reinterpret_cast<const REAL*>(a.pool.base[g] + a.pool.off_x) - ((size_t)g << a.pool.log2n);
+            const REAL* xg = reinterpret_cast<const REAL*>(a.pool.base[g] + a.pool.off_x);
+            const unsigned lmask = (1u << a.pool.log2n) - 1u;
 #pragma unroll
-            for (int j = 0; j < SB_ITEMS; ++j) xpar[j] = __ldg(xg + anc[j]);
+            for (int j = 0; j < SB_ITEMS; ++j) xpar[j] = __ldg(xg + ((unsigned)anc[j] & lmask));
         } else {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j)
