@@ -278,6 +278,14 @@ __device__ __forceinline__ void sb_store8_u32(uint32_t* p, const uint32_t v[8]) 
     reinterpret_cast<uint4*>(p)[1] = make_uint4(v[4], v[5], v[6], v[7]);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The kernels of a sweep alternate step -> scan -> step -> ...  Each is launched with programmatic stream
+// serialisation: it may become resident and run its prologue (stage model tables, build the weight table)
+// while its predecessor is still running, and calls sb_grid_dep_wait() before it touches anything the
+// predecessor wrote.  Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void sb_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void sb_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- asynchronous copies (TMA bulk, cp.async) and mbarrier
 __device__ __forceinline__ uint32_t sb_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sb_mbar_init(unsigned long long* bar, int count) {

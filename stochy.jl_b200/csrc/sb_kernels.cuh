@@ -234,8 +234,10 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     const unsigned rank = cl.block_rank();
     const int nthreads = SB_SCAN_THREADS * (int)cl.num_blocks();
     const int gtid = (int)rank * SB_SCAN_THREADS + threadIdx.x;
+    sb_grid_dep_launch();                                     // the next step kernel may start its prologue
     const unsigned long long R53 = __ldg(r53_ptr);            // host-drawn systematic offset (53-bit uniform)
     const int per = PER > 0 ? PER : (nt + nthreads - 1) / nthreads;
+    sb_grid_dep_wait();                                       // the pool's tile records are complete
     const int b0 = min(nt, gtid * per), b1 = min(nt, b0 + per);
     if (PEERS) {
         // every peer has finished the step kernel that produced this pool (and therefore also every
@@ -799,6 +801,7 @@ template <int ANC, bool FP32, bool PEERS, bool MULTI>
 __global__ void __launch_bounds__(SB_THREADS, 5)                  // 5 resident CTAs per SM: at most 48 registers
 k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     extern __shared__ __align__(16) unsigned char dyn[];
+    sb_grid_dep_launch();                                           // the scan that follows may be scheduled as SMs drain
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(dyn);             // rows * 256 (16-byte aligned: staged as uint4)
     double* s_l2 = reinterpret_cast<double*>(s_tab + (a.rows << SB_LG_BUCKETS));   // K   (float view when FP32)
     uint32_t* s_thr = reinterpret_cast<uint32_t*>(s_l2 + a.K);      // rows*K
@@ -834,6 +837,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         if (key) q = FP32 ? sb_q31_f32(__fsub_rn(reinterpret_cast<float*>(s_l2)[kx], (float)e)) : sb_q31_f64(__dsub_rn(s_l2[kx], (double)e));
         s_qtab[i] = q;
     }
+    sb_grid_dep_wait();                                           // everything above overlapped the previous scan
     SbStepInfo si;
     if (ANC == SB_ANC_PULL) {
         si = *a.info_prev;
@@ -890,6 +894,8 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     __shared__ SbHmmSmem sm;
     const int tid = threadIdx.x;
     const int N = (int)a.N;
+    sb_grid_dep_launch();
+    sb_grid_dep_wait();
     SbStepInfo si;
     if (ANC == SB_ANC_PULL) {
         si = *a.info_prev;

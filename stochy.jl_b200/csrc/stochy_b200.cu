@@ -63,6 +63,7 @@ struct sb_handle {
     size_t off_w32[2] = {0, 0}, off_x[2] = {0, 0}, off_wp[2] = {0, 0}, off_e[2] = {0, 0}, off_Q[2] = {0, 0}, off_flags = 0;
     char* peer_base[SB_MAX_PEERS] = {nullptr};
     unsigned epoch = 0;
+    int pdl = 1;                      // programmatic dependent launch between the kernels of a sweep (SB_NO_PDL=1 disables)
     int scan16 = -1;                  // 16-CTA scan cluster: -1 not probed, 0 unavailable, 1 available
     int* d_emax = nullptr;            // running max of the tile exponents of the pool in production (single GPU)
     DevBuf e_all;
@@ -287,10 +288,12 @@ int launch_tilescan_k(sb_handle* h, int ctas, const int* e, const unsigned long 
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas); cfg.blockDim = dim3(SB_SCAN_THREADS); cfg.stream = h->stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // may be scheduled while the step kernel drains
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl ? 2 : 1;
     long long nn = n, mm = m;
     CK(cudaLaunchKernelEx(&cfg, kern, e, Q, nt, nn, mm, d_r53, info, h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
                           h->child_start.as<int>(), h->first_tile.as<int>(), want_exact, h->d_err, h->d_emax, sp));
@@ -479,6 +482,7 @@ extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
         const int empty = SB_E_EMPTY;
         cudaMemcpy(h->d_emax, &empty, sizeof(int), cudaMemcpyHostToDevice);
     }
+    if (const char* np = getenv("SB_NO_PDL")) h->pdl = atoi(np) ? 0 : 1;
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, opt.device) != cudaSuccess || h->num_sms < 1)
         h->num_sms = 148;
     *out = h;
@@ -671,6 +675,21 @@ extern "C" int32_t sb_model_bayesnet(sb_handle* h, int32_t D, int32_t F, const u
 // ======================================================================= sweeps
 namespace {
 
+// A step kernel that pulls from the pool of the previous step follows that pool's tile scan in the stream:
+// launched with programmatic stream serialisation its prologue overlaps the scan (see sb_grid_dep_wait).
+template <typename Kern, typename Args>
+int launch_step(sb_handle* h, Kern kern, unsigned grid, size_t smem, bool after_scan, const Args& a) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SB_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (after_scan && h->pdl) ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kern, a));
+    return SB_OK;
+}
+
 template <bool FP32, bool MULTI>
 int launch_step_hmm_m(sb_handle* h, int anc_mode, const SbHmmStepArgs& a) {
     const size_t smem = ((size_t)a.rows << SB_LG_BUCKETS) * 4 + (size_t)a.K * 8 + (size_t)(a.rows * a.K + a.K + a.K * a.K) * 4;
@@ -679,7 +698,7 @@ int launch_step_hmm_m(sb_handle* h, int anc_mode, const SbHmmStepArgs& a) {
     do {                                                                                       \
         auto kern = k_step_hmm<ANC, FP32, PEERS, MULTI>;                                       \
         if ((rc = resident_ctas(h, kern, smem, &cap)) != SB_OK) return rc;                     \
-        kern<<<(unsigned)(a.ntiles < cap ? a.ntiles : cap), SB_THREADS, smem, h->stream>>>(a); \
+        if ((rc = launch_step(h, kern, (unsigned)(a.ntiles < cap ? a.ntiles : cap), smem, ANC == SB_ANC_PULL, a)) != SB_OK) return rc; \
     } while (0)
     if (h->dist_ready) {
         if (anc_mode == SB_ANC_NONE) SB_HMM_LAUNCH(SB_ANC_NONE, false);
@@ -710,7 +729,7 @@ int launch_step_lg(sb_handle* h, int anc_mode, const SbLgStepArgs& a) {
     do {                                                                                       \
         auto kern = k_step_lg<ANC, FP32, PEERS>;                                               \
         if ((rc = resident_ctas(h, kern, 0, &cap)) != SB_OK) return rc;                        \
-        kern<<<(unsigned)(a.ntiles < cap ? a.ntiles : cap), SB_THREADS, 0, h->stream>>>(a);    \
+        if ((rc = launch_step(h, kern, (unsigned)(a.ntiles < cap ? a.ntiles : cap), 0, ANC == SB_ANC_PULL, a)) != SB_OK) return rc; \
     } while (0)
     if (h->dist_ready) {
         if (anc_mode == SB_ANC_NONE) SB_LG_LAUNCH(SB_ANC_NONE, false);
