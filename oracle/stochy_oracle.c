@@ -586,18 +586,23 @@ int or_hmm_pmcmc(const or_hmm* m, const or_opts* o, int64_t iters, int64_t N,
 /* textbook Box-Muller and closed-form logpdf; parity unpinned.        */
 /* ------------------------------------------------------------------ */
 #define TWO_PI 6.283185307179586476925286766559
+/* Box-Muller, both branches used: particles 2q and 2q+1 share (u1, u2) and take r cos(theta), r sin(theta).
+ * fp64: one Philox block per pair (two 53-bit uniforms); fp32: one block per FOUR particles (four 24-bit
+ * uniforms).  Distributions.jl 0.6.3's rand(Normal) is not in the reference tree: stream unpinned. */
 static inline double normal_f64(uint64_t seed, uint64_t i, uint32_t t, uint32_t iter) {
     uint32_t o[4];
-    stream4(seed, i, t, iter, P_PROP, o);
+    stream4(seed, i >> 1, t, iter, P_PROP, o);
     double u1 = u53_from(o[0], o[1]), u2 = u53_from(o[2], o[3]);
-    return sqrt(-2.0 * log(1.0 - u1)) * cos(TWO_PI * u2);
+    double r = sqrt(-2.0 * log(1.0 - u1));
+    return (i & 1) ? r * sin(TWO_PI * u2) : r * cos(TWO_PI * u2);
 }
 static inline float normal_f32(uint64_t seed, uint64_t i, uint32_t t, uint32_t iter) {
     uint32_t o[4];
-    stream4(seed, i >> 1, t, iter, P_PROP, o);
-    int w = (int)(i & 1) * 2;
+    stream4(seed, i >> 2, t, iter, P_PROP, o);
+    int w = (int)((i >> 1) & 1) * 2;
     float u1 = (float)(o[w] >> 8) * 0x1p-24f, u2 = (float)(o[w + 1] >> 8) * 0x1p-24f;
-    return sqrtf(-2.0f * logf(1.0f - u1)) * cosf((float)TWO_PI * u2);
+    float r = sqrtf(-2.0f * logf(1.0f - u1));
+    return (i & 1) ? r * sinf((float)TWO_PI * u2) : r * cosf((float)TWO_PI * u2);
 }
 
 void or_lg_step(const or_lg* m, const or_opts* o, int64_t N, uint32_t t, uint32_t iter,

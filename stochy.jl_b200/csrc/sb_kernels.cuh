@@ -946,37 +946,51 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         if (FP32) {
             const float fa = (float)a.a, fsq = (float)a.sq, fsp = (float)a.sp, fc = (float)a.c, fy = (float)a.y;
             const float hr = -0.5f / (float)a.r, flc = (float)a.lc, fm0 = (float)a.m0;
+            // Box-Muller with both branches: one Philox block per FOUR particles (two pairs)
+            float z[SB_ITEMS];
+#pragma unroll
+            for (int p = 0; p < SB_ITEMS / 4; ++p) {
+                const SbU4 o = sb_stream4_rk(a.rk, (unsigned long long)((base >> 2) + p), (unsigned)a.t, a.iter, SB_P_PROP);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float u1 = (float)((h ? o.z : o.x) >> 8) * 0x1p-24f;
+                    const float u2 = (float)((h ? o.w : o.y) >> 8) * 0x1p-24f;
+                    const float r = sqrtf(-2.0f * logf(1.0f - u1));
+                    float sn, cs;
+                    sincospif(2.0f * u2, &sn, &cs);
+                    z[4 * p + 2 * h] = r * cs; z[4 * p + 2 * h + 1] = r * sn;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) {
+                float xv;
+                if (ANC == SB_ANC_NONE) xv = fm0 + fsp * z[j];
+                else xv = fa * (float)xpar[j] + fsq * z[j];
+                const float d = fy - fc * xv;
+                const float lw = hr * d * d + flc;
+                const bool live = base + j < N;
+                float v = live ? __fmul_rn(lw, SB_LOG2E_F) : -INFINITY;
+                if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
+                x[j] = (REAL)xv; l2[j] = (REAL)v;
+                mx = (REAL)fmaxf((float)mx, v);
+                if (a.lw_out && live) a.lw_out[lbase + j] = (double)lw;
+            }
+        } else {
+            double z[SB_ITEMS];
 #pragma unroll
             for (int p = 0; p < SB_ITEMS / 2; ++p) {
                 const SbU4 o = sb_stream4_rk(a.rk, (unsigned long long)((base >> 1) + p), (unsigned)a.t, a.iter, SB_P_PROP);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int j = 2 * p + h;
-                    const float u1 = (float)((h ? o.z : o.x) >> 8) * 0x1p-24f;
-                    const float u2 = (float)((h ? o.w : o.y) >> 8) * 0x1p-24f;
-                    const float z = sqrtf(-2.0f * logf(1.0f - u1)) * cosf((float)SB_TWO_PI * u2);
-                    float xv;
-                    if (ANC == SB_ANC_NONE) xv = fm0 + fsp * z;
-                    else xv = fa * (float)xpar[j] + fsq * z;
-                    const float d = fy - fc * xv;
-                    const float lw = hr * d * d + flc;
-                    const bool live = base + j < N;
-                    float v = live ? __fmul_rn(lw, SB_LOG2E_F) : -INFINITY;
-                    if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
-                    x[j] = (REAL)xv; l2[j] = (REAL)v;
-                    mx = (REAL)fmaxf((float)mx, v);
-                    if (a.lw_out && live) a.lw_out[lbase + j] = (double)lw;
-                }
+                const double u1 = sb_u53(o.x, o.y), u2 = sb_u53(o.z, o.w);
+                const double r = sqrt(-2.0 * log(1.0 - u1));
+                double sn, cs;
+                sincospi(2.0 * u2, &sn, &cs);
+                z[2 * p] = r * cs; z[2 * p + 1] = r * sn;
             }
-        } else {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) {
-                const SbU4 o = sb_stream4_rk(a.rk, (unsigned long long)(base + j), (unsigned)a.t, a.iter, SB_P_PROP);
-                const double u1 = sb_u53(o.x, o.y), u2 = sb_u53(o.z, o.w);
-                const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(SB_TWO_PI * u2);
                 double xv;
-                if (ANC == SB_ANC_NONE) xv = a.m0 + a.sp * z;
-                else xv = a.a * (double)xpar[j] + a.sq * z;
+                if (ANC == SB_ANC_NONE) xv = a.m0 + a.sp * z[j];
+                else xv = a.a * (double)xpar[j] + a.sq * z[j];
                 const double d = a.y - a.c * xv;
                 const double lw = -0.5 * d * d / a.r + a.lc;
                 const bool live = base + j < N;
