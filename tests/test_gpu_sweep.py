@@ -268,3 +268,55 @@ def test_erp_vocabulary():
         assert np.allclose(eng.erp_logpdf(nat.ERP_FLIP, [0.7], np.array([0.0, 1.0])), [np.log1p(-0.7), np.log(0.7)])
         xs = dsamp[:1000]
         assert np.allclose(eng.dirichlet_logpdf(alpha, xs), [stats.dirichlet.logpdf(v / v.sum(), alpha) for v in xs], rtol=1e-9, atol=1e-9)
+
+
+def test_full_size_sweep_properties(oracle, enumref):
+    """BASELINE size (2^24 particles): size-independent properties of a whole sweep.
+    (a) every ancestor row is sorted, in range, and its offspring counts are within one of N p_i
+        computed from that step's states; (b) the log-evidence is within 0.02 of the forward algorithm;
+    (c) the final particle set equals the one of a second handle with the same seed (determinism) and
+        differs under another seed; (d) the oracle agrees bit for bit at 2^20 (it finishes in seconds there)."""
+    sb = sb_mod()
+    T, N = 6, 1 << 24
+    A, logF, pi = cfg3_tables(T=T)
+    exact, _ = enumref.hmm_forward(A, logF, pi=pi)
+    with sb.Engine(precision="fp32", resample="systematic", seed=5) as eng:
+        eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+        lz = eng.smc_sweep(N, it=0, history=True)
+        assert abs(lz - exact) < 0.02, (lz, exact)
+        for t in range(T):
+            x, a, _ = eng.history(t, N)
+            assert x.min() >= 0 and x.max() < 16
+            assert a.min() >= 0 and a.max() < N and np.all(np.diff(a) >= 0)
+            w = np.exp(logF[t])[x]
+            cnt = np.bincount(a, minlength=N)
+            assert np.all(np.abs(cnt - N * w / w.sum()) < 1.0 + 1e-2), "offspring counts off at step %d" % t
+        xa = eng.particles(N)
+    with sb.Engine(precision="fp32", resample="systematic", seed=5) as e2:
+        e2.load(sb.DiscreteHMM(A, logF, pi=pi))
+        assert e2.smc_sweep(N, it=0) == lz
+        assert np.array_equal(e2.particles(N), xa)
+    with sb.Engine(precision="fp32", resample="systematic", seed=6) as e3:
+        e3.load(sb.DiscreteHMM(A, logF, pi=pi))
+        e3.smc_sweep(N, it=0)
+        assert not np.array_equal(e3.particles(N), xa)
+    M = 1 << 20
+    with sb.Engine(precision="fp32", resample="systematic", seed=5) as e4:
+        e4.load(sb.DiscreteHMM(A, logF, pi=pi))
+        lz4 = e4.smc_sweep(M, it=0)
+        ref = oracle.hmm_sweep(oracle.Hmm(A, logF, pi=pi), oracle.opts(oracle.SYSTEMATIC, fp32=True, seed=5), M)
+        assert np.array_equal(e4.particles(M), ref["x"][T - 1, :M])
+        assert lz4 == pytest.approx(ref["logZ"], rel=1e-9)
+
+
+def test_full_size_lg_vs_kalman(enumref):
+    """BASELINE config 4 at full particle count (2^24, reduced T): log-evidence against the Kalman filter.
+    At this N the Monte-Carlo error is ~1e-3 per sweep; fp32 weights add a rounding floor."""
+    sb = sb_mod()
+    d = cfg4_data(T=50)
+    exact, _ = enumref.kalman_loglik(d["a"], d["q"], d["c"], d["r"], d["m0"], d["P0"], d["y"])
+    for prec, tol in [("fp32", 2e-2), ("fp64", 1e-2)]:
+        with sb.Engine(precision=prec, seed=77) as eng:
+            eng.load(sb.LinearGaussian(**d))
+            lz = eng.smc_sweep(1 << 24)
+        assert abs(lz - exact) < tol, (prec, lz, exact)
