@@ -293,7 +293,7 @@ int launch_tilescan_k(sb_handle* h, int ctas, const int* e, const unsigned long 
     at[0].val.clusterDim.x = (unsigned)ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // may be scheduled while the step kernel drains
     at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = h->pdl ? 2 : 1;
+    cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->dist_ready) ? 2 : 1;     // measured: the overlap loses 7 us per step on sharded pools
     long long nn = n, mm = m;
     CK(cudaLaunchKernelEx(&cfg, kern, e, Q, nt, nn, mm, d_r53, info, h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
                           h->child_start.as<int>(), h->first_tile.as<int>(), want_exact, h->d_err, h->d_emax, sp));
@@ -685,7 +685,7 @@ int launch_step(sb_handle* h, Kern kern, unsigned grid, size_t smem, bool after_
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = (after_scan && h->pdl) ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = (after_scan && h->pdl && !h->dist_ready) ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kern, a));
     return SB_OK;
 }
