@@ -14,6 +14,7 @@
  *   sb_pmcmc_run        <- pmcmc(store,k,address,comp,numiterations,numparticles)  src/pmcmc.jl:78-99
  *   sb_smc_sweep        <- smc(store,k,a,comp,n) = pmcmc(...,1,n)                  src/pmcmc.jl:101-103
  *   sb_mh_run           <- mh(store,k,address,comp,numsteps)                       src/mh.jl:47-93
+ *   sb_enum_hmm         <- enum(store,k,address,comp) for the discrete descriptor  src/enumerate.jl:57-85
  *   sb_model_*          <- the @pp model closure `comp` restricted to fixed per-step structure
  *                          (examples/hmm.jl:4-25, examples/hmm2.jl:5-16); sample/factor/observe
  *                          dispatch src/Stochy.jl:47-56, src/pmcmc.jl:32-46
@@ -133,6 +134,13 @@ int32_t sb_smc_sweep(sb_handle* h, int64_t N, uint32_t iter, int32_t store_histo
  * (src/pmcmc.jl:90-92).  joint uses little-endian base-K codes (digit t = x_t) and needs K^T <= 2^26. */
 int32_t sb_pmcmc_run(sb_handle* h, int64_t numiterations, int64_t numparticles,
                      int64_t* marg, int64_t* joint);
+
+/* enum(comp) for the discrete model (src/enumerate.jl:57-85): exhaustive exploration.
+ * joint[K^T] (or NULL): UNNORMALISED mass exp(score) of every complete execution path, little-endian base-K
+ * trajectory codes -- the `returns` dictionary of enumerate.jl:66-72 before Discrete() normalises it; needs
+ * K^T <= 2^26.  marg[T*K] (or NULL): the same posterior marginalised per time step, computed exactly in
+ * O(T K^2) by forward-backward, for any T.  out_logZ = log of the total mass.  All-zero mass -> SB_EZEROMASS. */
+int32_t sb_enum_hmm(sb_handle* h, double* joint, double* marg, double* out_logZ);
 
 /* mh(comp, numsteps) batched: `chains` independent chains (global ids chain0..), counts[2^|query|]
  * is ADDED to with the value after every step of every chain (src/mh.jl:87). */

@@ -16,7 +16,7 @@
 # and the native handle is destroyed in a `finally` block (the reference restores `ctx` there).
 module StochyB200
 
-export DiscreteHMM, LinearGaussian, BayesNet, pmcmc, smc, mh, smc_logevidence, hmm2_example
+export DiscreteHMM, LinearGaussian, BayesNet, pmcmc, smc, mh, enum, smc_logevidence, hmm2_example
 
 const LIB = get(ENV, "STOCHY_B200_LIB", "libstochy_b200")
 
@@ -170,6 +170,29 @@ function smc_logevidence(comp::Model, n; iter=0, precision=SB_FP32, resample=SB_
     finally
         destroy(h)
     end
+end
+
+# ---- enum(store, k, address, comp)   (src/enumerate.jl:57-85): exhaustive, exact.  returns[value] += exp(score)
+function enum(store, k::Function, address, comp; kw...)
+    comp isa DiscreteHMM || error("enum: only the fixed-structure discrete model is enumerated on the GPU path")
+    h = create(; precision=SB_FP64, kw...)
+    returns = try
+        load!(h, comp)
+        K, T = size(comp.A, 1), size(comp.logF, 1)
+        joint = zeros(Float64, K^T)
+        lz = Ref{Float64}(0.0)
+        check(h, ccall((:sb_enum_hmm, LIB), Int32, (Handle, Ptr{Float64}, Ptr{Float64}, Ref{Float64}), h, joint, C_NULL, lz))
+        out = Dict{Any,Float64}()
+        for code in findall(!iszero, joint)
+            c = code - 1
+            v = comp.value(ntuple(t -> (c ÷ K^(t - 1)) % K + 1, T))
+            out[v] = get(out, v, 0.0) + joint[code]
+        end
+        out
+    finally
+        destroy(h)
+    end
+    k(store, discrete(returns))
 end
 
 # ---- mh(store, k, address, comp, numsteps=10)   (src/mh.jl:47-93), batched over `chains`

@@ -275,6 +275,16 @@ class Engine:
         self._chk(nat.lib().sb_pmcmc_run(self.h, iters, N, _ptr(marg), _ptr(joint)))
         return marg, joint
 
+    def enum_hmm(self, want_joint=True):
+        """Exhaustive enumeration of the loaded discrete model: (unnormalised joint masses or None,
+        exact per-time marginals [T, K], log total mass)."""
+        m = self.model
+        joint = np.zeros(m.K ** m.T, dtype=np.float64) if want_joint else None
+        marg = np.zeros((m.T, m.K), dtype=np.float64)
+        lz = C.c_double(0)
+        self._chk(nat.lib().sb_enum_hmm(self.h, _ptr(joint), _ptr(marg), C.byref(lz)))
+        return joint, marg, lz.value
+
     def mh_counts(self, chains, steps, chain0=0):
         nv = 1 << bin(self.model.query_mask).count("1")
         counts = np.zeros(nv, dtype=np.int64)
@@ -400,6 +410,28 @@ def pmcmc(comp, numiterations, numparticles, **engine_kw):
         return Discrete(_decode_joint(comp, joint))
     finally:
         eng.close()                      # `finally ctx = ctxold` (src/pmcmc.jl:95-97)
+
+
+def enum(comp, **engine_kw):
+    """enum(comp) -> Discrete(returns)   (src/enumerate.jl:57-85): exact posterior over the program's return
+    values by exhaustive exploration, for the fixed-structure discrete descriptor (K^T <= 2^26 paths)."""
+    engine_kw.setdefault("precision", "fp64")
+    eng = Engine(**engine_kw)
+    try:
+        eng.load(comp)
+        if not isinstance(comp, DiscreteHMM):
+            raise StochyError(nat.EUNSUPPORTED, "enum: only the fixed-structure discrete model is enumerated on the GPU path")
+        joint, _, _ = eng.enum_hmm(want_joint=True)
+        K, T = comp.K, comp.T
+        out = {}
+        for code in np.nonzero(joint)[0]:
+            c = int(code)
+            xs = tuple((c // K ** t) % K for t in range(T))
+            v = comp.value(xs) if comp.value else xs
+            out[v] = out.get(v, 0.0) + float(joint[code])             # returns[value] += exp(score)  (enumerate.jl:72)
+        return Discrete(out)
+    finally:
+        eng.close()
 
 
 def smc(comp, n, **engine_kw):

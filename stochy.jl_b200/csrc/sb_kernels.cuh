@@ -1106,6 +1106,76 @@ __global__ void k_fill_identity(int* __restrict__ a, long long n) {
 }
 
 // =====================================================================================
+// Enumerate for the fixed-structure discrete model (src/enumerate.jl:36-85).
+// k_enum_joint: one thread per complete execution path (trajectory code, little-endian base K); the score is
+// accumulated in program order -- sample adds score(e, val) (enumerate.jl:38), factor adds its score (:45) -- and
+// the path contributes exp(score) to its return value (:72).  Exhaustive: K^T <= 2^26 paths.
+// k_forward_backward: the same posterior marginalised per time step in O(T K^2) (scaled forward-backward): what
+// Enumerate would return for the per-time values of a model too long to enumerate.  One CTA, thread k = state k.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+k_enum_joint(const double* __restrict__ logA, const double* __restrict__ logp0, const double* __restrict__ logF,
+             const unsigned char* __restrict__ has_factor, int K, int T, long long ncodes, double* __restrict__ mass) {
+    const long long code = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (code >= ncodes) return;
+    long long c = code;
+    double score = 0.0;
+    int prev = 0;
+    for (int t = 0; t < T; ++t) {
+        const int x = (int)(c % K);
+        c /= K;
+        score += t == 0 ? __ldg(logp0 + x) : __ldg(logA + prev * K + x);       // sample: ctx.score + score(e, val)
+        if (has_factor[t]) score += __ldg(logF + (size_t)t * K + x);            // factor: ctx.score += score
+        prev = x;
+    }
+    mass[code] = exp(score);
+}
+
+__global__ void __launch_bounds__(64)
+k_forward_backward(const double* __restrict__ A, const double* __restrict__ p0, const double* __restrict__ logF,
+                   const unsigned char* __restrict__ has_factor, int K, int T, double* __restrict__ alpha /* [T*K] */,
+                   double* __restrict__ cnorm /* [T] */, double* __restrict__ marg /* [T*K] */, double* __restrict__ logZ) {
+    __shared__ double s_a[64], s_b[64], s_red[64];
+    const int k = threadIdx.x;
+    const bool live = k < K;
+    double lz = 0.0;
+    for (int t = 0; t < T; ++t) {                                   // forward pass, normalised at every step
+        double v = 0.0;
+        if (live) {
+            if (t == 0) v = p0[k];
+            else for (int j = 0; j < K; ++j) v += s_a[j] * __ldg(A + j * K + k);
+            if (has_factor[t]) v *= exp(__ldg(logF + (size_t)t * K + k));
+        }
+        __syncthreads();
+        s_red[k] = v;
+        __syncthreads();
+        double c = 0.0;
+        for (int j = 0; j < K; ++j) c += s_red[j];
+        const double a = c > 0.0 ? v / c : 0.0;
+        if (live) { s_a[k] = a; alpha[(size_t)t * K + k] = a; }
+        if (k == 0) cnorm[t] = c;
+        lz += log(c);
+        __syncthreads();
+    }
+    if (k == 0) *logZ = lz;
+    if (live) { s_b[k] = 1.0; marg[(size_t)(T - 1) * K + k] = alpha[(size_t)(T - 1) * K + k]; }
+    __syncthreads();
+    for (int t = T - 2; t >= 0; --t) {                              // backward pass with the forward normalisers
+        double v = 0.0;
+        if (live) {
+            for (int j = 0; j < K; ++j) {
+                const double f = has_factor[t + 1] ? exp(__ldg(logF + (size_t)(t + 1) * K + j)) : 1.0;
+                v += __ldg(A + k * K + j) * f * s_b[j];
+            }
+            v /= cnorm[t + 1];
+        }
+        __syncthreads();
+        if (live) { s_b[k] = v; marg[(size_t)t * K + k] = alpha[(size_t)t * K + k] * v; }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================
 // Batched single-site MH on a binary Bayes net: one thread = one chain, state in registers,
 // tables in shared memory, warp-aggregated histogram.  Replaces the loop src/mh.jl:61-88 and
 // log_mh_ratio src/mh.jl:95-111 for fixed-structure traces.  Not HBM-bound (INT/FP64 pipes).

@@ -76,7 +76,7 @@ struct sb_handle {
     int K = 0, T = 0, x0 = -1;
     bool hmm_multi = false;           // some lookup bucket holds several thresholds (slow scan needed)
     std::vector<uint8_t> has_factor;
-    DevBuf hmm_cumA, hmm_cumpi, hmm_tabA, hmm_tabpi, hmm_logF, hmm_expF, hmm_hasf;
+    DevBuf hmm_cumA, hmm_cumpi, hmm_tabA, hmm_tabpi, hmm_logF, hmm_expF, hmm_hasf, hmm_A, hmm_p0, hmm_logA, hmm_logp0, enum_buf;
     // LG
     double lg_a = 0, lg_q = 0, lg_c = 0, lg_r = 0, lg_m0 = 0, lg_P0 = 0;
     std::vector<double> lg_y;
@@ -494,7 +494,7 @@ extern "C" void sb_destroy(sb_handle* h) {
     cudaSetDevice(h->opt.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->d_r53, &h->d_info, &h->d_misc, &h->w32[0], &h->w32[1], &h->tile_e[0], &h->tile_e[1],
-                      &h->tile_Q[0], &h->tile_Q[1], &h->tile_wp[0], &h->tile_wp[1], &h->e_all, &h->hmm_tabA, &h->hmm_tabpi, &h->P, &h->Pt, &h->child_start, &h->first_tile, &h->cdf, &h->lit_acc, &h->lse_part,
+                      &h->tile_Q[0], &h->tile_Q[1], &h->tile_wp[0], &h->tile_wp[1], &h->e_all, &h->hmm_tabA, &h->hmm_tabpi, &h->hmm_A, &h->hmm_p0, &h->hmm_logA, &h->hmm_logp0, &h->enum_buf, &h->P, &h->Pt, &h->child_start, &h->first_tile, &h->cdf, &h->lit_acc, &h->lse_part,
                       &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
                       &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
                       &h->bn_fp, &h->bn_fac, &h->bn_counts, &h->xbuf, &h->ancbuf, &h->lwbuf, &h->wlit, &h->cnt[0],
@@ -619,6 +619,19 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
     CK(cudaMemcpyAsync(h->hmm_logF.p, logF, (size_t)T * K * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->hmm_expF.p, expF.data(), (size_t)T * K * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->hmm_hasf.p, h->has_factor.data(), (size_t)T, cudaMemcpyHostToDevice, h->stream));
+    {   // probabilities and their logs for Enumerate (score(e, val) = logpdf(Categorical), src/Stochy.jl:8)
+        std::vector<double> p0((size_t)K), lA((size_t)K * K), lp0((size_t)K);
+        for (int k = 0; k < K; ++k) p0[k] = x0 >= 0 ? A[(size_t)x0 * K + k] : pi[k];
+        for (size_t i = 0; i < (size_t)K * K; ++i) lA[i] = log(A[i]);
+        for (int k = 0; k < K; ++k) lp0[k] = log(p0[k]);
+        CK(h->hmm_A.ensure((size_t)K * K * 8)); CK(h->hmm_p0.ensure((size_t)K * 8));
+        CK(h->hmm_logA.ensure((size_t)K * K * 8)); CK(h->hmm_logp0.ensure((size_t)K * 8));
+        CK(cudaMemcpyAsync(h->hmm_A.p, A, (size_t)K * K * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->hmm_p0.p, p0.data(), (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->hmm_logA.p, lA.data(), (size_t)K * K * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->hmm_logp0.p, lp0.data(), (size_t)K * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));                      // the staging vectors go out of scope
+    }
     CK(cudaStreamSynchronize(h->stream));
     h->model = MODEL_HMM; h->K = K; h->T = T; h->x0 = x0;
     h->have_retained = false;
@@ -1041,6 +1054,48 @@ extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t*
         CK(cudaMemcpy(tmp.data(), h->joint.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < tmp.size(); ++i) joint[i] += (int64_t)tmp[i];
     }
+    return SB_OK;
+}
+
+extern "C" int32_t sb_enum_hmm(sb_handle* h, double* joint, double* marg, double* out_logZ) {
+    if (!h) return SB_EINVAL;
+    if (h->model != MODEL_HMM)
+        return fail(h, SB_EUNSUPPORTED, "enum: only the fixed-structure discrete model can be enumerated on the GPU (no CPU fallback)");
+    CK(cudaSetDevice(h->opt.device));
+    const int T = h->T, K = h->K;
+    int rc;
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    double lz = 0.0;
+    // exact per-time marginals and log-evidence (forward-backward)
+    CK(h->enum_buf.ensure(((size_t)2 * T * K + T + 1) * 8));
+    double* alpha = h->enum_buf.as<double>();
+    double* mg = alpha + (size_t)T * K;
+    double* cn = mg + (size_t)T * K;
+    double* d_lz = cn + T;
+    k_forward_backward<<<1, 64, 0, h->stream>>>(h->hmm_A.as<double>(), h->hmm_p0.as<double>(), h->hmm_logF.as<double>(),
+                                                h->hmm_hasf.as<unsigned char>(), K, T, alpha, cn, mg, d_lz);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(&lz, d_lz, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!(lz > -INFINITY) || lz != lz) return fail(h, SB_EZEROMASS, "Distribution has zero probability mass.");
+    if (marg) CK(cudaMemcpy(marg, mg, (size_t)T * K * 8, cudaMemcpyDeviceToHost));    // after the stream sync above
+    if (joint) {
+        if (T * log2((double)K) > 26.0) return fail(h, SB_EUNSUPPORTED, "enum: the joint needs K^T <= 2^26 paths; pass joint = NULL for per-time marginals");
+        long long nc = 1; for (int t = 0; t < T; ++t) nc *= K;
+        DevBuf tmp;
+        CK(tmp.ensure((size_t)nc * 8));
+        k_enum_joint<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(h->hmm_logA.as<double>(), h->hmm_logp0.as<double>(),
+                                                                       h->hmm_logF.as<double>(), h->hmm_hasf.as<unsigned char>(), K, T, nc, tmp.as<double>());
+        ++h->launches;
+        cudaError_t e1 = cudaGetLastError();
+        // the handle's stream does not synchronise with the default stream: copy on it, then wait
+        cudaError_t e2 = e1 == cudaSuccess ? cudaMemcpyAsync(joint, tmp.p, (size_t)nc * 8, cudaMemcpyDeviceToHost, h->stream) : e1;
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(h->stream);
+        tmp.release();
+        if (e2 != cudaSuccess) return fail(h, SB_ECUDA, std::string("enum joint: ") + cudaGetErrorString(e2));
+    }
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    if (out_logZ) *out_logZ = lz;
     return SB_OK;
 }
 

@@ -136,3 +136,37 @@ def test_gpu_frozen_pmcmc_and_mh():
         eng.load(sb.BayesNet(sites, factors, query))
         counts = eng.mh_counts(g["chains"], g["steps"])
         assert counts.tolist() == g["counts"] and eng.stats().accepts == g["accepts"]
+
+
+@pytest.mark.gpu
+def test_gpu_enumerate_matches_reference_kats(enumref):
+    """enum() on the GPU for the examples/hmm.jl and hmm2.jl descriptors == the hand enumerations, and the
+    exhaustive joint / forward-backward marginals == the CPU restatement of src/enumerate.jl on cfg2."""
+    need_gpu()
+    import stochy_jl_b200 as sb
+    d = sb.enum(sb.hmm2_example())
+    for key, p in KATS["hmm2_example_enum"]["p"].items():
+        v = (False,) + tuple(ch == "T" for ch in key[1:])
+        assert d.prob(v) == pytest.approx(p, rel=1e-12)
+    assert len(d.support()) == 16
+    d = sb.enum(sb.hmm_example(T=3))
+    for key, p in KATS["hmm_example_enum"]["p"].items():
+        assert d.prob(tuple(ch == "T" for ch in key)) == pytest.approx(p, rel=1e-12)
+    A, logF, pi = cfg2_tables()
+    Z, probs = enumref.hmm_enumerate_joint(A, logF, pi=pi)
+    with sb.Engine(precision="fp64") as eng:
+        eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+        joint, marg, lz = eng.enum_hmm()
+    assert lz == pytest.approx(math.log(Z), rel=1e-12)
+    assert np.allclose(joint / joint.sum(), probs, rtol=1e-11, atol=0)
+    K, T = 3, 10
+    codes = np.arange(K ** T)
+    for t in range(T):
+        ref = np.bincount((codes // K ** t) % K, weights=probs, minlength=K)
+        assert np.allclose(marg[t], ref, rtol=1e-10)
+    # zero mass: error("Distribution has zero probability mass.")  (test/inferencetests.jl:17-20)
+    with sb.Engine(precision="fp64") as eng:
+        eng.load(sb.DiscreteHMM([[0.5, 0.5], [0.5, 0.5]], [[-np.inf, -np.inf]], pi=[0.5, 0.5]))
+        with pytest.raises(sb.StochyError) as e:
+            eng.enum_hmm()
+        assert KATS["zero_mass"]["error"] in str(e.value)
