@@ -955,10 +955,14 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                 for (int h = 0; h < 2; ++h) {
                     const float u1 = (float)((h ? o.z : o.x) >> 8) * 0x1p-24f;
                     const float u2 = (float)((h ? o.w : o.y) >> 8) * 0x1p-24f;
-                    const float r = sqrtf(-2.0f * logf(1.0f - u1));
+                    // accurate log (its absolute error would otherwise dominate small radii), hardware sqrt and
+                    // sin/cos: the angle is taken in [-pi, pi), where MUFU.SIN/COS are good to 2^-21 absolute, and
+                    // cos(t + pi) = -cos t, sin(t + pi) = -sin t puts the sign on the radius
+                    float r;
+                    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(-2.0f * logf(1.0f - u1)));
                     float sn, cs;
-                    sincospif(2.0f * u2, &sn, &cs);
-                    z[4 * p + 2 * h] = r * cs; z[4 * p + 2 * h + 1] = r * sn;
+                    __sincosf((float)SB_TWO_PI * (u2 - 0.5f), &sn, &cs);
+                    z[4 * p + 2 * h] = -r * cs; z[4 * p + 2 * h + 1] = -r * sn;
                 }
             }
 #pragma unroll
@@ -970,7 +974,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                 const float lw = hr * d * d + flc;
                 const bool live = base + j < N;
                 float v = live ? __fmul_rn(lw, SB_LOG2E_F) : -INFINITY;
-                if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
+                if (!(v < INFINITY)) { bad = true; v = -INFINITY; }        // NaN or +Inf
                 x[j] = (REAL)xv; l2[j] = (REAL)v;
                 mx = (REAL)fmaxf((float)mx, v);
                 if (a.lw_out && live) a.lw_out[lbase + j] = (double)lw;
