@@ -63,7 +63,11 @@ struct sb_handle {
     size_t off_w32[2] = {0, 0}, off_x[2] = {0, 0}, off_wp[2] = {0, 0}, off_e[2] = {0, 0}, off_Q[2] = {0, 0}, off_flags = 0;
     char* peer_base[SB_MAX_PEERS] = {nullptr};
     unsigned epoch = 0;
-    int pdl = 1;                      // programmatic dependent launch between the kernels of a sweep (SB_NO_PDL=1 disables)
+    // programmatic dependent launch between the kernels of a sweep: bit 0 = the scan may be scheduled while the step
+    // kernel drains, bit 1 = the step kernel's prologue overlaps the scan.  Measured best: both on one GPU, only the
+    // second on sharded pools (the scan spins on peer flags there).  Overrides: SB_PDL, SB_PDL_DIST (0..3).
+    int pdl = 3;
+    int pdl_dist = 2;
     int scan16 = -1;                  // 16-CTA scan cluster: -1 not probed, 0 unavailable, 1 available
     int* d_emax = nullptr;            // running max of the tile exponents of the pool in production (single GPU)
     DevBuf e_all;
@@ -293,7 +297,7 @@ int launch_tilescan_k(sb_handle* h, int ctas, const int* e, const unsigned long 
     at[0].val.clusterDim.x = (unsigned)ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // may be scheduled while the step kernel drains
     at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = (h->pdl && !h->dist_ready) ? 2 : 1;     // measured: the overlap loses 7 us per step on sharded pools
+    cfg.attrs = at; cfg.numAttrs = ((h->dist_ready ? h->pdl_dist : h->pdl) & 1) ? 2 : 1;
     long long nn = n, mm = m;
     CK(cudaLaunchKernelEx(&cfg, kern, e, Q, nt, nn, mm, d_r53, info, h->P.as<unsigned long long>(), h->Pt.as<unsigned long long>(),
                           h->child_start.as<int>(), h->first_tile.as<int>(), want_exact, h->d_err, h->d_emax, sp));
@@ -482,7 +486,8 @@ extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
         const int empty = SB_E_EMPTY;
         cudaMemcpy(h->d_emax, &empty, sizeof(int), cudaMemcpyHostToDevice);
     }
-    if (const char* np = getenv("SB_NO_PDL")) h->pdl = atoi(np) ? 0 : 1;
+    if (const char* np = getenv("SB_PDL")) h->pdl = atoi(np) & 3;
+    if (const char* pd = getenv("SB_PDL_DIST")) h->pdl_dist = atoi(pd) & 3;
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, opt.device) != cudaSuccess || h->num_sms < 1)
         h->num_sms = 148;
     *out = h;
@@ -698,7 +703,7 @@ int launch_step(sb_handle* h, Kern kern, unsigned grid, size_t smem, bool after_
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = (after_scan && h->pdl && !h->dist_ready) ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = (after_scan && ((h->dist_ready ? h->pdl_dist : h->pdl) & 2)) ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kern, a));
     return SB_OK;
 }
