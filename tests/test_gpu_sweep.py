@@ -320,3 +320,32 @@ def test_full_size_lg_vs_kalman(enumref):
             eng.load(sb.LinearGaussian(**d))
             lz = eng.smc_sweep(1 << 24)
         assert abs(lz - exact) < tol, (prec, lz, exact)
+
+
+@pytest.mark.parametrize("K,N,T", [(1, 50, 3), (2, 1, 4), (37, 3000, 5), (64, 2500, 4), (64, 2048, 1), (5, 2047, 6), (5, 2049, 6)])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_hmm_edge_models_bitexact(oracle, K, N, T, precision):
+    """Edge shapes of the discrete model: one state, one particle, one step, the largest K (64 KB of lookup words:
+    opt-in shared memory), rows with zero and tiny probabilities (several thresholds inside one lookup bucket: the
+    scanning instantiation of the step kernel), pools that end exactly at / just past a tile boundary."""
+    sb = sb_mod()
+    rng = np.random.default_rng(1000 + K + N)
+    A = rng.random((K, K)) ** 6                      # a few large entries, many tiny ones
+    A[rng.random((K, K)) < 0.2] = 0.0                # exact zeros
+    A[np.arange(K), np.arange(K)] += 1e-3            # no empty row
+    A /= A.sum(axis=1, keepdims=True)
+    pi = rng.random(K) ** 4 + 1e-6
+    pi /= pi.sum()
+    logF = rng.normal(size=(T, K)) * 3.0
+    if K > 2:
+        logF[:, 0] = -np.inf                         # a state with no weight at all
+    fp32 = precision == "fp32"
+    ref = oracle.hmm_sweep(oracle.Hmm(A, logF, pi=pi), oracle.opts(oracle.SYSTEMATIC, fp32=fp32, seed=21), N)
+    with sb.Engine(precision=precision, resample="systematic", seed=21) as eng:
+        eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+        lz = eng.smc_sweep(N, it=0, history=True)
+        for t in range(T):
+            x, a, _ = eng.history(t, N)
+            assert np.array_equal(x, ref["x"][t, :N]), "states differ at step %d" % t
+            assert np.array_equal(a, ref["anc"][t, :N]), "ancestors differ at step %d" % t
+    assert lz == pytest.approx(ref["logZ"], rel=1e-9, abs=1e-12)
