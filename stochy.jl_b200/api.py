@@ -375,9 +375,13 @@ class Engine:
         self._chk(nat.lib().sb_get_retained(self.h, _ptr(xs)))
         return xs
 
-    def particles(self, count):
+    def particles(self, count, out=None):
+        """Final particle states of the last sweep.  out: optional destination array (e.g. page-locked memory,
+        which the device-to-host copy then reaches at full link speed)."""
         dt = np.int32 if isinstance(self.model, DiscreteHMM) else np.float64
-        x = np.empty(count, dtype=dt)
+        x = np.empty(count, dtype=dt) if out is None else out
+        if x.dtype != dt or x.size < count or not x.flags["C_CONTIGUOUS"]:
+            raise StochyError(nat.EINVAL, "particles: out must be a contiguous %s array of at least %d entries" % (np.dtype(dt).name, count))
         self._chk(nat.lib().sb_get_particles(self.h, count, _ptr(x)))
         return x
 
