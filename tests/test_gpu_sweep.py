@@ -349,3 +349,24 @@ def test_hmm_edge_models_bitexact(oracle, K, N, T, precision):
             assert np.array_equal(x, ref["x"][t, :N]), "states differ at step %d" % t
             assert np.array_equal(a, ref["anc"][t, :N]), "ancestors differ at step %d" % t
     assert lz == pytest.approx(ref["logZ"], rel=1e-9, abs=1e-12)
+
+
+def test_result_independent_of_grid(monkeypatch):
+    """The persistent step kernel walks tiles in an order that depends on the number of resident CTAs; the result
+    must not.  One CTA per SM at 2^25 particles gives every CTA 110 tiles (the per-CTA table of candidate parent
+    tiles is refilled every 64), the default grid gives 22: final particles and log-evidence must be identical."""
+    sb = sb_mod()
+    A, logF, pi = cfg3_tables(T=4)
+    N = 1 << 25
+    outs = []
+    for ctas in ["1", None]:
+        if ctas:
+            monkeypatch.setenv("SB_CTAS_PER_SM", ctas)
+        else:
+            monkeypatch.delenv("SB_CTAS_PER_SM", raising=False)
+        with sb.Engine(precision="fp32", resample="systematic", seed=9) as eng:
+            eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+            lz = eng.smc_sweep(N, it=0)
+            outs.append((lz, eng.particles(N)))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1])
