@@ -547,8 +547,8 @@ __device__ __forceinline__ double sb_block_max_f64_1(double v, double* sm) {
 }
 
 // Where the tile records (e, Q) of the pool being PRODUCED go (local tile index).  Single GPU: the
-// running maximum of the exponents is kept with atomicMax for the tile scan.  Sharded: k_signal copies
-// the records into every peer's replica after the step kernel (no remote stores inside the hot kernel).
+// running maximum of the exponents is kept with atomicMax for the tile scan.  Sharded: the scan of every
+// GPU reads the records from the owner's arena (no remote stores inside the hot kernel).
 struct SbRecOut {
     int* e;
     unsigned long long* Q;

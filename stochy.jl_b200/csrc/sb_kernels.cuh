@@ -241,7 +241,7 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     const int b0 = min(nt, gtid * per), b1 = min(nt, b0 + per);
     if (PEERS) {
         // every peer has finished the step kernel that produced this pool (and therefore also every
-        // read of the pool before it): flags are written by k_signal over NVLink
+        // read of the pool before it): the flags are raised over NVLink by the last CTA of that kernel
         if (threadIdx.x < sp.world) {
             const volatile unsigned* f = reinterpret_cast<const volatile unsigned*>(sp.base[sp.self] + sp.off_flags) + threadIdx.x;
             const long long t0 = clock64();

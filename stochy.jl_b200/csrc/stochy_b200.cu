@@ -1394,7 +1394,8 @@ extern "C" int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out) {
 // weights, states, warp prefixes, tile records) and a flag word per peer in ONE device allocation,
 // the arena, exported over CUDA IPC.  After the import every rank holds a mapping of every arena:
 // the fused step kernel reads parent weights and states of any GPU with ordinary loads over
-// NVLink, the tile scan reads every GPU's tile records behind a flag barrier (k_signal).  No NCCL
+// NVLink, the tile scan reads every GPU's tile records behind a flag barrier (raised by the last CTA of the
+// producing step kernel, sb_signal_done).  No NCCL
 // call sits on the data path; the 64-byte handles travel over the host's own plumbing
 // (torch.distributed.all_gather in the Python mirror).
 extern "C" int32_t sb_dist_init(sb_handle* h, int32_t rank, int32_t world) {
