@@ -12,6 +12,7 @@
  *
  * Reference interfaces replaced (paths relative to the Stochy.jl tree):
  *   sb_pmcmc_run        <- pmcmc(store,k,address,comp,numiterations,numparticles)  src/pmcmc.jl:78-99
+ *   sb_pmcmc_chains     <- many independent pmcmc(...) calls (one per chain)                       idem
  *   sb_smc_sweep        <- smc(store,k,a,comp,n) = pmcmc(...,1,n)                  src/pmcmc.jl:101-103
  *   sb_mh_run           <- mh(store,k,address,comp,numsteps)                       src/mh.jl:47-93
  *   sb_enum_hmm         <- enum(store,k,address,comp) for the discrete descriptor  src/enumerate.jl:57-85
@@ -134,6 +135,14 @@ int32_t sb_smc_sweep(sb_handle* h, int64_t N, uint32_t iter, int32_t store_histo
  * (src/pmcmc.jl:90-92).  joint uses little-endian base-K codes (digit t = x_t) and needs K^T <= 2^26. */
 int32_t sb_pmcmc_run(sb_handle* h, int64_t numiterations, int64_t numparticles,
                      int64_t* marg, int64_t* joint);
+
+/* A SET of independent PMCMC chains (global ids chain0 ..) of numparticles each, whose pool (numparticles + 1)
+ * fits one tile of 2048: one CTA per chain runs the chain's whole iteration loop (src/pmcmc.jl:83-94) in one
+ * kernel launch.  Chain c uses the Philox key seed + c * 0x9E3779B97F4A7C15; chain 0 reproduces sb_pmcmc_run.
+ * marg / joint are ADDED to with the pooled counts of all chains.  sb_pmcmc_run itself takes this route for
+ * numparticles <= 2047. */
+int32_t sb_pmcmc_chains(sb_handle* h, int64_t chains, int64_t numiterations, int64_t numparticles, int64_t chain0,
+                        int64_t* marg, int64_t* joint);
 
 /* enum(comp) for the discrete model (src/enumerate.jl:57-85): exhaustive exploration.
  * joint[K^T] (or NULL): UNNORMALISED mass exp(score) of every complete execution path, little-endian base-K

@@ -26,7 +26,7 @@ TILE = 2048
 EXPORTS = [
     "sb_version", "sb_options_default", "sb_create", "sb_destroy", "sb_last_error", "sb_get_stats", "sb_set_profile",
     "sb_model_discrete_hmm", "sb_model_linear_gaussian", "sb_model_bayesnet",
-    "sb_smc_sweep", "sb_pmcmc_run", "sb_mh_run", "sb_enum_hmm",
+    "sb_smc_sweep", "sb_pmcmc_run", "sb_pmcmc_chains", "sb_mh_run", "sb_enum_hmm",
     "sb_resample_systematic", "sb_resample_multinomial", "sb_resample_literal", "sb_logsumexp", "sb_gather",
     "sb_dev_resample_systematic", "sb_dev_gather", "sb_sync", "sb_timer_start", "sb_timer_stop",
     "sb_erp_sample", "sb_erp_logpdf", "sb_erp_sample_dirichlet", "sb_erp_logpdf_dirichlet",
@@ -94,6 +94,7 @@ def lib():
         "sb_model_bayesnet": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, u32]),
         "sb_smc_sweep": (i32, [vp, i64, u32, i32, C.POINTER(dbl)]),
         "sb_pmcmc_run": (i32, [vp, i64, i64, vp, vp]),
+        "sb_pmcmc_chains": (i32, [vp, i64, i64, i64, i64, vp, vp]),
         "sb_mh_run": (i32, [vp, i64, i64, i64, vp]),
         "sb_enum_hmm": (i32, [vp, vp, vp, C.POINTER(dbl)]),
         "sb_resample_systematic": (i32, [vp, vp, i32, i64, dbl, i64, vp]),

@@ -275,6 +275,14 @@ class Engine:
         self._chk(nat.lib().sb_pmcmc_run(self.h, iters, N, _ptr(marg), _ptr(joint)))
         return marg, joint
 
+    def pmcmc_chains_counts(self, chains, iters, N, chain0=0, want_joint=True):
+        """`chains` independent PMCMC chains (one CTA each, N <= 2047); pooled counts."""
+        m = self.model
+        marg = np.zeros((m.T, m.K), dtype=np.int64)
+        joint = np.zeros(m.K ** m.T, dtype=np.int64) if want_joint else None
+        self._chk(nat.lib().sb_pmcmc_chains(self.h, chains, iters, N, chain0, _ptr(marg), _ptr(joint)))
+        return marg, joint
+
     def enum_hmm(self, want_joint=True):
         """Exhaustive enumeration of the loaded discrete model: (unnormalised joint masses or None,
         exact per-time marginals [T, K], log total mass)."""
@@ -398,10 +406,11 @@ def _decode_joint(model, joint):
     return out
 
 
-def pmcmc(comp, numiterations, numparticles, **engine_kw):
+def pmcmc(comp, numiterations, numparticles, chains=1, **engine_kw):
     """pmcmc(comp, numiterations, numparticles) -> Discrete(counts)   (src/pmcmc.jl:78-99).
     Default numerics are the reference's (`resample="literal"`: plain exp weights, multinomial
-    draws on the sequential fp64 CDF, N+1 pool with the retained particle, retained = particle 1)."""
+    draws on the sequential fp64 CDF, N+1 pool with the retained particle, retained = particle 1).
+    chains > 1: that many independent chains side by side (numparticles <= 2047), counts pooled."""
     engine_kw.setdefault("resample", "literal")
     engine_kw.setdefault("precision", "fp64")
     eng = Engine(**engine_kw)
@@ -410,7 +419,10 @@ def pmcmc(comp, numiterations, numparticles, **engine_kw):
         if not isinstance(comp, DiscreteHMM):
             raise StochyError(nat.EUNSUPPORTED, "pmcmc: the return value of this model has no finite encoding; "
                                                 "use Engine.smc_sweep for its log-evidence")
-        _, joint = eng.pmcmc_counts(numiterations, numparticles, want_joint=True)
+        if chains > 1:
+            _, joint = eng.pmcmc_chains_counts(chains, numiterations, numparticles, want_joint=True)
+        else:
+            _, joint = eng.pmcmc_counts(numiterations, numparticles, want_joint=True)
         return Discrete(_decode_joint(comp, joint))
     finally:
         eng.close()                      # `finally ctx = ctxold` (src/pmcmc.jl:95-97)

@@ -187,6 +187,43 @@ __device__ __forceinline__ int sb_sys_F(unsigned long long C, unsigned long long
     return k >= (unsigned long long)m ? m : (int)k;
 }
 
+// Plan of the systematic rescale from the exact total of the pool (integers only after one fp64 division,
+// whose result is turned into a 26-bit multiplier with an explicit ceiling: every GPU, the tile scan and the
+// one-tile kernel get the same bits).  Child k's threshold is U + k * 2^s on the rescaled CDF.
+__device__ __forceinline__ void sb_plan_rescale(SbStepInfo& si, unsigned long long total, long long n, long long m,
+                                                int E, int LS, int nt) {
+    si.total = total; si.n = n; si.m = m; si.E = E; si.LS = LS; si.nt = nt;
+    si.Tt = 0ull; si.U = 0ull; si.R = 0u; si.r0 = 0; si.s = 0;
+    si.valid = (E != SB_E_EMPTY && total != 0ull) ? 1 : 0;
+    if (si.valid) {
+        const int clm = m <= 1 ? 0 : 64 - __clzll(m - 1);
+        int s = 62 - clm;
+        if (s > 36) s = 36;
+        const double ratio = __ddiv_rn(scalbn((double)m, s + LS), __ull2double_rn(total));
+        const unsigned long long rb_ = (unsigned long long)__double_as_longlong(ratio);
+        int x = (int)((rb_ >> 52) & 0x7ffull) - 1022;                      // ratio = f * 2^x, f in [0.5, 1)
+        const unsigned long long mant = (rb_ & 0xfffffffffffffull) | (1ull << 52);   // f * 2^53
+        unsigned long long R = (mant >> 27) + ((mant & ((1ull << 27) - 1ull)) ? 1ull : 0ull);   // ceil(f * 2^26)
+        if (R >= 67108864ull) { R = 33554432ull; x += 1; }
+        int r0 = 26 - x;
+        if (r0 < 0) { s += r0; r0 = 0; }
+        if (s < 0) si.valid = 0;
+        si.R = (unsigned)R; si.r0 = r0; si.s = s < 0 ? 0 : s;
+    }
+}
+// Tt: total of the rescaled CDF; R53: the step's 53-bit uniform.  The offset U is spread over the slack
+// Tt - (m - 1) 2^s.  Clears `valid` when the pool has no mass.
+__device__ __forceinline__ void sb_plan_offset(SbStepInfo& si, unsigned long long Tt, unsigned long long R53) {
+    const unsigned long long lastk = (unsigned long long)(si.m - 1) << si.s;
+    if (si.valid && Tt > lastk) {
+        const unsigned long long span = Tt - lastk;
+        si.U = (__umul64hi(R53, span) << 11) | ((R53 * span) >> 53);
+        si.Tt = Tt;
+    } else {
+        si.valid = 0;
+    }
+}
+
 // ---------------------------------------------------------------- block-level primitives (256 threads)
 __device__ __forceinline__ unsigned long long sb_shfl_up_u64(unsigned long long v, int d) {
     uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, d);

@@ -300,37 +300,13 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     }
     // plan of the systematic rescale (every thread computes the same few integers)
     SbStepInfo si;
-    si.total = total; si.n = n; si.m = m; si.E = E; si.LS = LS; si.nt = nt;
-    si.Tt = 0ull; si.U = 0ull; si.R = 0u; si.r0 = 0; si.s = 0;
-    si.valid = (E != SB_E_EMPTY && total != 0ull) ? 1 : 0;
-    if (si.valid) {
-        const int clm = m <= 1 ? 0 : 64 - __clzll(m - 1);
-        int s = 62 - clm;
-        if (s > 36) s = 36;
-        const double ratio = __ddiv_rn(scalbn((double)m, s + LS), __ull2double_rn(total));
-        const unsigned long long rb_ = (unsigned long long)__double_as_longlong(ratio);
-        int x = (int)((rb_ >> 52) & 0x7ffull) - 1022;                      // ratio = f * 2^x, f in [0.5, 1)
-        const unsigned long long mant = (rb_ & 0xfffffffffffffull) | (1ull << 52);   // f * 2^53
-        unsigned long long R = (mant >> 27) + ((mant & ((1ull << 27) - 1ull)) ? 1ull : 0ull);   // ceil(f * 2^26)
-        if (R >= 67108864ull) { R = 33554432ull; x += 1; }
-        int r0 = 26 - x;
-        if (r0 < 0) { s += r0; r0 = 0; }
-        if (s < 0) si.valid = 0;
-        si.R = (unsigned)R; si.r0 = r0; si.s = s < 0 ? 0 : s;
-    }
+    sb_plan_rescale(si, total, n, m, E, LS, nt);
     // rescaled CDF of tile sums (systematic)
     unsigned long long loc2 = 0;
     if (si.valid) { SB_TS_FOR((void)b; if (qv != 0ull) loc2 += sb_sys_delta(qv, si.R, si.r0 + (E - ev));) }
     unsigned long long Tt;
     unsigned long long run2 = sb_cluster_excl_scan(loc2, sm, cl, 1, &Tt);
-    const unsigned long long lastk = (unsigned long long)(m - 1) << si.s;
-    if (si.valid && Tt > lastk) {
-        const unsigned long long span = Tt - lastk;
-        si.U = (__umul64hi(R53, span) << 11) | ((R53 * span) >> 53);
-        si.Tt = Tt;
-    } else {
-        si.valid = 0;
-    }
+    sb_plan_offset(si, Tt, R53);
     if (gtid == 0) {
         if (!si.valid) atomicOr(err, SB_ERRBIT_ZERO);
         *info = si;

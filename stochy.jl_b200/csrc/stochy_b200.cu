@@ -3,6 +3,7 @@
 // entry point that computes launches CUDA kernels and fails with SB_ECUDA when it cannot.
 #include "../../include/stochy_b200.h"
 #include "sb_kernels.cuh"
+#include "sb_small.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -91,6 +92,9 @@ struct sb_handle {
 
     // sweep state
     DevBuf xbuf, ancbuf, lwbuf, wlit, cnt[2], xstar[2], marg, joint;
+    DevBuf sm_x, sm_a, sm_xs, sm_lz;  // one-tile chains (sb_small.cuh)
+    int small_cur = -1;               // >= 0: the retained particle of the last pmcmc call is in buffer small_cur of sm_xs
+    int use_small = 1;                // SB_NO_SMALL=1 keeps pmcmc on the tiled kernels
     int64_t sw_N = 0, sw_S = 0;       // particles and row stride of the last sweep
     int sw_hist = 0;                  // history rows kept
     int sw_cond = 0;
@@ -487,6 +491,7 @@ extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
         cudaMemcpy(h->d_emax, &empty, sizeof(int), cudaMemcpyHostToDevice);
     }
     if (const char* np = getenv("SB_PDL")) h->pdl = atoi(np) & 3;
+    if (const char* ns = getenv("SB_NO_SMALL")) h->use_small = atoi(ns) ? 0 : 1;
     if (const char* pd = getenv("SB_PDL_DIST")) h->pdl_dist = atoi(pd) & 3;
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, opt.device) != cudaSuccess || h->num_sms < 1)
         h->num_sms = 148;
@@ -503,7 +508,7 @@ extern "C" void sb_destroy(sb_handle* h) {
                       &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
                       &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
                       &h->bn_fp, &h->bn_fac, &h->bn_counts, &h->xbuf, &h->ancbuf, &h->lwbuf, &h->wlit, &h->cnt[0],
-                      &h->cnt[1], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint};
+                      &h->cnt[1], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint, &h->sm_x, &h->sm_a, &h->sm_xs, &h->sm_lz};
     for (DevBuf* b : bufs) b->release();
     for (int g = 0; g < SB_MAX_PEERS; ++g)
         if (h->peer_base[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_base[g]);
@@ -981,8 +986,83 @@ extern "C" int32_t sb_smc_sweep(sb_handle* h, int64_t N, uint32_t iter, int32_t 
     return check_err_word(h);
 }
 
+// `chains` independent PMCMC chains of numparticles each, one CTA per chain, the whole iteration loop on the device
+extern "C" int32_t sb_pmcmc_chains(sb_handle* h, int64_t chains, int64_t iters, int64_t N, int64_t chain0,
+                                   int64_t* marg, int64_t* joint) {
+    if (!h) return SB_EINVAL;
+    if (h->model != MODEL_HMM)
+        return fail(h, SB_EUNSUPPORTED, "pmcmc: only the fixed-structure discrete model is supported (no CPU fallback)");
+    if (chains < 1 || iters < 1 || N < 1 || chain0 < 0) return fail(h, SB_EINVAL, "pmcmc_chains: bad arguments");
+    if (N + 1 > SB_TILE) return fail(h, SB_EUNSUPPORTED, "pmcmc_chains: a chain's pool (numparticles + 1) must fit one tile of 2048; use sb_pmcmc_run");
+    if (h->dist_ready) return fail(h, SB_EUNSUPPORTED, "pmcmc_chains: chain sets run one handle per GPU, not on a sharded handle");
+    CK(cudaSetDevice(h->opt.device));
+    const int T = h->T, K = h->K;
+    int64_t njoint = 0;
+    if (joint) {
+        if (T * log2((double)K) > 26.0) return fail(h, SB_EUNSUPPORTED, "pmcmc: joint histogram needs K^T <= 2^26; pass joint = NULL");
+        njoint = 1; for (int t = 0; t < T; ++t) njoint *= K;
+    }
+    const int S = (int)((N + 1 + 7) & ~7LL);
+    CK(h->sm_x.ensure((size_t)chains * T * S * 4));
+    CK(h->sm_a.ensure((size_t)chains * T * S * 4));
+    CK(h->sm_xs.ensure((size_t)chains * 2 * T * 4));
+    CK(h->sm_lz.ensure((size_t)chains * 2 * 8));
+    CK(h->marg.ensure((size_t)T * K * 8));
+    CK(cudaMemsetAsync(h->marg.p, 0, (size_t)T * K * 8, h->stream));
+    if (joint) { CK(h->joint.ensure((size_t)njoint * 8)); CK(cudaMemsetAsync(h->joint.p, 0, (size_t)njoint * 8, h->stream)); }
+    int pick = h->opt.retained_pick;
+    if (pick < 0) pick = h->opt.resample_mode == SB_RESAMPLE_SYSTEMATIC ? 1 : 0;
+    SbSmallArgs a;
+    memset(&a, 0, sizeof(a));
+    const int G = 1 << SB_LG_BUCKETS;
+    a.K = K; a.T = T;
+    a.tabA = h->hmm_tabA.as<uint32_t>(); a.thrA = h->hmm_cumA.as<uint32_t>();
+    if (h->x0 >= 0) { a.tab0 = a.tabA + (size_t)h->x0 * G; a.thr0 = a.thrA + (size_t)h->x0 * K; }
+    else { a.tab0 = h->hmm_tabpi.as<uint32_t>(); a.thr0 = h->hmm_cumpi.as<uint32_t>(); }
+    a.logF = h->hmm_logF.as<double>(); a.expF = h->hmm_expF.as<double>(); a.has_factor = h->hmm_hasf.as<unsigned char>();
+    a.N = (int)N; a.S = S; a.iters = iters; a.chain0 = chain0; a.mode = h->opt.resample_mode; a.pick = pick; a.seed = h->opt.seed;
+    a.x_hist = h->sm_x.as<int>(); a.anc_hist = h->sm_a.as<int>(); a.xstar = h->sm_xs.as<int>();
+    a.marg = h->marg.as<unsigned long long>(); a.joint = joint ? h->joint.as<unsigned long long>() : nullptr;
+    a.logZ = h->sm_lz.as<double>(); a.err = h->d_err;
+    const size_t smem = sb_small_smem_bytes(K);
+    int rc;
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    const bool fp32 = h->opt.precision == SB_FP32;
+    if (fp32) {
+        CK(cudaFuncSetAttribute(k_pmcmc_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pmcmc_small<true><<<(unsigned)chains, SB_THREADS, smem, h->stream>>>(a);
+    } else {
+        CK(cudaFuncSetAttribute(k_pmcmc_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pmcmc_small<false><<<(unsigned)chains, SB_THREADS, smem, h->stream>>>(a);
+    }
+    LAUNCH_CHECK();
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    h->stats.particle_steps = chains * iters * N * (int64_t)T;
+    double lz[2] = {0.0, 0.0};
+    CK(cudaMemcpy(lz, h->sm_lz.p, sizeof(lz), cudaMemcpyDeviceToHost));      // chain chain0
+    h->stats.logZ_first = lz[0]; h->stats.logZ_last = lz[1];
+    h->small_cur = (int)(iters & 1);
+    h->have_retained = true;
+    if ((rc = check_err_word(h)) != SB_OK) return rc;
+    if (marg) {
+        std::vector<unsigned long long> tmp((size_t)T * K);
+        CK(cudaMemcpy(tmp.data(), h->marg.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) marg[i] += (int64_t)tmp[i];
+    }
+    if (joint) {
+        std::vector<unsigned long long> tmp((size_t)njoint);
+        CK(cudaMemcpy(tmp.data(), h->joint.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) joint[i] += (int64_t)tmp[i];
+    }
+    return SB_OK;
+}
+
 extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t* marg, int64_t* joint) {
     if (!h) return SB_EINVAL;
+    // a pool that fits one tile runs as a one-CTA chain: the whole iteration loop in one launch
+    if (h->use_small && h->model == MODEL_HMM && !h->dist_ready && iters >= 1 && N >= 1 && N + 1 <= SB_TILE && !h->opt.store_logw)
+        return sb_pmcmc_chains(h, 1, iters, N, 0, marg, joint);
+    h->small_cur = -1;
     if (h->model != MODEL_HMM)
         return fail(h, SB_EUNSUPPORTED, "pmcmc: only the fixed-structure discrete model is supported (no CPU fallback)");
     if (iters < 1 || N < 1) return fail(h, SB_EINVAL, "pmcmc: numiterations and numparticles must be >= 1");
@@ -1362,7 +1442,8 @@ extern "C" int32_t sb_get_retained(sb_handle* h, int32_t* xstar_out) {
     if (!xstar_out || !h->have_retained) return fail(h, SB_EINVAL, "get_retained: no retained particle");
     CK(cudaSetDevice(h->opt.device));
     CK(cudaStreamSynchronize(h->stream));
-    CK(cudaMemcpy(xstar_out, h->xstar[h->xstar_cur].p, (size_t)h->T * 4, cudaMemcpyDeviceToHost));
+    if (h->small_cur >= 0) CK(cudaMemcpy(xstar_out, h->sm_xs.as<int>() + (size_t)h->small_cur * h->T, (size_t)h->T * 4, cudaMemcpyDeviceToHost));
+    else CK(cudaMemcpy(xstar_out, h->xstar[h->xstar_cur].p, (size_t)h->T * 4, cudaMemcpyDeviceToHost));
     return SB_OK;
 }
 

@@ -370,3 +370,55 @@ def test_result_independent_of_grid(monkeypatch):
             outs.append((lz, eng.particles(N)))
     assert outs[0][0] == outs[1][0]
     assert np.array_equal(outs[0][1], outs[1][1])
+
+
+CHAIN_KEY = 0x9E3779B97F4A7C15
+
+
+@pytest.mark.parametrize("resample", ["systematic", "multinomial", "literal"])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_pmcmc_chain_set_bitexact(oracle, resample, precision):
+    """A set of independent PMCMC chains, one CTA per chain with the whole iteration loop on chip: the pooled
+    counts equal the sum of the oracle's runs with the chains' Philox keys (seed + c * 0x9E37...), bit for bit,
+    in all three numerics; chain 0 alone equals the tiled kernels (SB_NO_SMALL)."""
+    sb = sb_mod()
+    A, logF, pi = cfg2_tables()
+    iters, N, chains, seed = 6, 37, 5, 12
+    with sb.Engine(precision=precision, resample=resample, seed=seed) as eng:
+        eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+        marg, joint = eng.pmcmc_chains_counts(chains, iters, N)
+        lz0 = eng.stats().logZ_first
+    m = oracle.Hmm(A, logF, pi=pi)
+    rm = np.zeros_like(marg)
+    rj = np.zeros_like(joint)
+    for c in range(chains):
+        o = oracle.opts(MODES[resample], fp32=(precision == "fp32"), seed=(seed + c * CHAIN_KEY) % (1 << 64))
+        ref = oracle.hmm_pmcmc(m, o, iters, N)
+        rm += ref["marg"]
+        rj += ref["joint"]
+        if c == 0:
+            assert lz0 == pytest.approx(ref["logZ_first"], rel=1e-9 if resample != "literal" else 1e-6)
+    assert np.array_equal(marg, rm)
+    assert np.array_equal(joint, rj)
+
+
+@pytest.mark.parametrize("resample", ["systematic", "multinomial", "literal"])
+def test_pmcmc_one_tile_route_equals_tiled_kernels(monkeypatch, resample):
+    """sb_pmcmc_run sends pools that fit one tile to the one-CTA kernel; the tiled kernels (forced with
+    SB_NO_SMALL=1) must give identical counts, retained particle and log-evidence."""
+    sb = sb_mod()
+    A, logF, pi = cfg2_tables()
+    outs = []
+    for no_small in ["1", None]:
+        if no_small:
+            monkeypatch.setenv("SB_NO_SMALL", no_small)
+        else:
+            monkeypatch.delenv("SB_NO_SMALL", raising=False)
+        with sb.Engine(precision="fp64", resample=resample, seed=4) as eng:
+            eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+            marg, joint = eng.pmcmc_counts(8, 100)
+            outs.append((marg, joint, eng.retained(), eng.stats().logZ_first, eng.stats().kernel_launches))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+    assert outs[0][3] == pytest.approx(outs[1][3], rel=1e-12)
+    assert outs[1][4] == 1 and outs[0][4] > 100          # one launch instead of hundreds
