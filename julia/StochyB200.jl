@@ -140,7 +140,8 @@ function decode_joint(m::DiscreteHMM, joint::Vector{Int64})
 end
 
 # ---- pmcmc(store, k, address, comp, numiterations, numparticles)  -- ITERATIONS FIRST (src/pmcmc.jl:78)
-function pmcmc(store, k::Function, address, comp, numiterations, numparticles; kw...)
+# chains > 1: that many independent chains side by side on the GPU (numparticles <= 2047), counts pooled
+function pmcmc(store, k::Function, address, comp, numiterations, numparticles; chains=1, kw...)
     comp isa DiscreteHMM || error("pmcmc: only the fixed-structure discrete model has a finite value encoding " *
                                   "on the GPU path (no CPU fallback)")
     h = create(; kw...)
@@ -148,8 +149,13 @@ function pmcmc(store, k::Function, address, comp, numiterations, numparticles; k
         load!(h, comp)
         K, T = size(comp.A, 1), size(comp.logF, 1)
         joint = zeros(Int64, K^T)
-        check(h, ccall((:sb_pmcmc_run, LIB), Int32, (Handle, Int64, Int64, Ptr{Int64}, Ptr{Int64}),
-                       h, numiterations, numparticles, C_NULL, joint))
+        if chains > 1
+            check(h, ccall((:sb_pmcmc_chains, LIB), Int32, (Handle, Int64, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}),
+                           h, chains, numiterations, numparticles, 0, C_NULL, joint))
+        else
+            check(h, ccall((:sb_pmcmc_run, LIB), Int32, (Handle, Int64, Int64, Ptr{Int64}, Ptr{Int64}),
+                           h, numiterations, numparticles, C_NULL, joint))
+        end
         decode_joint(comp, joint)
     finally
         destroy(h)                       # `finally ctx = ctxold` (src/pmcmc.jl:95-97)

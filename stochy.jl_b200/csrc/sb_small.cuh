@@ -43,6 +43,8 @@ struct SbSmallArgs {
     unsigned long long* joint;       // [K^T] += trajectory counts, or nullptr
     double* logZ;                    // [chains][2]: log-evidence of the first and of the last sweep
     unsigned* err;
+    int hist_smem;                   // 1: the chain's history rows (T * S states + ancestors) live in shared memory
+    int marg_smem;                   // 1: per-time counts are accumulated in shared memory and flushed once per chain
 };
 
 struct SbSmallSmem {
@@ -51,13 +53,16 @@ struct SbSmallSmem {
     SbStepInfo si;
     unsigned long long Q;            // tile sum of the current pool
     int e;                           // tile exponent of the current pool
+    double lits;                     // literal numerics: sum(weights)
     double lz;
 };
 
-// dynamic shared memory: tabA | tab0 | l2[K] | thrA | thr0 | q[K] | x[SB_TILE] | w[SB_TILE] | anc[SB_TILE] | big[(SB_TILE+1) * 8] | wlit[(SB_TILE+1) * 8]
-__host__ __device__ inline size_t sb_small_smem_bytes(int K) {
-    return ((size_t)(K + 1) << SB_LG_BUCKETS) * 4 + (size_t)K * 8 + (size_t)(K * K + K + K) * 4 + (size_t)3 * SB_TILE * 4 +
-           (size_t)2 * (SB_TILE + 8) * 8;
+// dynamic shared memory (SP = pool slots rounded up to the 2048 / 8 blocked layout of the CTA, i.e. S8 = 8 * ceil(S / 8)):
+// tabA | tab0 | l2[K] | ef[K] | thrA | thr0 | q[K] | x[S8] | w[S8] | anc[S8] | big[(S8+8) * 8] | wlit[(S8+8) * 8] | marg[T*K] | hist[2*T*S]
+__host__ __device__ inline size_t sb_small_smem_bytes(int K, int T, int S, int hist_smem, int marg_smem) {
+    const size_t S8 = ((size_t)S + 7) & ~(size_t)7;
+    return ((size_t)(K + 1) << SB_LG_BUCKETS) * 4 + (size_t)2 * K * 8 + (size_t)(K * K + K + K) * 4 + 3 * S8 * 4 + 2 * (S8 + 8) * 8 + 16 +
+           (marg_smem ? (size_t)T * K * 4 : 0) + (hist_smem ? (size_t)2 * T * S * 4 : 0);
 }
 
 template <bool FP32>
@@ -70,24 +75,29 @@ k_pmcmc_small(const __grid_constant__ SbSmallArgs a) {
     uint32_t* s_tabA = reinterpret_cast<uint32_t*>(dyn);
     uint32_t* s_tab0 = s_tabA + (size_t)K * G;
     double* s_l2 = reinterpret_cast<double*>(s_tab0 + G);
-    uint32_t* s_thrA = reinterpret_cast<uint32_t*>(s_l2 + K);
+    double* s_ef = s_l2 + K;                                                    // exp(logF[t]) (literal numerics)
+    uint32_t* s_thrA = reinterpret_cast<uint32_t*>(s_ef + K);
     uint32_t* s_thr0 = s_thrA + K * K;
     uint32_t* s_q = s_thr0 + K;
+    const int S8 = (S + 7) & ~7;
     int* s_x = reinterpret_cast<int*>(s_q + K);
-    uint32_t* s_w = reinterpret_cast<uint32_t*>(s_x + SB_TILE);
-    int* s_anc = reinterpret_cast<int*>(s_w + SB_TILE);
-    unsigned char* p8 = reinterpret_cast<unsigned char*>(s_anc + SB_TILE);
+    uint32_t* s_w = reinterpret_cast<uint32_t*>(s_x + S8);
+    int* s_anc = reinterpret_cast<int*>(s_w + S8);
+    unsigned char* p8 = reinterpret_cast<unsigned char*>(s_anc + S8);
     p8 += (8 - (reinterpret_cast<size_t>(p8) & 7)) & 7;
     unsigned long long* s_cdf = reinterpret_cast<unsigned long long*>(p8);      // grid CDF (multinomial) ...
     double* s_acc = reinterpret_cast<double*>(p8);                              // ... or the literal running sum
-    double* s_wlit = reinterpret_cast<double*>(p8) + (SB_TILE + 8);
+    double* s_wlit = reinterpret_cast<double*>(p8) + (S8 + 8);
+    unsigned* s_marg = reinterpret_cast<unsigned*>(s_wlit + (S8 + 8));
+    int* s_hist = reinterpret_cast<int*>(s_marg + (a.marg_smem ? T * K : 0));
 
     const int tid = threadIdx.x;
     const int base = tid * SB_ITEMS;                                 // blocked: this thread's 8 pool slots
     const unsigned long long seed = a.seed + (unsigned long long)(a.chain0 + blockIdx.x) * SB_CHAIN_KEY;
-    int* xh = a.x_hist + (size_t)blockIdx.x * T * S;
-    int* ah = a.anc_hist + (size_t)blockIdx.x * T * S;
+    int* xh = a.hist_smem ? s_hist : a.x_hist + (size_t)blockIdx.x * T * S;
+    int* ah = a.hist_smem ? s_hist + (size_t)T * S : a.anc_hist + (size_t)blockIdx.x * T * S;
     int* xs = a.xstar + (size_t)blockIdx.x * 2 * T;
+    if (a.marg_smem) for (int i = tid; i < T * K; i += SB_THREADS) s_marg[i] = 0u;
 
     for (int i = tid; i < K * G; i += SB_THREADS) s_tabA[i] = __ldg(a.tabA + i);
     for (int i = tid; i < G; i += SB_THREADS) s_tab0[i] = __ldg(a.tab0 + i);
@@ -103,6 +113,9 @@ k_pmcmc_small(const __grid_constant__ SbSmallArgs a) {
         if (tid == 0) sm.lz = 0.0;
         // t runs to T inclusive: pass T only draws the ancestors after the last step (src/pmcmc.jl:42 at the last factor)
         for (int t = 0; t <= T; ++t) {
+            // this step's scores: requested now, needed after the resampling below
+            double lf = 0.0, ef = 0.0;
+            if (t < T && tid < K) { lf = __ldg(a.logF + (size_t)t * K + tid); ef = __ldg(a.expF + (size_t)t * K + tid); }
             // ------------------------------------------------------------ (1) resample the pool of step t-1
             if (t > 0) {
                 const int tp = t - 1;
@@ -165,12 +178,21 @@ k_pmcmc_small(const __grid_constant__ SbSmallArgs a) {
                         // literal reference numerics: sequentially rounded sum and running sum (src/pmcmc.jl:50, src/rand.jl:6-9)
                         if (tid == 0) {
                             double s = 0.0;
-                            for (int i = 0; i < n_pool; ++i) s = __dadd_rn(s, s_wlit[i]);
+                            for (int i = 0; i < n_pool; ++i) s = __dadd_rn(s, s_wlit[i]);      // sum(weights), one rounding per add
+                            sm.lits = s;
+                        }
+                        __syncthreads();
+                        {
+                            const double s = sm.lits;
+                            for (int i = tid; i < n_pool; i += SB_THREADS) s_acc[i] = __ddiv_rn(s_wlit[i], s);   // ps = weights / sum
+                        }
+                        __syncthreads();
+                        if (tid == 0) {
                             double acc = 0.0;
                             bool bad = false;
                             for (int i = 0; i < n_pool; ++i) {
-                                acc = __dadd_rn(acc, __ddiv_rn(s_wlit[i], s));
-                                if (isnan(acc) && (i < n_pool - 1 || n_pool == 1)) bad = true;
+                                acc = __dadd_rn(acc, s_acc[i]);                                  // src/rand.jl:7
+                                if (isnan(acc) && (i < n_pool - 1 || n_pool == 1)) bad = true;  // src/rand.jl:8,11
                                 s_acc[i] = acc;
                             }
                             if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
@@ -191,13 +213,20 @@ k_pmcmc_small(const __grid_constant__ SbSmallArgs a) {
             }
             // ------------------------------------------------------------ (2)+(3) gather parents, propagate (src/pmcmc.jl:32-34)
             int x[SB_ITEMS];
+            uint32_t r8[SB_ITEMS];
+            if (base < N) {                                               // one Philox block per four particles
+#pragma unroll
+                for (int p = 0; p < SB_ITEMS / 4; ++p) {
+                    const SbU4 o = sb_stream4(seed, (unsigned long long)((base >> 2) + p), (unsigned)t, iter, SB_P_PROP);
+                    r8[4 * p] = o.x; r8[4 * p + 1] = o.y; r8[4 * p + 2] = o.z; r8[4 * p + 3] = o.w;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) {
                 const int i = base + j;
                 int xv = 0;
                 if (i < N) {
-                    const SbU4 o = sb_stream4(seed, (unsigned long long)(i >> 2), (unsigned)t, iter, SB_P_PROP);
-                    const uint32_t R = (i & 3) == 0 ? o.x : ((i & 3) == 1 ? o.y : ((i & 3) == 2 ? o.z : o.w));
+                    const uint32_t R = r8[j];
                     const uint32_t* tab = t == 0 ? s_tab0 : s_tabA + ((size_t)s_x[s_anc[i]] << SB_LG_BUCKETS);
                     const uint32_t g = tab[R >> (32 - SB_LG_BUCKETS)];
                     xv = (int)(g & 63u) + (((R << SB_LG_BUCKETS) > g) ? 1 : 0);
@@ -213,14 +242,15 @@ k_pmcmc_small(const __grid_constant__ SbSmallArgs a) {
             }
             if (tid < K) {
                 if (FP32) {
-                    const float l2 = __fmul_rn((float)a.logF[(size_t)t * K + tid], SB_LOG2E_F);
+                    const float l2 = __fmul_rn((float)lf, SB_LOG2E_F);
                     if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
                     reinterpret_cast<float*>(s_l2)[tid] = l2;
                 } else {
-                    const double l2 = __dmul_rn(a.logF[(size_t)t * K + tid], SB_LOG2E_D);
+                    const double l2 = __dmul_rn(lf, SB_LOG2E_D);
                     if (isnan(l2) || l2 == INFINITY) atomicOr(a.err, SB_ERRBIT_NAN);
                     s_l2[tid] = l2;
                 }
+                s_ef[tid] = ef;
             }
             __syncthreads();                                             // every read of the old states is done; scores staged
             // ------------------------------------------------------------ (4)+(5) weight and quantise (one tile)
@@ -246,12 +276,12 @@ k_pmcmc_small(const __grid_constant__ SbSmallArgs a) {
             for (int j = 0; j < SB_ITEMS; ++j) {
                 const int i = base + j;
                 const uint32_t q = i < n_pool ? s_q[x[j]] : 0u;
-                s_x[i] = x[j];
-                s_w[i] = q;
                 tsum += q;
                 if (i < n_pool) {
+                    s_x[i] = x[j];
+                    s_w[i] = q;
                     xh[(size_t)t * S + i] = x[j];                        // Step push (src/pmcmc.jl:37)
-                    if (a.mode == SB_RESAMPLE_LITERAL) s_wlit[i] = a.expF[(size_t)t * K + x[j]];
+                    if (a.mode == SB_RESAMPLE_LITERAL) s_wlit[i] = s_ef[x[j]];
                 }
             }
             const unsigned long long Q = sb_block_sum_u64(tsum, sm.scan);
@@ -281,7 +311,8 @@ k_pmcmc_small(const __grid_constant__ SbSmallArgs a) {
             unsigned long long code = 0;
             for (int t = T - 1; t >= 0; --t) {
                 const int xv = xh[(size_t)t * S + j];
-                if (a.marg) atomicAdd(a.marg + (size_t)t * K + xv, 1ull);
+                if (a.marg_smem) atomicAdd(s_marg + t * K + xv, 1u);
+                else if (a.marg) atomicAdd(a.marg + (size_t)t * K + xv, 1ull);
                 code = code * (unsigned long long)K + (unsigned long long)xv;
                 if (t) j = ah[(size_t)(t - 1) * S + j];
             }
@@ -291,4 +322,6 @@ k_pmcmc_small(const __grid_constant__ SbSmallArgs a) {
         __syncthreads();                                                 // xstar of the next sweep is written; history may be overwritten
     }
     // the retained trajectory of the chain is now in buffer (iters & 1) of xstar
+    if (a.marg_smem && a.marg)
+        for (int i = tid; i < T * K; i += SB_THREADS) if (s_marg[i]) atomicAdd(a.marg + i, (unsigned long long)s_marg[i]);
 }

@@ -1024,7 +1024,12 @@ extern "C" int32_t sb_pmcmc_chains(sb_handle* h, int64_t chains, int64_t iters, 
     a.x_hist = h->sm_x.as<int>(); a.anc_hist = h->sm_a.as<int>(); a.xstar = h->sm_xs.as<int>();
     a.marg = h->marg.as<unsigned long long>(); a.joint = joint ? h->joint.as<unsigned long long>() : nullptr;
     a.logZ = h->sm_lz.as<double>(); a.err = h->d_err;
-    const size_t smem = sb_small_smem_bytes(K);
+    // history and per-time counts stay on chip when they are small (they then cost no global round trips in the
+    // lineage walks); counts: iters * N per cell must fit 32 bits
+    a.marg_smem = (marg && (size_t)T * K <= 4096 && (double)iters * (double)N < 4.0e9) ? 1 : 0;
+    a.hist_smem = ((size_t)2 * T * S * 4 <= 48 * 1024) ? 1 : 0;
+    const size_t smem = sb_small_smem_bytes(K, T, S, a.hist_smem, a.marg_smem);
+    if (smem > 200 * 1024) return fail(h, SB_EUNSUPPORTED, "pmcmc_chains: model tables do not fit in shared memory");
     int rc;
     if ((rc = begin_timed(h)) != SB_OK) return rc;
     const bool fp32 = h->opt.precision == SB_FP32;
