@@ -1278,6 +1278,82 @@ k_mh_bnet(const __grid_constant__ SbBnetArgs a) {
     if (live && acc) atomicAdd(a.accepts, acc);
 }
 
+// Same chains for nets of at most SB_MH_TABD sites: everything a step needs is a function of (site, state), so each
+// CTA tabulates it once -- P(site = 1 | parents) and the acceptance probability min(1, exp(log_mh_ratio)) of
+// src/mh.jl:78,95-111, computed with the SAME sequence of fp64 operations as k_mh_bnet -- and a step is one Philox
+// block, two shared-memory loads and two compares.  Bit-identical chains, about a quarter of the instructions.
+#define SB_MH_TABD 8
+__global__ void __launch_bounds__(128)
+k_mh_bnet_tab(const __grid_constant__ SbBnetArgs a) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const int D = a.D, F = a.F, st = a.stride;
+    const int NS = 1 << D;
+    double* s_p1 = reinterpret_cast<double*>(dyn);            // [D][NS]
+    double* s_acc = s_p1 + D * NS;                            // [D][NS][2]
+    double* s_score = s_acc + 2 * D * NS;                     // [NS]
+    double* s_cs = s_score + NS;                              // [D][NS]
+    unsigned* s_hist = reinterpret_cast<unsigned*>(s_cs + D * NS);
+    const int nq = __popc(a.query_mask), nv = 1 << nq;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < nwarps * nv; i += blockDim.x) s_hist[i] = 0u;
+    for (int s = threadIdx.x; s < NS; s += blockDim.x) {      // choice scores and total score of every state (src/mh.jl:33,42)
+        double sc = 0.0;
+        for (int d = 0; d < D; ++d) {
+            const unsigned idx = sb_pack_bits((unsigned)s, a.site_parents[d]);
+            const double c = ((s >> d) & 1) ? a.site_lp1[d * st + idx] : a.site_lp0[d * st + idx];
+            s_cs[d * NS + s] = c;
+            s_p1[d * NS + s] = a.site_cpt[d * st + idx];
+            sc = __dadd_rn(sc, c);
+        }
+        for (int f = 0; f < F; ++f) sc = __dadd_rn(sc, a.fac_logf[f * st + sb_pack_bits((unsigned)s, a.fac_parents[f])]);
+        s_score[s] = sc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D * NS * 2; i += blockDim.x) {
+        const int b = i & 1, s = (i >> 1) & (NS - 1), d = i >> (D + 1);
+        const int prop = (s & ~(1 << d)) | (b << d);
+        const double lr = __dsub_rn(__dadd_rn(__dsub_rn(s_score[prop], s_score[s]), s_cs[d * NS + s]), s_cs[d * NS + prop]);   // mh.jl:110
+        const double ar = exp(lr);
+        s_acc[i] = isnan(ar) ? -1.0 : (ar < 1.0 ? ar : 1.0);                                                                   // mh.jl:78
+    }
+    __syncthreads();
+    const long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = ch < a.chains;
+    const unsigned long long gch = (unsigned long long)(a.chain0 + ch);
+    unsigned state = 0;
+    unsigned long long acc = 0;
+#pragma unroll 1
+    for (int d = 0; d < D; ++d) {                              // src/mh.jl:57 -- run once from the prior
+        const SbU4 o = sb_stream4(a.seed, gch, (unsigned)d, 0u, SB_P_INIT);
+        if (__dmul_rn((double)o.x, 0x1p-32) < s_p1[d * NS + state]) state |= 1u << d;
+    }
+    unsigned* hist = s_hist + warp * nv;
+    for (long long s = 0; s < a.steps; ++s) {
+        const SbU4 o = sb_stream4(a.seed, gch, (unsigned)s, (unsigned)(s >> 32), SB_P_MH);
+        const int j = (int)__umulhi(o.x, (unsigned)D);                               // mh.jl:62
+        const double up = __dmul_rn((double)o.y, 0x1p-32), ua = __dmul_rn((double)o.z, 0x1p-32);
+        const int b = up < s_p1[j * NS + state] ? 1 : 0;                             // mh.jl:70-76
+        if (ua < s_acc[(((j << D) + (int)state) << 1) + b]) {
+            state = (state & ~(1u << j)) | ((unsigned)b << j);
+            ++acc;
+        }
+        const unsigned v = sb_pack_bits(state, a.query_mask);                        // mh.jl:87
+        const unsigned act = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const unsigned peers = __match_any_sync(act, v);
+            if (lane == __ffs(peers) - 1) hist[v] += __popc(peers);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        unsigned long long t = 0;
+        for (int w = 0; w < nwarps; ++w) t += s_hist[w * nv + v];
+        if (t) atomicAdd(a.counts + v, t);
+    }
+    if (live && acc) atomicAdd(a.accepts, acc);
+}
+
 // =====================================================================================
 // ERP vocabulary (src/erp.jl:1-30): samplers and log-densities.  Distributions.jl 0.6.3 is not
 // in the reference tree, so these are the textbook algorithms; validated statistically.

@@ -1209,7 +1209,15 @@ extern "C" int32_t sb_mh_run(sb_handle* h, int64_t chains, int64_t steps, int64_
     const size_t smem = (size_t)(3 * a.D + a.F) * a.stride * 8 + (size_t)(a.D + a.F) * 4 + (size_t)(threads / 32) * nv * 4;
     int rc;
     if ((rc = begin_timed(h)) != SB_OK) return rc;
-    k_mh_bnet<<<(unsigned)((chains + threads - 1) / threads), threads, smem, h->stream>>>(a);
+    if (a.D <= SB_MH_TABD && !getenv("SB_MH_NOTAB")) {
+        // small nets: per-(site, state) tables in shared memory (k_mh_bnet_tab); bit-identical chains
+        const size_t ns = (size_t)1 << a.D;
+        const size_t smem_t = (size_t)(4 * a.D + 1) * ns * 8 + (size_t)(threads / 32) * nv * 4;
+        if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(k_mh_bnet_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+        k_mh_bnet_tab<<<(unsigned)((chains + threads - 1) / threads), threads, smem_t, h->stream>>>(a);
+    } else {
+        k_mh_bnet<<<(unsigned)((chains + threads - 1) / threads), threads, smem, h->stream>>>(a);
+    }
     LAUNCH_CHECK();
     if ((rc = end_timed(h)) != SB_OK) return rc;
     std::vector<unsigned long long> tmp((size_t)nv + 1);

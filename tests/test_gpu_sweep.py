@@ -422,3 +422,39 @@ def test_pmcmc_one_tile_route_equals_tiled_kernels(monkeypatch, resample):
     assert np.array_equal(outs[0][2], outs[1][2])
     assert outs[0][3] == pytest.approx(outs[1][3], rel=1e-12)
     assert outs[1][4] == 1 and outs[0][4] > 100          # one launch instead of hundreds
+
+
+@pytest.mark.parametrize("D", [1, 5, 8, 10])
+def test_mh_random_nets_bitexact(oracle, monkeypatch, D):
+    """Random binary Bayes nets (up to three parents per site, two factor statements, one of them hard): the batched
+    chains equal the oracle's chain for chain, with the per-(site, state) tables (D <= 8) and without (SB_MH_NOTAB)."""
+    sb = sb_mod()
+    rng = np.random.default_rng(40 + D)
+    sites, factors = [], []
+    for d in range(D):
+        npar = min(d, int(rng.integers(0, 4)))
+        par = rng.choice(d, size=npar, replace=False) if npar else []
+        mask = int(sum(1 << int(p) for p in par))
+        sites.append((mask, rng.uniform(0.05, 0.95, size=1 << npar).tolist()))
+    for f in range(2):
+        npar = min(D, 2)
+        par = rng.choice(D, size=npar, replace=False)
+        mask = int(sum(1 << int(p) for p in par))
+        tab = rng.normal(size=1 << npar)
+        if f == 1 and D > 1:
+            tab[0] = -np.inf                                    # a hard factor: -Inf scores must reject, NaN ratios too
+        factors.append((mask, tab.tolist()))
+    query = sorted(set(int(q) for q in rng.choice(D, size=min(D, 2), replace=False)))
+    net = sb.BayesNet(sites, factors, query)
+    ob = oracle.Bnet([m for m, _ in sites], [c for _, c in sites], [m for m, _ in factors], [t for _, t in factors], net.query_mask)
+    ref, racc = oracle.bnet_mh(ob, 9, 1000, 150, chain0=3)
+    for notab in [None, "1"]:
+        if notab:
+            monkeypatch.setenv("SB_MH_NOTAB", notab)
+        else:
+            monkeypatch.delenv("SB_MH_NOTAB", raising=False)
+        with sb.Engine(precision="fp64", seed=9) as eng:
+            eng.load(net)
+            got = eng.mh_counts(1000, 150, chain0=3)
+            assert np.array_equal(got, ref), "counts differ (SB_MH_NOTAB=%s)" % notab
+            assert eng.stats().accepts == racc
