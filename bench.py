@@ -124,6 +124,9 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the reference arm is rank 0 alone and may use every host
+    # core (libgomp reads the variable when the oracle library is loaded, which has not happened yet)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     vals = []
     for i in range(args.warmup + args.steps):
         v, cores, dt, sample = cpu_sample(budget_log2n=21, T=8)
