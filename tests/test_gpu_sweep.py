@@ -458,3 +458,38 @@ def test_mh_random_nets_bitexact(oracle, monkeypatch, D):
             got = eng.mh_counts(1000, 150, chain0=3)
             assert np.array_equal(got, ref), "counts differ (SB_MH_NOTAB=%s)" % notab
             assert eng.stats().accepts == racc
+
+
+def test_handle_reuse_across_sizes_and_models():
+    """One handle, many calls: growing and shrinking pools, discrete and linear-Gaussian models, hooks in between.
+    Every result must equal the result of a fresh handle (buffers regrown, cached launch configurations, state left
+    behind by the previous call must not leak into the next)."""
+    sb = sb_mod()
+    A, logF, pi = cfg3_tables(T=5)
+    d = cfg4_data(T=5)
+    hmm, lg = sb.DiscreteHMM(A, logF, pi=pi), sb.LinearGaussian(**d)
+    plan = [("hmm", 100), ("hmm", 5000), ("lg", 70000), ("hmm", (1 << 20) + 5), ("hook", 30001), ("lg", 17),
+            ("hmm", 3000), ("pmcmc", 300), ("hmm", 2048), ("lg", 1 << 21), ("pmcmc", 2500), ("hmm", 17)]
+    rng = np.random.default_rng(3)
+    w = rng.random(30001)
+
+    def run(eng, what, n):
+        if what == "hmm":
+            eng.load(hmm)
+            return eng.smc_sweep(n, it=1), eng.particles(n)
+        if what == "lg":
+            eng.load(lg)
+            return eng.smc_sweep(n, it=1), eng.particles(n)
+        if what == "hook":
+            return 0.0, eng.resample_systematic(w, 0.77, n)
+        eng.load(hmm)
+        marg, _ = eng.pmcmc_counts(3, n, want_joint=False)
+        return eng.stats().logZ_last, marg
+
+    with sb.Engine(precision="fp32", resample="systematic", seed=8) as shared:
+        for what, n in plan:
+            got = run(shared, what, n)
+            with sb.Engine(precision="fp32", resample="systematic", seed=8) as fresh:
+                ref = run(fresh, what, n)
+            assert got[0] == ref[0], (what, n)
+            assert np.array_equal(got[1], ref[1]), (what, n)
