@@ -384,7 +384,7 @@ __device__ __forceinline__ int sb_pull_k(long long baseb, unsigned long long acc
     const long long D = baseb + (long long)(acc >> rb);
     if (S32) {
         const int k = (int)(D >> 32) >> (s - 32);
-        return min(max(k, 0), cw);
+        return __vimin_s32_relu(k, cw);                          // max(min(k, cw), 0) in one instruction
     }
     const long long k = D >> s;
     return k <= 0 ? 0 : (k >= (long long)cw ? cw : (int)k);
@@ -524,9 +524,8 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
         const int4 b = reinterpret_cast<const int4*>(sm.marker)[tid * 2 + 1];
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
-#pragma unroll
-    for (int j = 1; j < SB_ITEMS; ++j) v[j] = max(v[j], v[j - 1]);
-    int inc = v[SB_ITEMS - 1];
+    // the thread's largest marker (3-input max), for the scan across threads
+    int inc = __vimax3_s32(__vimax3_s32(v[0], v[1], v[2]), __vimax3_s32(v[3], v[4], v[5]), max(v[6], v[7]));
     const int lane = tid & 31;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -545,7 +544,7 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
     }
     prev = max(prev, 0);
 #pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) anc[j] = max(v[j], prev);
+    for (int j = 0; j < SB_ITEMS; ++j) { prev = max(v[j], prev); anc[j] = prev; }   // running max: each child takes the last head at or before it
 }
 
 // Candidate parent tiles of this CTA's next SB_FT_CHUNK + 1 children tiles (tile, tile + grid, ...), looked

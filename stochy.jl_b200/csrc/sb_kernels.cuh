@@ -740,8 +740,13 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     // (4)+(5) weight and quantise.  Only K distinct scores exist: the tile exponent is the largest
     // ceil(log2 weight) present (an integer max), and 2^(l2 - e) 2^27 comes from a K x K table.
     unsigned key = 0u;
+    if (!TAIL) {
+        key = __vimax3_u32(__vimax3_u32(s_key[x[0]], s_key[x[1]], s_key[x[2]]), __vimax3_u32(s_key[x[3]], s_key[x[4]], s_key[x[5]]),
+                           max(s_key[x[6]], s_key[x[7]]));
+    } else {
 #pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) if (!TAIL || base + j < a.n_out) key = max(key, s_key[x[j]]);
+        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) key = max(key, s_key[x[j]]);
+    }
     key = __reduce_max_sync(0xffffffffu, key);
     if ((tid & 31) == 0) reinterpret_cast<unsigned*>(sm.red)[tid >> 5] = key;
     __syncthreads();
