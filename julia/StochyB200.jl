@@ -181,7 +181,7 @@ end
 # ---- enum(store, k, address, comp)   (src/enumerate.jl:57-85): exhaustive, exact.  returns[value] += exp(score)
 function enum(store, k::Function, address, comp; kw...)
     comp isa DiscreteHMM || error("enum: only the fixed-structure discrete model is enumerated on the GPU path")
-    h = create(; precision=SB_FP64, kw...)
+    h = create(; kw..., precision=SB_FP64)
     returns = try
         load!(h, comp)
         K, T = size(comp.A, 1), size(comp.logF, 1)
