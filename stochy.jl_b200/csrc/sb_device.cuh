@@ -374,6 +374,11 @@ struct __align__(16) SbPullSmem {
     unsigned long long scan[SB_WARPS + 1];
     int wmax[SB_WARPS];
     int2 ft[SB_FT_CHUNK + 1];                // (first, last) candidate parent tile of this CTA's next children tiles
+    // per children tile, written by warp 0 before the tile's first barrier: the rescale constants of the two
+    // staged parent tiles and the child index (relative, clamped) at each of their 8 warp boundaries + end
+    long long seg_baseb[2];
+    int seg_rb[2];
+    int seg_k[2][SB_WARPS + 1];
 };
 
 // children (relative to c0, clamped to [0, cw]) whose threshold lies strictly below the CDF value
@@ -390,27 +395,33 @@ __device__ __forceinline__ int sb_pull_k(long long baseb, unsigned long long acc
     return k <= 0 ? 0 : (k >= (long long)cw ? cw : (int)k);
 }
 
+// 64-bit accumulate of a 32 x 32 -> 64 product in ONE instruction (IMAD.WIDE.U32 with a 64-bit addend)
+__device__ __forceinline__ unsigned long long sb_mad_wide(uint32_t a, uint32_t b, unsigned long long c) {
+    unsigned long long d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
 // One parent tile's contribution to the children [c0, c0 + cw): warp scan of its weights on top of
 // the warp prefix the producer left, then every parent that owns children in range writes its
 // index at its first child's slot ("head marker").  No block-level synchronisation.
-// A warp whose 256 parents own no child in range (known from its prefix and the next warp's) skips
-// everything: a children tile overlaps about one tile's worth of parents out of the two staged.
+// A warp whose 256 parents own no child in range (k1 <= k0: the child index at its prefix and at the next
+// warp's, looked up by the caller) skips everything: a children tile overlaps about one tile's worth of
+// parents out of the two staged.
 // wsrc: the tile's weights (shared-memory stage or global memory), read only by warps that work.
+//
+// Inside a thread the CDF is evaluated exactly ONCE with the full 64-bit formula (at the thread's own
+// exclusive prefix c):  D0 = baseb + (c R >> rb),  K = D0 >> s.  For the prefix c + a (a < 2^30: partial
+// sums of the thread's 8 weights) the nested-floor identity gives
+//     (baseb + ((c + a) R >> rb)) >> s  ==  K + ((Z0 + a R) >> (rb + s)),   Z0 = (D0 mod 2^s) 2^rb + (c R mod 2^rb),
+// so each further parent costs one multiply-accumulate into Z and one 32-bit shift of Z's high word
+// (rb + s in [32, 62], the ordinary case; other shifts take the literal formula).
 template <bool S32>
-__device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const uint32_t* __restrict__ wsrc, int eb,
-                                             unsigned long long Ptb, unsigned long long wbase, unsigned long long wnext,
-                                             int ce_rel, int c0, int cw, SbPullSmem& sm) {
+__device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const uint32_t* __restrict__ wsrc,
+                                             long long baseb, int rb, unsigned long long wbase, int cw, SbPullSmem& sm) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int s = si.s;
     const unsigned R = si.R;
-    // tile-uniform constants; rb < 64 because the tile owns children
-    const int rb = si.r0 + (si.E - eb);
-    const long long baseb = (long long)(Ptb - si.U) + ((1ll << s) - 1ll) - ((long long)c0 << s);
-    {
-        const int k0 = sb_pull_k<S32>(baseb, wbase * (unsigned long long)R, rb, s, cw);
-        const int k1 = (tid >> 5) == SB_WARPS - 1 ? ce_rel : sb_pull_k<S32>(baseb, wnext * (unsigned long long)R, rb, s, cw);
-        if (k1 <= k0) return;                                    // warp-uniform
-    }
     uint32_t w[SB_ITEMS];
     {
         const uint4 u = reinterpret_cast<const uint4*>(wsrc)[tid * 2], v = reinterpret_cast<const uint4*>(wsrc)[tid * 2 + 1];
@@ -425,16 +436,34 @@ __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const 
         const unsigned long long o = sb_shfl_up_u64(inc, d);
         if (lane >= d) inc += o;
     }
-    if (tsum != 0) {
-        const unsigned long long c = wbase + inc - tsum;        // tile-local exclusive prefix of this thread
-        unsigned long long acc = c * (unsigned long long)R;
-        int lo = sb_pull_k<S32>(baseb, acc, rb, s, cw);
-        const int hi_t = sb_pull_k<S32>(baseb, acc + (unsigned long long)tsum * R, rb, s, cw);
+    if (tsum == 0) return;
+    const unsigned long long c = wbase + inc - tsum;            // tile-local exclusive prefix of this thread
+    unsigned long long acc = c * (unsigned long long)R;
+    const int base = b * SB_TILE + tid * SB_ITEMS;
+    const int sh = rb + s;
+    if (S32 && sh <= 62) {
+        const long long D0 = baseb + (long long)(acc >> rb);
+        const int K = min((int)(D0 >> 32) >> (s - 32), 1 << 29);   // children below this thread: < 2^28, no overflow
+        unsigned long long Z = (((unsigned long long)D0 & ((1ull << s) - 1ull)) << rb) | (acc & ((1ull << rb) - 1ull));
+        const int sh32 = sh - 32;
+        int lo = __vimin_s32_relu(K, cw);
+        const int hi_t = __vimin_s32_relu(K + (int)((uint32_t)(sb_mad_wide(tsum, R, Z) >> 32) >> sh32), cw);
         if (hi_t > lo) {                                         // this thread's parents own children in range
-            const int base = b * SB_TILE + tid * SB_ITEMS;
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) {
-                acc += (unsigned long long)w[j] * R;             // one IMAD.WIDE with 64-bit accumulate
+                Z = sb_mad_wide(w[j], R, Z);
+                const int hi = (j == SB_ITEMS - 1) ? hi_t : __vimin_s32_relu(K + (int)((uint32_t)(Z >> 32) >> sh32), cw);
+                if (lo < hi) sm.marker[lo] = base + j;
+                lo = hi;
+            }
+        }
+    } else {
+        int lo = sb_pull_k<S32>(baseb, acc, rb, s, cw);
+        const int hi_t = sb_pull_k<S32>(baseb, acc + (unsigned long long)tsum * R, rb, s, cw);
+        if (hi_t > lo) {
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) {
+                acc += (unsigned long long)w[j] * R;
                 const int hi = (j == SB_ITEMS - 1) ? hi_t : sb_pull_k<S32>(baseb, acc, rb, s, cw);
                 if (lo < hi) sm.marker[lo] = base + j;
                 lo = hi;
@@ -487,7 +516,7 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
                                                   const int* __restrict__ child_start, int c0, int2 rng, int slot,
                                                   uint32_t parity, bool more, int next_b_lo, SbPullSmem& sm,
                                                   int anc[SB_ITEMS]) {
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = (int)si.m;
     const int c1 = min(c0 + SB_TILE, m);
     const int cw = max(c1 - c0, 0);
@@ -498,43 +527,69 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
         reinterpret_cast<int4*>(sm.marker)[tid * 2] = neg;
         reinterpret_cast<int4*>(sm.marker)[tid * 2 + 1] = neg;
     }
-    if (warp == 0) sb_cp_async_wait_all();
+    if (warp == 0) {
+        // the records of the two staged parent tiles have landed (this warp's own cp.async): 18 lanes evaluate
+        // the CDF at the 2 x (8 warp boundaries + tile end) ONCE for the CTA; every warp then decides from
+        // two table entries per tile whether its 256 parents own children here
+        sb_cp_async_wait_all();
+        __syncwarp();
+        if (lane < 2 * (SB_WARPS + 1)) {
+            const SbPullMeta& mt = sm.meta[slot];
+            const int which = lane >= SB_WARPS + 1 ? 1 : 0, bi = lane - which * (SB_WARPS + 1);
+            const int cs = mt.cs[which], ce = mt.ce[which];
+            bool use = !(ce <= c0 || cs >= c1 || ce == cs);
+            if (which) use = use && bB != bA && bB <= b_hi;
+            int kk = 0;
+            if (use) {
+                const int rb = si.r0 + (si.E - mt.e[which]);      // < 64 because the tile owns children
+                const long long baseb = (long long)(mt.Pt[which] - si.U) + ((1ll << si.s) - 1ll) - ((long long)c0 << si.s);
+                if (bi < SB_WARPS) kk = sb_pull_k<S32>(baseb, mt.wp[which][bi] * (unsigned long long)si.R, rb, si.s, cw);
+                else { kk = min(max(ce - c0, 0), cw); sm.seg_baseb[which] = baseb; sm.seg_rb[which] = rb; }
+            }
+            sm.seg_k[which][bi] = kk;
+        }
+    }
     sb_mbar_wait(&sm.bar, parity);
     __syncthreads();
-    const SbPullMeta& mt = sm.meta[slot];
-    const int csA = mt.cs[0], ceA = mt.ce[0], csB = mt.cs[1], ceB = mt.ce[1];
-    const bool useA = !(ceA <= c0 || csA >= c1 || ceA == csA);
-    const bool useB = bB != bA && bB <= b_hi && !(ceB <= c0 || csB >= c1 || ceB == csB);
-    const int wn = min(warp + 1, SB_WARPS - 1);                  // the last warp's end is the tile's own child_start
-    if (useA) sb_pull_tile<S32>(si, bA, sm.w[0], mt.e[0], mt.Pt[0], mt.wp[0][warp], mt.wp[0][wn], min(max(ceA - c0, 0), cw), c0, cw, sm);
-    if (useB) sb_pull_tile<S32>(si, bB, sm.w[1], mt.e[1], mt.Pt[1], mt.wp[1][warp], mt.wp[1][wn], min(max(ceB - c0, 0), cw), c0, cw, sm);
+    {
+        const SbPullMeta& mt = sm.meta[slot];
+        if (sm.seg_k[0][warp + 1] > sm.seg_k[0][warp])
+            sb_pull_tile<S32>(si, bA, sm.w[0], sm.seg_baseb[0], sm.seg_rb[0], mt.wp[0][warp], cw, sm);
+        if (sm.seg_k[1][warp + 1] > sm.seg_k[1][warp])
+            sb_pull_tile<S32>(si, bB, sm.w[1], sm.seg_baseb[1], sm.seg_rb[1], mt.wp[1][warp], cw, sm);
+    }
     for (int b = b_lo + 2; b <= b_hi; ++b) {
         const int cs = __ldg(child_start + b), ce = __ldg(child_start + b + 1);
         if (ce <= c0 || cs >= c1 || ce == cs) continue;          // no offspring in range (uniform branch)
         const unsigned long long* wpb = sb_pool_wp_ptr<PEERS>(pool, b);
-        sb_pull_tile<S32>(si, b, sb_pool_tile<PEERS>(pool, b), __ldg(e + b), __ldg(Pt + b), __ldg(wpb + warp), __ldg(wpb + wn),
-                          min(max(ce - c0, 0), cw), c0, cw, sm);
+        const int rb = si.r0 + (si.E - __ldg(e + b));
+        const long long baseb = (long long)(__ldg(Pt + b) - si.U) + ((1ll << si.s) - 1ll) - ((long long)c0 << si.s);
+        const unsigned long long wbase = __ldg(wpb + warp);
+        const int k0 = sb_pull_k<S32>(baseb, wbase * (unsigned long long)si.R, rb, si.s, cw);
+        const int k1 = warp == SB_WARPS - 1 ? min(max(ce - c0, 0), cw)
+                                            : sb_pull_k<S32>(baseb, __ldg(wpb + warp + 1) * (unsigned long long)si.R, rb, si.s, cw);
+        if (k1 > k0) sb_pull_tile<S32>(si, b, sb_pool_tile<PEERS>(pool, b), baseb, rb, wbase, cw, sm);
     }
     __syncthreads();                                             // markers complete; sm.w and sm.meta[slot] are free
     if (more && warp == 0) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, next_b_lo, slot ^ 1, sm);
-    // inclusive max-scan of the head markers fills every child slot with its parent
+    // every child takes the last head marker at or before its slot.  Markers ascend with the slot (the CDF is
+    // monotone), so the carry into a thread is the largest marker of the nearest earlier thread that has one:
+    // a ballot and one shuffle instead of a max-scan across the warp
     int v[SB_ITEMS];
     {
         const int4 a = reinterpret_cast<const int4*>(sm.marker)[tid * 2];
         const int4 b = reinterpret_cast<const int4*>(sm.marker)[tid * 2 + 1];
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
-    // the thread's largest marker (3-input max), for the scan across threads
-    int inc = __vimax3_s32(__vimax3_s32(v[0], v[1], v[2]), __vimax3_s32(v[3], v[4], v[5]), max(v[6], v[7]));
-    const int lane = tid & 31;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc = max(inc, o);
+    const int inc = __vimax3_s32(__vimax3_s32(v[0], v[1], v[2]), __vimax3_s32(v[3], v[4], v[5]), max(v[6], v[7]));
+    const unsigned has = __ballot_sync(0xffffffffu, inc >= 0);
+    const unsigned below = has & ((1u << lane) - 1u);
+    int prev = __shfl_sync(0xffffffffu, inc, (31 - __clz(below)) & 31);
+    if (!below) prev = -1;
+    {
+        const int last = __shfl_sync(0xffffffffu, inc, (31 - __clz(has)) & 31);
+        if (lane == 0) sm.wmax[warp] = has ? last : -1;
     }
-    if (lane == 31) sm.wmax[warp] = inc;
-    int prev = __shfl_up_sync(0xffffffffu, inc, 1);
-    if (lane == 0) prev = -1;
     __syncthreads();
     {
         const int4 a = reinterpret_cast<const int4*>(sm.wmax)[0], b = reinterpret_cast<const int4*>(sm.wmax)[1];
