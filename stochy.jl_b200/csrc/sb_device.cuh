@@ -494,13 +494,17 @@ __device__ __forceinline__ void sb_pull_prefetch(const SbStepInfo& si, const SbP
         sb_bulk_g2s(sm.w[0], sb_pool_tile<PEERS>(pool, bA), SB_TILE * 4u, &sm.bar);
         sb_bulk_g2s(sm.w[1], sb_pool_tile<PEERS>(pool, bB), SB_TILE * 4u, &sm.bar);
     }
+    // tile records: lanes 0-15 the 2 x 8 warp prefixes, 16-17 Pt (8 bytes each); 18-19 child_start, 20-21 child_start + 1,
+    // 22-23 e (4 bytes each).  Source and destination are selected per lane (no divergent branches).
     SbPullMeta& mt = sm.meta[slot];
-    const int which = (lane >> 3) & 1 ? 1 : 0;                   // lanes 0-7: A, 8-15: B (warp prefixes)
-    if (lane < 16) sb_cp_async8(&mt.wp[which][lane & 7], sb_pool_wp_ptr<PEERS>(pool, which ? bB : bA) + (lane & 7));
-    else if (lane < 18) sb_cp_async8(&mt.Pt[lane - 16], Pt + (lane == 16 ? bA : bB));
-    else if (lane < 20) sb_cp_async4(&mt.cs[lane - 18], child_start + (lane == 18 ? bA : bB));
-    else if (lane < 22) sb_cp_async4(&mt.ce[lane - 20], child_start + (lane == 20 ? bA : bB) + 1);
-    else if (lane < 24) sb_cp_async4(&mt.e[lane - 22], e + (lane == 22 ? bA : bB));
+    const int which = lane < 16 ? (lane >> 3) : (lane & 1);
+    const int bsel = which ? bB : bA;
+    const unsigned long long* src8 = lane < 16 ? sb_pool_wp_ptr<PEERS>(pool, bsel) + (lane & 7) : Pt + bsel;
+    unsigned long long* dst8 = lane < 16 ? &mt.wp[which][lane & 7] : &mt.Pt[which];
+    const int* src4 = lane < 22 ? child_start + bsel + (lane >= 20 ? 1 : 0) : e + bsel;
+    int* dst4 = lane < 20 ? &mt.cs[which] : (lane < 22 ? &mt.ce[which] : &mt.e[which]);
+    if (lane < 18) sb_cp_async8(dst8, src8);
+    else if (lane < 24) sb_cp_async4(dst4, src4);
     sb_cp_async_commit();
 }
 
@@ -529,25 +533,22 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
     }
     if (warp == 0) {
         // the records of the two staged parent tiles have landed (this warp's own cp.async): 18 lanes evaluate
-        // the CDF at the 2 x (8 warp boundaries + tile end) ONCE for the CTA; every warp then decides from
-        // two table entries per tile whether its 256 parents own children here
+        // the CDF at the 2 x (8 warp boundaries + tile end) ONCE for the CTA (straight-line code); every warp
+        // then decides from two table entries per tile whether its 256 parents own children here
         sb_cp_async_wait_all();
         __syncwarp();
-        if (lane < 2 * (SB_WARPS + 1)) {
-            const SbPullMeta& mt = sm.meta[slot];
-            const int which = lane >= SB_WARPS + 1 ? 1 : 0, bi = lane - which * (SB_WARPS + 1);
-            const int cs = mt.cs[which], ce = mt.ce[which];
-            bool use = !(ce <= c0 || cs >= c1 || ce == cs);
-            if (which) use = use && bB != bA && bB <= b_hi;
-            int kk = 0;
-            if (use) {
-                const int rb = si.r0 + (si.E - mt.e[which]);      // < 64 because the tile owns children
-                const long long baseb = (long long)(mt.Pt[which] - si.U) + ((1ll << si.s) - 1ll) - ((long long)c0 << si.s);
-                if (bi < SB_WARPS) kk = sb_pull_k<S32>(baseb, mt.wp[which][bi] * (unsigned long long)si.R, rb, si.s, cw);
-                else { kk = min(max(ce - c0, 0), cw); sm.seg_baseb[which] = baseb; sm.seg_rb[which] = rb; }
-            }
-            sm.seg_k[which][bi] = kk;
-        }
+        const SbPullMeta& mt = sm.meta[slot];
+        const int which = lane >= SB_WARPS + 1 ? 1 : 0, bi = lane - which * (SB_WARPS + 1);
+        const int cs = mt.cs[which], ce = mt.ce[which];
+        bool use = !(ce <= c0 || cs >= c1 || ce == cs);
+        if (which) use = use && bB != bA && bB <= b_hi;
+        const int rb = (si.r0 + (si.E - mt.e[which])) & 63;       // < 64 when the tile owns children (else unused)
+        const long long baseb = (long long)(mt.Pt[which] - si.U) + ((1ll << si.s) - 1ll) - ((long long)c0 << si.s);
+        int kk = sb_pull_k<S32>(baseb, mt.wp[which][bi & (SB_WARPS - 1)] * (unsigned long long)si.R, rb, si.s, cw);
+        if (bi == SB_WARPS) kk = min(max(ce - c0, 0), cw);         // the last warp ends at the tile's own child_start
+        if (!use) kk = 0;
+        if (lane < 2 * (SB_WARPS + 1)) sm.seg_k[which][bi] = kk;
+        if (bi == 0 && lane < 2 * (SB_WARPS + 1)) { sm.seg_baseb[which] = baseb; sm.seg_rb[which] = rb; }
     }
     sb_mbar_wait(&sm.bar, parity);
     __syncthreads();
