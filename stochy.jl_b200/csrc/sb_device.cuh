@@ -372,7 +372,6 @@ struct __align__(16) SbPullSmem {
     SbPullMeta meta[2];                      // double-buffered (cp.async, one tile ahead)
     unsigned long long bar;                  // mbarrier: the bytes of w have landed
     unsigned long long scan[SB_WARPS + 1];
-    int wmax[SB_WARPS];
     int2 ft[SB_FT_CHUNK + 1];                // (first, last) candidate parent tile of this CTA's next children tiles
     // per children tile, written by warp 0 before the tile's first barrier: the rescale constants of the two
     // staged parent tiles and the child index (relative, clamped) at each of their 8 warp boundaries + end
@@ -441,32 +440,51 @@ __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const 
     unsigned long long acc = c * (unsigned long long)R;
     const int base = b * SB_TILE + tid * SB_ITEMS;
     const int sh = rb + s;
+    // hi[j]: children (relative, clamped) below the END of parent j; parent j owns the slots [hi[j-1], hi[j])
+    int lo0, hi[SB_ITEMS];
     if (S32 && sh <= 62) {
         const long long D0 = baseb + (long long)(acc >> rb);
         const int K = min((int)(D0 >> 32) >> (s - 32), 1 << 29);   // children below this thread: < 2^28, no overflow
         unsigned long long Z = (((unsigned long long)D0 & ((1ull << s) - 1ull)) << rb) | (acc & ((1ull << rb) - 1ull));
         const int sh32 = sh - 32;
-        int lo = __vimin_s32_relu(K, cw);
-        const int hi_t = __vimin_s32_relu(K + (int)((uint32_t)(sb_mad_wide(tsum, R, Z) >> 32) >> sh32), cw);
-        if (hi_t > lo) {                                         // this thread's parents own children in range
+        lo0 = __vimin_s32_relu(K, cw);
+        hi[SB_ITEMS - 1] = __vimin_s32_relu(K + (int)((uint32_t)(sb_mad_wide(tsum, R, Z) >> 32) >> sh32), cw);
+        if (hi[SB_ITEMS - 1] <= lo0) return;                     // this thread's parents own no children in range
 #pragma unroll
-            for (int j = 0; j < SB_ITEMS; ++j) {
-                Z = sb_mad_wide(w[j], R, Z);
-                const int hi = (j == SB_ITEMS - 1) ? hi_t : __vimin_s32_relu(K + (int)((uint32_t)(Z >> 32) >> sh32), cw);
-                if (lo < hi) sm.marker[lo] = base + j;
-                lo = hi;
-            }
+        for (int j = 0; j < SB_ITEMS - 1; ++j) {
+            Z = sb_mad_wide(w[j], R, Z);
+            hi[j] = __vimin_s32_relu(K + (int)((uint32_t)(Z >> 32) >> sh32), cw);
         }
     } else {
-        int lo = sb_pull_k<S32>(baseb, acc, rb, s, cw);
-        const int hi_t = sb_pull_k<S32>(baseb, acc + (unsigned long long)tsum * R, rb, s, cw);
-        if (hi_t > lo) {
+        lo0 = sb_pull_k<S32>(baseb, acc, rb, s, cw);
+        hi[SB_ITEMS - 1] = sb_pull_k<S32>(baseb, acc + (unsigned long long)tsum * R, rb, s, cw);
+        if (hi[SB_ITEMS - 1] <= lo0) return;
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS - 1; ++j) {
+            acc += (unsigned long long)w[j] * R;
+            hi[j] = sb_pull_k<S32>(baseb, acc, rb, s, cw);
+        }
+    }
+    // head markers; and the owner of the first 256-slot boundary above lo0 (the first slot of the next warp of
+    // children) writes a marker there too, so the fill of the markers never has to look across warps:
+    // it is parent number #{j : hi[j] <= bnd} of this thread
+    const int bnd = (lo0 | 255) + 1;
+    int lo = lo0, nbelow = 0;
+#pragma unroll
+    for (int j = 0; j < SB_ITEMS; ++j) {
+        if (lo < hi[j]) sm.marker[lo] = base + j;
+        if (j < SB_ITEMS - 1) nbelow += hi[j] <= bnd ? 1 : 0;
+        lo = hi[j];
+    }
+    if (hi[SB_ITEMS - 1] > bnd) {
+        sm.marker[bnd] = base + nbelow;
+        if (hi[SB_ITEMS - 1] > bnd + 256) {                       // a parent with hundreds of children: every boundary it covers
+            lo = lo0;
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) {
-                acc += (unsigned long long)w[j] * R;
-                const int hi = (j == SB_ITEMS - 1) ? hi_t : sb_pull_k<S32>(baseb, acc, rb, s, cw);
-                if (lo < hi) sm.marker[lo] = base + j;
-                lo = hi;
+#pragma unroll 1
+                for (int q = (lo | 255) + 1; q < hi[j]; q += 256) sm.marker[q] = base + j;
+                lo = hi[j];
             }
         }
     }
@@ -508,12 +526,59 @@ __device__ __forceinline__ void sb_pull_prefetch(const SbStepInfo& si, const SbP
     sb_cp_async_commit();
 }
 
+// Warp 0 only, after the tile records of (rng, slot) were requested by this same warp (sb_pull_prefetch): wait for
+// them and evaluate the CDF at the 2 x (8 warp boundaries + tile end) ONCE for the CTA (18 lanes, straight-line
+// code).  A barrier must separate this from the sb_pull_ancestors call that consumes the table.
+template <bool S32>
+__device__ __forceinline__ void sb_pull_seg(const SbStepInfo& si, int c0, int2 rng, int slot, SbPullSmem& sm) {
+    const int lane = threadIdx.x & 31;
+    const int m = (int)si.m;
+    const int c1 = min(c0 + SB_TILE, m);
+    const int cw = max(c1 - c0, 0);
+    const int b_lo = rng.x, b_hi = rng.y;
+    const int bA = b_lo, bB = min(b_lo + 1, si.nt - 1);
+    sb_cp_async_wait_all();
+    __syncwarp();
+    const SbPullMeta& mt = sm.meta[slot];
+    const int which = lane >= SB_WARPS + 1 ? 1 : 0, bi = lane - which * (SB_WARPS + 1);
+    const int cs = mt.cs[which], ce = mt.ce[which];
+    bool use = !(ce <= c0 || cs >= c1 || ce == cs);
+    if (which) use = use && bB != bA && bB <= b_hi;
+    const int rb = (si.r0 + (si.E - mt.e[which])) & 63;           // < 64 when the tile owns children (else unused)
+    const long long baseb = (long long)(mt.Pt[which] - si.U) + ((1ll << si.s) - 1ll) - ((long long)c0 << si.s);
+    int kk = sb_pull_k<S32>(baseb, mt.wp[which][bi & (SB_WARPS - 1)] * (unsigned long long)si.R, rb, si.s, cw);
+    if (bi == SB_WARPS) kk = min(max(ce - c0, 0), cw);             // the last warp ends at the tile's own child_start
+    if (!use) kk = 0;
+    if (lane < 2 * (SB_WARPS + 1)) sm.seg_k[which][bi] = kk;
+    if (bi == 0 && lane < 2 * (SB_WARPS + 1)) { sm.seg_baseb[which] = baseb; sm.seg_rb[which] = rb; }
+}
+
+// Once per CTA, before its first children tile (the mbarrier is initialised and a barrier has passed): clear the
+// marker array, request the first tile's parents and build its boundary table.
+template <bool PEERS>
+__device__ __forceinline__ void sb_pull_first(const SbStepInfo& si, const SbPool& pool, const int* __restrict__ e,
+                                              const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
+                                              int c0, int2 rng, SbPullSmem& sm) {
+    const int tid = threadIdx.x;
+    const int4 neg = make_int4(-1, -1, -1, -1);
+    reinterpret_cast<int4*>(sm.marker)[tid * 2] = neg;
+    reinterpret_cast<int4*>(sm.marker)[tid * 2 + 1] = neg;
+    if (tid < 32) {
+        sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, rng.x, 0, sm);
+        if (si.s >= 32) sb_pull_seg<true>(si, c0, rng, 0, sm); else sb_pull_seg<false>(si, c0, rng, 0, sm);
+    }
+    __syncthreads();
+}
+
 // Computes, for the children [c0, c0+SB_TILE) of this CTA, the pool index of each child's parent
 // under systematic resampling on the weight grid; thread `tid` receives children c0+8*tid .. +7.
 // The weights and records of the candidate parent tiles [rng.x, rng.x+1] were requested one tile ahead
-// (sb_pull_prefetch, slot/parity of this tile); further candidates -- rare: a children tile that spans
+// (sb_pull_prefetch, slot/parity of this tile) and the boundary table of this tile was built behind an
+// earlier barrier (sb_pull_first / sb_pull_seg); further candidates -- rare: a children tile that spans
 // more than two parent tiles -- are read directly.  When `more`, the copies for the next children
 // tile (first candidate next_b_lo) are started as soon as this tile's staging buffers are free.
+// ONE barrier.  The marker array is all -1 on entry and on exit (every thread resets the slots it reads);
+// the caller runs sb_pull_seg for the next tile (warp 0) and at least one barrier before the next call.
 template <bool PEERS, bool S32>
 __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const SbPool& pool,
                                                   const int* __restrict__ e, const unsigned long long* __restrict__ Pt,
@@ -526,32 +591,7 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
     const int cw = max(c1 - c0, 0);
     const int b_lo = rng.x, b_hi = rng.y;
     const int bA = b_lo, bB = min(b_lo + 1, si.nt - 1);
-    {
-        const int4 neg = make_int4(-1, -1, -1, -1);
-        reinterpret_cast<int4*>(sm.marker)[tid * 2] = neg;
-        reinterpret_cast<int4*>(sm.marker)[tid * 2 + 1] = neg;
-    }
-    if (warp == 0) {
-        // the records of the two staged parent tiles have landed (this warp's own cp.async): 18 lanes evaluate
-        // the CDF at the 2 x (8 warp boundaries + tile end) ONCE for the CTA (straight-line code); every warp
-        // then decides from two table entries per tile whether its 256 parents own children here
-        sb_cp_async_wait_all();
-        __syncwarp();
-        const SbPullMeta& mt = sm.meta[slot];
-        const int which = lane >= SB_WARPS + 1 ? 1 : 0, bi = lane - which * (SB_WARPS + 1);
-        const int cs = mt.cs[which], ce = mt.ce[which];
-        bool use = !(ce <= c0 || cs >= c1 || ce == cs);
-        if (which) use = use && bB != bA && bB <= b_hi;
-        const int rb = (si.r0 + (si.E - mt.e[which])) & 63;       // < 64 when the tile owns children (else unused)
-        const long long baseb = (long long)(mt.Pt[which] - si.U) + ((1ll << si.s) - 1ll) - ((long long)c0 << si.s);
-        int kk = sb_pull_k<S32>(baseb, mt.wp[which][bi & (SB_WARPS - 1)] * (unsigned long long)si.R, rb, si.s, cw);
-        if (bi == SB_WARPS) kk = min(max(ce - c0, 0), cw);         // the last warp ends at the tile's own child_start
-        if (!use) kk = 0;
-        if (lane < 2 * (SB_WARPS + 1)) sm.seg_k[which][bi] = kk;
-        if (bi == 0 && lane < 2 * (SB_WARPS + 1)) { sm.seg_baseb[which] = baseb; sm.seg_rb[which] = rb; }
-    }
-    sb_mbar_wait(&sm.bar, parity);
-    __syncthreads();
+    sb_mbar_wait(&sm.bar, parity);                               // the two staged weight tiles have landed
     {
         const SbPullMeta& mt = sm.meta[slot];
         if (sm.seg_k[0][warp + 1] > sm.seg_k[0][warp])
@@ -574,31 +614,22 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
     __syncthreads();                                             // markers complete; sm.w and sm.meta[slot] are free
     if (more && warp == 0) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, next_b_lo, slot ^ 1, sm);
     // every child takes the last head marker at or before its slot.  Markers ascend with the slot (the CDF is
-    // monotone), so the carry into a thread is the largest marker of the nearest earlier thread that has one:
-    // a ballot and one shuffle instead of a max-scan across the warp
+    // monotone) and the first slot of every warp has one, so the carry into a thread is the largest marker of
+    // the nearest earlier thread OF ITS WARP that has one: a ballot and one shuffle
     int v[SB_ITEMS];
     {
         const int4 a = reinterpret_cast<const int4*>(sm.marker)[tid * 2];
         const int4 b = reinterpret_cast<const int4*>(sm.marker)[tid * 2 + 1];
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        const int4 neg = make_int4(-1, -1, -1, -1);
+        reinterpret_cast<int4*>(sm.marker)[tid * 2] = neg;        // left clean for the next children tile
+        reinterpret_cast<int4*>(sm.marker)[tid * 2 + 1] = neg;
     }
     const int inc = __vimax3_s32(__vimax3_s32(v[0], v[1], v[2]), __vimax3_s32(v[3], v[4], v[5]), max(v[6], v[7]));
     const unsigned has = __ballot_sync(0xffffffffu, inc >= 0);
     const unsigned below = has & ((1u << lane) - 1u);
     int prev = __shfl_sync(0xffffffffu, inc, (31 - __clz(below)) & 31);
-    if (!below) prev = -1;
-    {
-        const int last = __shfl_sync(0xffffffffu, inc, (31 - __clz(has)) & 31);
-        if (lane == 0) sm.wmax[warp] = has ? last : -1;
-    }
-    __syncthreads();
-    {
-        const int4 a = reinterpret_cast<const int4*>(sm.wmax)[0], b = reinterpret_cast<const int4*>(sm.wmax)[1];
-        const int wm[SB_WARPS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int w = 0; w < SB_WARPS; ++w) if (w < warp) prev = max(prev, wm[w]);
-    }
-    prev = max(prev, 0);
+    if (!below) prev = 0;
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) { prev = max(v[j], prev); anc[j] = prev; }   // running max: each child takes the last head at or before it
 }
@@ -615,7 +646,7 @@ __device__ __forceinline__ void sb_pull_ranges(const SbStepInfo& si, const SbPoo
         sm.ft[threadIdx.x] = tl < ntiles ? sb_pull_range(si, first_tile, pool.c_off + (int)tl * SB_TILE) : make_int2(0, -1);
     }
     __syncthreads();
-    if (first && threadIdx.x < 32) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, sm.ft[0].x, 0, sm);
+    if (first) sb_pull_first<PEERS>(si, pool, e, Pt, child_start, pool.c_off + tile * SB_TILE, sm.ft[0], sm);
 }
 
 // block maxima with ONE barrier (the caller's later barriers protect the scratch array)

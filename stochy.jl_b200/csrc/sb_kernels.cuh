@@ -345,7 +345,7 @@ k_pull(const SbStepInfo* __restrict__ info, const __grid_constant__ SbPool pool,
     if (threadIdx.x == 0) sb_mbar_init(&ps.bar, 1);
     const int2 rng = sb_pull_range(si, first_tile, c0);
     __syncthreads();
-    if (threadIdx.x < 32) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, rng.x, 0, ps);
+    sb_pull_first<PEERS>(si, pool, e, Pt, child_start, c0, rng, ps);
     int anc[SB_ITEMS];
     if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, pool, e, Pt, child_start, c0, rng, 0, 0u, false, 0, ps, anc);
     else            sb_pull_ancestors<PEERS, false>(si, pool, e, Pt, child_start, c0, rng, 0, 0u, false, 0, ps, anc);
@@ -749,6 +749,13 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     }
     key = __reduce_max_sync(0xffffffffu, key);
     if ((tid & 31) == 0) reinterpret_cast<unsigned*>(sm.red)[tid >> 5] = key;
+    if (ANC == SB_ANC_PULL && SB_ABLATE != 3 && tid < 32 && tile + (int)gridDim.x < a.ntiles) {
+        // warp 0: the next children tile's records have landed by now; its boundary table is built behind this barrier
+        const int kn = k % SB_FT_CHUNK + 1;
+        const int c0n = c0 + (int)gridDim.x * SB_TILE;
+        if (si.s >= 32) sb_pull_seg<true>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
+        else            sb_pull_seg<false>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
+    }
     __syncthreads();
     {
         const uint4 u = reinterpret_cast<const uint4*>(sm.red)[0], v = reinterpret_cast<const uint4*>(sm.red)[1];
@@ -985,6 +992,13 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                 mx = (REAL)fmax((double)mx, v);
                 if (a.lw_out && live) a.lw_out[lbase + j] = lw;
             }
+        }
+        if (ANC == SB_ANC_PULL && tid < 32 && tile + (int)gridDim.x < a.ntiles) {
+            // warp 0: the next children tile's boundary table, built behind the barrier of the block maximum
+            const int kn = k % SB_FT_CHUNK + 1;
+            const int c0n = c0 + (int)gridDim.x * SB_TILE;
+            if (si.s >= 32) sb_pull_seg<true>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
+            else            sb_pull_seg<false>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
         }
         int e;
         if (FP32) { const float m2 = sb_block_max_f32_1((float)mx, reinterpret_cast<float*>(sm.red)); e = m2 > -INFINITY ? (int)ceilf(m2) : SB_E_EMPTY; }
