@@ -876,7 +876,7 @@ struct SbLgStepArgs {
 #define SB_TWO_PI 6.283185307179586476925286766559
 
 template <int ANC, bool FP32, bool PEERS>
-__global__ void __launch_bounds__(SB_THREADS)
+__global__ void __launch_bounds__(SB_THREADS, FP32 ? 5 : 3)       // fp32: 48 registers (5 CTAs per SM); fp64: 80 (3)
 k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     typedef typename std::conditional<FP32, float, double>::type REAL;
     __shared__ SbHmmSmem sm;

@@ -53,6 +53,12 @@ def test_systematic_degenerate(eng, oracle):
     w = np.full(n, 1e-12); w[::4099] = 1.0; cases.append((w, 0))                 # one child per ~2 tiles
     lw = rng.normal(size=n) * 200.0; cases.append((lw, 1))
     lw = np.full(n, -np.inf); lw[77] = -1e4; lw[n - 5] = -1e4 - 3; cases.append((lw, 1))
+    # parents with hundreds of children each (one parent covers several 256-slot warp boundaries of a children
+    # tile), alone in their thread, two in one thread, and with light neighbours that still own a child
+    w = np.full(n, 1e-9); w[::300] = 1.0; cases.append((w, 0))
+    w = np.full(n, 1e-9); w[5::997] = 1.0; w[6::997] = 0.7; cases.append((w, 0))
+    w = np.full(n, 0.004); w[3::640] = 1.0; w[7::640] = 0.45; cases.append((w, 0))
+    w = rng.random(n) ** 40; cases.append((w, 0))
     for w, kind in cases:
         got = eng.resample_systematic(w, 0.37, n, kind=kind)
         assert np.array_equal(got, oracle.resample_systematic(w, 0.37, n, kind=kind))
