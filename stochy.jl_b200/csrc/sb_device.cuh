@@ -333,6 +333,9 @@ __device__ __forceinline__ void sb_mbar_init(unsigned long long* bar, int count)
 __device__ __forceinline__ void sb_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb_smem_addr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void sb_mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sb_smem_addr(bar)) : "memory");
+}
 __device__ __forceinline__ void sb_mbar_wait(unsigned long long* bar, uint32_t parity) {
     asm volatile(
         "{\n"

@@ -622,6 +622,10 @@ struct SbHmmStepArgs {
 struct SbHmmSmem {
     SbPullSmem ps;
     double red[SB_WARPS];
+    unsigned long long tot[2][SB_WARPS];   // warp totals of the tile just produced, by tile parity: with the split barrier a
+                                           // fast warp may finish tile k+1 before warp 0 has flushed the totals of tile k
+    unsigned long long bar2;    // split-phase barrier of the fused HMM kernel: one arrival per warp and children tile
+    unsigned kmax;              // largest exponent key any state of this step can have
 };
 
 // k: how many tiles this CTA has done before this one (staging slot / mbarrier parity of the pull)
@@ -646,6 +650,9 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         const int2 rng = sm.ps.ft[kk];
         const bool more = tile + (int)gridDim.x < a.ntiles;
         const int nb = sm.ps.ft[kk + 1].x;
+        // every warp has finished the previous tile's marker slots and exponent key, and warp 0 this tile's boundary
+        // table (the wait half of the split barrier; most of its skew was absorbed by the previous tile's epilogue)
+        if (k > 0) sb_mbar_wait(&sm.bar2, (uint32_t)((k - 1) & 1));
         if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
         else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
 #endif
@@ -736,7 +743,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     }
     // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
     if (ANC != SB_ANC_PULL) __syncthreads();                     // the pull has its own barriers
-    if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
+    if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
     // (4)+(5) weight and quantise.  Only K distinct scores exist: the tile exponent is the largest
     // ceil(log2 weight) present (an integer max), and 2^(l2 - e) 2^27 comes from a K x K table.
     unsigned key = 0u;
@@ -749,15 +756,26 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     }
     key = __reduce_max_sync(0xffffffffu, key);
     if ((tid & 31) == 0) reinterpret_cast<unsigned*>(sm.red)[tid >> 5] = key;
-    if (ANC == SB_ANC_PULL && SB_ABLATE != 3 && tid < 32 && tile + (int)gridDim.x < a.ntiles) {
-        // warp 0: the next children tile's records have landed by now; its boundary table is built behind this barrier
-        const int kn = k % SB_FT_CHUNK + 1;
-        const int c0n = c0 + (int)gridDim.x * SB_TILE;
-        if (si.s >= 32) sb_pull_seg<true>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
-        else            sb_pull_seg<false>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
-    }
-    __syncthreads();
-    {
+    if (ANC == SB_ANC_PULL && SB_ABLATE != 3) {
+        if (tid < 32 && tile + (int)gridDim.x < a.ntiles) {
+            // warp 0: the next children tile's records have landed by now; its boundary table is built behind the barrier
+            const int kn = k % SB_FT_CHUNK + 1;
+            const int c0n = c0 + (int)gridDim.x * SB_TILE;
+            if (si.s >= 32) sb_pull_seg<true>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
+            else            sb_pull_seg<false>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
+        }
+        // split-phase barrier: arrive now, wait at the start of the next tile.  The tile exponent needs the other
+        // warps' keys only when this warp's own maximum is below the largest key the model can produce this
+        // step -- otherwise the tile maximum is already known and the warp goes on without waiting.
+        __syncwarp();
+        if ((tid & 31) == 0) sb_mbar_arrive(&sm.bar2);
+        if (TAIL || key != sm.kmax) {
+            sb_mbar_wait(&sm.bar2, (uint32_t)(k & 1));
+            const uint4 u = reinterpret_cast<const uint4*>(sm.red)[0], v = reinterpret_cast<const uint4*>(sm.red)[1];
+            key = max(max(max(u.x, u.y), max(u.z, u.w)), max(max(v.x, v.y), max(v.z, v.w)));
+        }
+    } else {
+        __syncthreads();
         const uint4 u = reinterpret_cast<const uint4*>(sm.red)[0], v = reinterpret_cast<const uint4*>(sm.red)[1];
         key = max(max(max(u.x, u.y), max(u.z, u.w)), max(max(v.x, v.y), max(v.z, v.w)));
     }
@@ -780,7 +798,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.wlit_out[lbase + j] = a.expF_t[x[j]];
     }
-    sb_warp_total(tsum, sm.ps.scan);                              // flushed after the next barrier (next tile / kernel end)
+    sb_warp_total(tsum, sm.tot[k & 1]);                           // flushed after the next barrier (next tile / kernel end)
     if (tid == 0) sb_put_e(a.rec, tile, e);
     // no barrier here: every shared scratch array is rewritten only after a later barrier of the next tile
 }
@@ -817,6 +835,11 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         s_key[tid] = live ? (((unsigned)(ce + SB_KEY_BIAS) << 6) | (unsigned)tid) : 0u;
     }
     __syncthreads();
+    if (tid == 0) {
+        unsigned km = 0u;
+        for (int i = 0; i < K; ++i) km = max(km, s_key[i]);
+        sm.kmax = km;
+    }
     for (int i = tid; i < K * K; i += SB_THREADS) {
         const int ks = i / K, kx = i - ks * K;
         const unsigned key = s_key[ks];
@@ -829,7 +852,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     SbStepInfo si;
     if (ANC == SB_ANC_PULL) {
         si = *a.info_prev;
-        if (tid == 0) sb_mbar_init(&sm.ps.bar, 1);
+        if (tid == 0) { sb_mbar_init(&sm.ps.bar, 1); sb_mbar_init(&sm.bar2, SB_WARPS); }
     }
     __syncthreads();                                              // tables staged
     int k = 0;
@@ -843,7 +866,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     if (k > 0) {                                                  // the last tile's totals
         __syncthreads();
         const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
-        sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
+        sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
     }
     sb_signal_done(a.sig);
 }
