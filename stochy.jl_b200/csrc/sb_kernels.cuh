@@ -1068,22 +1068,43 @@ k_count_final(const int* __restrict__ anc_last, long long N, int* __restrict__ c
 // cnt_t[j] lineages pass through pool entry j at step t.  anc_prev = ancestors drawn after step
 // t-1 (nullptr at t == 0; identity when that step had no factor).  Also walks the retained
 // lineage one step (thread 0 of block 0) so no separate pointer chase is needed.
+// Eight consecutive entries per thread (128-bit loads); cnt_clear (the buffer the launch after next accumulates
+// into) is zeroed on the way, so the T launches of a backward pass need no memset between them.  Lineages coalesce
+// quickly going backwards: most entries are zero and cost one 4-byte read.
 __global__ void __launch_bounds__(256)
 k_count_back(const int* __restrict__ x_t, const int* __restrict__ cnt_t, const int* __restrict__ anc_prev,
              int identity_prev, long long n_pool, long long N, int K, int t,
-             int* __restrict__ cnt_prev, unsigned long long* __restrict__ marg,
+             int* __restrict__ cnt_prev, int* __restrict__ cnt_clear, unsigned long long* __restrict__ marg,
              int* __restrict__ lineage, int* __restrict__ xstar_out) {
     extern __shared__ unsigned int s_hist[];
     for (int k = threadIdx.x; k < K; k += blockDim.x) s_hist[k] = 0u;
     __syncthreads();
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_pool) {
-        const int c = cnt_t[j];
-        if (c) {
-            atomicAdd(&s_hist[x_t[j]], (unsigned)c);
-            if (cnt_prev) {
-                const int pj = (j >= N || identity_prev) ? (int)j : anc_prev[j];
-                atomicAdd(cnt_prev + pj, c);
+    const long long j0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (j0 < n_pool) {
+        int c[8];
+        if (j0 + 8 <= n_pool) {
+            const int4 u = __ldg(reinterpret_cast<const int4*>(cnt_t + j0)), v = __ldg(reinterpret_cast<const int4*>(cnt_t + j0) + 1);
+            c[0] = u.x; c[1] = u.y; c[2] = u.z; c[3] = u.w; c[4] = v.x; c[5] = v.y; c[6] = v.z; c[7] = v.w;
+            if (cnt_clear) {
+                reinterpret_cast<int4*>(cnt_clear + j0)[0] = make_int4(0, 0, 0, 0);
+                reinterpret_cast<int4*>(cnt_clear + j0)[1] = make_int4(0, 0, 0, 0);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                c[i] = j0 + i < n_pool ? cnt_t[j0 + i] : 0;
+                if (cnt_clear && j0 + i < n_pool) cnt_clear[j0 + i] = 0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (c[i]) {
+                const long long j = j0 + i;
+                atomicAdd(&s_hist[x_t[j]], (unsigned)c[i]);
+                if (cnt_prev) {
+                    const int pj = (j >= N || identity_prev) ? (int)j : anc_prev[j];
+                    atomicAdd(cnt_prev + pj, c[i]);
+                }
             }
         }
     }

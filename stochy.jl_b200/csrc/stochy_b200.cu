@@ -91,7 +91,7 @@ struct sb_handle {
     DevBuf bn_sp, bn_cpt, bn_lp1, bn_lp0, bn_fp, bn_fac, bn_counts;
 
     // sweep state
-    DevBuf xbuf, ancbuf, lwbuf, wlit, cnt[2], xstar[2], marg, joint;
+    DevBuf xbuf, ancbuf, lwbuf, wlit, cnt[3], xstar[2], marg, joint;
     DevBuf sm_x, sm_a, sm_xs, sm_lz;  // one-tile chains (sb_small.cuh)
     int small_cur = -1;               // >= 0: the retained particle of the last pmcmc call is in buffer small_cur of sm_xs
     int use_small = 1;                // SB_NO_SMALL=1 keeps pmcmc on the tiled kernels
@@ -508,7 +508,7 @@ extern "C" void sb_destroy(sb_handle* h) {
                       &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
                       &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
                       &h->bn_fp, &h->bn_fac, &h->bn_counts, &h->xbuf, &h->ancbuf, &h->lwbuf, &h->wlit, &h->cnt[0],
-                      &h->cnt[1], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint, &h->sm_x, &h->sm_a, &h->sm_xs, &h->sm_lz};
+                      &h->cnt[1], &h->cnt[2], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint, &h->sm_x, &h->sm_a, &h->sm_xs, &h->sm_lz};
     for (DevBuf* b : bufs) b->release();
     for (int g = 0; g < SB_MAX_PEERS; ++g)
         if (h->peer_base[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_base[g]);
@@ -1082,7 +1082,7 @@ extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t*
     }
     const int64_t S = tiles_of(N + 1) * SB_TILE;
     CK(h->xstar[0].ensure((size_t)T * 4)); CK(h->xstar[1].ensure((size_t)T * 4));
-    CK(h->cnt[0].ensure((size_t)S * 4)); CK(h->cnt[1].ensure((size_t)S * 4));
+    for (int i = 0; i < 3; ++i) CK(h->cnt[i].ensure((size_t)S * 4));
     CK(h->marg.ensure((size_t)T * K * 8));
     CK(cudaMemsetAsync(h->marg.p, 0, (size_t)T * K * 8, h->stream));
     if (joint) { CK(h->joint.ensure((size_t)njoint * 8)); CK(cudaMemsetAsync(h->joint.p, 0, (size_t)njoint * 8, h->stream)); }
@@ -1100,18 +1100,21 @@ extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t*
         k_lineage_start<<<1, 1, 0, h->stream>>>(ab + (size_t)(T - 1) * S, N, pick, h->opt.seed, (unsigned)T, (unsigned)it, lineage);
         LAUNCH_CHECK();
         // src/pmcmc.jl:90-92 -- count every particle's value
-        int* cnt_t = h->cnt[(T - 1) & 1].as<int>();
+        // three count buffers in rotation: step t reads buf[t % 3], accumulates into buf[(t - 1) % 3] and clears
+        // buf[(t + 1) % 3] (read by the previous launch) for the step after next -- no memset between the T launches
+        int* cnt_t = h->cnt[(T - 1) % 3].as<int>();
         CK(cudaMemsetAsync(cnt_t, 0, (size_t)S * 4, h->stream));
+        if (T > 1) CK(cudaMemsetAsync(h->cnt[(T - 2) % 3].p, 0, (size_t)S * 4, h->stream));
         k_count_final<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(ab + (size_t)(T - 1) * S, N, cnt_t);
         LAUNCH_CHECK();
         int* xs_next = h->xstar[h->xstar_cur ^ 1].as<int>();
         for (int t = T - 1; t >= 0; --t) {
-            int* c_t = h->cnt[t & 1].as<int>();
-            int* c_p = t ? h->cnt[(t - 1) & 1].as<int>() : nullptr;
-            if (c_p) CK(cudaMemsetAsync(c_p, 0, (size_t)S * 4, h->stream));
-            k_count_back<<<(unsigned)((n_pool + 255) / 256), 256, (size_t)K * 4, h->stream>>>(
+            int* c_t = h->cnt[t % 3].as<int>();
+            int* c_p = t ? h->cnt[(t - 1) % 3].as<int>() : nullptr;
+            int* c_clear = t >= 2 ? h->cnt[(t + 1) % 3].as<int>() : nullptr;
+            k_count_back<<<(unsigned)((n_pool + 2047) / 2048), 256, (size_t)K * 4, h->stream>>>(
                 xb + (size_t)t * S, c_t, t ? ab + (size_t)(t - 1) * S : nullptr, t ? !h->has_factor[t - 1] : 0,
-                n_pool, N, K, t, c_p, h->marg.as<unsigned long long>(), lineage, xs_next);
+                n_pool, N, K, t, c_p, c_clear, h->marg.as<unsigned long long>(), lineage, xs_next);
             LAUNCH_CHECK();
         }
         if (joint) {
