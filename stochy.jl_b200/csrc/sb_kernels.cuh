@@ -573,6 +573,13 @@ k_lse_final(const SbLse* __restrict__ partial, int np, double* __restrict__ out)
 // factor's Step push (src/pmcmc.jl:37), and resample + deepcopy (src/pmcmc.jl:42,48-66).
 // Algorithmic bytes per particle-step: read w32 (4) + read parent state (S) + write state (S)
 // + write w32 (4) [+ 4 for the ancestor row when history is kept].
+//
+// Synchronisation per children tile of k_step_hmm (pull instantiation): ONE CTA barrier (all head markers written)
+// and ONE split-phase mbarrier (sm.bar2, one arrival per warp): a warp arrives once its exponent key is published
+// -- warp 0 also the next tile's boundary table -- and waits at the start of the next tile; the tile exponent itself
+// needs the wait only when the warp's own key is below the model's largest key (sm.kmax).  What the split barrier
+// lets run ahead is buffered by tile parity (sm.tot, the meta slots); everything else is rewritten only behind the
+// next full barrier ("How k_step_hmm is built").  k_step_lg keeps a full barrier for its block maximum.
 // =====================================================================================
 #define SB_ANC_NONE     0   // first step: no parents
 #define SB_ANC_PULL     1   // systematic resampling fused in
@@ -742,7 +749,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         }
     }
     // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
-    if (ANC != SB_ANC_PULL) __syncthreads();                     // the pull has its own barriers
+    if (ANC != SB_ANC_PULL) __syncthreads();                     // the pull has its own barrier
     if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
     // (4)+(5) weight and quantise.  Only K distinct scores exist: the tile exponent is the largest
     // ceil(log2 weight) present (an integer max), and 2^(l2 - e) 2^27 comes from a K x K table.
@@ -936,7 +943,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;
         }
         // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
-        if (ANC != SB_ANC_PULL) __syncthreads();                 // the pull has its own barriers
+        if (ANC != SB_ANC_PULL) __syncthreads();                 // the pull has its own barrier
         if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
         REAL xpar[SB_ITEMS];
         if (PEERS && base + SB_ITEMS <= N && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
