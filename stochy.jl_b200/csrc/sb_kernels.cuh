@@ -917,9 +917,13 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     SbStepInfo si;
     if (ANC == SB_ANC_PULL) {
         si = *a.info_prev;
-        if (tid == 0) sb_mbar_init(&sm.ps.bar, 1);
+        if (tid == 0) { sb_mbar_init(&sm.ps.bar, 1); sb_mbar_init(&sm.bar2, SB_WARPS); }
         __syncthreads();
     }
+    // no particle of this step can weigh more than the density's mode: lw <= lc, and the roundings below are monotone,
+    // so every log2-weight is <= vmax.  A warp whose own maximum already reaches ceil(vmax) knows the tile exponent.
+    const REAL vmax = FP32 ? (REAL)__fmul_rn((float)a.lc, SB_LOG2E_F) : (REAL)__dmul_rn(a.lc, SB_LOG2E_D);
+    const int e_top = FP32 ? (int)ceilf((float)vmax) : (int)ceil((double)vmax);
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
         if (ANC == SB_ANC_PULL && (k % SB_FT_CHUNK) == 0)
@@ -933,6 +937,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             const int2 rng = sm.ps.ft[kk];
             const bool more = tile + (int)gridDim.x < a.ntiles;
             const int nb = sm.ps.ft[kk + 1].x;
+            if (k > 0) sb_mbar_wait(&sm.bar2, (uint32_t)((k - 1) & 1));   // wait half of the previous tile's split barrier (see k_step_hmm)
             if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
             else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
         } else if (ANC == SB_ANC_EXPLICIT) {
@@ -944,7 +949,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         }
         // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
         if (ANC != SB_ANC_PULL) __syncthreads();                 // the pull has its own barrier
-        if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
+        if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
         REAL xpar[SB_ITEMS];
         if (PEERS && base + SB_ITEMS <= N && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
             const int g = anc[0] >> a.pool.log2n;               // ascending parents: all eight on GPU g
@@ -1031,8 +1036,31 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             else            sb_pull_seg<false>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
         }
         int e;
-        if (FP32) { const float m2 = sb_block_max_f32_1((float)mx, reinterpret_cast<float*>(sm.red)); e = m2 > -INFINITY ? (int)ceilf(m2) : SB_E_EMPTY; }
-        else      { const double m2 = sb_block_max_f64_1((double)mx, sm.red); e = m2 > -INFINITY ? (int)ceil(m2) : SB_E_EMPTY; }
+        if (ANC == SB_ANC_PULL) {
+            // split-phase barrier as in k_step_hmm: publish the warp maximum, arrive, and wait for the other warps only
+            // if this warp's own maximum does not already reach the top exponent (m_w <= tile max <= vmax)
+#pragma unroll
+            for (int d = 16; d; d >>= 1) mx = FP32 ? (REAL)fmaxf((float)mx, __shfl_xor_sync(0xffffffffu, (float)mx, d))
+                                                   : (REAL)fmax((double)mx, __shfl_xor_sync(0xffffffffu, (double)mx, d));
+            if ((tid & 31) == 0) { if (FP32) reinterpret_cast<float*>(sm.red)[tid >> 5] = (float)mx; else sm.red[tid >> 5] = (double)mx; }
+            __syncwarp();
+            if ((tid & 31) == 0) sb_mbar_arrive(&sm.bar2);
+            e = mx > -INFINITY ? (FP32 ? (int)ceilf((float)mx) : (int)ceil((double)mx)) : SB_E_EMPTY;
+            if (e != e_top) {
+                sb_mbar_wait(&sm.bar2, (uint32_t)(k & 1));
+                if (FP32) {
+                    const float4 u = reinterpret_cast<const float4*>(sm.red)[0], v = reinterpret_cast<const float4*>(sm.red)[1];
+                    const float m2 = fmaxf(fmaxf(fmaxf(u.x, u.y), fmaxf(u.z, u.w)), fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+                    e = m2 > -INFINITY ? (int)ceilf(m2) : SB_E_EMPTY;
+                } else {
+                    double m2 = sm.red[0];
+#pragma unroll
+                    for (int w = 1; w < SB_WARPS; ++w) m2 = fmax(m2, sm.red[w]);
+                    e = m2 > -INFINITY ? (int)ceil(m2) : SB_E_EMPTY;
+                }
+            }
+        } else if (FP32) { const float m2 = sb_block_max_f32_1((float)mx, reinterpret_cast<float*>(sm.red)); e = m2 > -INFINITY ? (int)ceilf(m2) : SB_E_EMPTY; }
+        else             { const double m2 = sb_block_max_f64_1((double)mx, sm.red); e = m2 > -INFINITY ? (int)ceil(m2) : SB_E_EMPTY; }
         uint32_t q[SB_ITEMS];
         unsigned tsum = 0;
 #pragma unroll
@@ -1050,14 +1078,14 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             for (int j = 0; j < SB_ITEMS; j += 2) reinterpret_cast<double2*>(xo)[j / 2] = make_double2((double)x[j], (double)x[j + 1]);
         }
         sb_store8_u32(a.w32_out + lbase, q);
-        sb_warp_total(tsum, sm.ps.scan);                          // flushed after the next barrier (next tile / kernel end)
+        sb_warp_total(tsum, sm.tot[k & 1]);                       // flushed after the next barrier (next tile / kernel end)
         if (tid == 0) sb_put_e(a.rec, tile, e);
         if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
     }
     if (k > 0) {
         __syncthreads();
         const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
-        sb_flush_totals(sm.ps.scan, a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
+        sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
     }
     sb_signal_done(a.sig);
 }
