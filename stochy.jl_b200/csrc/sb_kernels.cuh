@@ -579,7 +579,8 @@ k_lse_final(const SbLse* __restrict__ partial, int np, double* __restrict__ out)
 // -- warp 0 also the next tile's boundary table -- and waits at the start of the next tile; the tile exponent itself
 // needs the wait only when the warp's own key is below the model's largest key (sm.kmax).  What the split barrier
 // lets run ahead is buffered by tile parity (sm.tot, the meta slots); everything else is rewritten only behind the
-// next full barrier ("How k_step_hmm is built").  k_step_lg keeps a full barrier for its block maximum.
+// next full barrier ("How k_step_hmm is built").  k_step_lg follows the same protocol; its shortcut is
+// the mode of the observation density (no log2-weight exceeds log2e * lc).
 // =====================================================================================
 #define SB_ANC_NONE     0   // first step: no parents
 #define SB_ANC_PULL     1   // systematic resampling fused in
