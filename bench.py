@@ -142,7 +142,7 @@ def run_reference(args):
                                    "bounded sample N=2^21 x 8 steps per bench step"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -249,7 +249,7 @@ def run_ours(args):
                 line["roofline"]["traffic"] = json.load(open(tr)).get("k_step_hmm_bytes_per_launch")
             except Exception:
                 pass
-        print(json.dumps(line))
+        emit(line)
     barrier()                                       # no rank unmaps its arena while a peer may still read it
     eng.close()
     if world > 1:
@@ -266,10 +266,29 @@ def main():
     ap.add_argument("--T", type=int, default=T_STEPS)
     ap.add_argument("--force-shard", action="store_true", help="run the sharded (peer-addressed) kernels even on one GPU")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line on the first
+    # collective when NCCL_DEBUG=VERSION): everything but the result line goes to stderr.
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    """The result line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
 
 
 if __name__ == "__main__":
