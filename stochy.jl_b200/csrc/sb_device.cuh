@@ -501,19 +501,26 @@ __device__ __forceinline__ int2 sb_pull_range(const SbStepInfo& si, const int* _
     return make_int2(__ldg(first_tile + cb), (c0 + SB_TILE < m) ? __ldg(first_tile + cb + 1) : si.nt - 1);
 }
 
-// Warp 0 (all 32 lanes): start the copies of the two candidate parent tiles b_lo, b_lo+1 of an upcoming
-// children tile -- weights by TMA bulk copy (one lane), tile records by 4/8-byte cp.async -- into
-// sm.w / sm.meta[slot].  The pool may live on a peer GPU: the copies then run over NVLink.
+// Warps 0 and SB_META_WARP (all 32 lanes each): start the copies of the two candidate parent tiles b_lo, b_lo+1 of
+// an upcoming children tile -- weights by TMA bulk copy (one lane of warp 0), tile records by 4/8-byte cp.async
+// (warp SB_META_WARP, which later waits for them and builds the boundary table: sb_pull_seg) -- into
+// sm.w / sm.meta[slot].  The per-tile serial duties are spread over three warps (the third flushes the tile totals).
+// The pool may live on a peer GPU: the copies then run over NVLink.
+#define SB_META_WARP  1
+#define SB_FLUSH_WARP 2
 template <bool PEERS>
 __device__ __forceinline__ void sb_pull_prefetch(const SbStepInfo& si, const SbPool& pool, const int* __restrict__ e,
                                                  const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
                                                  int b_lo, int slot, SbPullSmem& sm) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int bA = b_lo, bB = min(b_lo + 1, si.nt - 1);
-    if (lane == 0) {
-        sb_mbar_expect_tx(&sm.bar, 2u * SB_TILE * 4u);
-        sb_bulk_g2s(sm.w[0], sb_pool_tile<PEERS>(pool, bA), SB_TILE * 4u, &sm.bar);
-        sb_bulk_g2s(sm.w[1], sb_pool_tile<PEERS>(pool, bB), SB_TILE * 4u, &sm.bar);
+    if (warp == 0) {
+        if (lane == 0) {
+            sb_mbar_expect_tx(&sm.bar, 2u * SB_TILE * 4u);
+            sb_bulk_g2s(sm.w[0], sb_pool_tile<PEERS>(pool, bA), SB_TILE * 4u, &sm.bar);
+            sb_bulk_g2s(sm.w[1], sb_pool_tile<PEERS>(pool, bB), SB_TILE * 4u, &sm.bar);
+        }
+        return;
     }
     // tile records: lanes 0-15 the 2 x 8 warp prefixes, 16-17 Pt (8 bytes each); 18-19 child_start, 20-21 child_start + 1,
     // 22-23 e (4 bytes each).  Source and destination are selected per lane (no divergent branches).
@@ -529,7 +536,7 @@ __device__ __forceinline__ void sb_pull_prefetch(const SbStepInfo& si, const SbP
     sb_cp_async_commit();
 }
 
-// Warp 0 only, after the tile records of (rng, slot) were requested by this same warp (sb_pull_prefetch): wait for
+// Warp SB_META_WARP only, after the tile records of (rng, slot) were requested by this same warp (sb_pull_prefetch): wait for
 // them and evaluate the CDF at the 2 x (8 warp boundaries + tile end) ONCE for the CTA (18 lanes, straight-line
 // code).  A barrier must separate this from the sb_pull_ancestors call that consumes the table.
 template <bool S32>
@@ -566,8 +573,8 @@ __device__ __forceinline__ void sb_pull_first(const SbStepInfo& si, const SbPool
     const int4 neg = make_int4(-1, -1, -1, -1);
     reinterpret_cast<int4*>(sm.marker)[tid * 2] = neg;
     reinterpret_cast<int4*>(sm.marker)[tid * 2 + 1] = neg;
-    if (tid < 32) {
-        sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, rng.x, 0, sm);
+    if ((tid >> 5) == 0 || (tid >> 5) == SB_META_WARP) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, rng.x, 0, sm);
+    if ((tid >> 5) == SB_META_WARP) {
         if (si.s >= 32) sb_pull_seg<true>(si, c0, rng, 0, sm); else sb_pull_seg<false>(si, c0, rng, 0, sm);
     }
     __syncthreads();
@@ -615,7 +622,7 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
         if (k1 > k0) sb_pull_tile<S32>(si, b, sb_pool_tile<PEERS>(pool, b), baseb, rb, wbase, cw, sm);
     }
     __syncthreads();                                             // markers complete; sm.w and sm.meta[slot] are free
-    if (more && warp == 0) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, next_b_lo, slot ^ 1, sm);
+    if (more && (warp == 0 || warp == SB_META_WARP)) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, next_b_lo, slot ^ 1, sm);
     // every child takes the last head marker at or before its slot.  Markers ascend with the slot (the CDF is
     // monotone) and the first slot of every warp has one, so the carry into a thread is the largest marker of
     // the nearest earlier thread OF ITS WARP that has one: a ballot and one shuffle
@@ -724,11 +731,12 @@ __device__ __forceinline__ void sb_warp_total(unsigned tsum, unsigned long long*
 }
 __device__ __forceinline__ void sb_flush_totals(const unsigned long long* sm, unsigned long long* __restrict__ wp_tile,
                                                 const SbRecOut& rec, int tile) {
-    if (threadIdx.x <= SB_WARPS) {                               // thread w < 8: prefix of warp w; thread 8: the tile sum
+    const int t = (int)threadIdx.x - 32 * SB_FLUSH_WARP;          // lanes 0-8 of warp SB_FLUSH_WARP
+    if (t >= 0 && t <= SB_WARPS) {                               // lane w < 8: prefix of warp w; lane 8: the tile sum
         unsigned long long pre = 0;
 #pragma unroll
-        for (int w = 0; w < SB_WARPS; ++w) if (w < (int)threadIdx.x) pre += sm[w];
-        if (threadIdx.x < SB_WARPS) wp_tile[threadIdx.x] = pre; else sb_put_Q(rec, tile, pre);
+        for (int w = 0; w < SB_WARPS; ++w) if (w < t) pre += sm[w];
+        if (t < SB_WARPS) wp_tile[t] = pre; else sb_put_Q(rec, tile, pre);
     }
 }
 

@@ -765,8 +765,8 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     key = __reduce_max_sync(0xffffffffu, key);
     if ((tid & 31) == 0) reinterpret_cast<unsigned*>(sm.red)[tid >> 5] = key;
     if (ANC == SB_ANC_PULL && SB_ABLATE != 3) {
-        if (tid < 32 && tile + (int)gridDim.x < a.ntiles) {
-            // warp 0: the next children tile's records have landed by now; its boundary table is built behind the barrier
+        if ((tid >> 5) == SB_META_WARP && tile + (int)gridDim.x < a.ntiles) {
+            // one warp: the next children tile's records have landed by now; its boundary table is built behind the barrier
             const int kn = k % SB_FT_CHUNK + 1;
             const int c0n = c0 + (int)gridDim.x * SB_TILE;
             if (si.s >= 32) sb_pull_seg<true>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
@@ -1029,8 +1029,8 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                 if (a.lw_out && live) a.lw_out[lbase + j] = lw;
             }
         }
-        if (ANC == SB_ANC_PULL && tid < 32 && tile + (int)gridDim.x < a.ntiles) {
-            // warp 0: the next children tile's boundary table, built behind the barrier of the block maximum
+        if (ANC == SB_ANC_PULL && (tid >> 5) == SB_META_WARP && tile + (int)gridDim.x < a.ntiles) {
+            // one warp: the next children tile's boundary table, built behind the split barrier of the block maximum
             const int kn = k % SB_FT_CHUNK + 1;
             const int c0n = c0 + (int)gridDim.x * SB_TILE;
             if (si.s >= 32) sb_pull_seg<true>(si, c0n, sm.ps.ft[kn], (k + 1) & 1, sm.ps);
