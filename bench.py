@@ -137,9 +137,14 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "discrete HMM K=16 T=1000 SMC sweep, systematic resampling; reference arm: "
-                                   "C restatement of Stochy.jl src/pmcmc.jl + src/rand.jl (Julia 0.3 cannot run here), "
-                                   "bounded sample N=2^21 x 8 steps per bench step"},
+            # the same workload as our arm's line (same keys), plus what the CPU arm actually runs per bench step
+            "config": {"workload": "discrete HMM K=%d T=%d, 2^%d particles per GPU, one SMC sweep per step "
+                                   "(propagate + weight + normalise + systematic resample + gather every t), "
+                                   "history off" % (K_STATES, args.T, args.log2n),
+                       "particles_per_gpu": 1 << args.log2n, "T": args.T, "K": K_STATES, "resample": "systematic",
+                       "reference_arm": "C restatement of Stochy.jl src/pmcmc.jl + src/rand.jl on the host cores (Julia 0.3, "
+                                        "REQUIRE:1, cannot run here); each bench step is a bounded sample of the workload: "
+                                        "N=2^21 particles x the first 8 steps"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
