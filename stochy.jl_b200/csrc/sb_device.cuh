@@ -376,7 +376,7 @@ struct __align__(16) SbPullSmem {
     unsigned long long bar;                  // mbarrier: the bytes of w have landed
     unsigned long long scan[SB_WARPS + 1];
     int2 ft[SB_FT_CHUNK + 1];                // (first, last) candidate parent tile of this CTA's next children tiles
-    // per children tile, written by warp 0 before the tile's first barrier: the rescale constants of the two
+    // per children tile, written by warp SB_META_WARP one tile ahead (sb_pull_seg): the rescale constants of the two
     // staged parent tiles and the child index (relative, clamped) at each of their 8 warp boundaries + end
     long long seg_baseb[2];
     int seg_rb[2];
@@ -588,7 +588,7 @@ __device__ __forceinline__ void sb_pull_first(const SbStepInfo& si, const SbPool
 // more than two parent tiles -- are read directly.  When `more`, the copies for the next children
 // tile (first candidate next_b_lo) are started as soon as this tile's staging buffers are free.
 // ONE barrier.  The marker array is all -1 on entry and on exit (every thread resets the slots it reads);
-// the caller runs sb_pull_seg for the next tile (warp 0) and at least one barrier before the next call.
+// the caller runs sb_pull_seg for the next tile (warp SB_META_WARP) and at least one barrier before the next call.
 template <bool PEERS, bool S32>
 __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const SbPool& pool,
                                                   const int* __restrict__ e, const unsigned long long* __restrict__ Pt,

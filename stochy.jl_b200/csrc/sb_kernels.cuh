@@ -576,7 +576,7 @@ k_lse_final(const SbLse* __restrict__ partial, int np, double* __restrict__ out)
 //
 // Synchronisation per children tile of k_step_hmm (pull instantiation): ONE CTA barrier (all head markers written)
 // and ONE split-phase mbarrier (sm.bar2, one arrival per warp): a warp arrives once its exponent key is published
-// -- warp 0 also the next tile's boundary table -- and waits at the start of the next tile; the tile exponent itself
+// -- warp SB_META_WARP also the next tile's boundary table -- and waits at the start of the next tile; the tile exponent itself
 // needs the wait only when the warp's own key is below the model's largest key (sm.kmax).  What the split barrier
 // lets run ahead is buffered by tile parity (sm.tot, the meta slots); everything else is rewritten only behind the
 // next full barrier ("How k_step_hmm is built").  k_step_lg follows the same protocol; its shortcut is
@@ -631,7 +631,7 @@ struct SbHmmSmem {
     SbPullSmem ps;
     double red[SB_WARPS];
     unsigned long long tot[2][SB_WARPS];   // warp totals of the tile just produced, by tile parity: with the split barrier a
-                                           // fast warp may finish tile k+1 before warp 0 has flushed the totals of tile k
+                                           // fast warp may finish tile k+1 before the flushing warp has written out the totals of tile k
     unsigned long long bar2;    // split-phase barrier of the fused HMM kernel: one arrival per warp and children tile
     unsigned kmax;              // largest exponent key any state of this step can have
 };
@@ -658,7 +658,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         const int2 rng = sm.ps.ft[kk];
         const bool more = tile + (int)gridDim.x < a.ntiles;
         const int nb = sm.ps.ft[kk + 1].x;
-        // every warp has finished the previous tile's marker slots and exponent key, and warp 0 this tile's boundary
+        // every warp has finished the previous tile's marker slots and exponent key, and the records warp this tile's boundary
         // table (the wait half of the split barrier; most of its skew was absorbed by the previous tile's epilogue)
         if (k > 0) sb_mbar_wait(&sm.bar2, (uint32_t)((k - 1) & 1));
         if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
