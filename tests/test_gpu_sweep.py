@@ -494,3 +494,31 @@ def test_handle_reuse_across_sizes_and_models():
                 ref = run(fresh, what, n)
             assert got[0] == ref[0], (what, n)
             assert np.array_equal(got[1], ref[1]), (what, n)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_lg_outlier_takes_the_waiting_path(monkeypatch, enumref, precision):
+    """The linear-Gaussian step kernel skips the wait for the tile exponent when a warp's own maximum already reaches
+    the density's mode.  An outlying observation (40 standard deviations) puts every particle far below the mode, so
+    every warp has to wait for the other warps' maxima; with several tiles per CTA the split barrier's phases are
+    exercised too.  The result must not depend on the grid.  (No particle reaches an observation that far out, so
+    the estimate of the evidence falls short of the Kalman filter's by a wide margin - it can only be bounded above.)"""
+    sb = sb_mod()
+    d = cfg4_data(T=6)
+    d["y"] = d["y"].copy()
+    d["y"][3] = 40.0
+    exact, _ = enumref.kalman_loglik(d["a"], d["q"], d["c"], d["r"], d["m0"], d["P0"], d["y"])
+    N = 1 << 22
+    outs = []
+    for ctas in ["1", None]:
+        if ctas:
+            monkeypatch.setenv("SB_CTAS_PER_SM", ctas)
+        else:
+            monkeypatch.delenv("SB_CTAS_PER_SM", raising=False)
+        with sb.Engine(precision=precision, seed=4) as eng:
+            eng.load(sb.LinearGaussian(**d))
+            lz = eng.smc_sweep(N)
+            outs.append((lz, eng.particles(N)))
+    assert outs[0][0] == outs[1][0]
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.isfinite(outs[0][0]) and outs[0][0] < exact + 1.0, (outs[0][0], exact)
