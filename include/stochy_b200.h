@@ -186,6 +186,13 @@ int32_t sb_erp_logpdf(sb_handle* h, int32_t erp, const double* params, const dou
 int32_t sb_erp_sample_dirichlet(sb_handle* h, const double* alpha, int32_t k, int64_t n, uint64_t seed, double* out);
 int32_t sb_erp_logpdf_dirichlet(sb_handle* h, const double* alpha, int32_t k, const double* x, int64_t n, double* out);
 
+/* Discrete(x, p) as a model primitive (src/erp.jl:39-59): p[k] = values(dict), possibly un-normalised (divided by
+ * z = sum(p) when z != 1, :46-49; z == 0 -> SB_EZEROMASS, :47).  rand(erp) = x[rand(p)] with the inverse-CDF scan of
+ * src/rand.jl:2-13 (NaN -> SB_ENAN): out_index[n] are 1-based positions in the support x.  score(erp, x) =
+ * log(dict[x] / z) (:56): index[n] 1-based, -inf outside 1..k. */
+int32_t sb_erp_sample_discrete(sb_handle* h, const double* p, int32_t k, int64_t n, uint64_t seed, int32_t* out_index);
+int32_t sb_erp_logpdf_discrete(sb_handle* h, const double* p, int32_t k, const int32_t* index, int64_t n, double* out);
+
 /* ---- state access (debug / parity / results) ---- */
 /* rows of the last sweep's history at step t: x (int32 for discrete, double for LG), anc (ancestors
  * drawn AFTER step t), lw (needs store_logw).  Any out pointer may be NULL.  `count` entries each. */

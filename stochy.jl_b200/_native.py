@@ -30,6 +30,7 @@ EXPORTS = [
     "sb_resample_systematic", "sb_resample_multinomial", "sb_resample_literal", "sb_logsumexp", "sb_gather",
     "sb_dev_resample_systematic", "sb_dev_gather", "sb_sync", "sb_timer_start", "sb_timer_stop",
     "sb_erp_sample", "sb_erp_logpdf", "sb_erp_sample_dirichlet", "sb_erp_logpdf_dirichlet",
+    "sb_erp_sample_discrete", "sb_erp_logpdf_discrete",
     "sb_get_history", "sb_get_retained", "sb_get_particles",
     "sb_dist_init", "sb_dist_ipc_export", "sb_dist_ipc_import",
 ]
@@ -111,6 +112,8 @@ def lib():
         "sb_erp_logpdf": (i32, [vp, i32, vp, vp, i64, vp]),
         "sb_erp_sample_dirichlet": (i32, [vp, vp, i32, i64, u64, vp]),
         "sb_erp_logpdf_dirichlet": (i32, [vp, vp, i32, vp, i64, vp]),
+        "sb_erp_sample_discrete": (i32, [vp, vp, i32, i64, u64, vp]),
+        "sb_erp_logpdf_discrete": (i32, [vp, vp, i32, vp, i64, vp]),
         "sb_get_history": (i32, [vp, i32, i64, vp, vp, vp]),
         "sb_get_retained": (i32, [vp, vp]),
         "sb_get_particles": (i32, [vp, i64, vp]),

@@ -365,6 +365,21 @@ class Engine:
         self._chk(nat.lib().sb_erp_logpdf_dirichlet(self.h, _ptr(a), len(a), _ptr(x), len(x), _ptr(out)))
         return out
 
+    def discrete_sample(self, p, n, seed=1):
+        """rand(Discrete(x, p)) (src/erp.jl:52): 1-based positions in the support, n draws."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        out = np.empty(n, dtype=np.int32)
+        self._chk(nat.lib().sb_erp_sample_discrete(self.h, _ptr(p), len(p), n, seed, _ptr(out)))
+        return out
+
+    def discrete_logpdf(self, p, index):
+        """score(Discrete(x, p), x[index]) = log(p[index] / sum(p)) (src/erp.jl:56), index 1-based."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        idx = np.ascontiguousarray(index, dtype=np.int32)
+        out = np.empty(len(idx))
+        self._chk(nat.lib().sb_erp_logpdf_discrete(self.h, _ptr(p), len(p), _ptr(idx), len(idx), _ptr(out)))
+        return out
+
     # ---- state access
     def history(self, t, count, want_lw=False):
         x = np.empty(count, dtype=np.int32)

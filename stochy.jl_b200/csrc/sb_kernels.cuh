@@ -1519,6 +1519,34 @@ k_erp_logpdf(int erp, double p0, double p1, const double* __restrict__ x, long l
     }
     out[i] = lp;
 }
+// Discrete ERP (src/erp.jl:39-56): rand(erp) = erp.x[rand(erp.p)] with p = values(dict), divided by z = sum(p) when
+// z != 1.0 (:49); rand(ps) is the inverse-CDF scan of src/rand.jl:2-13 (sequential fp64 adds, strict `r < acc`, last
+// index as fallback, NaN -> error).  score(erp, x) = log(dict[x] / z) (:56).  Draws are 1-based positions in the support.
+__global__ void __launch_bounds__(256)
+k_discrete_sample(const double* __restrict__ p, int k, double z, long long n, unsigned long long seed,
+                  int* __restrict__ out, unsigned* __restrict__ err) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SbRng g{seed, (unsigned long long)i, 0u};
+    const double r = g.next();
+    double acc = 0.0;
+    int draw = k;
+    for (int j = 0; j < k - 1; ++j) {
+        const double pj = z != 1.0 ? __ddiv_rn(p[j], z) : p[j];
+        acc = __dadd_rn(acc, pj);
+        if (isnan(acc)) { atomicOr(err, SB_ERRBIT_NAN); break; }
+        if (r < acc) { draw = j + 1; break; }
+    }
+    if (k == 1 && isnan(z != 1.0 ? __ddiv_rn(p[0], z) : p[0])) atomicOr(err, SB_ERRBIT_NAN);
+    out[i] = draw;
+}
+__global__ void __launch_bounds__(256)
+k_discrete_logpdf(const double* __restrict__ p, int k, double z, const int* __restrict__ x, long long n, double* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int v = x[i];
+    out[i] = (v >= 1 && v <= k) ? log(__ddiv_rn(p[v - 1], z)) : -INFINITY;       // outside the support: no mass
+}
 #define SB_DIR_MAXK 32
 __global__ void __launch_bounds__(256)
 k_dirichlet_sample(const double* __restrict__ alpha, int k, long long n, unsigned long long seed, double* __restrict__ out) {

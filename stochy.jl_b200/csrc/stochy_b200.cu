@@ -1401,6 +1401,48 @@ extern "C" int32_t sb_erp_logpdf(sb_handle* h, int32_t erp, const double* params
     CK(cudaMemcpy(out, h->hk_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return SB_OK;
 }
+// z = sum(values(dict)) (src/erp.jl:46), accumulated in order like the oracle; zero mass is the reference's error (:47)
+static int discrete_z(sb_handle* h, const double* p, int32_t k, double* z) {
+    double acc = 0.0;
+    for (int32_t j = 0; j < k; ++j) acc += p[j];
+    if (acc == 0.0) return fail(h, SB_EZEROMASS, "Distribution has zero probability mass.");
+    *z = acc;
+    return SB_OK;
+}
+extern "C" int32_t sb_erp_sample_discrete(sb_handle* h, const double* p, int32_t k, int64_t n, uint64_t seed, int32_t* out_index) {
+    if (!h) return SB_EINVAL;
+    if (!p || !out_index || n < 1 || k < 1) return fail(h, SB_EINVAL, "discrete: bad arguments");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    double z;
+    if ((rc = discrete_z(h, p, k, &z)) != SB_OK) return rc;
+    if ((rc = stage_in(h, h->hk_in, p, (size_t)k * 8)) != SB_OK) return rc;
+    CK(h->hk_anc.ensure((size_t)n * 4));
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    k_discrete_sample<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->hk_in.as<double>(), k, z, n, seed, h->hk_anc.as<int>(), h->d_err);
+    LAUNCH_CHECK();
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    if ((rc = check_err_word(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(out_index, h->hk_anc.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
+extern "C" int32_t sb_erp_logpdf_discrete(sb_handle* h, const double* p, int32_t k, const int32_t* index, int64_t n, double* out) {
+    if (!h) return SB_EINVAL;
+    if (!p || !index || !out || n < 1 || k < 1) return fail(h, SB_EINVAL, "discrete: bad arguments");
+    CK(cudaSetDevice(h->opt.device));
+    int rc;
+    double z;
+    if ((rc = discrete_z(h, p, k, &z)) != SB_OK) return rc;
+    if ((rc = stage_in(h, h->hk_in, p, (size_t)k * 8)) != SB_OK) return rc;
+    if ((rc = stage_in(h, h->hk_src, index, (size_t)n * 4)) != SB_OK) return rc;
+    CK(h->hk_out.ensure((size_t)n * 8));
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    k_discrete_logpdf<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->hk_in.as<double>(), k, z, h->hk_src.as<int>(), n, h->hk_out.as<double>());
+    LAUNCH_CHECK();
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    CK(cudaMemcpy(out, h->hk_out.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return SB_OK;
+}
 extern "C" int32_t sb_erp_sample_dirichlet(sb_handle* h, const double* alpha, int32_t k, int64_t n, uint64_t seed, double* out) {
     if (!h) return SB_EINVAL;
     if (!alpha || !out || n < 1 || k < 1 || k > SB_DIR_MAXK) return fail(h, SB_EINVAL, "dirichlet: bad arguments (k <= 32)");

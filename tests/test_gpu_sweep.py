@@ -522,3 +522,36 @@ def test_lg_outlier_takes_the_waiting_path(monkeypatch, enumref, precision):
     assert outs[0][0] == outs[1][0]
     assert np.array_equal(outs[0][1], outs[1][1])
     assert np.isfinite(outs[0][0]) and outs[0][0] < exact + 1.0, (outs[0][0], exact)
+
+
+def test_discrete_erp_hooks(oracle):
+    """Discrete(x, p) as a model primitive (src/erp.jl:39-59): draws are bit-exact against the oracle's rand(ps)
+    (src/rand.jl:2-13) on the same Philox uniforms, after the reference's normalisation p /= z (only when z != 1);
+    score = log(dict[x] / z); zero mass and NaN raise the reference's errors."""
+    sb = sb_mod()
+    from stochy_jl_b200 import _native as nat
+    rng = np.random.default_rng(3)
+    with sb.Engine(precision="fp64") as eng:
+        for p in ([0.2, 0.5, 0.3], [3.0, 1.0, 0.0, 4.0, 2.0], [1.0], [0.0, 0.0, 7.0], list(rng.random(37)), [0.25, 0.25, 0.5]):
+            p = np.array(p, dtype=np.float64)
+            z = 0.0
+            for v in p:
+                z += v
+            ps = p / z if z != 1.0 else p
+            n = 2500
+            got = eng.discrete_sample(p, n, seed=8)
+            ref = np.array([oracle.rand_categorical(ps, oracle.uniform53(8, i, 0, 0, 5, 0)) + 1 for i in range(n)])
+            assert np.array_equal(got, ref)
+            freq = np.bincount(got, minlength=len(p) + 1)[1:] / n
+            assert np.abs(freq - p / z).max() < 0.05
+            idx = np.arange(0, len(p) + 2)
+            with np.errstate(divide="ignore"):
+                want = np.concatenate([[-np.inf], np.log(p / z), [-np.inf]])
+            assert np.array_equal(eng.discrete_logpdf(p, idx), want)
+        with pytest.raises(sb.StochyError) as ei:
+            eng.discrete_sample([0.0, 0.0], 10)
+        assert ei.value.code == nat.EZEROMASS and "zero probability mass" in str(ei.value)
+        with pytest.raises(sb.StochyError) as ei:
+            eng.discrete_sample([0.3, float("nan"), 0.2], 1000)
+        assert ei.value.code == nat.ENAN and "unexpected nan in rand" in str(ei.value)
+        assert np.array_equal(eng.discrete_sample([0.5, 0.5], 4, seed=1), eng.discrete_sample([0.5, 0.5], 4, seed=1))
