@@ -16,7 +16,7 @@
 # and the native handle is destroyed in a `finally` block (the reference restores `ctx` there).
 module StochyB200
 
-export DiscreteHMM, LinearGaussian, BayesNet, pmcmc, smc, mh, enum, smc_logevidence, hmm2_example
+export DiscreteHMM, LinearGaussian, BayesNet, pmcmc, smc, mh, enum, smc_logevidence, hmm2_example, rand_discrete, score_discrete
 
 const LIB = get(ENV, "STOCHY_B200_LIB", "libstochy_b200")
 
@@ -220,6 +220,35 @@ function mh(store, k::Function, address, comp, numsteps=10; chains=1, kw...)
         destroy(h)
     end
     k(store, discrete(counts))
+end
+
+# Discrete(x, p) as a model primitive (src/erp.jl:39-59) drawn / scored on the device: `dict` is the possibly
+# un-normalised Dict the reference's constructor takes; draws come back as elements of keys(dict).
+function rand_discrete(dict::Dict, n::Integer; seed=1, kw...)
+    xs = collect(keys(dict)); ps = Vector{Float64}(collect(values(dict)))
+    h = create(; kw...)
+    try
+        idx = Vector{Int32}(undef, n)
+        check(h, ccall((:sb_erp_sample_discrete, LIB), Int32, (Handle, Ptr{Float64}, Int32, Int64, UInt64, Ptr{Int32}),
+                       h, ps, length(ps), n, seed, idx))
+        [xs[i] for i in idx]                       # rand(erp::Discrete) = erp.x[rand(erp.p)]  (src/erp.jl:52)
+    finally
+        destroy(h)
+    end
+end
+function score_discrete(dict::Dict, values::Vector; kw...)
+    xs = collect(keys(dict)); ps = Vector{Float64}(collect(values(dict)))
+    pos = Dict(x => Int32(i) for (i, x) in enumerate(xs))
+    idx = Int32[get(pos, v, Int32(0)) for v in values]          # 0 = outside the support: -Inf
+    h = create(; kw...)
+    try
+        out = Vector{Float64}(undef, length(idx))
+        check(h, ccall((:sb_erp_logpdf_discrete, LIB), Int32, (Handle, Ptr{Float64}, Int32, Ptr{Int32}, Int64, Ptr{Float64}),
+                       h, ps, length(ps), idx, length(idx), out))
+        out                                        # score(erp::Discrete, x) = log(erp.dict[x]/erp.z)  (src/erp.jl:56)
+    finally
+        destroy(h)
+    end
 end
 
 # examples/hmm2.jl:5-24 as a descriptor: init false; state ~ flip(prev ? .9 : .1);
