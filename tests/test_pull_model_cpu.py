@@ -3,7 +3,8 @@ oracle's systematic-resampling formula (stochy.jl_b200/csrc/sb_device.cuh, sb_pu
 
  1. the nested-floor form: inside a thread the CDF is evaluated once in 64 bits, K = (baseb + (c R >> rb)) >> s, and the
     child index at the prefix c + a is K + ((Z0 + a R) >> (rb + s)) with Z0 = (D0 mod 2^s) 2^rb + (c R mod 2^rb);
- 2. head markers + boundary owners + warp-local fill: every parent that owns children writes its index at its first
+ 2. the boundary table (a warp skips its 256 parents when the child index at its prefix equals the one at the next
+    warp's) + head markers + boundary owners + warp-local fill: every parent that owns children writes its index at its first
     child's slot; the owner of the first 256-slot boundary above a thread's first child writes one there too (all of
     them when a parent covers several boundaries); each warp of 256 child slots then fills from its own markers only.
 
@@ -82,11 +83,16 @@ def kernel_model(w, R, rb, s, U, c0, cw):
         wt = w[which * TILE:(which + 1) * TILE]
         Ptb = (sum(w[:TILE]) * R >> rb) if which else 0       # rescaled prefix of the tile (same exponent: one shift)
         baseb = Ptb - U + (1 << s) - 1 - (c0 << s)
+        # the boundary table (sb_pull_seg): child index at the 8 warp prefixes and at the tile's end; a warp whose two
+        # entries coincide skips its 256 parents
+        wpre = [sum(wt[:256 * g]) for g in range(8)]
+        segk = [literal_k(baseb, wpre[g] * R, rb, s, cw) for g in range(8)] + [literal_k(baseb, sum(wt) * R, rb, s, cw)]
         c = 0
         for t in range(TILE // ITEMS):
             ws = wt[t * ITEMS:(t + 1) * ITEMS]
             base = which * TILE + t * ITEMS
-            if sum(ws):
+            g = t // WARP
+            if segk[g + 1] > segk[g] and sum(ws):
                 lo0, his = thread_his(baseb, c, ws, R, rb, s, cw)
                 if his[-1] > lo0:
                     lo = lo0
