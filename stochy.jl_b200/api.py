@@ -60,6 +60,20 @@ class Discrete:
         return "\n".join("%s | %s" % (k.ljust(w), p) for p, k in rows)
 
 
+class Categorical:
+    """Categorical(p) as the reference sees it through Distributions.jl (src/erp.jl:1-16): support 1..k (1-based,
+    like randominteger, src/erp.jl:28-30), score = logpdf.  Host-side value type for hellingerdistance / kl."""
+
+    def __init__(self, p):
+        self.p = [float(v) for v in p]
+
+    def support(self):
+        return list(range(1, len(self.p) + 1))
+
+    def score(self, x):
+        return math.log(self.p[x - 1]) if 1 <= x <= len(self.p) and self.p[x - 1] > 0 else -math.inf
+
+
 def support(d):
     return d.support()
 
@@ -81,7 +95,14 @@ def hellingerdistance(p, q):
 
 
 def kl(p, q):
-    return sum(math.exp(p.score(x)) * (p.score(x) - q.score(x)) for x in p.support())
+    """kl(p, q) (src/erp.jl:113-118): both supports must hold the same values (the reference's two asserts)."""
+    ps, qs = list(p.support()), list(q.support())
+    if len(ps) != len(qs):
+        raise AssertionError("length(psupp) == length(qsupp)")
+    for x in ps:
+        if x not in qs:
+            raise AssertionError("x in qsupp")
+    return sum(math.exp(p.score(x)) * (p.score(x) - q.score(x)) for x in ps)
 
 
 # ------------------------------------------------------------------ model descriptors
@@ -199,7 +220,17 @@ class Engine:
         self.model = None
 
     def close(self):
+        """Release the native handle.  A sharded handle first waits at a group barrier: a peer's last tile scan may
+        still be reading this rank's arena, which sb_destroy frees (every rank must therefore call close())."""
         if self.h:
+            grp = getattr(self, "_shard_group", False)
+            if grp is not False:
+                try:
+                    from . import dist as sbdist
+                    sbdist.barrier(grp)
+                except Exception:
+                    pass
+                self._shard_group = False
             nat.lib().sb_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -260,6 +291,7 @@ class Engine:
         self._chk(nat.lib().sb_dist_ipc_import(self.h, buf))
         sbdist.barrier(group)                                       # every arena is mapped everywhere
         self.rank, self.world, self.N_local = rank, world, N_local
+        self._shard_group = group                                   # close() meets the peers at a barrier first
         return self
 
     # ---- inference
@@ -336,6 +368,17 @@ class Engine:
         dst = np.empty(len(anc), dtype=src.dtype)
         self._chk(nat.lib().sb_gather(self.h, _ptr(src), src.dtype.itemsize, len(src), _ptr(anc), len(anc), _ptr(dst)))
         return dst
+
+    # ---- the same operations on DEVICE-resident buffers (raw device addresses, e.g. torch tensors' data_ptr());
+    # asynchronous on the handle's stream: call sync() before reading the results
+    def dev_resample_systematic(self, d_weights, kind, n, u, m, d_anc):
+        self._chk(nat.lib().sb_dev_resample_systematic(self.h, C.c_void_p(d_weights), kind, n, float(u), m, C.c_void_p(d_anc)))
+
+    def dev_gather(self, d_src, elem_bytes, n, d_anc, m, d_dst):
+        self._chk(nat.lib().sb_dev_gather(self.h, C.c_void_p(d_src), elem_bytes, n, C.c_void_p(d_anc), m, C.c_void_p(d_dst)))
+
+    def sync(self):
+        self._chk(nat.lib().sb_sync(self.h))
 
     def erp_sample(self, erp, params, n, seed=1):
         p = np.zeros(2)

@@ -589,7 +589,13 @@ __device__ __forceinline__ void sb_pull_first(const SbStepInfo& si, const SbPool
 // tile (first candidate next_b_lo) are started as soon as this tile's staging buffers are free.
 // ONE barrier.  The marker array is all -1 on entry and on exit (every thread resets the slots it reads);
 // the caller runs sb_pull_seg for the next tile (warp SB_META_WARP) and at least one barrier before the next call.
-template <bool PEERS, bool S32>
+// GEN: the record arrays (e, Pt, child_start, warp prefixes) may be shared memory or memory written earlier in the
+// same launch (the resident sweep kernel): ordinary coherent loads instead of ld.global.nc.
+template <bool GEN, typename T>
+__device__ __forceinline__ T sb_ld_rec(const T* p) { return GEN ? *p : __ldg(p); }          // Pt, child_start: shared memory when GEN
+template <bool GEN, typename T>
+__device__ __forceinline__ T sb_ld_recg(const T* p) { return GEN ? __ldcg(p) : __ldg(p); }  // e, warp prefixes: always global
+template <bool PEERS, bool S32, bool GEN = false>
 __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const SbPool& pool,
                                                   const int* __restrict__ e, const unsigned long long* __restrict__ Pt,
                                                   const int* __restrict__ child_start, int c0, int2 rng, int slot,
@@ -610,15 +616,15 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
             sb_pull_tile<S32>(si, bB, sm.w[1], sm.seg_baseb[1], sm.seg_rb[1], mt.wp[1][warp], cw, sm);
     }
     for (int b = b_lo + 2; b <= b_hi; ++b) {
-        const int cs = __ldg(child_start + b), ce = __ldg(child_start + b + 1);
+        const int cs = sb_ld_rec<GEN>(child_start + b), ce = sb_ld_rec<GEN>(child_start + b + 1);
         if (ce <= c0 || cs >= c1 || ce == cs) continue;          // no offspring in range (uniform branch)
         const unsigned long long* wpb = sb_pool_wp_ptr<PEERS>(pool, b);
-        const int rb = si.r0 + (si.E - __ldg(e + b));
-        const long long baseb = (long long)(__ldg(Pt + b) - si.U) + ((1ll << si.s) - 1ll) - ((long long)c0 << si.s);
-        const unsigned long long wbase = __ldg(wpb + warp);
+        const int rb = si.r0 + (si.E - sb_ld_recg<GEN>(e + b));
+        const long long baseb = (long long)(sb_ld_rec<GEN>(Pt + b) - si.U) + ((1ll << si.s) - 1ll) - ((long long)c0 << si.s);
+        const unsigned long long wbase = sb_ld_recg<GEN>(wpb + warp);
         const int k0 = sb_pull_k<S32>(baseb, wbase * (unsigned long long)si.R, rb, si.s, cw);
         const int k1 = warp == SB_WARPS - 1 ? min(max(ce - c0, 0), cw)
-                                            : sb_pull_k<S32>(baseb, __ldg(wpb + warp + 1) * (unsigned long long)si.R, rb, si.s, cw);
+                                            : sb_pull_k<S32>(baseb, sb_ld_recg<GEN>(wpb + warp + 1) * (unsigned long long)si.R, rb, si.s, cw);
         if (k1 > k0) sb_pull_tile<S32>(si, b, sb_pool_tile<PEERS>(pool, b), baseb, rb, wbase, cw, sm);
     }
     __syncthreads();                                             // markers complete; sm.w and sm.meta[slot] are free

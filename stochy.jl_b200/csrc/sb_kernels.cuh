@@ -1283,6 +1283,18 @@ __device__ __forceinline__ unsigned sb_pack_bits(unsigned state, unsigned mask) 
     return idx;
 }
 #define SB_MH_MAXD 16
+// The per-warp histogram words are 32 bits and grow by at most 32 per step: every 2^26 steps the CTA adds them to
+// the 64-bit global counters and clears them (uniform over the CTA: every thread runs the same number of steps).
+#define SB_MH_FLUSH_MASK ((1ll << 26) - 1ll)
+__device__ __forceinline__ void sb_mh_flush(unsigned* s_hist, int nwarps, int nv, unsigned long long* counts) {
+    __syncthreads();
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        unsigned long long t = 0;
+        for (int w = 0; w < nwarps; ++w) { t += s_hist[w * nv + v]; s_hist[w * nv + v] = 0u; }
+        if (t) atomicAdd(counts + v, t);
+    }
+    __syncthreads();
+}
 __global__ void __launch_bounds__(128)
 k_mh_bnet(const __grid_constant__ SbBnetArgs a) {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -1367,13 +1379,9 @@ k_mh_bnet(const __grid_constant__ SbBnetArgs a) {
             if (lane == __ffs(peers) - 1) hist[v] += __popc(peers);
         }
         __syncwarp();
+        if ((s & SB_MH_FLUSH_MASK) == SB_MH_FLUSH_MASK) sb_mh_flush(s_hist, nwarps, nv, a.counts);
     }
-    __syncthreads();
-    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
-        unsigned long long t = 0;
-        for (int w = 0; w < nwarps; ++w) t += s_hist[w * nv + v];
-        if (t) atomicAdd(a.counts + v, t);
-    }
+    sb_mh_flush(s_hist, nwarps, nv, a.counts);
     if (live && acc) atomicAdd(a.accepts, acc);
 }
 
@@ -1443,13 +1451,9 @@ k_mh_bnet_tab(const __grid_constant__ SbBnetArgs a) {
             if (lane == __ffs(peers) - 1) hist[v] += __popc(peers);
         }
         __syncwarp();
+        if ((s & SB_MH_FLUSH_MASK) == SB_MH_FLUSH_MASK) sb_mh_flush(s_hist, nwarps, nv, a.counts);
     }
-    __syncthreads();
-    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
-        unsigned long long t = 0;
-        for (int w = 0; w < nwarps; ++w) t += s_hist[w * nv + v];
-        if (t) atomicAdd(a.counts + v, t);
-    }
+    sb_mh_flush(s_hist, nwarps, nv, a.counts);
     if (live && acc) atomicAdd(a.accepts, acc);
 }
 

@@ -4,6 +4,7 @@
 #include "../../include/stochy_b200.h"
 #include "sb_kernels.cuh"
 #include "sb_small.cuh"
+#include "sb_resident.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -64,6 +65,10 @@ struct sb_handle {
     size_t off_w32[2] = {0, 0}, off_x[2] = {0, 0}, off_wp[2] = {0, 0}, off_e[2] = {0, 0}, off_Q[2] = {0, 0}, off_flags = 0;
     char* peer_base[SB_MAX_PEERS] = {nullptr};
     unsigned epoch = 0;
+    // Sharded pools: pool slot of step t is (slot_base + t) & 1 and slot_base advances by T per sweep, so the first
+    // step kernel of a sweep never writes the slot whose tile records a slower peer's LAST scan of the previous sweep
+    // may still be reading (every later overwrite is ordered behind the peers' flags; see DESIGN.md "Multi-GPU").
+    unsigned slot_base = 0;
     // programmatic dependent launch between the kernels of a sweep: bit 0 = the scan may be scheduled while the step
     // kernel drains, bit 1 = the step kernel's prologue overlaps the scan.  Measured best: both on one GPU, only the
     // second on sharded pools (the scan spins on peer flags there).  Overrides: SB_PDL, SB_PDL_DIST (0..3).
@@ -95,7 +100,12 @@ struct sb_handle {
     DevBuf sm_x, sm_a, sm_xs, sm_lz;  // one-tile chains (sb_small.cuh)
     int small_cur = -1;               // >= 0: the retained particle of the last pmcmc call is in buffer small_cur of sm_xs
     int use_small = 1;                // SB_NO_SMALL=1 keeps pmcmc on the tiled kernels
+    int use_resident = 1;             // SB_NO_RESIDENT=1 keeps mid-size sweeps on the tiled kernels (one launch per step and scan)
+    int coop = -1;                    // cooperative launch: -1 not probed, 0 unavailable, 1 available
+    int last_route = 0;               // 0 tiled kernels, 1 resident sweep kernel, 2 one-tile chain kernel (last run call)
     int64_t sw_N = 0, sw_S = 0;       // particles and row stride of the last sweep
+    int sw_T = 0;                     // steps of the last sweep (rows that exist in xbuf / ancbuf / lwbuf)
+    int sw_slot = 0;                  // pool slot that holds the last sweep's final particle set
     int sw_hist = 0;                  // history rows kept
     int sw_cond = 0;
     int xstar_cur = 0;
@@ -129,6 +139,10 @@ int fail(sb_handle* h, int code, const std::string& msg) {
     } while (0)
 
 inline int64_t tiles_of(int64_t n) { return (n + SB_TILE - 1) / SB_TILE; }
+
+// No sweep of the tiled kernels is current any more (a model was loaded, or the one-tile chain kernel ran, whose
+// history lives in its own buffers): sb_get_history / sb_get_particles must not read stale rows.
+inline void invalidate_sweep(sb_handle* h) { h->sw_N = 0; h->sw_S = 0; h->sw_T = 0; h->sw_hist = 0; h->sw_cond = 0; }
 
 // ---- where the grid arrays of pool slot `slot` live (plain buffers, or the shared arena when sharded)
 inline uint32_t* W32(sb_handle* h, int slot) {
@@ -492,6 +506,7 @@ extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
     }
     if (const char* np = getenv("SB_PDL")) h->pdl = atoi(np) & 3;
     if (const char* ns = getenv("SB_NO_SMALL")) h->use_small = atoi(ns) ? 0 : 1;
+    if (const char* nr = getenv("SB_NO_RESIDENT")) h->use_resident = atoi(nr) ? 0 : 1;
     if (const char* pd = getenv("SB_PDL_DIST")) h->pdl_dist = atoi(pd) & 3;
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, opt.device) != cudaSuccess || h->num_sms < 1)
         h->num_sms = 148;
@@ -604,11 +619,20 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
         double acc = 0.0;
         for (int k = 0; k < K; ++k) {
             const double p = A[(size_t)r * K + k];
-            if (!(p >= 0.0)) return fail(h, SB_EINVAL, "discrete_hmm: negative or NaN transition probability");
+            if (p != p) return fail(h, SB_ENAN, "unexpected nan in rand");
+            if (!(p >= 0.0)) return fail(h, SB_EINVAL, "discrete_hmm: negative transition probability");
             acc += p; cumA[(size_t)r * K + k] = thr_of(acc);
         }
     }
-    if (x0 < 0) { double acc = 0.0; for (int k = 0; k < K; ++k) { acc += pi[k]; cumpi[k] = thr_of(acc); } }
+    if (x0 < 0) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) {
+            // rand(ps) on a NaN entry is the reference's error (src/rand.jl:8,15); a negative entry is a caller bug
+            if (pi[k] != pi[k]) return fail(h, SB_ENAN, "unexpected nan in rand");
+            if (!(pi[k] >= 0.0)) return fail(h, SB_EINVAL, "discrete_hmm: negative initial probability");
+            acc += pi[k]; cumpi[k] = thr_of(acc);
+        }
+    }
     for (int r = 0; r < K; ++r) fill_tab(cumA.data() + (size_t)r * K, tabA.data() + (size_t)r * G);
     fill_tab(cumpi.data(), tabpi.data());
     h->hmm_multi = multi;
@@ -645,6 +669,7 @@ extern "C" int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int
     CK(cudaStreamSynchronize(h->stream));
     h->model = MODEL_HMM; h->K = K; h->T = T; h->x0 = x0;
     h->have_retained = false;
+    invalidate_sweep(h);
     return SB_OK;
 }
 
@@ -656,6 +681,7 @@ extern "C" int32_t sb_model_linear_gaussian(sb_handle* h, int32_t T, double a, d
     h->lg_a = a; h->lg_q = q; h->lg_c = c; h->lg_r = r; h->lg_m0 = m0; h->lg_P0 = P0;
     h->lg_y.assign(y, y + T);
     h->have_retained = false;
+    invalidate_sweep(h);
     return SB_OK;
 }
 
@@ -675,6 +701,8 @@ extern "C" int32_t sb_model_bayesnet(sb_handle* h, int32_t D, int32_t F, const u
         if (fac_parents[f] >> D) return fail(h, SB_EINVAL, "bayesnet: factor parent outside the sites");
         if ((1 << __builtin_popcount(fac_parents[f])) > cpt_stride) return fail(h, SB_EINVAL, "bayesnet: cpt_stride too small");
     }
+    if (D > SB_MH_TABD && (size_t)(3 * D + F) * cpt_stride * 8 > 190 * 1024)
+        return fail(h, SB_EUNSUPPORTED, "bayesnet: conditional tables exceed the shared memory of one SM (no CPU fallback)");
     CK(cudaSetDevice(h->opt.device));
     const size_t ns = (size_t)D * cpt_stride, nf = (size_t)(F > 0 ? F : 1) * cpt_stride;
     std::vector<double> lp1(ns), lp0(ns), fac(nf, 0.0);
@@ -692,6 +720,7 @@ extern "C" int32_t sb_model_bayesnet(sb_handle* h, int32_t D, int32_t F, const u
     CK(cudaMemcpyAsync(h->bn_fac.p, fac.data(), nf * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->model = MODEL_BNET; h->bn_D = D; h->bn_F = F; h->bn_stride = cpt_stride; h->bn_query = query_mask;
+    invalidate_sweep(h);
     return SB_OK;
 }
 
@@ -791,6 +820,53 @@ int upload_offsets(sb_handle* h, unsigned iter) {
     return SB_OK;
 }
 
+// The whole sweep as ONE cooperative launch (sb_resident.cuh) when every tile of the pool fits on the GPU at once.
+// *done = 0: not eligible here (too many tiles for the resident grid, no cooperative launch): the caller runs the
+// tiled kernels.  Buffers, offsets and the per-step records were prepared by sweep_hmm.
+template <bool FP32, bool MULTI>
+int sweep_hmm_resident_k(sb_handle* h, const SbResArgs& a, int* done) {
+    auto kern = k_sweep_hmm<FP32, MULTI>;
+    const size_t smem = sb_res_smem_bytes(a.K, a.ntiles, MULTI);
+    if (smem > 160 * 1024) return SB_OK;
+    int cap = 0, rc;
+    if ((rc = resident_ctas(h, kern, smem, &cap)) != SB_OK) { h->err.clear(); return SB_OK; }
+    if (a.ntiles > cap) return SB_OK;
+    void* args[] = {(void*)&a};
+    CK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)a.ntiles), dim3(SB_THREADS), args, smem, h->stream));
+    ++h->launches;
+    *done = 1;
+    return SB_OK;
+}
+int sweep_hmm_resident(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool history, bool final_anc, int64_t S, int* done) {
+    *done = 0;
+    if (h->coop < 0) {
+        int v = 0;
+        h->coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->opt.device) == cudaSuccess && v) ? 1 : 0;
+    }
+    if (!h->coop) return SB_OK;
+    const int n_out = (int)(N + (conditional ? 1 : 0));
+    const int nt = (int)tiles_of(n_out);
+    if (nt > SB_RES_MAXPER * SB_THREADS) return SB_OK;
+    SbResArgs a;
+    memset(&a, 0, sizeof(a));
+    const int G = 1 << SB_LG_BUCKETS;
+    a.tabA = h->hmm_tabA.as<uint32_t>(); a.thrA = h->hmm_cumA.as<uint32_t>();
+    if (h->x0 >= 0) { a.tab0 = a.tabA + (size_t)h->x0 * G; a.thr0 = a.thrA + (size_t)h->x0 * h->K; }
+    else { a.tab0 = h->hmm_tabpi.as<uint32_t>(); a.thr0 = h->hmm_cumpi.as<uint32_t>(); }
+    a.logF = h->hmm_logF.as<double>();
+    a.K = h->K; a.T = h->T;
+    for (int sl = 0; sl < 2; ++sl) { a.w32[sl] = W32(h, sl); a.e[sl] = TE(h, sl); a.Q[sl] = TQ(h, sl); a.wp[sl] = WP(h, sl); }
+    a.xbuf = h->xbuf.as<int>(); a.ancbuf = h->ancbuf.as<int>(); a.S = S;
+    a.history = history ? 1 : 0; a.final_anc = final_anc ? 1 : 0;
+    a.xstar = conditional ? h->xstar[h->xstar_cur].as<int>() : nullptr;
+    a.N = N; a.n_out = n_out; a.ntiles = nt;
+    a.r53 = h->d_r53.as<unsigned long long>(); a.info = h->d_info.as<SbStepInfo>();
+    a.iter = iter; a.rk = round_keys(h->opt.seed); a.err = h->d_err;
+    const bool fp32 = h->opt.precision == SB_FP32;
+    if (h->hmm_multi) return fp32 ? sweep_hmm_resident_k<true, true>(h, a, done) : sweep_hmm_resident_k<false, true>(h, a, done);
+    return fp32 ? sweep_hmm_resident_k<true, false>(h, a, done) : sweep_hmm_resident_k<false, false>(h, a, done);
+}
+
 // One sweep of the discrete model.  conditional: pool of N+1 with the retained particle appended.
 // Sharded handle: N is the GLOBAL particle count (world x N_local); this GPU produces its own share.
 int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool history, bool final_anc) {
@@ -817,13 +893,26 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
     h->sw_N = dist ? h->NL : N; h->sw_S = S; h->sw_hist = history ? 1 : 0; h->sw_cond = conditional ? 1 : 0;
     int* xb = h->xbuf.as<int>();
     int* ab = h->ancbuf.as<int>();
+    const unsigned sb0 = dist ? h->slot_base : 0u;
     auto xrow = [&](int t) -> int* {
-        if (dist) return reinterpret_cast<int*>((char*)h->arena + h->off_x[t & 1]);
+        if (dist) return reinterpret_cast<int*>((char*)h->arena + h->off_x[(sb0 + (unsigned)t) & 1u]);
         return xb + (size_t)(history ? t : (t & 1)) * S;
     };
     const int ntiles = dist ? (int)(h->NL / SB_TILE) : (int)tiles_of(n_out);
+    h->sw_T = T; h->sw_slot = (int)((sb0 + (unsigned)(T - 1)) & 1u);
+    if (dist) h->slot_base += (unsigned)T;
+    h->last_route = 0;
+    if (!dist && h->use_resident && mode == SB_RESAMPLE_SYSTEMATIC && !h->opt.store_logw && !h->profile) {
+        bool all_factors = true;
+        for (int t = 0; t < T; ++t) all_factors = all_factors && h->has_factor[t];
+        if (all_factors) {
+            int done = 0;
+            if ((rc = sweep_hmm_resident(h, N, iter, conditional, history, final_anc, S, &done)) != SB_OK) return rc;
+            if (done) { h->last_route = 1; return SB_OK; }
+        }
+    }
     for (int t = 0; t < T; ++t) {
-        const int cur = t & 1, prev = cur ^ 1;
+        const int cur = (int)((sb0 + (unsigned)t) & 1u), prev = cur ^ 1;
         int anc_mode = SB_ANC_NONE;
         int* anc_row_prev = (t && !dist) ? ab + (size_t)(history ? (t - 1) : 0) * S : nullptr;
         if (t > 0) {
@@ -874,7 +963,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         }
     }
     if (final_anc) {
-        const int t = T - 1, cur = t & 1;
+        const int t = T - 1, cur = (int)((sb0 + (unsigned)t) & 1u);
         int* row = ab + (size_t)(history ? t : 0) * S;
         if (!h->has_factor[t]) {
             k_fill_identity<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(row, N);
@@ -913,8 +1002,11 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
     char* xb = h->xbuf.as<char>();
     auto xrow = [&](int slot) -> char* { return dist ? (char*)h->arena + h->off_x[slot] : xb + (size_t)slot * S * sz; };
     const int ntiles = (int)(S / SB_TILE);
+    const unsigned sb0 = dist ? h->slot_base : 0u;
+    h->sw_T = T; h->sw_slot = (int)((sb0 + (unsigned)(T - 1)) & 1u);
+    if (dist) h->slot_base += (unsigned)T;
     for (int t = 0; t < T; ++t) {
-        const int cur = t & 1, prev = cur ^ 1;
+        const int cur = (int)((sb0 + (unsigned)t) & 1u), prev = cur ^ 1;
         int anc_mode = t ? (mode == SB_RESAMPLE_SYSTEMATIC ? SB_ANC_PULL : SB_ANC_EXPLICIT) : SB_ANC_NONE;
         if (anc_mode == SB_ANC_EXPLICIT)
             if ((rc = explicit_resample(h, prev, t - 1, iter, N, N, h->ancbuf.as<int>())) != SB_OK) return rc;
@@ -1003,6 +1095,7 @@ extern "C" int32_t sb_pmcmc_chains(sb_handle* h, int64_t chains, int64_t iters, 
         njoint = 1; for (int t = 0; t < T; ++t) njoint *= K;
     }
     const int S = (int)((N + 1 + 7) & ~7LL);
+    invalidate_sweep(h);                                            // the chain kernel keeps its history in its own buffers
     CK(h->sm_x.ensure((size_t)chains * T * S * 4));
     CK(h->sm_a.ensure((size_t)chains * T * S * 4));
     CK(h->sm_xs.ensure((size_t)chains * 2 * T * 4));
@@ -1219,6 +1312,9 @@ extern "C" int32_t sb_mh_run(sb_handle* h, int64_t chains, int64_t steps, int64_
         if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(k_mh_bnet_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         k_mh_bnet_tab<<<(unsigned)((chains + threads - 1) / threads), threads, smem_t, h->stream>>>(a);
     } else {
+        if (smem > 200 * 1024)
+            return fail(h, SB_EUNSUPPORTED, "mh: the net's tables do not fit in shared memory (no CPU fallback)");
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_mh_bnet, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_mh_bnet<<<(unsigned)((chains + threads - 1) / threads), threads, smem, h->stream>>>(a);
     }
     LAUNCH_CHECK();
@@ -1476,7 +1572,10 @@ extern "C" int32_t sb_erp_logpdf_dirichlet(sb_handle* h, const double* alpha, in
 // ======================================================================= state access
 extern "C" int32_t sb_get_history(sb_handle* h, int32_t t, int64_t count, void* x_out, int32_t* anc_out, double* lw_out) {
     if (!h) return SB_EINVAL;
-    if (h->sw_N == 0 || t < 0 || t >= h->T || count < 1 || count > h->sw_S) return fail(h, SB_EINVAL, "get_history: no sweep / bad index");
+    if (h->sw_N == 0)
+        return fail(h, SB_EINVAL, h->small_cur >= 0 ? "get_history: history not available (the last call ran as a one-tile chain set, whose history stays on chip)"
+                                                    : "get_history: no sweep has run since the model was loaded");
+    if (t < 0 || t >= h->sw_T || count < 1 || count > h->sw_S) return fail(h, SB_EINVAL, "get_history: bad index");
     CK(cudaSetDevice(h->opt.device));
     CK(cudaStreamSynchronize(h->stream));
     const int64_t S = h->sw_S;
@@ -1510,16 +1609,16 @@ extern "C" int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out) {
     if (!x_out || h->sw_N == 0 || count < 1 || count > h->sw_N) return fail(h, SB_EINVAL, "get_particles: no sweep / bad count");
     CK(cudaSetDevice(h->opt.device));
     CK(cudaStreamSynchronize(h->stream));
-    const int t = h->T - 1;
+    const int t = h->sw_T - 1;
     if (h->model == MODEL_HMM) {
-        const int row = h->sw_hist ? t : (t & 1);
-        const int* src = h->dist_ready ? reinterpret_cast<const int*>((char*)h->arena + h->off_x[t & 1])
+        const int row = h->sw_hist ? t : h->sw_slot;
+        const int* src = h->dist_ready ? reinterpret_cast<const int*>((char*)h->arena + h->off_x[h->sw_slot])
                                        : h->xbuf.as<int>() + (size_t)row * h->sw_S;
         CK(cudaMemcpy(x_out, src, (size_t)count * 4, cudaMemcpyDeviceToHost));
     } else {
         const size_t sz = h->opt.precision == SB_FP32 ? 4 : 8;
         std::vector<char> tmp((size_t)count * sz);
-        const char* src = h->dist_ready ? (char*)h->arena + h->off_x[t & 1] : h->xbuf.as<char>() + (size_t)(t & 1) * h->sw_S * sz;
+        const char* src = h->dist_ready ? (char*)h->arena + h->off_x[h->sw_slot] : h->xbuf.as<char>() + (size_t)h->sw_slot * h->sw_S * sz;
         CK(cudaMemcpy(tmp.data(), src, tmp.size(), cudaMemcpyDeviceToHost));
         double* o = (double*)x_out;
         if (sz == 4) for (int64_t i = 0; i < count; ++i) o[i] = (double)((float*)tmp.data())[i];

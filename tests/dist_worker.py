@@ -20,8 +20,18 @@ def main():
     import stochy_jl_b200 as sb
     from gpu_util import cfg3_tables, cfg4_data
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    # SB_DIST_SAME_GPU=1: every rank on device 0 (a one-GPU box): the ranks are separate processes whose arenas
+    # are mapped into each other over CUDA IPC exactly as across GPUs; the host plumbing is gloo (NCCL refuses two
+    # ranks on one device).  The kernels of the ranks are time-sliced, the flag barrier still holds.
+    same = os.environ.get("SB_DIST_SAME_GPU") == "1"
+    if same:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if same:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tdev = "cpu" if same else "cuda"
     log2n = int(sys.argv[1]) if len(sys.argv) > 1 else 14
     NL = 1 << log2n
     fails = []
@@ -36,11 +46,13 @@ def main():
         eng = sb.Engine(device=local, precision=prec, resample="systematic", seed=11)
         eng.load(mk())
         eng.shard(NL)
-        lz = [eng.smc_sweep(NL, it=i) for i in range(2)]            # two sweeps: the flag epochs keep counting
-        x = torch.from_numpy(eng.particles(NL).astype(np.float64)).cuda()
+        nsw = int(os.environ.get("SB_DIST_SWEEPS", "2"))
+        lz = [eng.smc_sweep(NL, it=i) for i in range(nsw)]          # several sweeps, no barrier between them: the flag epochs keep
+                                                                    # counting and (odd T) the starting pool slot alternates
+        x = torch.from_numpy(eng.particles(NL).astype(np.float64)).to(tdev)
         allx = [torch.empty_like(x) for _ in range(world)]
         dist.all_gather(allx, x)
-        lzt = torch.tensor(lz, dtype=torch.float64, device="cuda")
+        lzt = torch.tensor(lz, dtype=torch.float64, device=tdev)
         alllz = [torch.empty_like(lzt) for _ in range(world)]
         dist.all_gather(alllz, lzt)
         dist.barrier()
@@ -51,7 +63,7 @@ def main():
                     fails.append("%s: logZ differs between rank 0 and rank %d" % (name, r))
             ref = sb.Engine(device=local, precision=prec, resample="systematic", seed=11)
             ref.load(mk())
-            lz_ref = [ref.smc_sweep(NL * world, it=i) for i in range(2)]
+            lz_ref = [ref.smc_sweep(NL * world, it=i) for i in range(nsw)]
             x_ref = ref.particles(NL * world).astype(np.float64)
             ref.close()
             got = torch.cat(allx).cpu().numpy()

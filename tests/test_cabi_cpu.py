@@ -92,3 +92,40 @@ def test_hmm_example_descriptor_matches_enumerate(sb, enumref):
     assert post[(F, F, F)] == pytest.approx(0.8296918550634872, rel=1e-12)
     assert post[(T, F, F)] == pytest.approx(0.09218798389594302, rel=1e-12)
     assert post[(T, T, T)] == pytest.approx(0.0026556209352740765, rel=1e-12)
+
+
+def test_product_hellinger_kat(sb):
+    """test/erptests.jl:12-17 against the PRODUCT's hellingerdistance (src/erp.jl:100-111), not the oracle's."""
+    import json, os
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))["hellinger"]
+    p = sb.Categorical(kat["p"])
+    q = sb.Discrete({int(k): v for k, v in kat["q_counts"].items()})
+    assert sb.hellingerdistance(p, q) == pytest.approx(kat["value"], abs=kat["tol"])
+    assert sb.hellingerdistance(q, q) == 0.0
+    with pytest.raises(AssertionError):                     # @assert issubset(qsupp, psupp), src/erp.jl:103
+        sb.hellingerdistance(p, sb.Discrete({4: 1}))
+
+
+def test_product_kl_and_asserts(sb):
+    """kl(p, q) = sum_x p(x) (log p(x) - log q(x)) over a COMMON support (src/erp.jl:113-118)."""
+    import math
+    p = sb.Discrete({"a": 1, "b": 3})
+    q = sb.Discrete({"b": 1, "a": 1})
+    want = 0.25 * math.log(0.25 / 0.5) + 0.75 * math.log(0.75 / 0.5)
+    assert sb.kl(p, q) == pytest.approx(want, rel=1e-14)
+    assert sb.kl(p, p) == 0.0
+    c = sb.Categorical([0.5, 0.5])
+    assert sb.kl(sb.Discrete({1: 1, 2: 3}), c) == pytest.approx(want, rel=1e-14)
+    with pytest.raises(AssertionError):                     # @assert length(psupp) == length(qsupp)
+        sb.kl(p, sb.Discrete({"a": 1}))
+    with pytest.raises(AssertionError):                     # @assert x in qsupp
+        sb.kl(p, sb.Discrete({"a": 1, "c": 1}))
+
+
+def test_product_discrete_show_order(sb):
+    """show(io, ::Discrete) (src/erp.jl:80-96): rows sorted by descending probability, keys padded to one width."""
+    d = sb.Discrete({"x": 1, "long": 6, "yy": 3})
+    rows = repr(d).split("\n")
+    assert [r.split("|")[0].strip() for r in rows] == ["'long'", "'yy'", "'x'"]
+    assert len({r.index("|") for r in rows}) == 1
+    assert [float(r.split("|")[1]) for r in rows] == pytest.approx([0.6, 0.3, 0.1])

@@ -19,3 +19,21 @@ def test_sharded_sweep_equals_single_gpu(log2n):
            "--master-port", "29611", os.path.join(ROOT, "tests", "dist_worker.py"), str(log2n)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_PARITY_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,log2n", [(2, 11), (2, 13), (4, 12)])
+def test_sharded_sweep_ranks_on_one_gpu(world, log2n):
+    """The same parity on a ONE-GPU box: `world` rank processes, all on device 0, each with its own arena mapped into
+    the others over CUDA IPC exactly as across GPUs (gloo is the host plumbing; NCCL refuses two ranks on a device).
+    The ranks' kernels are time-sliced, so every flag wait really waits for another context.  The sharded sweeps
+    (HMM and linear-Gaussian, fp32 and fp64, odd T, several sweeps per handle) must equal the single-handle sweep of
+    the same global pool bit for bit."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    env = dict(os.environ, SB_DIST_SAME_GPU="1", SB_DIST_SWEEPS="4")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
+           "--master-port", str(29620 + world + log2n), os.path.join(ROOT, "tests", "dist_worker.py"), str(log2n)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "DIST_PARITY_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -555,3 +555,54 @@ def test_discrete_erp_hooks(oracle):
             eng.discrete_sample([0.3, float("nan"), 0.2], 1000)
         assert ei.value.code == nat.ENAN and "unexpected nan in rand" in str(ei.value)
         assert np.array_equal(eng.discrete_sample([0.5, 0.5], 4, seed=1), eng.discrete_sample([0.5, 0.5], 4, seed=1))
+
+
+@pytest.mark.parametrize("log2n", [16, 20])
+def test_tiled_conditional_smc_with_history_full_size(oracle, log2n):
+    """BASELINE cfg3's shape at its full particle count (K = 16 sticky HMM, N = 2^20, conditional SMC with
+    history; T reduced to 8 so the oracle finishes in seconds): iteration 0 is a plain sweep, iteration 1 a
+    CONDITIONAL sweep whose pool of N+1 carries the retained particle (src/pmcmc.jl:59-66).  Every history
+    row (states and ancestors, including the retained slot N), the next retained trajectory (src/pmcmc.jl:89)
+    and the per-time value counts over all N particles of both iterations (src/pmcmc.jl:90-92) must equal
+    the oracle's, bit for bit."""
+    sb = sb_mod()
+    T, N = 8, 1 << log2n
+    A, logF, pi = cfg3_tables(T=T)
+    om = oracle.Hmm(A, logF, pi=pi)
+    oo = oracle.opts(oracle.SYSTEMATIC, fp32=True, seed=9)
+    ref0 = oracle.hmm_sweep(om, oo, N, it=0)
+    ref1 = oracle.hmm_sweep(om, oo, N, it=1, xstar=ref0["xstar"])
+    refc = oracle.hmm_pmcmc(om, oo, 2, N, want_joint=False)
+    with sb.Engine(precision="fp32", resample="systematic", seed=9) as eng:
+        eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+        marg, _ = eng.pmcmc_counts(2, N, want_joint=False)
+        st = eng.stats()
+        assert np.array_equal(marg, refc["marg"])
+        assert marg.sum() == 2 * N * T
+        for t in range(T):
+            x, a, _ = eng.history(t, N + 1)
+            assert np.array_equal(x, ref1["x"][t, :N + 1]), t          # slot N = the retained particle's state
+            assert np.array_equal(a[:N], ref1["anc"][t, :N]), t
+        assert np.array_equal(eng.retained(), ref1["xstar"])
+        assert st.logZ_first == pytest.approx(ref0["logZ"], rel=1e-9)
+        assert st.logZ_last == pytest.approx(ref1["logZ"], rel=1e-9)
+
+
+def test_cfg1_hmm_example_pmcmc_vs_enumerate():
+    """BASELINE cfg1: examples/hmm.jl with line 27's enum() replaced by pmcmc(1000, 100) (iterations first,
+    src/pmcmc.jl:78), reference numerics; total variation against exhaustive enumeration (the product's own
+    enum on the GPU, and the hand-derived goldens of SURVEY section 4)."""
+    import json
+    import os
+    sb = sb_mod()
+    m = sb.hmm_example(3)
+    d = sb.pmcmc(m, 1000, 100, seed=1)
+    exact = sb.enum(m)
+    keys = set(d.support()) | set(exact.support())
+    tv = 0.5 * sum(abs(d.prob(k) - exact.prob(k)) for k in keys)
+    assert tv <= 0.02, tv
+    kat = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))["hmm_example_enum"]["p"]
+    for name, p in kat.items():
+        key = tuple(c == "T" for c in name)
+        assert exact.prob(key) == pytest.approx(p, rel=1e-10)
+        assert abs(d.prob(key) - p) <= 0.02
