@@ -14,7 +14,7 @@ _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("STOCHY_B200_LIB") or os.path.join(_PKG, "libstochy_b200.so")   # same override as the Julia shim
 SOURCES = ["stochy_b200.cu"]
-HEADERS = ["sb_device.cuh", "sb_kernels.cuh", "sb_small.cuh"]
+HEADERS = ["sb_device.cuh", "sb_kernels.cuh", "sb_small.cuh", "sb_resident.cuh"]
 
 OK, ENAN, EZEROMASS, EINVAL, EUNSUPPORTED, ECUDA, EPEER, ENOMEM = range(8)
 FP32, FP64 = 0, 1

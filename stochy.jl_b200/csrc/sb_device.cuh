@@ -77,6 +77,14 @@ __device__ __forceinline__ const unsigned long long* sb_pool_wp_ptr(const SbPool
     const int ts = p.log2n - 11;
     return reinterpret_cast<const unsigned long long*>(p.base[b >> ts] + p.off_wp) + (size_t)(b & ((1 << ts) - 1)) * SB_WARPS;
 }
+// the 2048 states of parent tile b (4-byte states: the discrete model), read by the parents themselves when the head
+// markers carry the state (CARRY): coalesced 128-bit loads instead of the children's scattered gather
+template <bool PEERS>
+__device__ __forceinline__ const int* sb_pool_xtile(const SbPool& p, int b) {
+    if (!PEERS) return reinterpret_cast<const int*>(p.x) + (size_t)b * SB_TILE;
+    const int ts = p.log2n - 11;
+    return reinterpret_cast<const int*>(p.base[b >> ts] + p.off_x) + (size_t)(b & ((1 << ts) - 1)) * SB_TILE;
+}
 template <typename T, bool PEERS>
 __device__ __forceinline__ T sb_pool_x(const SbPool& p, int i) {
     if (!PEERS) return __ldg(reinterpret_cast<const T*>(p.x) + i);
@@ -347,11 +355,28 @@ __device__ __forceinline__ void sb_mbar_wait(unsigned long long* bar, uint32_t p
         "SB_DONE:\n"
         "}\n" ::"r"(sb_smem_addr(bar)), "r"(parity) : "memory");
 }
+// Split-phase CTA barrier on the hardware named barriers 1..SB_WARPS (no spinning: a waiting warp is descheduled and
+// costs no issue slots -- an mbarrier try_wait loop re-issues itself every few dozen cycles, which was a fifth of
+// all instructions the step kernels executed).  Barrier 1 + w belongs to warp w: every warp ARRIVES on all of them
+// (non-blocking) once it has published what the others need, and later WAITS on its own -- which completes when all
+// SB_WARPS warps have arrived.  One wait per arrive; a full CTA barrier separates consecutive arrives (callers'
+// invariant), so phases cannot overlap.  Writes before the arrive are visible after the wait (bar.arrive / bar.sync).
+__device__ __forceinline__ void sb_split_arrive() {
+#pragma unroll
+    for (int j = 0; j < SB_WARPS; ++j) asm volatile("bar.arrive %0, %1;" ::"r"(j + 1), "r"(32 * SB_WARPS + 32) : "memory");
+}
+__device__ __forceinline__ void sb_split_wait() {
+    asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x >> 5) + 1), "r"(32 * SB_WARPS + 32) : "memory");
+}
 // one thread: `bytes` (multiple of 16, 16-byte aligned both sides) from global memory -- local HBM or a
 // peer GPU's arena over NVLink -- into shared memory; completion is counted on the mbarrier
 __device__ __forceinline__ void sb_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(sb_smem_addr(dst)), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(sb_smem_addr(bar)) : "memory");
+}
+// one thread: ask for `bytes` (multiple of 16) of global memory to be brought into L2
+__device__ __forceinline__ void sb_bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void sb_cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sb_smem_addr(dst)), "l"(__cvta_generic_to_global(src)) : "memory");
@@ -418,9 +443,19 @@ __device__ __forceinline__ unsigned long long sb_mad_wide(uint32_t a, uint32_t b
 //     (baseb + ((c + a) R >> rb)) >> s  ==  K + ((Z0 + a R) >> (rb + s)),   Z0 = (D0 mod 2^s) 2^rb + (c R mod 2^rb),
 // so each further parent costs one multiply-accumulate into Z and one 32-bit shift of Z's high word
 // (rb + s in [32, 62], the ordinary case; other shifts take the literal formula).
-template <bool S32>
+// CARRY: a head marker is (parent index << xb) | parent state, so the child that takes the marker has its parent's
+// state without a gather; the parent reads its own 8 states (xsrc: the tile's state array, global memory) with two
+// coalesced 128-bit loads issued behind the warp scan.  Markers still ascend with the slot (the index dominates).
+// XPRE: the caller loaded the states already (xpa, xpc: in flight since before the weights landed).
+template <bool COH>
+__device__ __forceinline__ int4 sb_ld_x4(const int* p, int i) {
+    return COH ? __ldcg(reinterpret_cast<const int4*>(p) + i) : __ldg(reinterpret_cast<const int4*>(p) + i);
+}
+template <bool S32, bool CARRY, bool COH = false, bool XPRE = false>
 __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const uint32_t* __restrict__ wsrc,
-                                             long long baseb, int rb, unsigned long long wbase, int cw, SbPullSmem& sm) {
+                                             long long baseb, int rb, unsigned long long wbase, int cw, SbPullSmem& sm,
+                                             const int* __restrict__ xsrc = nullptr, int xb = 0,
+                                             int4 xpa = make_int4(0, 0, 0, 0), int4 xpc = make_int4(0, 0, 0, 0)) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int s = si.s;
     const unsigned R = si.R;
@@ -439,6 +474,12 @@ __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const 
         if (lane >= d) inc += o;
     }
     if (tsum == 0) return;
+    int4 xa = xpa, xc = xpc;
+    if (CARRY && !XPRE) {                                        // in flight during the CDF evaluation below
+        // COH: the states were written earlier in this same launch (resident sweep kernel): coherent loads
+        xa = sb_ld_x4<COH>(xsrc, tid * 2);
+        xc = sb_ld_x4<COH>(xsrc, tid * 2 + 1);
+    }
     const unsigned long long c = wbase + inc - tsum;            // tile-local exclusive prefix of this thread
     unsigned long long acc = c * (unsigned long long)R;
     const int base = b * SB_TILE + tid * SB_ITEMS;
@@ -472,6 +513,40 @@ __device__ __forceinline__ void sb_pull_tile(const SbStepInfo& si, int b, const 
     // children) writes a marker there too, so the fill of the markers never has to look across warps:
     // it is parent number #{j : hi[j] <= bnd} of this thread
     const int bnd = (lo0 | 255) + 1;
+    if (CARRY) {
+        const int xs[SB_ITEMS] = {xa.x, xa.y, xa.z, xa.w, xc.x, xc.y, xc.z, xc.w};
+        const int bsh = base << xb;
+        int mk[SB_ITEMS];
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) mk[j] = bsh + (j << xb) + xs[j];
+        int lo = lo0, bv = mk[0];
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) {
+#if !(defined(SB_ABLATE) && (SB_ABLATE == 6 || SB_ABLATE == 7))     /* diagnostics: 6 = no head-marker stores (wrong results) */
+            if (lo < hi[j]) sm.marker[lo] = mk[j];
+#elif SB_ABLATE == 6
+            if (lo < hi[j] && mk[j] == -12345) sm.marker[lo] = mk[j];
+#endif
+#if defined(SB_ABLATE) && SB_ABLATE == 7                            /* diagnostics: 7 = head markers at conflict-free slots (wrong results) */
+            if (lo < hi[j]) sm.marker[(lo & 0x700) + j * 32 + lane] = mk[j];
+#endif
+            if (j < SB_ITEMS - 1 && hi[j] <= bnd) bv = mk[j + 1];  // hi ascends: the last assignment is parent #{j : hi[j] <= bnd}
+            lo = hi[j];
+        }
+        if (hi[SB_ITEMS - 1] > bnd) {
+            sm.marker[bnd] = bv;
+            if (hi[SB_ITEMS - 1] > bnd + 256) {
+                lo = lo0;
+#pragma unroll
+                for (int j = 0; j < SB_ITEMS; ++j) {
+#pragma unroll 1
+                    for (int q = (lo | 255) + 1; q < hi[j]; q += 256) sm.marker[q] = mk[j];
+                    lo = hi[j];
+                }
+            }
+        }
+        return;
+    }
     int lo = lo0, nbelow = 0;
 #pragma unroll
     for (int j = 0; j < SB_ITEMS; ++j) {
@@ -508,7 +583,7 @@ __device__ __forceinline__ int2 sb_pull_range(const SbStepInfo& si, const int* _
 // The pool may live on a peer GPU: the copies then run over NVLink.
 #define SB_META_WARP  1
 #define SB_FLUSH_WARP 2
-template <bool PEERS>
+template <bool PEERS, bool CARRY = false>
 __device__ __forceinline__ void sb_pull_prefetch(const SbStepInfo& si, const SbPool& pool, const int* __restrict__ e,
                                                  const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
                                                  int b_lo, int slot, SbPullSmem& sm) {
@@ -519,6 +594,13 @@ __device__ __forceinline__ void sb_pull_prefetch(const SbStepInfo& si, const SbP
             sb_mbar_expect_tx(&sm.bar, 2u * SB_TILE * 4u);
             sb_bulk_g2s(sm.w[0], sb_pool_tile<PEERS>(pool, bA), SB_TILE * 4u, &sm.bar);
             sb_bulk_g2s(sm.w[1], sb_pool_tile<PEERS>(pool, bB), SB_TILE * 4u, &sm.bar);
+            if (CARRY) {
+                // the parents read their own states one tile from now (sb_pull_tile): have them in L2 by then
+                // (local memory only: a peer's memory is not cached here)
+                const int ts = pool.log2n - 11, self = PEERS ? (pool.tile_off >> ts) : 0;
+                if (!PEERS || (bA >> ts) == self) sb_bulk_prefetch_l2(sb_pool_xtile<PEERS>(pool, bA), SB_TILE * 4u);
+                if (bB != bA && (!PEERS || (bB >> ts) == self)) sb_bulk_prefetch_l2(sb_pool_xtile<PEERS>(pool, bB), SB_TILE * 4u);
+            }
         }
         return;
     }
@@ -565,7 +647,7 @@ __device__ __forceinline__ void sb_pull_seg(const SbStepInfo& si, int c0, int2 r
 
 // Once per CTA, before its first children tile (the mbarrier is initialised and a barrier has passed): clear the
 // marker array, request the first tile's parents and build its boundary table.
-template <bool PEERS>
+template <bool PEERS, bool CARRY = false>
 __device__ __forceinline__ void sb_pull_first(const SbStepInfo& si, const SbPool& pool, const int* __restrict__ e,
                                               const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
                                               int c0, int2 rng, SbPullSmem& sm) {
@@ -573,7 +655,7 @@ __device__ __forceinline__ void sb_pull_first(const SbStepInfo& si, const SbPool
     const int4 neg = make_int4(-1, -1, -1, -1);
     reinterpret_cast<int4*>(sm.marker)[tid * 2] = neg;
     reinterpret_cast<int4*>(sm.marker)[tid * 2 + 1] = neg;
-    if ((tid >> 5) == 0 || (tid >> 5) == SB_META_WARP) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, rng.x, 0, sm);
+    if ((tid >> 5) == 0 || (tid >> 5) == SB_META_WARP) sb_pull_prefetch<PEERS, CARRY>(si, pool, e, Pt, child_start, rng.x, 0, sm);
     if ((tid >> 5) == SB_META_WARP) {
         if (si.s >= 32) sb_pull_seg<true>(si, c0, rng, 0, sm); else sb_pull_seg<false>(si, c0, rng, 0, sm);
     }
@@ -595,12 +677,13 @@ template <bool GEN, typename T>
 __device__ __forceinline__ T sb_ld_rec(const T* p) { return GEN ? *p : __ldg(p); }          // Pt, child_start: shared memory when GEN
 template <bool GEN, typename T>
 __device__ __forceinline__ T sb_ld_recg(const T* p) { return GEN ? __ldcg(p) : __ldg(p); }  // e, warp prefixes: always global
-template <bool PEERS, bool S32, bool GEN = false>
+// CARRY: anc[] receives (parent index << xb) | parent state (see sb_pull_tile).
+template <bool PEERS, bool S32, bool GEN = false, bool CARRY = false>
 __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const SbPool& pool,
                                                   const int* __restrict__ e, const unsigned long long* __restrict__ Pt,
                                                   const int* __restrict__ child_start, int c0, int2 rng, int slot,
                                                   uint32_t parity, bool more, int next_b_lo, SbPullSmem& sm,
-                                                  int anc[SB_ITEMS]) {
+                                                  int anc[SB_ITEMS], int xb = 0) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m = (int)si.m;
     const int c1 = min(c0 + SB_TILE, m);
@@ -609,11 +692,17 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
     const int bA = b_lo, bB = min(b_lo + 1, si.nt - 1);
     sb_mbar_wait(&sm.bar, parity);                               // the two staged weight tiles have landed
     {
+        // (requesting the parents' states here, before the wait for the weights, was measured: 80.0 vs 76.4 us per launch)
         const SbPullMeta& mt = sm.meta[slot];
         if (sm.seg_k[0][warp + 1] > sm.seg_k[0][warp])
-            sb_pull_tile<S32>(si, bA, sm.w[0], sm.seg_baseb[0], sm.seg_rb[0], mt.wp[0][warp], cw, sm);
+            sb_pull_tile<S32, CARRY, GEN>(si, bA, sm.w[0], sm.seg_baseb[0], sm.seg_rb[0], mt.wp[0][warp], cw, sm,
+                                     CARRY ? sb_pool_xtile<PEERS>(pool, bA) : nullptr, xb);
+#if defined(SB_ABLATE) && SB_ABLATE == 4                              /* diagnostics: at most one parent segment per warp (wrong results) */
+        if (!(sm.seg_k[0][warp + 1] > sm.seg_k[0][warp]))
+#endif
         if (sm.seg_k[1][warp + 1] > sm.seg_k[1][warp])
-            sb_pull_tile<S32>(si, bB, sm.w[1], sm.seg_baseb[1], sm.seg_rb[1], mt.wp[1][warp], cw, sm);
+            sb_pull_tile<S32, CARRY, GEN>(si, bB, sm.w[1], sm.seg_baseb[1], sm.seg_rb[1], mt.wp[1][warp], cw, sm,
+                                     CARRY ? sb_pool_xtile<PEERS>(pool, bB) : nullptr, xb);
     }
     for (int b = b_lo + 2; b <= b_hi; ++b) {
         const int cs = sb_ld_rec<GEN>(child_start + b), ce = sb_ld_rec<GEN>(child_start + b + 1);
@@ -625,10 +714,11 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
         const int k0 = sb_pull_k<S32>(baseb, wbase * (unsigned long long)si.R, rb, si.s, cw);
         const int k1 = warp == SB_WARPS - 1 ? min(max(ce - c0, 0), cw)
                                             : sb_pull_k<S32>(baseb, sb_ld_recg<GEN>(wpb + warp + 1) * (unsigned long long)si.R, rb, si.s, cw);
-        if (k1 > k0) sb_pull_tile<S32>(si, b, sb_pool_tile<PEERS>(pool, b), baseb, rb, wbase, cw, sm);
+        if (k1 > k0) sb_pull_tile<S32, CARRY, GEN>(si, b, sb_pool_tile<PEERS>(pool, b), baseb, rb, wbase, cw, sm,
+                                              CARRY ? sb_pool_xtile<PEERS>(pool, b) : nullptr, xb);
     }
     __syncthreads();                                             // markers complete; sm.w and sm.meta[slot] are free
-    if (more && (warp == 0 || warp == SB_META_WARP)) sb_pull_prefetch<PEERS>(si, pool, e, Pt, child_start, next_b_lo, slot ^ 1, sm);
+    if (more && (warp == 0 || warp == SB_META_WARP)) sb_pull_prefetch<PEERS, CARRY>(si, pool, e, Pt, child_start, next_b_lo, slot ^ 1, sm);
     // every child takes the last head marker at or before its slot.  Markers ascend with the slot (the CDF is
     // monotone) and the first slot of every warp has one, so the carry into a thread is the largest marker of
     // the nearest earlier thread OF ITS WARP that has one: a ballot and one shuffle
@@ -652,7 +742,7 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
 
 // Candidate parent tiles of this CTA's next SB_FT_CHUNK + 1 children tiles (tile, tile + grid, ...), looked
 // up once per chunk; on the CTA's first tile also starts the copies for that tile.
-template <bool PEERS>
+template <bool PEERS, bool CARRY = false>
 __device__ __forceinline__ void sb_pull_ranges(const SbStepInfo& si, const SbPool& pool, const int* __restrict__ e,
                                                const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
                                                const int* __restrict__ first_tile, int tile, int ntiles, bool first, SbPullSmem& sm) {
@@ -662,7 +752,7 @@ __device__ __forceinline__ void sb_pull_ranges(const SbStepInfo& si, const SbPoo
         sm.ft[threadIdx.x] = tl < ntiles ? sb_pull_range(si, first_tile, pool.c_off + (int)tl * SB_TILE) : make_int2(0, -1);
     }
     __syncthreads();
-    if (first) sb_pull_first<PEERS>(si, pool, e, Pt, child_start, pool.c_off + tile * SB_TILE, sm.ft[0], sm);
+    if (first) sb_pull_first<PEERS, CARRY>(si, pool, e, Pt, child_start, pool.c_off + tile * SB_TILE, sm.ft[0], sm);
 }
 
 // block maxima with ONE barrier (the caller's later barriers protect the scratch array)

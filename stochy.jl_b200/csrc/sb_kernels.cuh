@@ -621,6 +621,7 @@ struct SbHmmStepArgs {
     int n_out;                  // N (+1 with a retained particle)
     int ntiles;                 // local tiles to produce
     int K, rows, t;
+    int xb;                     // CARRY instantiations: state bits of a head marker ((parent << xb) | state)
     unsigned iter;
     unsigned long long seed;
     SbRoundKeys rk;             // Philox round keys of `seed`
@@ -634,10 +635,12 @@ struct SbHmmSmem {
                                            // fast warp may finish tile k+1 before the flushing warp has written out the totals of tile k
     unsigned long long bar2;    // split-phase barrier of the fused HMM kernel: one arrival per warp and children tile
     unsigned kmax;              // largest exponent key any state of this step can have
+    unsigned qthr;              // largest grid weight, in kmax's row of the weight table, of a state BELOW the top exponent:
+                                // a particle weighing more proves that the tile exponent is the top one
 };
 
 // k: how many tiles this CTA has done before this one (staging slot / mbarrier parity of the pull)
-template <int ANC, bool FP32, bool PEERS, bool MULTI, bool TAIL>
+template <int ANC, bool FP32, bool PEERS, bool MULTI, bool TAIL, bool CARRY>
 __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStepInfo& si, int tile, int k, SbHmmSmem& sm,
                                             const uint32_t* s_thr, const uint32_t* s_key, const uint32_t* s_qtab, const uint32_t* s_tab) {
     const int tid = threadIdx.x;
@@ -660,9 +663,9 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         const int nb = sm.ps.ft[kk + 1].x;
         // every warp has finished the previous tile's marker slots and exponent key, and the records warp this tile's boundary
         // table (the wait half of the split barrier; most of its skew was absorbed by the previous tile's epilogue)
-        if (k > 0) sb_mbar_wait(&sm.bar2, (uint32_t)((k - 1) & 1));
-        if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
-        else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
+        if (k > 0) sb_split_wait();
+        if (si.s >= 32) sb_pull_ancestors<PEERS, true, false, CARRY>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc, a.xb);
+        else            sb_pull_ancestors<PEERS, false, false, CARRY>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc, a.xb);
 #endif
     } else if (ANC == SB_ANC_EXPLICIT) {
         if (!TAIL) {
@@ -677,15 +680,17 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
 #pragma unroll
         for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;
     }
+    // CARRY: the pull returned (parent << xb) | parent state
+    const int xsh = (CARRY && ANC == SB_ANC_PULL) ? a.xb : 0;
     if (ANC != SB_ANC_NONE && ANC != SB_ANC_EXPLICIT && a.anc_out) {
         if (!TAIL) {
-            reinterpret_cast<int4*>(a.anc_out + lbase)[0] = make_int4(anc[0], anc[1], anc[2], anc[3]);
-            reinterpret_cast<int4*>(a.anc_out + lbase)[1] = make_int4(anc[4], anc[5], anc[6], anc[7]);
+            reinterpret_cast<int4*>(a.anc_out + lbase)[0] = make_int4(anc[0] >> xsh, anc[1] >> xsh, anc[2] >> xsh, anc[3] >> xsh);
+            reinterpret_cast<int4*>(a.anc_out + lbase)[1] = make_int4(anc[4] >> xsh, anc[5] >> xsh, anc[6] >> xsh, anc[7] >> xsh);
         } else {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) {
                 const int i = base + j;
-                if (i < N) a.anc_out[lbase + j] = anc[j];
+                if (i < N) a.anc_out[lbase + j] = anc[j] >> xsh;
                 else if (i == N) a.anc_out[lbase + j] = N;       // the retained slot descends from itself
             }
         }
@@ -698,7 +703,11 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         for (int j = 0; j < SB_ITEMS; ++j) xp[j] = anc[j] & 15;
     } else
 #endif
-    if (PEERS && !TAIL && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
+    if (CARRY && ANC == SB_ANC_PULL) {                            // the head markers carried the parents' states: no gather
+        const int xm = (1 << xsh) - 1;
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) xp[j] = (!TAIL || base + j < N) ? (anc[j] & xm) : 0;
+    } else if (PEERS && !TAIL && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
         // the pull returns parents in ascending order: first and last on the same GPU means all eight are,
         // and one base pointer serves them (the usual case; only shard boundaries take the general path)
         const int g = anc[0] >> a.pool.log2n;
@@ -731,7 +740,13 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
             const int j = 4 * p + h;
             const int ri = a.rows > 1 ? xp[j] : 0;
             const uint32_t R = r4[h];
+#if SB_ABLATE == 8                                                  /* diagnostics: 8 = no draw-table lookup (wrong results) */
+            const uint32_t g = ((uint32_t)ri + (R >> 29)) & 7u;
+#elif SB_ABLATE == 9                                                /* diagnostics: 9 = conflict-free draw-table lookup (wrong results) */
+            const uint32_t g = s_tab[(ri << SB_LG_BUCKETS) + ((R >> (32 - SB_LG_BUCKETS)) & ~31u) + (tid & 31)];
+#else
             const uint32_t g = s_tab[(ri << SB_LG_BUCKETS) + (R >> (32 - SB_LG_BUCKETS))];
+#endif
             int lo = (int)(g & 63u) + (((R << SB_LG_BUCKETS) > g) ? 1 : 0);
             if (MULTI && (g & 128u)) {                           // several thresholds inside one bucket: scan
                 const uint32_t* row = s_thr + ri * K;
@@ -754,16 +769,33 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
     // (4)+(5) weight and quantise.  Only K distinct scores exist: the tile exponent is the largest
     // ceil(log2 weight) present (an integer max), and 2^(l2 - e) 2^27 comes from a K x K table.
+    // The weights are looked up at once in the row of the LARGEST key the model can produce this step (sm.kmax): a
+    // particle heavier than every below-top state of that row (sm.qthr) proves that the tile exponent is the top
+    // one, and then these weights are final -- the usual case, no per-particle key lookup.  Otherwise the exact keys
+    // are reduced as before and, should the tile exponent turn out lower, the weights are looked up again.
+    const unsigned kmax = sm.kmax;
+    constexpr bool SPEC = !TAIL && ANC == SB_ANC_PULL && SB_ABLATE != 3;
+    uint32_t q[SB_ITEMS];
     unsigned key = 0u;
-    if (!TAIL) {
-        key = __vimax3_u32(__vimax3_u32(s_key[x[0]], s_key[x[1]], s_key[x[2]]), __vimax3_u32(s_key[x[3]], s_key[x[4]], s_key[x[5]]),
-                           max(s_key[x[6]], s_key[x[7]]));
+    if (SPEC) {
+        const uint32_t* qtop = s_qtab + (kmax & 63u) * K;
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) q[j] = qtop[x[j]];
+        unsigned wm = __vimax3_u32(__vimax3_u32(q[0], q[1], q[2]), __vimax3_u32(q[3], q[4], q[5]), max(q[6], q[7]));
+        wm = __reduce_max_sync(0xffffffffu, wm);
+        if (wm > sm.qthr) key = kmax;
+        else {
+            key = __vimax3_u32(__vimax3_u32(s_key[x[0]], s_key[x[1]], s_key[x[2]]), __vimax3_u32(s_key[x[3]], s_key[x[4]], s_key[x[5]]),
+                               max(s_key[x[6]], s_key[x[7]]));
+            key = __reduce_max_sync(0xffffffffu, key);
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) key = max(key, s_key[x[j]]);
+        for (int j = 0; j < SB_ITEMS; ++j) if (!TAIL || base + j < a.n_out) key = max(key, s_key[x[j]]);
+        key = __reduce_max_sync(0xffffffffu, key);
     }
-    key = __reduce_max_sync(0xffffffffu, key);
     if ((tid & 31) == 0) reinterpret_cast<unsigned*>(sm.red)[tid >> 5] = key;
+    bool final_q = SPEC;                                        // q[] already holds the weights of the tile's row
     if (ANC == SB_ANC_PULL && SB_ABLATE != 3) {
         if ((tid >> 5) == SB_META_WARP && tile + (int)gridDim.x < a.ntiles) {
             // one warp: the next children tile's records have landed by now; its boundary table is built behind the barrier
@@ -776,26 +808,29 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         // warps' keys only when this warp's own maximum is below the largest key the model can produce this
         // step -- otherwise the tile maximum is already known and the warp goes on without waiting.
         __syncwarp();
-        if ((tid & 31) == 0) sb_mbar_arrive(&sm.bar2);
-        if (TAIL || key != sm.kmax) {
+        sb_split_arrive();                                        // waited for at the start of the next tile (hardware barrier, no spin)
+        if ((tid & 31) == 0) sb_mbar_arrive(&sm.bar2);            // the same event for the rare waiters just below
+        if (TAIL || key != kmax) {
             sb_mbar_wait(&sm.bar2, (uint32_t)(k & 1));
             const uint4 u = reinterpret_cast<const uint4*>(sm.red)[0], v = reinterpret_cast<const uint4*>(sm.red)[1];
             key = max(max(max(u.x, u.y), max(u.z, u.w)), max(max(v.x, v.y), max(v.z, v.w)));
+            final_q = false;
         }
     } else {
         __syncthreads();
         const uint4 u = reinterpret_cast<const uint4*>(sm.red)[0], v = reinterpret_cast<const uint4*>(sm.red)[1];
         key = max(max(max(u.x, u.y), max(u.z, u.w)), max(max(v.x, v.y), max(v.z, v.w)));
+        final_q = false;
     }
     const int e = key ? (int)(key >> 6) - SB_KEY_BIAS : SB_E_EMPTY;
-    const uint32_t* qrow = s_qtab + (key & 63u) * K;
-    uint32_t q[SB_ITEMS];
+    if (!final_q) {
+        const uint32_t* qrow = s_qtab + (key & 63u) * K;
+#pragma unroll
+        for (int j = 0; j < SB_ITEMS; ++j) q[j] = (key != 0u && (!TAIL || base + j < a.n_out)) ? qrow[x[j]] : 0u;
+    }
     unsigned tsum = 0;
 #pragma unroll
-    for (int j = 0; j < SB_ITEMS; ++j) {
-        q[j] = (key != 0u && (!TAIL || base + j < a.n_out)) ? qrow[x[j]] : 0u;
-        tsum += q[j];
-    }
+    for (int j = 0; j < SB_ITEMS; ++j) tsum += q[j];
     sb_store8_u32(reinterpret_cast<uint32_t*>(a.x_out) + lbase, reinterpret_cast<const uint32_t*>(x));
     sb_store8_u32(a.w32_out + lbase, q);
     if (a.lw_out) {
@@ -811,7 +846,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     // no barrier here: every shared scratch array is rewritten only after a later barrier of the next tile
 }
 
-template <int ANC, bool FP32, bool PEERS, bool MULTI>
+template <int ANC, bool FP32, bool PEERS, bool MULTI, bool CARRY = false>
 __global__ void __launch_bounds__(SB_THREADS, 5)                  // 5 resident CTAs per SM: at most 48 registers
 k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -843,11 +878,8 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         s_key[tid] = live ? (((unsigned)(ce + SB_KEY_BIAS) << 6) | (unsigned)tid) : 0u;
     }
     __syncthreads();
-    if (tid == 0) {
-        unsigned km = 0u;
-        for (int i = 0; i < K; ++i) km = max(km, s_key[i]);
-        sm.kmax = km;
-    }
+    unsigned km = 0u;
+    for (int i = 0; i < K; ++i) km = max(km, s_key[i]);
     for (int i = tid; i < K * K; i += SB_THREADS) {
         const int ks = i / K, kx = i - ks * K;
         const unsigned key = s_key[ks];
@@ -855,6 +887,13 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         uint32_t q = 0u;
         if (key) q = FP32 ? sb_q31_f32(__fsub_rn(reinterpret_cast<float*>(s_l2)[kx], (float)e)) : sb_q31_f64(__dsub_rn(s_l2[kx], (double)e));
         s_qtab[i] = q;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned qt = 0u;                                         // heaviest below-top state in the top row (0xffffffff: no shortcut)
+        if (km == 0u) qt = 0xffffffffu;
+        for (int i = 0; i < K; ++i) if ((s_key[i] >> 6) != (km >> 6)) qt = max(qt, s_qtab[(km & 63u) * K + i]);
+        sm.kmax = km; sm.qthr = qt;
     }
     sb_grid_dep_wait();                                           // everything above overlapped the previous scan
     SbStepInfo si;
@@ -866,10 +905,10 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
         if (ANC == SB_ANC_PULL && (k % SB_FT_CHUNK) == 0 && SB_ABLATE != 3)
-            sb_pull_ranges<PEERS>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, tile, a.ntiles, k == 0, sm.ps);
+            sb_pull_ranges<PEERS, CARRY>(si, a.pool, a.e_prev, a.Pt, a.child_start, a.first_tile, tile, a.ntiles, k == 0, sm.ps);
         const bool tail = a.pool.c_off + (tile + 1) * SB_TILE > a.N;   // only the last tile(s) see padding / the retained slot
-        if (!tail) sb_hmm_tile<ANC, FP32, PEERS, MULTI, false>(a, si, tile, k, sm, s_thr, s_key, s_qtab, s_tab);
-        else       sb_hmm_tile<ANC, FP32, PEERS, MULTI, true>(a, si, tile, k, sm, s_thr, s_key, s_qtab, s_tab);
+        if (!tail) sb_hmm_tile<ANC, FP32, PEERS, MULTI, false, CARRY>(a, si, tile, k, sm, s_thr, s_key, s_qtab, s_tab);
+        else       sb_hmm_tile<ANC, FP32, PEERS, MULTI, true, CARRY>(a, si, tile, k, sm, s_thr, s_key, s_qtab, s_tab);
     }
     if (k > 0) {                                                  // the last tile's totals
         __syncthreads();
@@ -938,7 +977,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             const int2 rng = sm.ps.ft[kk];
             const bool more = tile + (int)gridDim.x < a.ntiles;
             const int nb = sm.ps.ft[kk + 1].x;
-            if (k > 0) sb_mbar_wait(&sm.bar2, (uint32_t)((k - 1) & 1));   // wait half of the previous tile's split barrier (see k_step_hmm)
+            if (k > 0) sb_split_wait();                           // wait half of the previous tile's split barrier (see k_step_hmm)
             if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
             else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
         } else if (ANC == SB_ANC_EXPLICIT) {
@@ -1045,6 +1084,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                                                    : (REAL)fmax((double)mx, __shfl_xor_sync(0xffffffffu, (double)mx, d));
             if ((tid & 31) == 0) { if (FP32) reinterpret_cast<float*>(sm.red)[tid >> 5] = (float)mx; else sm.red[tid >> 5] = (double)mx; }
             __syncwarp();
+            sb_split_arrive();
             if ((tid & 31) == 0) sb_mbar_arrive(&sm.bar2);
             e = mx > -INFINITY ? (FP32 ? (int)ceilf((float)mx) : (int)ceil((double)mx)) : SB_E_EMPTY;
             if (e != e_top) {

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -100,6 +101,7 @@ struct sb_handle {
     DevBuf sm_x, sm_a, sm_xs, sm_lz;  // one-tile chains (sb_small.cuh)
     int small_cur = -1;               // >= 0: the retained particle of the last pmcmc call is in buffer small_cur of sm_xs
     int use_small = 1;                // SB_NO_SMALL=1 keeps pmcmc on the tiled kernels
+    int use_carry = 1;                // SB_NO_CARRY=1: the step kernel gathers parent states instead of carrying them in the head markers
     int use_resident = 1;             // SB_NO_RESIDENT=1 keeps mid-size sweeps on the tiled kernels (one launch per step and scan)
     int coop = -1;                    // cooperative launch: -1 not probed, 0 unavailable, 1 available
     int last_route = 0;               // 0 tiled kernels, 1 resident sweep kernel, 2 one-tile chain kernel (last run call)
@@ -267,7 +269,18 @@ int resident_ctas(sb_handle* h, Kern kern, size_t smem, int* out) {
     const std::pair<const void*, size_t> key((const void*)kern, smem);
     auto it = h->occ.find(key);
     if (it == h->occ.end()) {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // static + dynamic shared memory above 48 KB needs the opt-in even when the dynamic part alone is small; the
+        // attribute belongs to the kernel, not to this (kernel, size) entry: only ever raise it
+        if (smem > 16 * 1024) {
+            static std::mutex mu;
+            static std::map<std::pair<int, const void*>, size_t> optin;   // (device, kernel) -> largest size opted into
+            std::lock_guard<std::mutex> lk(mu);
+            size_t& have = optin[std::make_pair(h->opt.device, (const void*)kern)];
+            if (smem > have) {
+                CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                have = smem;
+            }
+        }
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SB_THREADS, smem));
         if (nb < 1) return fail(h, SB_ECUDA, "step kernel does not fit on an SM");
@@ -507,6 +520,7 @@ extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
     if (const char* np = getenv("SB_PDL")) h->pdl = atoi(np) & 3;
     if (const char* ns = getenv("SB_NO_SMALL")) h->use_small = atoi(ns) ? 0 : 1;
     if (const char* nr = getenv("SB_NO_RESIDENT")) h->use_resident = atoi(nr) ? 0 : 1;
+    if (const char* nc = getenv("SB_NO_CARRY")) h->use_carry = atoi(nc) ? 0 : 1;
     if (const char* pd = getenv("SB_PDL_DIST")) h->pdl_dist = atoi(pd) & 3;
     if (cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, opt.device) != cudaSuccess || h->num_sms < 1)
         h->num_sms = 148;
@@ -746,22 +760,23 @@ template <bool FP32, bool MULTI>
 int launch_step_hmm_m(sb_handle* h, int anc_mode, const SbHmmStepArgs& a) {
     const size_t smem = ((size_t)a.rows << SB_LG_BUCKETS) * 4 + (size_t)a.K * 8 + (size_t)(a.rows * a.K + a.K + a.K * a.K) * 4;
     int cap = 0, rc;
-#define SB_HMM_LAUNCH(ANC, PEERS)                                                              \
+#define SB_HMM_LAUNCH(ANC, PEERS, CARRY)                                                       \
     do {                                                                                       \
-        auto kern = k_step_hmm<ANC, FP32, PEERS, MULTI>;                                       \
+        auto kern = k_step_hmm<ANC, FP32, PEERS, MULTI, CARRY>;                                \
         if ((rc = resident_ctas(h, kern, smem, &cap)) != SB_OK) return rc;                     \
         if ((rc = launch_step(h, kern, (unsigned)(a.ntiles < cap ? a.ntiles : cap), smem, ANC == SB_ANC_PULL, a)) != SB_OK) return rc; \
     } while (0)
+    const bool carry = a.xb > 0;
     if (h->dist_ready) {
-        if (anc_mode == SB_ANC_NONE) SB_HMM_LAUNCH(SB_ANC_NONE, false);
-        else if (anc_mode == SB_ANC_PULL) SB_HMM_LAUNCH(SB_ANC_PULL, true);
+        if (anc_mode == SB_ANC_NONE) SB_HMM_LAUNCH(SB_ANC_NONE, false, false);
+        else if (anc_mode == SB_ANC_PULL) { if (carry) SB_HMM_LAUNCH(SB_ANC_PULL, true, true); else SB_HMM_LAUNCH(SB_ANC_PULL, true, false); }
         else return fail(h, SB_EUNSUPPORTED, "sharded pools resample systematically at every step");
     } else {
         switch (anc_mode) {
-            case SB_ANC_NONE:     SB_HMM_LAUNCH(SB_ANC_NONE, false); break;
-            case SB_ANC_PULL:     SB_HMM_LAUNCH(SB_ANC_PULL, false); break;
-            case SB_ANC_EXPLICIT: SB_HMM_LAUNCH(SB_ANC_EXPLICIT, false); break;
-            default:              SB_HMM_LAUNCH(SB_ANC_IDENTITY, false); break;
+            case SB_ANC_NONE:     SB_HMM_LAUNCH(SB_ANC_NONE, false, false); break;
+            case SB_ANC_PULL:     if (carry) SB_HMM_LAUNCH(SB_ANC_PULL, false, true); else SB_HMM_LAUNCH(SB_ANC_PULL, false, false); break;
+            case SB_ANC_EXPLICIT: SB_HMM_LAUNCH(SB_ANC_EXPLICIT, false, false); break;
+            default:              SB_HMM_LAUNCH(SB_ANC_IDENTITY, false, false); break;
         }
     }
 #undef SB_HMM_LAUNCH
@@ -830,6 +845,7 @@ int sweep_hmm_resident_k(sb_handle* h, const SbResArgs& a, int* done) {
     if (smem > 160 * 1024) return SB_OK;
     int cap = 0, rc;
     if ((rc = resident_ctas(h, kern, smem, &cap)) != SB_OK) { h->err.clear(); return SB_OK; }
+    if (getenv("SB_DEBUG")) fprintf(stderr, "[sb] resident sweep: tiles %d, cap %d, dynamic smem %zu\n", a.ntiles, cap, smem);
     if (a.ntiles > cap) return SB_OK;
     void* args[] = {(void*)&a};
     CK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)a.ntiles), dim3(SB_THREADS), args, smem, h->stream));
@@ -951,6 +967,12 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.expF_t = h->hmm_expF.as<double>() + (size_t)t * K;
         a.xstar = conditional ? h->xstar[h->xstar_cur].as<int>() : nullptr;
         a.N = N; a.n_out = n_out; a.ntiles = ntiles; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed); a.err = h->d_err;
+        // head markers that carry the parent's state ((parent << xb) | state must stay below 2^31): no gather
+        a.xb = 0;
+        if (anc_mode == SB_ANC_PULL && h->use_carry) {
+            const int xb = K <= 16 ? 4 : 6;
+            if (K <= 64 && ((tiles_of(n_out) * SB_TILE) << xb) <= (1ll << 31)) a.xb = xb;
+        }
         {
             ProfScope ps(h, t ? t : -1);                               // t = 0 has no resample/gather: not sampled
             rc = launch_step_hmm(h, anc_mode, a);

@@ -606,3 +606,37 @@ def test_cfg1_hmm_example_pmcmc_vs_enumerate():
         key = tuple(c == "T" for c in name)
         assert exact.prob(key) == pytest.approx(p, rel=1e-10)
         assert abs(d.prob(key) - p) <= 0.02
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("N", [5000, 70001, 1 << 20])
+def test_resident_sweep_equals_tiled_kernels(monkeypatch, precision, N):
+    """Pools whose tiles are all resident at once run a whole sweep as ONE cooperative launch (sb_resident.cuh).  The
+    tiled kernels (forced with SB_NO_RESIDENT=1: one step kernel + one tile scan per step) must give identical
+    states and ancestors at every step, log-evidence, PMCMC counts and retained trajectory -- plain and conditional
+    sweeps (src/pmcmc.jl:59-66, 83-94)."""
+    sb = sb_mod()
+    A, logF, pi = cfg3_tables(T=7)
+    outs = []
+    for no_res in ["1", None]:
+        if no_res:
+            monkeypatch.setenv("SB_NO_RESIDENT", no_res)
+        else:
+            monkeypatch.delenv("SB_NO_RESIDENT", raising=False)
+        with sb.Engine(precision=precision, resample="systematic", seed=21) as eng:
+            eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+            lz = eng.smc_sweep(N, it=3, history=True)
+            launches = eng.stats().kernel_launches
+            rows = [eng.history(t, N) for t in range(7)]
+            lz2 = eng.smc_sweep(N, it=4)
+            parts = eng.particles(N)
+            marg, _ = eng.pmcmc_counts(3, N, want_joint=False)
+            outs.append((lz, launches, rows, lz2, parts, marg, eng.retained(), eng.stats().logZ_last))
+    a, b = outs
+    assert a[0] == b[0] and a[3] == b[3] and a[7] == b[7]
+    assert b[1] == 1 and a[1] >= 14                                   # one launch instead of 2 per step
+    for t in range(7):
+        assert np.array_equal(a[2][t][0], b[2][t][0]), "states differ at step %d" % t
+        assert np.array_equal(a[2][t][1], b[2][t][1]), "ancestors differ at step %d" % t
+    assert np.array_equal(a[4], b[4])
+    assert np.array_equal(a[5], b[5]) and np.array_equal(a[6], b[6])
