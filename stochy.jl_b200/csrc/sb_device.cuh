@@ -357,16 +357,41 @@ __device__ __forceinline__ void sb_mbar_wait(unsigned long long* bar, uint32_t p
 }
 // Split-phase CTA barrier on the hardware named barriers 1..SB_WARPS (no spinning: a waiting warp is descheduled and
 // costs no issue slots -- an mbarrier try_wait loop re-issues itself every few dozen cycles, which was a fifth of
-// all instructions the step kernels executed).  Barrier 1 + w belongs to warp w: every warp ARRIVES on all of them
+// all instructions the step kernels executed).  MEASURED SLOWER than the spinning mbarrier (76.4 vs 73.9 us per launch
+// of k_step_hmm: the spinning warp resumes sooner, and the issue slots it burns are free ones), so it is compiled out
+// by default (SB_OPT_NAMEDBAR 0); kept for the record.  Barrier 1 + w belongs to warp w: every warp ARRIVES on all of them
 // (non-blocking) once it has published what the others need, and later WAITS on its own -- which completes when all
 // SB_WARPS warps have arrived.  One wait per arrive; a full CTA barrier separates consecutive arrives (callers'
 // invariant), so phases cannot overlap.  Writes before the arrive are visible after the wait (bar.arrive / bar.sync).
+#ifndef SB_OPT_NAMEDBAR
+#define SB_OPT_NAMEDBAR 0       // 0: the split barrier waits on its mbarrier (try_wait spin) instead of a hardware named barrier
+#endif
+#ifndef SB_OPT_XPREFETCH
+#define SB_OPT_XPREFETCH 1      // 0: no L2 prefetch of the parent tiles' states
+#endif
 __device__ __forceinline__ void sb_split_arrive() {
+#if SB_OPT_NAMEDBAR
 #pragma unroll
     for (int j = 0; j < SB_WARPS; ++j) asm volatile("bar.arrive %0, %1;" ::"r"(j + 1), "r"(32 * SB_WARPS + 32) : "memory");
+#endif
 }
 __device__ __forceinline__ void sb_split_wait() {
     asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x >> 5) + 1), "r"(32 * SB_WARPS + 32) : "memory");
+}
+// Grid-wide barrier of a cooperative launch (all CTAs resident): one release-add per CTA on a counter that only ever
+// grows, one thread per CTA spinning on an acquire-load until the counter reaches `target` = (count before the
+// launch) + (barriers so far + 1) * gridDim.x -- the host hands out the base, so nothing is reset between launches.
+// Measured against cooperative_groups' grid.sync() at 513 CTAs: see profiles/r02_notes.md.
+__device__ __forceinline__ void sb_grid_barrier(unsigned* counter, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
 }
 // one thread: `bytes` (multiple of 16, 16-byte aligned both sides) from global memory -- local HBM or a
 // peer GPU's arena over NVLink -- into shared memory; completion is counted on the mbarrier
@@ -594,7 +619,7 @@ __device__ __forceinline__ void sb_pull_prefetch(const SbStepInfo& si, const SbP
             sb_mbar_expect_tx(&sm.bar, 2u * SB_TILE * 4u);
             sb_bulk_g2s(sm.w[0], sb_pool_tile<PEERS>(pool, bA), SB_TILE * 4u, &sm.bar);
             sb_bulk_g2s(sm.w[1], sb_pool_tile<PEERS>(pool, bB), SB_TILE * 4u, &sm.bar);
-            if (CARRY) {
+            if (CARRY && SB_OPT_XPREFETCH) {
                 // the parents read their own states one tile from now (sb_pull_tile): have them in L2 by then
                 // (local memory only: a peer's memory is not cached here)
                 const int ts = pool.log2n - 11, self = PEERS ? (pool.tile_off >> ts) : 0;
@@ -717,7 +742,9 @@ __device__ __forceinline__ void sb_pull_ancestors(const SbStepInfo& si, const Sb
         if (k1 > k0) sb_pull_tile<S32, CARRY, GEN>(si, b, sb_pool_tile<PEERS>(pool, b), baseb, rb, wbase, cw, sm,
                                               CARRY ? sb_pool_xtile<PEERS>(pool, b) : nullptr, xb);
     }
-    __syncthreads();                                             // markers complete; sm.w and sm.meta[slot] are free
+    // markers complete; sm.w and sm.meta[slot] are free.  (An mbarrier with a try_wait spin here instead of BAR.SYNC was
+    // measured: 75.4 vs 73.9 us per launch; for the split barrier it is the other way round, see sb_split_arrive.)
+    __syncthreads();
     if (more && (warp == 0 || warp == SB_META_WARP)) sb_pull_prefetch<PEERS, CARRY>(si, pool, e, Pt, child_start, next_b_lo, slot ^ 1, sm);
     // every child takes the last head marker at or before its slot.  Markers ascend with the slot (the CDF is
     // monotone) and the first slot of every warp has one, so the carry into a thread is the largest marker of

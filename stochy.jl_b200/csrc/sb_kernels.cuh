@@ -663,7 +663,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         const int nb = sm.ps.ft[kk + 1].x;
         // every warp has finished the previous tile's marker slots and exponent key, and the records warp this tile's boundary
         // table (the wait half of the split barrier; most of its skew was absorbed by the previous tile's epilogue)
-        if (k > 0) sb_split_wait();
+        if (k > 0) { if (SB_OPT_NAMEDBAR) sb_split_wait(); else sb_mbar_wait(&sm.bar2, (uint32_t)((k - 1) & 1)); }
         if (si.s >= 32) sb_pull_ancestors<PEERS, true, false, CARRY>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc, a.xb);
         else            sb_pull_ancestors<PEERS, false, false, CARRY>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc, a.xb);
 #endif
@@ -977,7 +977,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             const int2 rng = sm.ps.ft[kk];
             const bool more = tile + (int)gridDim.x < a.ntiles;
             const int nb = sm.ps.ft[kk + 1].x;
-            if (k > 0) sb_split_wait();                           // wait half of the previous tile's split barrier (see k_step_hmm)
+            if (k > 0) { if (SB_OPT_NAMEDBAR) sb_split_wait(); else sb_mbar_wait(&sm.bar2, (uint32_t)((k - 1) & 1)); }   // wait half of the previous tile's split barrier (see k_step_hmm)
             if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
             else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
         } else if (ANC == SB_ANC_EXPLICIT) {
@@ -1192,6 +1192,78 @@ k_count_back(const int* __restrict__ x_t, const int* __restrict__ cnt_t, const i
         const int r = *lineage;
         xstar_out[t] = x_t[r];
         if (t > 0) *lineage = (r >= N || identity_prev) ? r : anc_prev[r];
+    }
+}
+// The whole backward pass of one PMCMC iteration in ONE cooperative launch: the loop over t of k_count_back with a
+// grid-wide barrier between steps (the counts of step t-1 are complete before anybody reads them) instead of T
+// launches -- at BASELINE cfg3's size a launch costs more than the work of a step (6.5 us against ~1 us).  Three count
+// buffers in rotation as on the host path: step t reads buf[t % 3], accumulates into buf[(t - 1) % 3] and clears
+// buf[(t + 1) % 3]; same integers as k_count_back (atomic adds of integers commute).
+struct SbCountArgs {
+    const int* x_hist;                  // [T][S]
+    const int* anc_hist;                // [T][S]
+    const unsigned char* has_factor;    // [T]
+    int* cnt[3];
+    long long S, n_pool, N;
+    int K, T;
+    unsigned long long* marg;           // [T*K]
+    int* lineage;
+    int* xstar_out;                     // [T]
+    unsigned* bar;                      // grid barrier counter (sb_grid_barrier) and its value before this launch
+    unsigned bar0;
+};
+__global__ void __launch_bounds__(256)
+k_count_back_all(const __grid_constant__ SbCountArgs a) {
+    extern __shared__ unsigned int s_hist[];
+    const int K = a.K;
+    for (int t = a.T - 1; t >= 0; --t) {
+        const int* x_t = a.x_hist + (size_t)t * a.S;
+        const int* anc_prev = t ? a.anc_hist + (size_t)(t - 1) * a.S : nullptr;
+        const int identity_prev = t ? !a.has_factor[t - 1] : 0;
+        const int* cnt_t = a.cnt[t % 3];
+        int* cnt_prev = t ? a.cnt[(t - 1) % 3] : nullptr;
+        int* cnt_clear = t >= 2 ? a.cnt[(t + 1) % 3] : nullptr;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) s_hist[k] = 0u;
+        __syncthreads();
+        for (long long j0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; j0 < a.n_pool; j0 += (long long)gridDim.x * blockDim.x * 8) {
+            int c[8];
+            if (j0 + 8 <= a.n_pool) {
+                // the counts were written by other CTAs earlier in this launch: coherent loads
+                const int4 u = __ldcg(reinterpret_cast<const int4*>(cnt_t + j0)), v = __ldcg(reinterpret_cast<const int4*>(cnt_t + j0) + 1);
+                c[0] = u.x; c[1] = u.y; c[2] = u.z; c[3] = u.w; c[4] = v.x; c[5] = v.y; c[6] = v.z; c[7] = v.w;
+                if (cnt_clear) {
+                    reinterpret_cast<int4*>(cnt_clear + j0)[0] = make_int4(0, 0, 0, 0);
+                    reinterpret_cast<int4*>(cnt_clear + j0)[1] = make_int4(0, 0, 0, 0);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    c[i] = j0 + i < a.n_pool ? __ldcg(cnt_t + j0 + i) : 0;
+                    if (cnt_clear && j0 + i < a.n_pool) cnt_clear[j0 + i] = 0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (c[i]) {
+                    const long long j = j0 + i;
+                    atomicAdd(&s_hist[x_t[j]], (unsigned)c[i]);
+                    if (cnt_prev) {
+                        const int pj = (j >= a.N || identity_prev) ? (int)j : anc_prev[j];
+                        atomicAdd(cnt_prev + pj, c[i]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (a.marg)
+            for (int k = threadIdx.x; k < K; k += blockDim.x)
+                if (s_hist[k]) atomicAdd(a.marg + (size_t)t * K + k, (unsigned long long)s_hist[k]);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.lineage) {
+            const int r = *a.lineage;
+            a.xstar_out[t] = x_t[r];
+            if (t > 0) *a.lineage = (r >= a.N || identity_prev) ? r : anc_prev[r];
+        }
+        if (t > 0) sb_grid_barrier(a.bar, a.bar0 + (unsigned)(a.T - t) * gridDim.x);
     }
 }
 // start of the retained lineage: child c* of the final resample (src/pmcmc.jl:89 or uniform pick, H4)

@@ -6,6 +6,7 @@
 #include "sb_small.cuh"
 #include "sb_resident.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -98,6 +99,10 @@ struct sb_handle {
 
     // sweep state
     DevBuf xbuf, ancbuf, lwbuf, wlit, cnt[3], xstar[2], marg, joint;
+    DevBuf res_trace;                 // SB_RES_TRACE diagnostics
+    DevBuf res_rec;                   // resident sweep kernel: the tile records its CTAs exchange (two slots)
+    unsigned bar_count = 0;           // arrivals the grid barrier counter (d_err + 1) has seen: base of the next cooperative launch
+    unsigned res_epoch = 0;           // epoch stamps handed out so far (fresh ones for every launch)
     DevBuf sm_x, sm_a, sm_xs, sm_lz;  // one-tile chains (sb_small.cuh)
     int small_cur = -1;               // >= 0: the retained particle of the last pmcmc call is in buffer small_cur of sm_xs
     int use_small = 1;                // SB_NO_SMALL=1 keeps pmcmc on the tiled kernels
@@ -262,6 +267,9 @@ int ensure_grid(sb_handle* h, int64_t n_pool, int64_t m) {
     CK(h->first_tile.ensure((size_t)(tiles_of(m) + 1) * 4));
     return SB_OK;
 }
+
+// counter of sb_grid_barrier: the word behind the error word (allocated and zeroed together in sb_create)
+inline unsigned* grid_bar(sb_handle* h) { return h->d_err + 1; }
 
 // resident CTAs of a persistent kernel (cached per kernel and shared-memory size)
 template <typename Kern>
@@ -505,8 +513,8 @@ extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
         cudaEventCreate(&h->evt0) != cudaSuccess || cudaEventCreate(&h->evt1) != cudaSuccess ||
-        cudaMalloc(&h->d_err, sizeof(unsigned)) != cudaSuccess ||
-        cudaMemset(h->d_err, 0, sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&h->d_err, 16 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(h->d_err, 0, 16 * sizeof(unsigned)) != cudaSuccess ||
         cudaMalloc(&h->d_emax, sizeof(int)) != cudaSuccess ||
         h->d_misc.ensure(64) != cudaSuccess) {
         g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -537,7 +545,7 @@ extern "C" void sb_destroy(sb_handle* h) {
                       &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
                       &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
                       &h->bn_fp, &h->bn_fac, &h->bn_counts, &h->xbuf, &h->ancbuf, &h->lwbuf, &h->wlit, &h->cnt[0],
-                      &h->cnt[1], &h->cnt[2], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint, &h->sm_x, &h->sm_a, &h->sm_xs, &h->sm_lz};
+                      &h->cnt[1], &h->cnt[2], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint, &h->sm_x, &h->sm_a, &h->sm_xs, &h->sm_lz, &h->res_trace, &h->res_rec};
     for (DevBuf* b : bufs) b->release();
     for (int g = 0; g < SB_MAX_PEERS; ++g)
         if (h->peer_base[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_base[g]);
@@ -838,9 +846,9 @@ int upload_offsets(sb_handle* h, unsigned iter) {
 // The whole sweep as ONE cooperative launch (sb_resident.cuh) when every tile of the pool fits on the GPU at once.
 // *done = 0: not eligible here (too many tiles for the resident grid, no cooperative launch): the caller runs the
 // tiled kernels.  Buffers, offsets and the per-step records were prepared by sweep_hmm.
-template <bool FP32, bool MULTI>
+template <bool FP32, bool MULTI, bool CARRY>
 int sweep_hmm_resident_k(sb_handle* h, const SbResArgs& a, int* done) {
-    auto kern = k_sweep_hmm<FP32, MULTI>;
+    auto kern = k_sweep_hmm<FP32, MULTI, CARRY>;
     const size_t smem = sb_res_smem_bytes(a.K, a.ntiles, MULTI);
     if (smem > 160 * 1024) return SB_OK;
     int cap = 0, rc;
@@ -848,9 +856,40 @@ int sweep_hmm_resident_k(sb_handle* h, const SbResArgs& a, int* done) {
     if (getenv("SB_DEBUG")) fprintf(stderr, "[sb] resident sweep: tiles %d, cap %d, dynamic smem %zu\n", a.ntiles, cap, smem);
     if (a.ntiles > cap) return SB_OK;
     void* args[] = {(void*)&a};
+    // cooperative launch: the CTAs exchange records among themselves, so all of them must be resident at once
     CK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)a.ntiles), dim3(SB_THREADS), args, smem, h->stream));
     ++h->launches;
+    h->res_epoch += (unsigned)a.T + 1u;
+    h->bar_count += (unsigned)a.T * (unsigned)a.ntiles;            // one barrier per step, one arrival per CTA
     *done = 1;
+    if (a.dbg) {                                                    // diagnostics: phase stamps of CTA 0, steps 8..15 (ns)
+        std::vector<unsigned long long> ts(1024 + 4096);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(ts.data(), a.dbg, ts.size() * 8, cudaMemcpyDeviceToHost));
+        if (a.T > 12 && a.ntiles <= 1024) {
+            // when each CTA published step 11, relative to the first: distribution, and the mean per number of CTAs on its SM
+            std::vector<long long> d; std::map<unsigned, int> per_sm;
+            unsigned long long t0 = ~0ull;
+            for (int i = 0; i < a.ntiles; ++i) { t0 = std::min(t0, ts[1024 + 2048 + 2 * i]); per_sm[(unsigned)ts[1024 + 2048 + 2 * i + 1]]++; }
+            double sum[8] = {0}; int cnt[8] = {0};
+            for (int i = 0; i < a.ntiles; ++i) {
+                const long long v = (long long)(ts[1024 + 2048 + 2 * i] - t0);
+                d.push_back(v);
+                const int c = std::min(7, per_sm[(unsigned)ts[1024 + 2048 + 2 * i + 1]]);
+                sum[c] += (double)v; cnt[c]++;
+            }
+            std::sort(d.begin(), d.end());
+            fprintf(stderr, "[sb trace] publish times of step 11 over %d CTAs (ns after the first): p10 %lld p50 %lld p90 %lld p99 %lld max %lld; step-to-step of CTA0 %lld\n",
+                    a.ntiles, d[d.size() / 10], d[d.size() / 2], d[d.size() * 9 / 10], d[d.size() * 99 / 100], d.back(),
+                    (long long)(ts[1024 + 2048] - ts[1024]));
+            for (int c = 1; c < 8; ++c) if (cnt[c]) fprintf(stderr, "[sb trace]   SMs holding %d CTAs: %d CTAs, mean publish time %+.0f ns\n", c, cnt[c], sum[c] / cnt[c]);
+        }
+        for (int t = 8; t < 16 && t + 1 < a.T; ++t) {
+            fprintf(stderr, "[sb trace] t=%d:", t);
+            for (int i = 1; i <= 7; ++i) fprintf(stderr, " p%d %+lld", i, (long long)(ts[t * 16 + i] - ts[t * 16 + i - 1]));
+            fprintf(stderr, "  | step %lld ns\n", (long long)(ts[(t + 1) * 16] - ts[t * 16]));
+        }
+    }
     return SB_OK;
 }
 int sweep_hmm_resident(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool history, bool final_anc, int64_t S, int* done) {
@@ -878,9 +917,23 @@ int sweep_hmm_resident(sb_handle* h, int64_t N, unsigned iter, bool conditional,
     a.N = N; a.n_out = n_out; a.ntiles = nt;
     a.r53 = h->d_r53.as<unsigned long long>(); a.info = h->d_info.as<SbStepInfo>();
     a.iter = iter; a.rk = round_keys(h->opt.seed); a.err = h->d_err;
+    if (getenv("SB_RES_TRACE")) { CK(h->res_trace.ensure((1024 + 4096) * 8)); a.dbg = h->res_trace.as<unsigned long long>(); }
+    // the records the CTAs exchange (zeroed once: epoch 0 is never waited for)
+    const size_t rec_bytes = (size_t)2 * SB_RES_MAXPER * SB_THREADS * sizeof(ulonglong2);
+    if (h->res_rec.cap < rec_bytes) {
+        CK(h->res_rec.ensure(rec_bytes));
+        CK(cudaMemsetAsync(h->res_rec.p, 0, h->res_rec.cap, h->stream));
+    }
+    a.rec[0] = h->res_rec.as<ulonglong2>(); a.rec[1] = a.rec[0] + SB_RES_MAXPER * SB_THREADS;
+    a.epoch0 = h->res_epoch;
+    a.bar = grid_bar(h); a.bar0 = h->bar_count;
+    a.xb = 0;
+    if (h->use_carry && h->K <= 64) a.xb = h->K <= 16 ? 4 : 6;      // n_out <= 2^21 here: (parent << xb) | state fits 31 bits
     const bool fp32 = h->opt.precision == SB_FP32;
-    if (h->hmm_multi) return fp32 ? sweep_hmm_resident_k<true, true>(h, a, done) : sweep_hmm_resident_k<false, true>(h, a, done);
-    return fp32 ? sweep_hmm_resident_k<true, false>(h, a, done) : sweep_hmm_resident_k<false, false>(h, a, done);
+#define SB_RES_GO(F, M) (a.xb ? sweep_hmm_resident_k<F, M, true>(h, a, done) : sweep_hmm_resident_k<F, M, false>(h, a, done))
+    if (h->hmm_multi) return fp32 ? SB_RES_GO(true, true) : SB_RES_GO(false, true);
+    return fp32 ? SB_RES_GO(true, false) : SB_RES_GO(false, false);
+#undef SB_RES_GO
 }
 
 // One sweep of the discrete model.  conditional: pool of N+1 with the retained particle appended.
@@ -1223,7 +1276,31 @@ extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t*
         k_count_final<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(ab + (size_t)(T - 1) * S, N, cnt_t);
         LAUNCH_CHECK();
         int* xs_next = h->xstar[h->xstar_cur ^ 1].as<int>();
-        for (int t = T - 1; t >= 0; --t) {
+        // the whole backward pass as one cooperative launch when its grid fits the device at once
+        bool counted = false;
+        if (h->use_resident && h->coop != 0) {
+            if (h->coop < 0) {
+                int v = 0;
+                h->coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->opt.device) == cudaSuccess && v) ? 1 : 0;
+            }
+            int cap = 0;
+            if (h->coop && resident_ctas(h, k_count_back_all, (size_t)K * 4, &cap) == SB_OK) {
+                SbCountArgs ca;
+                ca.x_hist = xb; ca.anc_hist = ab; ca.has_factor = h->hmm_hasf.as<unsigned char>();
+                for (int i = 0; i < 3; ++i) ca.cnt[i] = h->cnt[i].as<int>();
+                ca.S = S; ca.n_pool = n_pool; ca.N = N; ca.K = K; ca.T = T;
+                ca.marg = h->marg.as<unsigned long long>(); ca.lineage = lineage; ca.xstar_out = xs_next;
+                const int want = (int)((n_pool + 2047) / 2048);
+                const unsigned ctas = (unsigned)(want < cap ? want : cap);
+                ca.bar = grid_bar(h); ca.bar0 = h->bar_count;
+                void* args[] = {(void*)&ca};
+                CK(cudaLaunchCooperativeKernel((const void*)k_count_back_all, dim3(ctas), dim3(256), args, (size_t)K * 4, h->stream));
+                h->bar_count += (unsigned)(T - 1) * ctas;
+                ++h->launches;
+                counted = true;
+            } else h->err.clear();
+        }
+        for (int t = T - 1; t >= 0 && !counted; --t) {
             int* c_t = h->cnt[t % 3].as<int>();
             int* c_p = t ? h->cnt[(t - 1) % 3].as<int>() : nullptr;
             int* c_clear = t >= 2 ? h->cnt[(t + 1) % 3].as<int>() : nullptr;
