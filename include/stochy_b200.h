@@ -209,8 +209,19 @@ int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out);
  * weights / states on other GPUs are read over NVLink by the fused step kernel itself, tile records
  * are exchanged through peer memory behind a flag barrier.  out_logZ is identical on every rank.
  * All ranks must make the same sequence of sweep calls, and must not destroy their handle before every
- * rank has finished (barrier first). */
+ * rank has finished (barrier first).
+ *
+ * Conditional SMC / PMCMC on the sharded pool (src/pmcmc.jl:59-66, 83-94 across GPUs): call
+ * sb_dist_reserve_history(h, T) between sb_dist_init and sb_dist_ipc_export (the state history rows then live in
+ * the exported allocation: the parents of step t are read from row t-1 of the owning GPU), load the discrete model
+ * (T steps at most), and call sb_pmcmc_run(h, iters, world x N_local - 1, marg, NULL) on every rank: the pool of
+ * numparticles + 1 entries fills the shards exactly, the retained particle is the last entry of the last GPU,
+ * ancestor rows hold GLOBAL indices, the backward pass (counts of every particle's value, the next retained
+ * trajectory) follows the lineages across GPUs with peer atomics behind the same flag barrier.  `marg` receives
+ * THIS rank's share of the counts (the particles it owns at each step): the host sums the ranks.  Bit-identical
+ * to the single-GPU sb_pmcmc_run of the same particle count and seed. */
 int32_t sb_dist_init(sb_handle* h, int32_t rank, int32_t world);
+int32_t sb_dist_reserve_history(sb_handle* h, int32_t rows);
 int32_t sb_dist_ipc_export(sb_handle* h, int64_t N_local, uint8_t out_handle[64]);
 int32_t sb_dist_ipc_import(sb_handle* h, const uint8_t* all_handles /* [world][64] */);
 

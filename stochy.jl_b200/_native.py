@@ -32,7 +32,7 @@ EXPORTS = [
     "sb_erp_sample", "sb_erp_logpdf", "sb_erp_sample_dirichlet", "sb_erp_logpdf_dirichlet",
     "sb_erp_sample_discrete", "sb_erp_logpdf_discrete",
     "sb_get_history", "sb_get_retained", "sb_get_particles",
-    "sb_dist_init", "sb_dist_ipc_export", "sb_dist_ipc_import",
+    "sb_dist_init", "sb_dist_reserve_history", "sb_dist_ipc_export", "sb_dist_ipc_import",
 ]
 
 
@@ -118,6 +118,7 @@ def lib():
         "sb_get_retained": (i32, [vp, vp]),
         "sb_get_particles": (i32, [vp, i64, vp]),
         "sb_dist_init": (i32, [vp, i32, i32]),
+        "sb_dist_reserve_history": (i32, [vp, i32]),
         "sb_dist_ipc_export": (i32, [vp, i64, vp]),
         "sb_dist_ipc_import": (i32, [vp, vp]),
     }

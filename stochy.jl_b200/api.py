@@ -276,14 +276,18 @@ class Engine:
         return self
 
     # ---- multi-GPU: ONE pool sharded over the ranks of a torch.distributed group (one process per GPU)
-    def shard(self, N_local, group=None):
+    def shard(self, N_local, group=None, history_rows=0):
         """Make this handle rank `dist.get_rank()`'s share of a global pool of world x N_local particles.
         torch.distributed is only the plumbing (the 64-byte CUDA-IPC handles travel through one
         all_gather); afterwards smc_sweep(N_local) sweeps the GLOBAL pool, with resampled particles
-        read across GPUs by the step kernel itself (NVLink peer loads)."""
+        read across GPUs by the step kernel itself (NVLink peer loads).
+        history_rows = T reserves the state history inside the shared allocation: needed for conditional SMC /
+        pmcmc_counts on the sharded pool (src/pmcmc.jl:59-66, 83-94 across GPUs)."""
         from . import dist as sbdist
         rank, world = sbdist.rank_world(group)
         self._chk(nat.lib().sb_dist_init(self.h, rank, world))
+        if history_rows:
+            self._chk(nat.lib().sb_dist_reserve_history(self.h, int(history_rows)))
         mine = (C.c_uint8 * 64)()
         self._chk(nat.lib().sb_dist_ipc_export(self.h, N_local, mine))
         allh = sbdist.exchange_handles(bytes(mine), group)          # rank order
@@ -301,10 +305,16 @@ class Engine:
         return lz.value
 
     def pmcmc_counts(self, iters, N, want_joint=True):
+        """src/pmcmc.jl:78-99.  On a sharded handle (shard(..., history_rows=T)): N = world x N_local - 1 GLOBAL
+        particles, every rank calls it, and the ranks' shares of the counts are summed over the group."""
         m = self.model
         marg = np.zeros((m.T, m.K), dtype=np.int64)
-        joint = np.zeros(m.K ** m.T, dtype=np.int64) if want_joint else None
+        sharded = getattr(self, "_shard_group", False) is not False
+        joint = np.zeros(m.K ** m.T, dtype=np.int64) if (want_joint and not sharded) else None
         self._chk(nat.lib().sb_pmcmc_run(self.h, iters, N, _ptr(marg), _ptr(joint)))
+        if sharded:
+            from . import dist as sbdist
+            marg = sbdist.sum_over_ranks(marg, self._shard_group)
         return marg, joint
 
     def pmcmc_chains_counts(self, chains, iters, N, chain0=0, want_joint=True):

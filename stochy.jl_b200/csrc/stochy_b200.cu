@@ -5,6 +5,7 @@
 #include "sb_kernels.cuh"
 #include "sb_small.cuh"
 #include "sb_resident.cuh"
+#include "sb_dist_back.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -67,6 +68,10 @@ struct sb_handle {
     size_t off_w32[2] = {0, 0}, off_x[2] = {0, 0}, off_wp[2] = {0, 0}, off_e[2] = {0, 0}, off_Q[2] = {0, 0}, off_flags = 0;
     char* peer_base[SB_MAX_PEERS] = {nullptr};
     unsigned epoch = 0;
+    // sharded conditional SMC / PMCMC (sb_dist_reserve_history): state history rows, the backward pass's count
+    // buffers, the retained lineage's index words and both retained trajectories live in the arena too
+    int hist_rows = 0;                // rows reserved (0: plain SMC sweeps only)
+    size_t off_xh = 0, off_cnt[2] = {0, 0}, off_lin = 0, off_xstar[2] = {0, 0};
     // Sharded pools: pool slot of step t is (slot_base + t) & 1 and slot_base advances by T per sweep, so the first
     // step kernel of a sweep never writes the slot whose tile records a slower peer's LAST scan of the previous sweep
     // may still be reading (every later overwrite is ordered behind the peers' flags; see DESIGN.md "Multi-GPU").
@@ -188,7 +193,7 @@ inline unsigned long long* WP(sb_handle* h, int slot) {
 inline const int* TE_pull(sb_handle* h, int slot) { return TE(h, slot); }
 
 // the pool held in slot `slot` whose particle states are at `x` (single GPU) / in the arena (sharded)
-inline SbPool make_pool(sb_handle* h, int slot, const void* x) {
+inline SbPool make_pool(sb_handle* h, int slot, const void* x, size_t off_x_override = 0) {
     SbPool p;
     memset(&p, 0, sizeof(p));
     p.w32 = W32(h, slot); p.x = x; p.wp = WP(h, slot);
@@ -200,6 +205,7 @@ inline SbPool make_pool(sb_handle* h, int slot, const void* x) {
         p.c_off = (int)(h->rank * h->NL);
         p.tile_off = (int)(h->rank * (h->NL / SB_TILE));
         p.x = (char*)h->arena + h->off_x[slot];
+        if (off_x_override) { p.off_x = off_x_override; p.x = (char*)h->arena + off_x_override; }   // a history row
     }
     return p;
 }
@@ -251,8 +257,8 @@ int ensure_grid(sb_handle* h, int64_t n_pool, int64_t m) {
     const int64_t nt = tiles_of(n_pool);
     if (nt > (1 << 20) || m > 0x7fffffffLL - SB_TILE) return fail(h, SB_EINVAL, "pool too large (max 2^31 particles)");
     if (h->dist_ready) {
-        if (n_pool != h->NL * h->world || m != n_pool)
-            return fail(h, SB_EINVAL, "sharded handle: the pool is fixed at world x N_local particles");
+        if (n_pool != h->NL * h->world || (m != n_pool && m != n_pool - 1))
+            return fail(h, SB_EINVAL, "sharded handle: the pool is fixed at world x N_local entries (particles, or particles + the retained one)");
     } else {
         for (int i = 0; i < 2; ++i) {
             CK(h->w32[i].ensure((size_t)nt * SB_TILE * 4));
@@ -941,19 +947,28 @@ int sweep_hmm_resident(sb_handle* h, int64_t N, unsigned iter, bool conditional,
 int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool history, bool final_anc) {
     const int T = h->T, K = h->K;
     const bool dist = h->dist_ready;
-    if (dist && (conditional || history || final_anc || h->opt.store_logw || h->opt.resample_mode != SB_RESAMPLE_SYSTEMATIC))
-        return fail(h, SB_EUNSUPPORTED, "sharded pools run plain SMC sweeps with systematic resampling and no history");
+    if (dist && (h->opt.store_logw || h->opt.resample_mode != SB_RESAMPLE_SYSTEMATIC))
+        return fail(h, SB_EUNSUPPORTED, "sharded pools resample systematically and keep no log-weight history");
+    // sharded conditional SMC: the history rows live in the arena (the parents of step t are read from row t-1 of the
+    // owning GPU), reserved before the arena was exported
+    const bool dhist = dist && (conditional || history || final_anc);
+    if (dhist && h->hist_rows < T)
+        return fail(h, SB_EUNSUPPORTED, "sharded conditional SMC / history: call sb_dist_reserve_history(h, T) before sb_dist_ipc_export");
+    if (dhist) history = true;
     const int64_t S = dist ? h->NL : tiles_of(N + 1) * SB_TILE;        // row stride (slot N = retained)
     const int n_out = (int)(N + (conditional ? 1 : 0));
     const int mode = h->opt.resample_mode;
     const bool literal = mode == SB_RESAMPLE_LITERAL;
     int rc;
-    if ((rc = ensure_grid(h, dist ? N : N + 1, N)) != SB_OK) return rc;
+    if (dist && n_out > h->NL * h->world) return fail(h, SB_EINVAL, "sharded handle: the pool (particles + the retained one) exceeds world x N_local entries");
+    if ((rc = ensure_grid(h, dist ? h->NL * h->world : N + 1, N)) != SB_OK) return rc;
     const int xrows = history ? T : 2;
     const int arows = history ? T : 1;
     if (!dist) {
         CK(h->xbuf.ensure((size_t)xrows * S * 4));
         CK(h->ancbuf.ensure((size_t)arows * S * 4));
+    } else if (dhist) {
+        CK(h->ancbuf.ensure((size_t)arows * S * 4));                   // local rows of GLOBAL parent indices
     }
     CK(h->d_info.ensure(sizeof(SbStepInfo) * (size_t)T));
     if (h->opt.store_logw) CK(h->lwbuf.ensure((size_t)T * S * 8));
@@ -963,8 +978,9 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
     int* xb = h->xbuf.as<int>();
     int* ab = h->ancbuf.as<int>();
     const unsigned sb0 = dist ? h->slot_base : 0u;
+    auto xoff = [&](int t) -> size_t { return dhist ? h->off_xh + (size_t)t * (size_t)S * 4 : h->off_x[(sb0 + (unsigned)t) & 1u]; };   // sharded: inside the arena
     auto xrow = [&](int t) -> int* {
-        if (dist) return reinterpret_cast<int*>((char*)h->arena + h->off_x[(sb0 + (unsigned)t) & 1u]);
+        if (dist) return reinterpret_cast<int*>((char*)h->arena + xoff(t));
         return xb + (size_t)(history ? t : (t & 1)) * S;
     };
     const int ntiles = dist ? (int)(h->NL / SB_TILE) : (int)tiles_of(n_out);
@@ -983,7 +999,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
     for (int t = 0; t < T; ++t) {
         const int cur = (int)((sb0 + (unsigned)t) & 1u), prev = cur ^ 1;
         int anc_mode = SB_ANC_NONE;
-        int* anc_row_prev = (t && !dist) ? ab + (size_t)(history ? (t - 1) : 0) * S : nullptr;
+        int* anc_row_prev = (t && (!dist || dhist)) ? ab + (size_t)(history ? (t - 1) : 0) * S : nullptr;
         if (t > 0) {
             if (!h->has_factor[t - 1]) anc_mode = SB_ANC_IDENTITY;
             else if (mode == SB_RESAMPLE_SYSTEMATIC) anc_mode = SB_ANC_PULL;
@@ -997,7 +1013,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
             return fail(h, SB_EUNSUPPORTED, "sharded pools need a factor statement at every step");
         SbHmmStepArgs a;
         memset(&a, 0, sizeof(a));
-        a.pool = make_pool(h, prev, t ? xrow(t - 1) : nullptr);
+        a.pool = make_pool(h, prev, t ? xrow(t - 1) : nullptr, (dhist && t) ? xoff(t - 1) : 0);
         a.e_prev = TE_pull(h, prev);
         a.Pt = h->Pt.as<unsigned long long>();
         a.child_start = h->child_start.as<int>();
@@ -1018,7 +1034,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         else { a.thr = h->hmm_cumA.as<uint32_t>(); a.tab = h->hmm_tabA.as<uint32_t>(); a.rows = K; }
         a.logF_t = h->hmm_logF.as<double>() + (size_t)t * K;
         a.expF_t = h->hmm_expF.as<double>() + (size_t)t * K;
-        a.xstar = conditional ? h->xstar[h->xstar_cur].as<int>() : nullptr;
+        a.xstar = conditional ? (dist ? reinterpret_cast<const int*>((char*)h->arena + h->off_xstar[h->xstar_cur]) : h->xstar[h->xstar_cur].as<int>()) : nullptr;
         a.N = N; a.n_out = n_out; a.ntiles = ntiles; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed); a.err = h->d_err;
         // head markers that carry the parent's state ((parent << xb) | state must stay below 2^31): no gather
         a.xb = 0;
@@ -1041,10 +1057,11 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         const int t = T - 1, cur = (int)((sb0 + (unsigned)t) & 1u);
         int* row = ab + (size_t)(history ? t : 0) * S;
         if (!h->has_factor[t]) {
+            if (dist) return fail(h, SB_EUNSUPPORTED, "sharded pools need a factor statement at every step");
             k_fill_identity<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(row, N);
             LAUNCH_CHECK();
         } else if (mode == SB_RESAMPLE_SYSTEMATIC) {
-            if ((rc = launch_pull(h, cur, h->d_info.as<SbStepInfo>() + t, N, row)) != SB_OK) return rc;
+            if ((rc = launch_pull(h, cur, h->d_info.as<SbStepInfo>() + t, dist ? h->NL : N, row)) != SB_OK) return rc;
         } else {
             if ((rc = explicit_resample(h, cur, t, iter, n_out, N, row)) != SB_OK) return rc;
         }
@@ -1230,6 +1247,87 @@ extern "C" int32_t sb_pmcmc_chains(sb_handle* h, int64_t chains, int64_t iters, 
     return SB_OK;
 }
 
+namespace {
+// PMCMC on a pool sharded over the GPUs (iterated conditional SMC, src/pmcmc.jl:78-99): every rank calls this with the
+// same arguments.  N = world x N_local - 1 particles, so the pool of N + 1 entries fills the shards and the retained
+// particle is the last entry of the last GPU.  marg receives this rank's share of the counts.
+int pmcmc_run_dist(sb_handle* h, int64_t iters, int64_t N, int64_t* marg, int64_t* joint) {
+    if (joint) return fail(h, SB_EUNSUPPORTED, "pmcmc on a sharded pool: the joint histogram is not kept (pass joint = NULL)");
+    if (N + 1 != h->NL * h->world)
+        return fail(h, SB_EINVAL, "pmcmc on a sharded pool: numparticles must be world x N_local - 1 (the retained particle takes the last entry)");
+    if (h->opt.resample_mode != SB_RESAMPLE_SYSTEMATIC)
+        return fail(h, SB_EUNSUPPORTED, "sharded pools resample systematically");
+    CK(cudaSetDevice(h->opt.device));
+    const int T = h->T, K = h->K;
+    if (h->hist_rows < T)
+        return fail(h, SB_EUNSUPPORTED, "pmcmc on a sharded pool: call sb_dist_reserve_history(h, T) before sb_dist_ipc_export");
+    const int64_t S = h->NL;
+    CK(h->marg.ensure((size_t)T * K * 8));
+    CK(cudaMemsetAsync(h->marg.p, 0, (size_t)T * K * 8, h->stream));
+    int pick = h->opt.retained_pick;
+    if (pick < 0) pick = 1;                                           // systematic: uniform pick (as on one GPU)
+    int rc;
+    if ((rc = begin_timed(h)) != SB_OK) return rc;
+    SbBackArgs b;
+    memset(&b, 0, sizeof(b));
+    for (int g = 0; g < h->world; ++g) b.base[g] = h->peer_base[g];
+    b.off_cnt[0] = h->off_cnt[0]; b.off_cnt[1] = h->off_cnt[1]; b.off_lin = h->off_lin; b.off_flags = h->off_flags;
+    b.world = h->world; b.self = h->rank; b.log2n = 0; while ((1ll << b.log2n) < h->NL) ++b.log2n;
+    b.N = N; b.K = K; b.T = T; b.marg = h->marg.as<unsigned long long>(); b.err = h->d_err;
+    const unsigned grid8 = (unsigned)((h->NL / 8 + 255) / 256), grid1 = (unsigned)((h->NL + 255) / 256);
+    for (int64_t it = 0; it < iters; ++it) {
+        if ((rc = sweep_hmm(h, N, (unsigned)it, it > 0, true, true)) != SB_OK) return rc;
+        const int* ab = h->ancbuf.as<int>();
+        b.n_pool = N + (it > 0 ? 1 : 0);
+        b.off_xstar = h->off_xstar[h->xstar_cur ^ 1];
+        // src/pmcmc.jl:89 -- the child whose lineage is retained (k_lineage_start's arithmetic, on the host)
+        b.pick = 0;
+        if (pick) {
+            const double u = (double)host_r53(h->opt.seed, 0, (uint32_t)T, (uint32_t)it, SB_P_PICK) * 0x1p-53;
+            long long c = (long long)(u * (double)N);
+            b.pick = c >= N ? N - 1 : c;
+        }
+        // the forward sweep's last kernels (final pull) read the peers' pools, not their count buffers: no wait
+        b.t = T - 1; b.x_t = nullptr; b.anc_prev = ab + (size_t)(T - 1) * S; b.identity_prev = 0;
+        b.wait_epoch = 0u; b.sig_epoch = ++h->epoch;
+        k_count_final_dist<<<grid1, 256, 0, h->stream>>>(b);
+        LAUNCH_CHECK();
+        for (int t = T - 1; t >= 0; --t) {
+            b.t = t;
+            b.x_t = reinterpret_cast<const int*>((char*)h->arena + h->off_xh + (size_t)t * (size_t)S * 4);
+            b.anc_prev = t ? ab + (size_t)(t - 1) * S : nullptr;
+            b.identity_prev = t ? !h->has_factor[t - 1] : 0;
+            b.wait_epoch = h->epoch; b.sig_epoch = ++h->epoch;
+            k_count_back_dist<<<grid8, 256, (size_t)K * 4, h->stream>>>(b);
+            LAUNCH_CHECK();
+        }
+        b.wait_epoch = h->epoch;
+        k_flag_wait<<<1, 32, 0, h->stream>>>(b);
+        LAUNCH_CHECK();
+        h->xstar_cur ^= 1;
+        h->have_retained = true;
+        if (it == 0) {
+            double lz;
+            if ((rc = fetch_logZ(h, &lz)) != SB_OK) return rc;
+            h->stats.logZ_first = lz;
+            if ((rc = check_err_word(h)) != SB_OK) return rc;
+        }
+    }
+    if ((rc = end_timed(h)) != SB_OK) return rc;
+    h->stats.particle_steps = iters * h->NL * (int64_t)T;
+    double lz;
+    if ((rc = fetch_logZ(h, &lz)) != SB_OK) return rc;
+    h->stats.logZ_last = lz;
+    if ((rc = check_err_word(h)) != SB_OK) return rc;
+    if (marg) {
+        std::vector<unsigned long long> tmp((size_t)T * K);
+        CK(cudaMemcpy(tmp.data(), h->marg.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) marg[i] += (int64_t)tmp[i];
+    }
+    return SB_OK;
+}
+}  // namespace
+
 extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t* marg, int64_t* joint) {
     if (!h) return SB_EINVAL;
     // a pool that fits one tile runs as a one-CTA chain: the whole iteration loop in one launch
@@ -1239,7 +1337,7 @@ extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t*
     if (h->model != MODEL_HMM)
         return fail(h, SB_EUNSUPPORTED, "pmcmc: only the fixed-structure discrete model is supported (no CPU fallback)");
     if (iters < 1 || N < 1) return fail(h, SB_EINVAL, "pmcmc: numiterations and numparticles must be >= 1");
-    if (h->dist_ready) return fail(h, SB_EUNSUPPORTED, "pmcmc: independent chains run one handle per GPU, not on a sharded handle");
+    if (h->dist_ready) return pmcmc_run_dist(h, iters, N, marg, joint);
     CK(cudaSetDevice(h->opt.device));
     const int T = h->T, K = h->K;
     int64_t njoint = 0;
@@ -1680,7 +1778,8 @@ extern "C" int32_t sb_get_history(sb_handle* h, int32_t t, int64_t count, void* 
     const int64_t S = h->sw_S;
     if (x_out) {
         if (h->model != MODEL_HMM || !h->sw_hist) return fail(h, SB_EINVAL, "get_history: state history was not kept");
-        CK(cudaMemcpy(x_out, h->xbuf.as<int>() + (size_t)t * S, (size_t)count * 4, cudaMemcpyDeviceToHost));
+        const int* src = h->dist_ready ? reinterpret_cast<const int*>((char*)h->arena + h->off_xh) : h->xbuf.as<int>();
+        CK(cudaMemcpy(x_out, src + (size_t)t * S, (size_t)count * 4, cudaMemcpyDeviceToHost));
     }
     if (anc_out) {
         if (h->model != MODEL_HMM || !h->sw_hist) return fail(h, SB_EINVAL, "get_history: ancestor history was not kept");
@@ -1699,6 +1798,7 @@ extern "C" int32_t sb_get_retained(sb_handle* h, int32_t* xstar_out) {
     CK(cudaSetDevice(h->opt.device));
     CK(cudaStreamSynchronize(h->stream));
     if (h->small_cur >= 0) CK(cudaMemcpy(xstar_out, h->sm_xs.as<int>() + (size_t)h->small_cur * h->T, (size_t)h->T * 4, cudaMemcpyDeviceToHost));
+    else if (h->dist_ready) CK(cudaMemcpy(xstar_out, (char*)h->arena + h->off_xstar[h->xstar_cur], (size_t)h->T * 4, cudaMemcpyDeviceToHost));
     else CK(cudaMemcpy(xstar_out, h->xstar[h->xstar_cur].p, (size_t)h->T * 4, cudaMemcpyDeviceToHost));
     return SB_OK;
 }
@@ -1711,7 +1811,7 @@ extern "C" int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out) {
     const int t = h->sw_T - 1;
     if (h->model == MODEL_HMM) {
         const int row = h->sw_hist ? t : h->sw_slot;
-        const int* src = h->dist_ready ? reinterpret_cast<const int*>((char*)h->arena + h->off_x[h->sw_slot])
+        const int* src = h->dist_ready ? reinterpret_cast<const int*>((char*)h->arena + (h->sw_hist ? h->off_xh + (size_t)t * (size_t)h->sw_S * 4 : h->off_x[h->sw_slot]))
                                        : h->xbuf.as<int>() + (size_t)row * h->sw_S;
         CK(cudaMemcpy(x_out, src, (size_t)count * 4, cudaMemcpyDeviceToHost));
     } else {
@@ -1744,6 +1844,14 @@ extern "C" int32_t sb_dist_init(sb_handle* h, int32_t rank, int32_t world) {
     return SB_OK;
 }
 
+extern "C" int32_t sb_dist_reserve_history(sb_handle* h, int32_t rows) {
+    if (!h) return SB_EINVAL;
+    if (h->arena) return fail(h, SB_EINVAL, "dist_reserve_history: call it before sb_dist_ipc_export (the rows live in the exported allocation)");
+    if (rows < 0) return fail(h, SB_EINVAL, "dist_reserve_history: rows must be >= 0");
+    h->hist_rows = rows;
+    return SB_OK;
+}
+
 extern "C" int32_t sb_dist_ipc_export(sb_handle* h, int64_t N_local, uint8_t out_handle[64]) {
     if (!h || !out_handle) return SB_EINVAL;
     if (h->arena) return fail(h, SB_EINVAL, "dist_ipc_export: arena already allocated");
@@ -1762,6 +1870,12 @@ extern "C" int32_t sb_dist_ipc_export(sb_handle* h, int64_t N_local, uint8_t out
         h->off_Q[sl] = take(ntl * h->world * 8);
     }
     h->off_flags = take((SB_MAX_PEERS + 1) * sizeof(unsigned));     // flags[8] + the CTA counter of the step kernel
+    if (h->hist_rows > 0) {                                         // sharded conditional SMC / PMCMC (sb_dist_back.cuh)
+        h->off_xh = take((size_t)h->hist_rows * (size_t)N_local * 4);
+        h->off_cnt[0] = take((size_t)N_local * 4); h->off_cnt[1] = take((size_t)N_local * 4);
+        h->off_lin = take(2 * sizeof(int));
+        h->off_xstar[0] = take((size_t)h->hist_rows * 4); h->off_xstar[1] = take((size_t)h->hist_rows * 4);
+    }
     CK(cudaMalloc(&h->arena, off));
     h->arena_bytes = off;
     CK(cudaMemset(h->arena, 0, off));

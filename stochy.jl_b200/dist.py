@@ -76,3 +76,16 @@ def max_over_ranks(value, group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=_device_for(group))
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def sum_over_ranks(arr, group=None):
+    """Integer histograms kept per rank (each rank counts the particles it owns) summed over the group."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank, world = rank_world(group)
+    if world == 1:
+        return arr
+    t = torch.from_numpy(np.ascontiguousarray(arr)).to(_device_for(group))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()

@@ -37,3 +37,31 @@ def test_sharded_sweep_ranks_on_one_gpu(world, log2n):
            "--master-port", str(29620 + world + log2n), os.path.join(ROOT, "tests", "dist_worker.py"), str(log2n)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0 and "DIST_PARITY_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,log2n,T", [(2, 11, 9), (2, 13, 16), (4, 12, 7)])
+def test_sharded_pmcmc_ranks_on_one_gpu(world, log2n, T):
+    """Iterated conditional SMC on a SHARDED pool (src/pmcmc.jl:59-66, 83-94 across GPUs; retained entry in the last
+    slot of the last rank, history rows sharded, the backward pass's counts and the retained lineage hopping between
+    ranks through peer atomics) == sb_pmcmc_run on one handle: counts, retained trajectory, log-evidence and the
+    history rows, bit for bit.  Rank processes share device 0 (CUDA IPC as across GPUs)."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    env = dict(os.environ, SB_DIST_SAME_GPU="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % world, "--master-addr", "127.0.0.1",
+           "--master-port", str(29650 + world + log2n), os.path.join(ROOT, "tests", "dist_pmcmc_worker.py"), str(log2n), str(T), "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0 and "DIST_PMCMC_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_sharded_pmcmc_two_gpus():
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641", os.path.join(ROOT, "tests", "dist_pmcmc_worker.py"), "14", "25", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_PMCMC_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
