@@ -114,6 +114,31 @@ int32_t sb_model_discrete_hmm(sb_handle* h, int32_t K, int32_t T, int32_t x0, co
 int32_t sb_model_linear_gaussian(sb_handle* h, int32_t T, double a, double q, double c, double r,
                                  double m0, double P0, const double* y);
 
+/* Fixed-structure ERP program with ONE real-valued latent per particle ("op list"): step t draws x_t from an ERP
+ * whose parameters may depend (affinely) on x_{t-1}, then conditions on that step's observations with
+ * observe(erp, ys...) = factor(sum of score(erp, y)) (src/Stochy.jl:55-56; ERPs: src/erp.jl:1-30 -- every
+ * Distributions.jl distribution is an ERP there; these are the ones of the north star: flip, gaussian, beta, gamma,
+ * uniform; poisson as a second observation family).  Replaces sample(...)/factor(...) of src/pmcmc.jl:32-46 for such
+ * programs, e.g.  p = ~Beta(a, b); observe(Bernoulli(p), ys_1...); observe(Bernoulli(p), ys_2...); ...
+ * Computed in fp64 whatever the handle's precision.  Rejection samplers (Beta, Gamma: Marsaglia-Tsang) draw from the
+ * particle's own Philox counter stream (particle, draw number, step, iteration). */
+#define SB_DRAW_KEEP      0   /* x_t = x_{t-1} (a statement-free step of the program between two observe calls) */
+#define SB_DRAW_NORMAL    1   /* x_t ~ Normal(dp[0] x_{t-1} + dp[1], dp[2])   (standard deviation) */
+#define SB_DRAW_BETA      2   /* x_t ~ Beta(dp[0], dp[1]) */
+#define SB_DRAW_GAMMA     3   /* x_t ~ Gamma(shape dp[0], scale dp[1]) */
+#define SB_DRAW_UNIFORM   4   /* x_t ~ Uniform(dp[0], dp[1]) */
+#define SB_DRAW_FLIP      5   /* x_t = flip(dp[0] x_{t-1} + dp[1]) as 0.0 / 1.0 */
+#define SB_SCORE_ZERO      0  /* factor(0.0): the step still resamples */
+#define SB_SCORE_NORMAL    1  /* observe(Normal(sp[0] x_t + sp[1], sp[2]), ys...) */
+#define SB_SCORE_BERNOULLI 2  /* observe(Bernoulli(sp[0] x_t + sp[1]), ys...), ys in {0, 1} */
+#define SB_SCORE_POISSON   3  /* observe(Poisson(sp[0] x_t + sp[1]), ys...), ys non-negative integers */
+typedef struct sb_op_step {
+    int32_t draw, score;
+    double  dp[4], sp[4];
+    int32_t obs_off, obs_n;   /* this step's observations: obs[obs_off .. obs_off + obs_n) */
+} sb_op_step;
+int32_t sb_model_ops(sb_handle* h, int32_t T, const sb_op_step* steps, const double* obs, int64_t n_obs);
+
 /* Binary Bayes net for MH: D sampled flip sites in topological order, site d ~ flip(cpt[d][parents]),
  * F factor statements factor(logf[f][parents]); parents are bitmasks over sites, table index = the
  * parent bits packed in ascending site order; both tables have row stride cpt_stride.

@@ -76,6 +76,10 @@ def lib():
         L.or_lg_step.restype = None
         L.or_lg_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p,
                                  C.c_void_p, C.c_void_p]
+        L.or_ops_sweep.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.or_ops_step.restype = None
+        L.or_ops_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]
         L.or_bnet_mh.argtypes = [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.or_philox4x32_10.restype = None
         L.or_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -217,6 +221,51 @@ def lg_step(m, o, N, t, it, x_prev_gathered):
     x = np.empty(N, dtype=np.float64)
     lw = np.empty(N, dtype=np.float64)
     lib().or_lg_step(C.byref(m.c), C.byref(o), N, t, it, _p(xp), _p(x), _p(lw))
+    return x, lw
+
+
+class OrOpStep(C.Structure):
+    _fields_ = [("draw", C.c_int32), ("score", C.c_int32), ("dp", C.c_double * 4), ("sp", C.c_double * 4),
+                ("obs_off", C.c_int32), ("obs_n", C.c_int32)]
+
+
+class OrOps(C.Structure):
+    _fields_ = [("T", C.c_int32), ("steps", C.c_void_p), ("obs", C.c_void_p)]
+
+
+class Ops:
+    """steps: list of (draw, dp, score, sp, ys) with the integer codes of include/stochy_b200.h (SB_DRAW_*, SB_SCORE_*)."""
+
+    def __init__(self, steps):
+        self.T = len(steps)
+        self.steps = (OrOpStep * self.T)()
+        obs = []
+        for t, (draw, dp, score, sp, ys) in enumerate(steps):
+            st = self.steps[t]
+            st.draw, st.score = int(draw), int(score)
+            for i, v in enumerate(dp):
+                st.dp[i] = float(v)
+            for i, v in enumerate(sp):
+                st.sp[i] = float(v)
+            st.obs_off, st.obs_n = len(obs), len(ys)
+            obs.extend(float(y) for y in ys)
+        self.obs = np.ascontiguousarray(obs if obs else [0.0], dtype=np.float64)
+        self.c = OrOps(self.T, C.cast(self.steps, C.c_void_p), _p(self.obs))
+
+
+def ops_sweep(m, o, N, it=0):
+    x = np.empty(N, dtype=np.float64)
+    lw = np.empty(N, dtype=np.float64)
+    lz = C.c_double(0)
+    _chk(lib().or_ops_sweep(C.byref(m.c), C.byref(o), N, it, _p(x), C.byref(lz), _p(lw)))
+    return dict(x=x, lw=lw, logZ=lz.value)
+
+
+def ops_step(m, o, N, t, it, x_prev_gathered):
+    xp = np.ascontiguousarray(x_prev_gathered, dtype=np.float64) if x_prev_gathered is not None else np.zeros(N)
+    x = np.empty(N, dtype=np.float64)
+    lw = np.empty(N, dtype=np.float64)
+    lib().or_ops_step(C.byref(m.c), C.byref(o), N, t, it, _p(xp), _p(x), _p(lw))
     return x, lw
 
 

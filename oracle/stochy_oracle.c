@@ -661,6 +661,103 @@ int or_lg_sweep(const or_lg* m, const or_opts* o, int64_t N, uint32_t iter,
 }
 
 /* ------------------------------------------------------------------ */
+/* Op-list programs: a real latent, per step one draw statement         */
+/* (sample = rand(e), src/pmcmc.jl:32-34) and one observe statement     */
+/* (factor of the summed scores, src/Stochy.jl:55-56, src/pmcmc.jl:36). */
+/* Random stream of particle i at step t: Philox counter                */
+/* (i | (draw pair) << 32, t, iter, PROP), two 53-bit uniforms a block. */
+/* Distributions.jl 0.6.3's samplers are not in the tree: Beta = ratio  */
+/* of Gammas, Gamma = Marsaglia-Tsang, Normal = Box-Muller (cos branch).*/
+/* ------------------------------------------------------------------ */
+typedef struct { uint64_t seed, idx; uint32_t t, iter, n; } ops_rng;
+static inline double ops_next(ops_rng* g) {
+    uint32_t o[4];
+    stream4(g->seed, g->idx | ((uint64_t)(g->n >> 1) << 32), g->t, g->iter, P_PROP, o);
+    double u = (g->n & 1) ? u53_from(o[2], o[3]) : u53_from(o[0], o[1]);
+    ++g->n;
+    return u;
+}
+static inline double ops_normal(ops_rng* g) {
+    double u1 = ops_next(g), u2 = ops_next(g);
+    return sqrt(-2.0 * log(1.0 - u1)) * cos(TWO_PI * u2);
+}
+static double ops_gamma(ops_rng* g, double shape) {
+    double boost = 1.0;
+    if (shape < 1.0) { boost = pow(1.0 - ops_next(g), 1.0 / shape); shape += 1.0; }
+    const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (int it = 0; it < 1000; ++it) {
+        const double z = ops_normal(g);
+        double v = 1.0 + c * z;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        const double u = 1.0 - ops_next(g);
+        if (log(u) < 0.5 * z * z + d - d * v + d * log(v)) return boost * d * v;
+    }
+    return boost * d;
+}
+/* score(erp, y): logpdf of Distributions.jl (textbook forms) */
+static inline double lp_normal(double mu, double sd, double y) { double z = (y - mu) / sd; return (-0.5 * z * z - log(sd)) - 0.9189385332046727418; }
+static inline double lp_bernoulli(double p, double y) { return y != 0.0 ? log(p) : log(1.0 - p); }
+static inline double lp_poisson(double lam, double y) { return (y * log(lam) - lam) - lgamma(y + 1.0); }
+
+void or_ops_step(const or_ops* m, const or_opts* o, int64_t N, uint32_t t, uint32_t iter,
+                 const double* xpg, double* x_out, double* lw_out) {
+    const or_op_step* s = &m->steps[t];
+    #pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        ops_rng g = {o->seed, (uint64_t)i, t, iter, 0u};
+        const double xprev = (t == 0 || !xpg) ? 0.0 : xpg[i];
+        double x = xprev;
+        switch (s->draw) {                                           /* sample: rand(e) */
+            case 1: x = (s->dp[0] * xprev + s->dp[1]) + s->dp[2] * ops_normal(&g); break;
+            case 2: { double X = ops_gamma(&g, s->dp[0]), Y = ops_gamma(&g, s->dp[1]); x = X / (X + Y); } break;
+            case 3: x = s->dp[1] * ops_gamma(&g, s->dp[0]); break;
+            case 4: x = s->dp[0] + (s->dp[1] - s->dp[0]) * ops_next(&g); break;
+            case 5: x = ops_next(&g) < (s->dp[0] * xprev + s->dp[1]) ? 1.0 : 0.0; break;
+            default: break;
+        }
+        const double par = s->sp[0] * x + s->sp[1];
+        double lw = 0.0;                                             /* observe(erp, ys...): sum([score(erp, y) for y in ys]) */
+        for (int k = 0; k < s->obs_n; ++k) {
+            const double y = m->obs[s->obs_off + k];
+            if (s->score == 1) lw += lp_normal(par, s->sp[2], y);
+            else if (s->score == 2) lw += lp_bernoulli(par, y);
+            else if (s->score == 3) lw += lp_poisson(par, y);
+        }
+        x_out[i] = x;
+        lw_out[i] = lw;
+    }
+}
+
+int or_ops_sweep(const or_ops* m, const or_opts* o, int64_t N, uint32_t iter,
+                 double* x_last, double* logZ, double* lw_last) {
+    double* x = (double*)malloc(sizeof(double) * (size_t)N);
+    double* xg = (double*)malloc(sizeof(double) * (size_t)N);
+    double* lw = (double*)malloc(sizeof(double) * (size_t)N);
+    int64_t* anc = (int64_t*)malloc(sizeof(int64_t) * (size_t)N);
+    double lz = 0.0; int rc = OR_OK;
+    or_opts o64 = *o; o64.fp32 = 0;                                  /* op-list programs are computed in fp64 */
+    for (int t = 0; t < m->T; ++t) {
+        if (t) {
+            #pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < N; ++i) xg[i] = x[anc[i]];       /* pmcmc.jl:51 deepcopy(particles[a]) */
+        }
+        or_ops_step(m, &o64, N, (uint32_t)t, iter, xg, x, lw);
+        double lm;
+        rc = resample_pool(&o64, lw, N, N, (uint32_t)t, iter, anc, &lm);
+        if (rc) break;
+        lz += lm;
+    }
+    if (rc == OR_OK) {
+        if (x_last) memcpy(x_last, x, sizeof(double) * (size_t)N);
+        if (lw_last) memcpy(lw_last, lw, sizeof(double) * (size_t)N);
+        if (logZ) *logZ = lz;
+    }
+    free(x); free(xg); free(lw); free(anc);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ */
 /* Bayes-net single-site MH: src/mh.jl:22-43 (sample/factor),          */
 /* :47-93 (mh loop), :95-111 (log_mh_ratio) specialised to a           */
 /* fixed-structure trace (every address present in both traces, only   */

@@ -126,6 +126,26 @@ int or_lg_sweep(const or_lg* m, const or_opts* o, int64_t N, uint32_t iter,
 void or_lg_step(const or_lg* m, const or_opts* o, int64_t N, uint32_t t, uint32_t iter,
                 const double* x_prev_gathered, double* x_out, double* lw_out);
 
+/* ---- op-list program: one real latent per particle, per step a draw statement and an observe statement
+ * (src/pmcmc.jl:32-46 for sample/factor; observe(erp, xs...) = factor(sum of scores) src/Stochy.jl:55-56;
+ * ERPs src/erp.jl:1-30 = Distributions.jl's: logpdf forms textbook, unpinned by the reference's tests).
+ * Codes and parameter meaning as sb_op_step in include/stochy_b200.h. ---- */
+typedef struct {
+    int32_t draw, score;
+    double  dp[4], sp[4];
+    int32_t obs_off, obs_n;
+} or_op_step;
+typedef struct {
+    int32_t T;
+    const or_op_step* steps;  /* [T] */
+    const double* obs;
+} or_ops;
+/* one propagate+weight step from given parents */
+void or_ops_step(const or_ops* m, const or_opts* o, int64_t N, uint32_t t, uint32_t iter,
+                 const double* x_prev_gathered, double* x_out, double* lw_out);
+int or_ops_sweep(const or_ops* m, const or_opts* o, int64_t N, uint32_t iter,
+                 double* x_last, double* logZ, double* lw_last);
+
 /* ---- Bayes net single-site MH (src/mh.jl:47-111) ---- */
 typedef struct {
     int32_t D;                /* sampled binary sites, topological order */

@@ -4,8 +4,8 @@ The directory name carries a dot, so import it through the `stochy_jl_b200` shim
 """
 from . import _native, dist
 from ._native import build, lib
-from .api import (BayesNet, Categorical, Discrete, DiscreteHMM, Engine, LinearGaussian, StochyError, enum, hellingerdistance,
+from .api import (BayesNet, Categorical, Discrete, DiscreteHMM, Engine, LinearGaussian, OpsProgram, StochyError, enum, hellingerdistance,
                   hmm2_example, hmm_example, kl, mh, pmcmc, score, smc, support)
 
-__all__ = ["build", "lib", "Engine", "Discrete", "Categorical", "DiscreteHMM", "LinearGaussian", "BayesNet", "StochyError",
+__all__ = ["build", "lib", "Engine", "Discrete", "Categorical", "DiscreteHMM", "LinearGaussian", "OpsProgram", "BayesNet", "StochyError",
            "pmcmc", "smc", "mh", "enum", "hellingerdistance", "kl", "support", "score", "hmm2_example", "hmm_example"]

@@ -25,7 +25,7 @@ TILE = 2048
 
 EXPORTS = [
     "sb_version", "sb_options_default", "sb_create", "sb_destroy", "sb_last_error", "sb_get_stats", "sb_set_profile",
-    "sb_model_discrete_hmm", "sb_model_linear_gaussian", "sb_model_bayesnet",
+    "sb_model_discrete_hmm", "sb_model_linear_gaussian", "sb_model_bayesnet", "sb_model_ops",
     "sb_smc_sweep", "sb_pmcmc_run", "sb_pmcmc_chains", "sb_mh_run", "sb_enum_hmm",
     "sb_resample_systematic", "sb_resample_multinomial", "sb_resample_literal", "sb_logsumexp", "sb_gather",
     "sb_dev_resample_systematic", "sb_dev_gather", "sb_sync", "sb_timer_start", "sb_timer_stop",
@@ -40,6 +40,11 @@ class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("precision", C.c_int32), ("resample_mode", C.c_int32),
                 ("retained_pick", C.c_int32), ("store_logw", C.c_int32), ("use_graph", C.c_int32),
                 ("seed", C.c_uint64)]
+
+
+class OpStep(C.Structure):
+    _fields_ = [("draw", C.c_int32), ("score", C.c_int32), ("dp", C.c_double * 4), ("sp", C.c_double * 4),
+                ("obs_off", C.c_int32), ("obs_n", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -93,6 +98,7 @@ def lib():
         "sb_model_discrete_hmm": (i32, [vp, i32, i32, i32, vp, vp, vp, vp]),
         "sb_model_linear_gaussian": (i32, [vp, i32, dbl, dbl, dbl, dbl, dbl, dbl, vp]),
         "sb_model_bayesnet": (i32, [vp, i32, i32, vp, vp, vp, vp, i32, u32]),
+        "sb_model_ops": (i32, [vp, i32, vp, vp, i64]),
         "sb_smc_sweep": (i32, [vp, i64, u32, i32, C.POINTER(dbl)]),
         "sb_pmcmc_run": (i32, [vp, i64, i64, vp, vp]),
         "sb_pmcmc_chains": (i32, [vp, i64, i64, i64, i64, vp, vp]),

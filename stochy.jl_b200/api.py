@@ -146,6 +146,43 @@ class LinearGaussian:
                                                     self.P0, _ptr(self.y)))
 
 
+class OpsProgram:
+    """Fixed-structure ERP program with ONE real latent per particle (sb_model_ops): a list of steps, each
+    `(draw, score)` where
+      draw  = ("normal", a, b, sd)   x ~ Normal(a x_prev + b, sd)         | ("beta", a, b) | ("gamma", shape, scale)
+              | ("uniform", lo, hi) | ("flip", a, b)  x = flip(a x_prev + b) | ("keep",)
+      score = ("normal", c, d, sd, ys)  observe(Normal(c x + d, sd), ys...) | ("bernoulli", c, d, ys)
+              | ("poisson", c, d, ys) | ("zero",)  factor(0.0)
+    -- sample / observe of src/pmcmc.jl:32-46 and src/Stochy.jl:55-56 for programs such as
+       p = ~Beta(2, 3); observe(Bernoulli(p), true, false, true); observe(Bernoulli(p), false, ...)."""
+    DRAWS = {"keep": 0, "normal": 1, "beta": 2, "gamma": 3, "uniform": 4, "flip": 5}
+    SCORES = {"zero": 0, "normal": 1, "bernoulli": 2, "poisson": 3}
+
+    def __init__(self, steps):
+        self.T = len(steps)
+        self.K = 0
+        self.steps = (nat.OpStep * self.T)()
+        obs = []
+        for t, (draw, score) in enumerate(steps):
+            st = self.steps[t]
+            st.draw = self.DRAWS[draw[0]]
+            for i, v in enumerate(draw[1:]):
+                st.dp[i] = float(v)
+            st.score = self.SCORES[score[0]]
+            ys = []
+            if score[0] != "zero":
+                *par, ys = score[1:]
+                for i, v in enumerate(par):
+                    st.sp[i] = float(v)
+            st.obs_off, st.obs_n = len(obs), len(ys)
+            obs.extend(float(y) for y in ys)
+        self.obs = np.ascontiguousarray(obs if obs else [0.0], dtype=np.float64)
+        self.n_obs = len(obs)
+
+    def load(self, eng):
+        eng._chk(nat.lib().sb_model_ops(eng.h, self.T, C.cast(self.steps, C.c_void_p), _ptr(self.obs), self.n_obs))
+
+
 class BayesNet:
     """Binary Bayes net: sites[d] = (parent_mask, cpt) with cpt[i] = P(site=1 | packed parent bits i);
     factors[f] = (parent_mask, logf table).  query: iterable of site indices whose values are returned."""

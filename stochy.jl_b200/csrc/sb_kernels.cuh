@@ -1,6 +1,7 @@
 // sb_kernels.cuh -- the kernels of libstochy_b200 (sm_100a).  See DESIGN.md for the per-kernel
 // byte counts and rooflines.  Reference lines each kernel replaces are cited at the kernel.
 #pragma once
+#include "stochy_b200.h"
 #include "sb_device.cuh"
 #include <cfloat>
 #include <cmath>
@@ -941,13 +942,86 @@ struct SbLgStepArgs {
     SbRoundKeys rk;             // Philox round keys of `seed`
     double a, sq, sp, c, r, m0, y, lc;   // sq = sqrt(q), sp = sqrt(P0), lc = -0.5 log(2 pi r)
     unsigned* err;
+    // OPS instantiations (sb_model_ops): this step's draw / score statement and the observations (device memory)
+    sb_op_step op;
+    const double* obs;          // [n_obs] observations
+    const double* obs_aux;      // [n_obs] lgamma(y + 1) (Poisson), computed on the host
 };
+
+// Sequential draws of ONE particle at one step of an op-list program: Philox counter (particle | draw pair << 32,
+// step, iteration, PROP), two 53-bit uniforms per block (the CPU checker used by the tests restates the same stream).
+struct SbOpsRng {
+    const SbRoundKeys& rk;
+    unsigned long long idx;
+    unsigned t, iter, n;
+    __device__ __forceinline__ double next() {
+        const SbU4 o = sb_stream4_rk(rk, idx | ((unsigned long long)(n >> 1) << 32), t, iter, SB_P_PROP);
+        const double u = (n & 1) ? sb_u53(o.z, o.w) : sb_u53(o.x, o.y);
+        ++n;
+        return u;
+    }
+    __device__ __forceinline__ double normal() {
+        const double u1 = next(), u2 = next();
+        return sqrt(-2.0 * log(1.0 - u1)) * cos(6.283185307179586476925286766559 * u2);
+    }
+    // Marsaglia-Tsang (2000); shape < 1 boosted by u^(1/shape) -- as SbRng::gamma (the standalone ERP hooks)
+    __device__ double gamma(double shape) {
+        double boost = 1.0;
+        if (shape < 1.0) { boost = pow(1.0 - next(), 1.0 / shape); shape += 1.0; }
+        const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+        for (int it = 0; it < 1000; ++it) {
+            const double z = normal();
+            double v = 1.0 + c * z;
+            if (v <= 0.0) continue;
+            v = v * v * v;
+            const double u = 1.0 - next();
+            if (log(u) < 0.5 * z * z + d - d * v + d * log(v)) return boost * d * v;
+        }
+        return boost * d;
+    }
+};
+// one particle: the step's draw (src/pmcmc.jl:32-34: sample = rand(e)) and the score of its observe statement
+// (src/Stochy.jl:55-56: the scores of the observations summed in order).  log(p), log(1 - p), log(lambda) do not
+// depend on the observation: evaluated once, the sum then adds the same doubles the literal loop would.
+__device__ __forceinline__ void sb_ops_particle(const sb_op_step& op, const double* __restrict__ obs, const double* __restrict__ obs_aux,
+                                                SbOpsRng& g, double xprev, double* x_out, double* lw_out) {
+    double xv = xprev;
+    switch (op.draw) {
+        case SB_DRAW_NORMAL:  xv = (op.dp[0] * xprev + op.dp[1]) + op.dp[2] * g.normal(); break;
+        case SB_DRAW_BETA:    { const double X = g.gamma(op.dp[0]), Y = g.gamma(op.dp[1]); xv = X / (X + Y); } break;
+        case SB_DRAW_GAMMA:   xv = op.dp[1] * g.gamma(op.dp[0]); break;
+        case SB_DRAW_UNIFORM: xv = op.dp[0] + (op.dp[1] - op.dp[0]) * g.next(); break;
+        case SB_DRAW_FLIP:    xv = g.next() < (op.dp[0] * xprev + op.dp[1]) ? 1.0 : 0.0; break;
+        default: break;
+    }
+    double lw = 0.0;
+    const double par = op.sp[0] * xv + op.sp[1];
+    const double* y = obs + op.obs_off;
+    switch (op.score) {
+        case SB_SCORE_NORMAL: {
+            const double lsd = log(op.sp[2]);
+            for (int i = 0; i < op.obs_n; ++i) { const double z = (__ldg(y + i) - par) / op.sp[2]; lw += (-0.5 * z * z - lsd) - 0.9189385332046727418; }
+        } break;
+        case SB_SCORE_BERNOULLI: {
+            const double l1 = log(par), l0 = log(1.0 - par);
+            for (int i = 0; i < op.obs_n; ++i) lw += __ldg(y + i) != 0.0 ? l1 : l0;
+        } break;
+        case SB_SCORE_POISSON: {
+            const double ll = log(par);
+            const double* ya = obs_aux + op.obs_off;
+            for (int i = 0; i < op.obs_n; ++i) lw += (__ldg(y + i) * ll - par) - __ldg(ya + i);
+        } break;
+        default: break;
+    }
+    *x_out = xv; *lw_out = lw;
+}
 
 #define SB_TWO_PI 6.283185307179586476925286766559
 
-template <int ANC, bool FP32, bool PEERS>
+template <int ANC, bool FP32, bool PEERS, bool OPS = false>
 __global__ void __launch_bounds__(SB_THREADS, FP32 ? 5 : 3)       // fp32: 48 registers (5 CTAs per SM); fp64: 80 (3)
 k_step_lg(const __grid_constant__ SbLgStepArgs a) {
+    static_assert(!(OPS && FP32), "op-list programs are computed in fp64");
     typedef typename std::conditional<FP32, float, double>::type REAL;
     __shared__ SbHmmSmem sm;
     const int tid = threadIdx.x;
@@ -962,8 +1036,9 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     }
     // no particle of this step can weigh more than the density's mode: lw <= lc, and the roundings below are monotone,
     // so every log2-weight is <= vmax.  A warp whose own maximum already reaches ceil(vmax) knows the tile exponent.
+    // (an op-list program has no such bound: every warp waits for the tile maximum)
     const REAL vmax = FP32 ? (REAL)__fmul_rn((float)a.lc, SB_LOG2E_F) : (REAL)__dmul_rn(a.lc, SB_LOG2E_D);
-    const int e_top = FP32 ? (int)ceilf((float)vmax) : (int)ceil((double)vmax);
+    const int e_top = OPS ? 0x7fffffff : (FP32 ? (int)ceilf((float)vmax) : (int)ceil((double)vmax));
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
         if (ANC == SB_ANC_PULL && (k % SB_FT_CHUNK) == 0)
@@ -1041,6 +1116,21 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                 x[j] = (REAL)xv; l2[j] = (REAL)v;
                 mx = (REAL)fmaxf((float)mx, v);
                 if (a.lw_out && live) a.lw_out[lbase + j] = (double)lw;
+            }
+        } else if (OPS) {
+#pragma unroll 1
+            for (int j = 0; j < SB_ITEMS; ++j) {
+                const bool live = base + j < N;
+                double xv = 0.0, lw = 0.0;
+                if (live) {
+                    SbOpsRng g{a.rk, (unsigned long long)(base + j), (unsigned)a.t, a.iter, 0u};
+                    sb_ops_particle(a.op, a.obs, a.obs_aux, g, (double)xpar[j], &xv, &lw);
+                }
+                double v = live ? __dmul_rn(lw, SB_LOG2E_D) : -INFINITY;
+                if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
+                x[j] = (REAL)xv; l2[j] = (REAL)v;
+                mx = (REAL)fmax((double)mx, v);
+                if (a.lw_out && live) a.lw_out[lbase + j] = lw;
             }
         } else {
             double z[SB_ITEMS];

@@ -34,7 +34,7 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum ModelKind { MODEL_NONE = 0, MODEL_HMM = 1, MODEL_LG = 2, MODEL_BNET = 3 };
+enum ModelKind { MODEL_NONE = 0, MODEL_HMM = 1, MODEL_LG = 2, MODEL_BNET = 3, MODEL_OPS = 4 };
 
 }  // namespace
 
@@ -97,6 +97,9 @@ struct sb_handle {
     // LG
     double lg_a = 0, lg_q = 0, lg_c = 0, lg_r = 0, lg_m0 = 0, lg_P0 = 0;
     std::vector<double> lg_y;
+    // OPS (op-list program, sb_model_ops)
+    std::vector<sb_op_step> ops;
+    DevBuf ops_obs, ops_aux;
     // BNET
     int bn_D = 0, bn_F = 0, bn_stride = 0;
     unsigned bn_query = 0;
@@ -551,7 +554,7 @@ extern "C" void sb_destroy(sb_handle* h) {
                       &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
                       &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
                       &h->bn_fp, &h->bn_fac, &h->bn_counts, &h->xbuf, &h->ancbuf, &h->lwbuf, &h->wlit, &h->cnt[0],
-                      &h->cnt[1], &h->cnt[2], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint, &h->sm_x, &h->sm_a, &h->sm_xs, &h->sm_lz, &h->res_trace, &h->res_rec};
+                      &h->cnt[1], &h->cnt[2], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint, &h->sm_x, &h->sm_a, &h->sm_xs, &h->sm_lz, &h->res_trace, &h->res_rec, &h->ops_obs, &h->ops_aux};
     for (DevBuf* b : bufs) b->release();
     for (int g = 0; g < SB_MAX_PEERS; ++g)
         if (h->peer_base[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_base[g]);
@@ -713,6 +716,49 @@ extern "C" int32_t sb_model_linear_gaussian(sb_handle* h, int32_t T, double a, d
     return SB_OK;
 }
 
+extern "C" int32_t sb_model_ops(sb_handle* h, int32_t T, const sb_op_step* steps, const double* obs, int64_t n_obs) {
+    if (!h) return SB_EINVAL;
+    if (!steps || T < 1 || n_obs < 0 || (n_obs > 0 && !obs)) return fail(h, SB_EINVAL, "ops: bad arguments");
+    CK(cudaSetDevice(h->opt.device));
+    for (int t = 0; t < T; ++t) {
+        const sb_op_step& s = steps[t];
+        if (s.draw < SB_DRAW_KEEP || s.draw > SB_DRAW_FLIP || s.score < SB_SCORE_ZERO || s.score > SB_SCORE_POISSON)
+            return fail(h, SB_EUNSUPPORTED, "ops: unknown draw / score statement (no CPU fallback)");
+        if (t == 0 && s.draw == SB_DRAW_KEEP) return fail(h, SB_EINVAL, "ops: the first step must draw the latent");
+        if (s.obs_n < 0 || s.obs_off < 0 || (int64_t)s.obs_off + s.obs_n > n_obs) return fail(h, SB_EINVAL, "ops: observation range outside obs[]");
+        bool ok = true;
+        switch (s.draw) {
+            case SB_DRAW_NORMAL:  ok = s.dp[2] > 0; break;
+            case SB_DRAW_BETA:    ok = s.dp[0] > 0 && s.dp[1] > 0; break;
+            case SB_DRAW_GAMMA:   ok = s.dp[0] > 0 && s.dp[1] > 0; break;
+            case SB_DRAW_UNIFORM: ok = s.dp[1] > s.dp[0]; break;
+            default: break;
+        }
+        if (s.score == SB_SCORE_NORMAL) ok = ok && s.sp[2] > 0;
+        if (!ok) return fail(h, SB_EINVAL, "ops: distribution parameter out of range");
+        for (int i = 0; i < s.obs_n; ++i) {
+            const double y = obs[s.obs_off + i];
+            if (std::isnan(y)) return fail(h, SB_ENAN, "ops: NaN observation");
+            if (s.score == SB_SCORE_BERNOULLI && y != 0.0 && y != 1.0) return fail(h, SB_EINVAL, "ops: Bernoulli observations must be 0 or 1");
+            if (s.score == SB_SCORE_POISSON && (y < 0.0 || y != floor(y))) return fail(h, SB_EINVAL, "ops: Poisson observations must be non-negative integers");
+        }
+    }
+    std::vector<double> aux((size_t)(n_obs > 0 ? n_obs : 1), 0.0);
+    for (int64_t i = 0; i < n_obs; ++i) aux[(size_t)i] = obs[i] >= 0.0 ? lgamma(obs[i] + 1.0) : 0.0;
+    CK(h->ops_obs.ensure((size_t)(n_obs > 0 ? n_obs : 1) * 8));
+    CK(h->ops_aux.ensure((size_t)(n_obs > 0 ? n_obs : 1) * 8));
+    if (n_obs > 0) {
+        CK(cudaMemcpyAsync(h->ops_obs.p, obs, (size_t)n_obs * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->ops_aux.p, aux.data(), (size_t)n_obs * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->ops.assign(steps, steps + T);
+    h->model = MODEL_OPS; h->T = T; h->K = 0;
+    h->have_retained = false;
+    invalidate_sweep(h);
+    return SB_OK;
+}
+
 extern "C" int32_t sb_model_bayesnet(sb_handle* h, int32_t D, int32_t F, const uint32_t* site_parents,
                                      const double* site_cpt, const uint32_t* fac_parents, const double* fac_logf,
                                      int32_t cpt_stride, uint32_t query_mask) {
@@ -803,12 +849,12 @@ int launch_step_hmm(sb_handle* h, int anc_mode, const SbHmmStepArgs& a) {
     return fp32 ? launch_step_hmm_m<true, false>(h, anc_mode, a) : launch_step_hmm_m<false, false>(h, anc_mode, a);
 }
 
-template <bool FP32>
+template <bool FP32, bool OPS = false>
 int launch_step_lg(sb_handle* h, int anc_mode, const SbLgStepArgs& a) {
     int cap = 0, rc;
 #define SB_LG_LAUNCH(ANC, PEERS)                                                               \
     do {                                                                                       \
-        auto kern = k_step_lg<ANC, FP32, PEERS>;                                               \
+        auto kern = k_step_lg<ANC, FP32, PEERS, OPS>;                                          \
         if ((rc = resident_ctas(h, kern, 0, &cap)) != SB_OK) return rc;                        \
         if ((rc = launch_step(h, kern, (unsigned)(a.ntiles < cap ? a.ntiles : cap), 0, ANC == SB_ANC_PULL, a)) != SB_OK) return rc; \
     } while (0)
@@ -1072,7 +1118,8 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
 // Sharded handle: N is the GLOBAL particle count.
 int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
     const int T = h->T;
-    const bool fp32 = h->opt.precision == SB_FP32;
+    const bool ops = h->model == MODEL_OPS;                         // op-list program: same sweep, fp64, its own propagate + weight
+    const bool fp32 = h->opt.precision == SB_FP32 && !ops;
     const bool dist = h->dist_ready;
     const size_t sz = fp32 ? 4 : 8;
     const int64_t S = dist ? h->NL : tiles_of(N) * SB_TILE;
@@ -1118,12 +1165,16 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.N = N; a.ntiles = ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed);
-        a.a = h->lg_a; a.sq = sqrt(h->lg_q); a.sp = sqrt(h->lg_P0); a.c = h->lg_c; a.r = h->lg_r; a.m0 = h->lg_m0;
-        a.y = h->lg_y[t]; a.lc = -0.5 * log(SB_TWO_PI * h->lg_r);
+        if (ops) {
+            a.op = h->ops[(size_t)t]; a.obs = h->ops_obs.as<double>(); a.obs_aux = h->ops_aux.as<double>();
+        } else {
+            a.a = h->lg_a; a.sq = sqrt(h->lg_q); a.sp = sqrt(h->lg_P0); a.c = h->lg_c; a.r = h->lg_r; a.m0 = h->lg_m0;
+            a.y = h->lg_y[t]; a.lc = -0.5 * log(SB_TWO_PI * h->lg_r);
+        }
         a.err = h->d_err;
         {
             ProfScope ps(h, t ? t : -1);
-            rc = fp32 ? launch_step_lg<true>(h, anc_mode, a) : launch_step_lg<false>(h, anc_mode, a);
+            rc = ops ? launch_step_lg<false, true>(h, anc_mode, a) : (fp32 ? launch_step_lg<true>(h, anc_mode, a) : launch_step_lg<false>(h, anc_mode, a));
         }
         if (rc != SB_OK) return rc;
         if ((rc = launch_tilescan(h, cur, N, N, h->d_r53.as<unsigned long long>() + t,
@@ -1151,7 +1202,7 @@ int fetch_logZ(sb_handle* h, double* out) {
 extern "C" int32_t sb_smc_sweep(sb_handle* h, int64_t N, uint32_t iter, int32_t store_history, double* out_logZ) {
     if (!h) return SB_EINVAL;
     if (N < 1) return fail(h, SB_EINVAL, "smc: N must be >= 1");
-    if (h->model != MODEL_HMM && h->model != MODEL_LG)
+    if (h->model != MODEL_HMM && h->model != MODEL_LG && h->model != MODEL_OPS)
         return fail(h, SB_EUNSUPPORTED, "smc: no fixed-structure state-space model is loaded (no CPU fallback)");
     CK(cudaSetDevice(h->opt.device));
     int rc;
@@ -1815,7 +1866,7 @@ extern "C" int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out) {
                                        : h->xbuf.as<int>() + (size_t)row * h->sw_S;
         CK(cudaMemcpy(x_out, src, (size_t)count * 4, cudaMemcpyDeviceToHost));
     } else {
-        const size_t sz = h->opt.precision == SB_FP32 ? 4 : 8;
+        const size_t sz = (h->opt.precision == SB_FP32 && h->model != MODEL_OPS) ? 4 : 8;
         std::vector<char> tmp((size_t)count * sz);
         const char* src = h->dist_ready ? (char*)h->arena + h->off_x[h->sw_slot] : h->xbuf.as<char>() + (size_t)h->sw_slot * h->sw_S * sz;
         CK(cudaMemcpy(tmp.data(), src, tmp.size(), cudaMemcpyDeviceToHost));
