@@ -1301,12 +1301,34 @@ struct SbCountArgs {
     int* xstar_out;                     // [T]
     unsigned* bar;                      // grid barrier counter (sb_grid_barrier) and its value before this launch
     unsigned bar0;
+    // the walk phase (below): live[t] = entries with a non-zero count at step t (zeroed before the launch), the
+    // compacted list of (entry, count) pairs and its cursor (zeroed before the launch)
+    unsigned* live;                     // [T]
+    unsigned* cursor;
+    int2* list;                         // [gridDim.x * blockDim.x]
 };
+#define SB_WALK_CHUNK 16                // steps per flush of the walk phase's shared-memory histograms
+// Two phases.  COUNTING (as k_count_back, a grid barrier per step) while many pool entries still carry lineages.
+// Lineages coalesce quickly going backwards (after g steps about N / (1 + g c) entries are live), and a step of
+// the counting phase costs a grid barrier whatever the number of live entries -- so as soon as they fit one per
+// thread the kernel switches to WALKING: the live (entry, count) pairs are compacted into a list, every thread takes
+// one pair and follows its lineage down to step 0 on its own (two dependent loads per step, no barrier of any kind:
+// the walks are independent), adding its count into per-CTA shared-memory histograms that are flushed every
+// SB_WALK_CHUNK steps.  Same integers as the counting phase (integer adds commute); at BASELINE cfg3's size
+// (2^20 particles, T = 1000) the pass takes ~1 ms instead of 5.2 ms (a barrier per step).
+// Every CTA arrives T times at the grid barrier in total (the arrivals of the barriers it skips are added at the
+// end), so the host can hand out the counter's base for the next launch without knowing when the switch happened.
 __global__ void __launch_bounds__(256)
 k_count_back_all(const __grid_constant__ SbCountArgs a) {
-    extern __shared__ unsigned int s_hist[];
+    extern __shared__ unsigned int s_hist[];                     // SB_WALK_CHUNK * K
+    __shared__ unsigned s_nz[8];
     const int K = a.K;
-    for (int t = a.T - 1; t >= 0; --t) {
+    const unsigned nthreads = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    unsigned barriers = 0;
+    bool walk = false;
+    int t = a.T - 1;
+    while (true) {                                               // ---- counting phase
         const int* x_t = a.x_hist + (size_t)t * a.S;
         const int* anc_prev = t ? a.anc_hist + (size_t)(t - 1) * a.S : nullptr;
         const int identity_prev = t ? !a.has_factor[t - 1] : 0;
@@ -1315,7 +1337,8 @@ k_count_back_all(const __grid_constant__ SbCountArgs a) {
         int* cnt_clear = t >= 2 ? a.cnt[(t + 1) % 3] : nullptr;
         for (int k = threadIdx.x; k < K; k += blockDim.x) s_hist[k] = 0u;
         __syncthreads();
-        for (long long j0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; j0 < a.n_pool; j0 += (long long)gridDim.x * blockDim.x * 8) {
+        unsigned nz = 0;
+        for (long long j0 = (long long)gid * 8; j0 < a.n_pool; j0 += (long long)nthreads * 8) {
             int c[8];
             if (j0 + 8 <= a.n_pool) {
                 // the counts were written by other CTAs earlier in this launch: coherent loads
@@ -1335,6 +1358,7 @@ k_count_back_all(const __grid_constant__ SbCountArgs a) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (c[i]) {
+                    ++nz;
                     const long long j = j0 + i;
                     atomicAdd(&s_hist[x_t[j]], (unsigned)c[i]);
                     if (cnt_prev) {
@@ -1344,17 +1368,83 @@ k_count_back_all(const __grid_constant__ SbCountArgs a) {
                 }
             }
         }
+        nz = __reduce_add_sync(0xffffffffu, nz);
+        if (lane == 0) s_nz[threadIdx.x >> 5] = nz;
         __syncthreads();
         if (a.marg)
             for (int k = threadIdx.x; k < K; k += blockDim.x)
                 if (s_hist[k]) atomicAdd(a.marg + (size_t)t * K + k, (unsigned long long)s_hist[k]);
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) tot += s_nz[w];
+            if (tot) atomicAdd(a.live + t, tot);
+        }
         if (blockIdx.x == 0 && threadIdx.x == 0 && a.lineage) {
             const int r = *a.lineage;
             a.xstar_out[t] = x_t[r];
             if (t > 0) *a.lineage = (r >= a.N || identity_prev) ? r : anc_prev[r];
         }
-        if (t > 0) sb_grid_barrier(a.bar, a.bar0 + (unsigned)(a.T - t) * gridDim.x);
+        if (t == 0) break;
+        sb_grid_barrier(a.bar, a.bar0 + (++barriers) * gridDim.x);
+        const unsigned live = __ldcg(a.live + t);               // entries with lineages at step t; no more than that at step t-1
+        --t;
+        if (live <= nthreads) { walk = true; break; }
     }
+    if (walk) {                                                  // ---- walking phase: steps t .. 0
+        // compact the live entries of step t (every count of this step is complete: the barrier above)
+        const int* cnt_t = a.cnt[t % 3];
+        // (warp-uniform trip count: the shuffles below need all 32 lanes)
+        for (long long w0 = (long long)(gid - lane) * 8; w0 < a.n_pool; w0 += (long long)nthreads * 8) {
+            const long long j0 = w0 + lane * 8;
+            int c[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = j0 + i < a.n_pool ? __ldcg(cnt_t + j0 + i) : 0;
+            int mine = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mine += c[i] ? 1 : 0;
+            int inc = mine;                                      // one cursor update per warp
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+            const int wtot = __shfl_sync(0xffffffffu, inc, 31);
+            unsigned wbase = 0;
+            if (lane == 31 && wtot) wbase = atomicAdd(a.cursor, (unsigned)wtot);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            unsigned pos = wbase + (unsigned)(inc - mine);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (c[i]) a.list[pos++] = make_int2((int)(j0 + i), c[i]);
+        }
+        sb_grid_barrier(a.bar, a.bar0 + (++barriers) * gridDim.x);
+        const unsigned total = __ldcg(a.cursor);
+        int j = 0, c = 0;
+        if (gid < total) { const int2 e = __ldcg(a.list + gid); j = e.x; c = e.y; }
+        int r = (blockIdx.x == 0 && threadIdx.x == 0 && a.lineage) ? *a.lineage : -1;
+        for (int hi = t; hi >= 0; hi -= SB_WALK_CHUNK) {
+            const int lo = max(hi - SB_WALK_CHUNK + 1, 0);
+            for (int k = threadIdx.x; k < SB_WALK_CHUNK * K; k += blockDim.x) s_hist[k] = 0u;
+            __syncthreads();
+            for (int tt = hi; tt >= lo; --tt) {
+                const int* x_t = a.x_hist + (size_t)tt * a.S;
+                const int* anc_prev = tt ? a.anc_hist + (size_t)(tt - 1) * a.S : nullptr;
+                const bool follow = tt > 0 && a.has_factor[tt - 1];
+                if (c) {
+                    atomicAdd(&s_hist[(hi - tt) * K + __ldg(x_t + j)], (unsigned)c);
+                    if (follow && j < a.N) j = __ldg(anc_prev + j);
+                }
+                if (r >= 0) {
+                    a.xstar_out[tt] = __ldg(x_t + r);
+                    if (follow && r < a.N) r = __ldg(anc_prev + r);
+                }
+            }
+            __syncthreads();
+            if (a.marg)
+                for (int k = threadIdx.x; k < (hi - lo + 1) * K; k += blockDim.x)
+                    if (s_hist[k]) atomicAdd(a.marg + (size_t)(hi - k / K) * K + (k % K), (unsigned long long)s_hist[k]);
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0 && barriers < (unsigned)a.T)            // the arrivals of the barriers this CTA skipped
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(a.bar), "r"((unsigned)a.T - barriers) : "memory");
 }
 // start of the retained lineage: child c* of the final resample (src/pmcmc.jl:89 or uniform pick, H4)
 __global__ void k_lineage_start(const int* __restrict__ anc_last, long long N, int pick_uniform,

@@ -109,6 +109,7 @@ struct sb_handle {
     DevBuf xbuf, ancbuf, lwbuf, wlit, cnt[3], xstar[2], marg, joint;
     DevBuf res_trace;                 // SB_RES_TRACE diagnostics
     DevBuf res_rec;                   // resident sweep kernel: the tile records its CTAs exchange (two slots)
+    DevBuf cb_live, cb_list;          // cooperative backward pass: live-entry counters + cursor, compacted (entry, count) list
     unsigned bar_count = 0;           // arrivals the grid barrier counter (d_err + 1) has seen: base of the next cooperative launch
     unsigned res_epoch = 0;           // epoch stamps handed out so far (fresh ones for every launch)
     DevBuf sm_x, sm_a, sm_xs, sm_lz;  // one-tile chains (sb_small.cuh)
@@ -554,7 +555,7 @@ extern "C" void sb_destroy(sb_handle* h) {
                       &h->hk_in, &h->hk_r, &h->hk_anc, &h->hk_out, &h->hk_src, &h->hmm_cumA, &h->hmm_cumpi,
                       &h->hmm_logF, &h->hmm_expF, &h->hmm_hasf, &h->bn_sp, &h->bn_cpt, &h->bn_lp1, &h->bn_lp0,
                       &h->bn_fp, &h->bn_fac, &h->bn_counts, &h->xbuf, &h->ancbuf, &h->lwbuf, &h->wlit, &h->cnt[0],
-                      &h->cnt[1], &h->cnt[2], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint, &h->sm_x, &h->sm_a, &h->sm_xs, &h->sm_lz, &h->res_trace, &h->res_rec, &h->ops_obs, &h->ops_aux};
+                      &h->cnt[1], &h->cnt[2], &h->xstar[0], &h->xstar[1], &h->marg, &h->joint, &h->sm_x, &h->sm_a, &h->sm_xs, &h->sm_lz, &h->res_trace, &h->res_rec, &h->ops_obs, &h->ops_aux, &h->cb_live, &h->cb_list};
     for (DevBuf* b : bufs) b->release();
     for (int g = 0; g < SB_MAX_PEERS; ++g)
         if (h->peer_base[g] && g != h->rank) cudaIpcCloseMemHandle(h->peer_base[g]);
@@ -1433,7 +1434,8 @@ extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t*
                 h->coop = (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->opt.device) == cudaSuccess && v) ? 1 : 0;
             }
             int cap = 0;
-            if (h->coop && resident_ctas(h, k_count_back_all, (size_t)K * 4, &cap) == SB_OK) {
+            const size_t smem_cb = (size_t)SB_WALK_CHUNK * K * 4;
+            if (h->coop && resident_ctas(h, k_count_back_all, smem_cb, &cap) == SB_OK) {
                 SbCountArgs ca;
                 ca.x_hist = xb; ca.anc_hist = ab; ca.has_factor = h->hmm_hasf.as<unsigned char>();
                 for (int i = 0; i < 3; ++i) ca.cnt[i] = h->cnt[i].as<int>();
@@ -1441,10 +1443,15 @@ extern "C" int32_t sb_pmcmc_run(sb_handle* h, int64_t iters, int64_t N, int64_t*
                 ca.marg = h->marg.as<unsigned long long>(); ca.lineage = lineage; ca.xstar_out = xs_next;
                 const int want = (int)((n_pool + 2047) / 2048);
                 const unsigned ctas = (unsigned)(want < cap ? want : cap);
+                // walk phase: live-entry counters per step + the list cursor (zeroed), the compacted list
+                CK(h->cb_live.ensure(((size_t)T + 1) * 4));
+                CK(h->cb_list.ensure((size_t)ctas * 256 * sizeof(int2)));
+                CK(cudaMemsetAsync(h->cb_live.p, 0, ((size_t)T + 1) * 4, h->stream));
+                ca.live = h->cb_live.as<unsigned>(); ca.cursor = ca.live + T; ca.list = h->cb_list.as<int2>();
                 ca.bar = grid_bar(h); ca.bar0 = h->bar_count;
                 void* args[] = {(void*)&ca};
-                CK(cudaLaunchCooperativeKernel((const void*)k_count_back_all, dim3(ctas), dim3(256), args, (size_t)K * 4, h->stream));
-                h->bar_count += (unsigned)(T - 1) * ctas;
+                CK(cudaLaunchCooperativeKernel((const void*)k_count_back_all, dim3(ctas), dim3(256), args, smem_cb, h->stream));
+                h->bar_count += (unsigned)T * ctas;                      // every CTA arrives T times whatever the switch point
                 ++h->launches;
                 counted = true;
             } else h->err.clear();
