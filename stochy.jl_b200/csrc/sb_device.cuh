@@ -393,6 +393,18 @@ __device__ __forceinline__ void sb_grid_barrier(unsigned* counter, unsigned targ
     }
     __syncthreads();
 }
+// The same barrier in two halves (thread 0 of the CTA calls both; the caller puts a __syncthreads() before the arrive
+// -- every thread's writes are then ordered before the release -- and one after the wait): work that needs nothing
+// from the other CTAs goes between the two and is off the critical path of the step.
+__device__ __forceinline__ void sb_grid_arrive(unsigned* counter) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ void sb_grid_wait(unsigned* counter, unsigned target) {
+    unsigned v;
+    do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while ((int)(v - target) < 0);
+}
 // one thread: `bytes` (multiple of 16, 16-byte aligned both sides) from global memory -- local HBM or a
 // peer GPU's arena over NVLink -- into shared memory; completion is counted on the mbarrier
 __device__ __forceinline__ void sb_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {

@@ -87,16 +87,21 @@ __device__ __forceinline__ void sb_st_rec_volatile(ulonglong2* p, unsigned long 
 // (child_start), and the candidate parent tiles of the children tile starting at c0 (what k_tilescan's first_tile
 // table holds): sm.bA = the tile b with cs[b] <= c0 < cs[b+1], sm.bLast likewise for c0 + SB_TILE (or nt - 1).
 // Thread r owns the `per` consecutive tiles from r * per.  Four CTA barriers.
+// (One warp doing this scan for the CTA, the other seven parked at the barrier, was measured: the CTAs publish closer
+// together -- max 4.4 us behind the first instead of 6.0: an SM holding four CTAs is issue-bound and the redundant scan
+// is a third of its instructions -- but a lone warp issues one dependent instruction every 5-10 cycles: 10 us per scan
+// against 2.9 us.  profiles/r02_notes.md.)
+template <int PER>
 __device__ __forceinline__ void sb_res_scan(const ulonglong2* rec, unsigned epoch, int nt, long long n, long long m,
                                             unsigned long long R53, int c0, SbResSmem& sm, unsigned long long* s_Pt, int* s_cs,
                                             SbStepInfo* info_out, unsigned* err) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (nt + SB_THREADS - 1) / SB_THREADS;          // <= SB_RES_MAXPER
+    const int per = PER;                                          // tiles per thread (>= ceil(nt / SB_THREADS))
     const int b0 = min(nt, tid * per), b1 = min(nt, b0 + per);
-    unsigned long long qr[SB_RES_MAXPER];
-    int er[SB_RES_MAXPER];
+    unsigned long long qr[PER];
+    int er[PER];
 #pragma unroll
-    for (int i = 0; i < SB_RES_MAXPER; ++i) {
+    for (int i = 0; i < PER; ++i) {
         const int b = b0 + i;
         qr[i] = 0ull; er[i] = SB_E_EMPTY;
         if (b < b1) {
@@ -110,7 +115,7 @@ __device__ __forceinline__ void sb_res_scan(const ulonglong2* rec, unsigned epoc
     if (tid == 0) { sm.bA = 0; sm.bLast = nt - 1; }
     int E = SB_E_EMPTY;
 #pragma unroll
-    for (int i = 0; i < SB_RES_MAXPER; ++i) if (qr[i] != 0ull) E = max(E, er[i]);
+    for (int i = 0; i < PER; ++i) if (qr[i] != 0ull) E = max(E, er[i]);
     E = __reduce_max_sync(0xffffffffu, E);
     if (lane == 0) sm.redi[warp] = E;
     __syncthreads();                                              // (1)
@@ -121,7 +126,7 @@ __device__ __forceinline__ void sb_res_scan(const ulonglong2* rec, unsigned epoc
     const int LS = 24 - (nt <= 1 ? 0 : 32 - __clz(nt - 1));
     unsigned long long loc = 0;
 #pragma unroll
-    for (int i = 0; i < SB_RES_MAXPER; ++i)
+    for (int i = 0; i < PER; ++i)
         if (qr[i] != 0ull) { const int sh = E - er[i]; loc += sh >= 63 ? 0ull : ((qr[i] << LS) >> sh); }
     unsigned long long inc = loc;
 #pragma unroll
@@ -136,7 +141,7 @@ __device__ __forceinline__ void sb_res_scan(const ulonglong2* rec, unsigned epoc
     unsigned long long loc2 = 0;
     if (si.valid) {
 #pragma unroll
-        for (int i = 0; i < SB_RES_MAXPER; ++i) if (qr[i] != 0ull) loc2 += sb_sys_delta(qr[i], si.R, si.r0 + (E - er[i]));
+        for (int i = 0; i < PER; ++i) if (qr[i] != 0ull) loc2 += sb_sys_delta(qr[i], si.R, si.r0 + (E - er[i]));
     }
     unsigned long long inc2 = loc2;
 #pragma unroll
@@ -150,7 +155,7 @@ __device__ __forceinline__ void sb_res_scan(const ulonglong2* rec, unsigned epoc
     const int mi = (int)m;
     int cs = si.valid ? sb_sys_F(run2, si.U, si.s, mi) : 0;
 #pragma unroll
-    for (int i = 0; i < SB_RES_MAXPER; ++i) {
+    for (int i = 0; i < PER; ++i) {
         const int b = b0 + i;
         if (b < b1) {
             s_Pt[b] = run2;
@@ -406,9 +411,12 @@ k_sweep_hmm(const __grid_constant__ SbResArgs a) {
             unsigned long long Qt = 0;
 #pragma unroll
             for (int w = 0; w < SB_WARPS; ++w) Qt += sm.tot[w];
-            __threadfence();
+            // the record, then the ARRIVE half of the grid barrier (release at GPU scope: the barrier above ordered every
+            // thread's stores of this step before it; the records are only read behind the barrier, so no fence of
+            // their own).  The wait half comes after the work below, which needs nothing from the other CTAs.
             sb_st_rec_volatile(a.rec[cur] + tile, Qt | ((unsigned long long)(epoch & 0xffffu) << 48),
                                (unsigned long long)(unsigned)e | ((unsigned long long)epoch << 32));
+            sb_grid_arrive(a.bar);
             if (a.dbg && (t == 10 || t == 11)) {                         // diagnostics: when (and where) every CTA published step 10 / 11
                 unsigned long long ts_; unsigned smid_;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_));
@@ -424,11 +432,18 @@ k_sweep_hmm(const __grid_constant__ SbResArgs a) {
             for (int p = 0; p < SB_ITEMS / 4; ++p) rnd[p] = sb_stream4_rk(a.rk, (unsigned long long)((base >> 2) + p), (unsigned)(t + 1), a.iter, SB_P_PROP);
         }
         SB_RES_STAMP(5);
-        // ---- the barrier of `factor` (src/pmcmc.jl:36-46) + the normalisation (src/pmcmc.jl:50), by every CTA for itself
-        sb_grid_barrier(a.bar, a.bar0 + (unsigned)(t + 1) * gridDim.x);
+        // ---- the barrier of `factor` (src/pmcmc.jl:36-46), wait half, + the normalisation (src/pmcmc.jl:50), by every CTA for itself
+        if (tid == 0) sb_grid_wait(a.bar, a.bar0 + (unsigned)(t + 1) * gridDim.x);
+        __syncthreads();
         SB_RES_STAMP(6);
-        sb_res_scan(a.rec[cur], epoch, nt, (long long)a.n_out, a.N, __ldg(a.r53 + t), c0, sm, s_Pt, s_cs,
-                    tile == 0 ? a.info + t : nullptr, a.err);
+        {
+            // (records per thread as a compile-time bound: at 2^20 particles two, not SB_RES_MAXPER's four)
+            SbStepInfo* io = tile == 0 ? a.info + t : nullptr;
+            const unsigned long long R53 = __ldg(a.r53 + t);
+            if (nt <= SB_THREADS)          sb_res_scan<1>(a.rec[cur], epoch, nt, (long long)a.n_out, a.N, R53, c0, sm, s_Pt, s_cs, io, a.err);
+            else if (nt <= 2 * SB_THREADS) sb_res_scan<2>(a.rec[cur], epoch, nt, (long long)a.n_out, a.N, R53, c0, sm, s_Pt, s_cs, io, a.err);
+            else                           sb_res_scan<SB_RES_MAXPER>(a.rec[cur], epoch, nt, (long long)a.n_out, a.N, R53, c0, sm, s_Pt, s_cs, io, a.err);
+        }
         SB_RES_STAMP(7);
     }
     if (a.final_anc && c0 < N) {                                         // the resample after the last step (src/pmcmc.jl:42)

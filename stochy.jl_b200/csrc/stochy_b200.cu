@@ -936,6 +936,22 @@ int sweep_hmm_resident_k(sb_handle* h, const SbResArgs& a, int* done) {
                     a.ntiles, d[d.size() / 10], d[d.size() / 2], d[d.size() * 9 / 10], d[d.size() * 99 / 100], d.back(),
                     (long long)(ts[1024 + 2048] - ts[1024]));
             for (int c = 1; c < 8; ++c) if (cnt[c]) fprintf(stderr, "[sb trace]   SMs holding %d CTAs: %d CTAs, mean publish time %+.0f ns\n", c, cnt[c], sum[c] / cnt[c]);
+            {   // the latest publishers: (tile, SM, CTAs on that SM, +ns)
+                std::vector<std::pair<long long, int>> late;
+                for (int i = 0; i < a.ntiles; ++i) late.push_back(std::make_pair((long long)(ts[1024 + 2048 + 2 * i] - t0), i));
+                std::sort(late.begin(), late.end());
+                fprintf(stderr, "[sb trace]   latest:");
+                for (int q = 0; q < 24 && q < (int)late.size(); ++q) {
+                    const int i = late[late.size() - 1 - q].second;
+                    fprintf(stderr, " t%d/sm%u/%d/+%lld", i, (unsigned)ts[1024 + 2048 + 2 * i + 1], per_sm[(unsigned)ts[1024 + 2048 + 2 * i + 1]], late[late.size() - 1 - q].first);
+                }
+                fprintf(stderr, "\n[sb trace]   earliest:");
+                for (int q = 0; q < 12 && q < (int)late.size(); ++q) {
+                    const int i = late[q].second;
+                    fprintf(stderr, " t%d/sm%u/%d/+%lld", i, (unsigned)ts[1024 + 2048 + 2 * i + 1], per_sm[(unsigned)ts[1024 + 2048 + 2 * i + 1]], late[q].first);
+                }
+                fprintf(stderr, "\n");
+            }
         }
         for (int t = 8; t < 16 && t + 1 < a.T; ++t) {
             fprintf(stderr, "[sb trace] t=%d:", t);
