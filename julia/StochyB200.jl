@@ -16,7 +16,7 @@
 # and the native handle is destroyed in a `finally` block (the reference restores `ctx` there).
 module StochyB200
 
-export DiscreteHMM, LinearGaussian, BayesNet, pmcmc, smc, mh, enum, smc_logevidence, hmm2_example, rand_discrete, score_discrete
+export DiscreteHMM, LinearGaussian, BayesNet, OpsProgram, OpStep, pmcmc, smc, mh, enum, smc_logevidence, hmm2_example, rand_discrete, score_discrete
 
 const LIB = get(ENV, "STOCHY_B200_LIB", "libstochy_b200")
 
@@ -98,6 +98,21 @@ struct BayesNet <: Model
     query::Vector{Int}             # 1-based site indices returned by the program
 end
 
+# One real latent per particle; per step a draw statement and an observe statement (include/stochy_b200.h: sb_op_step;
+# src/pmcmc.jl:32-46, src/Stochy.jl:55-56 with the continuous ERPs of src/erp.jl:1-30).  isbits, C layout.
+struct OpStep
+    draw::Int32; score::Int32          # SB_DRAW_* / SB_SCORE_* codes
+    dp::NTuple{4,Float64}; sp::NTuple{4,Float64}
+    obs_off::Int32; obs_n::Int32
+end
+struct OpsProgram <: Model
+    steps::Vector{OpStep}
+    obs::Vector{Float64}
+end
+# e.g. p = ~Beta(2, 3); observe(Bernoulli(p), ys...):
+#   OpsProgram([OpStep(2, 2, (2., 3., 0., 0.), (1., 0., 0., 0.), 0, length(ys))], Float64.(ys))
+# smc_logevidence(prog, n) then returns the log-evidence estimate of one sweep.
+
 # Row-major tables cross the ABI; Julia matrices are column-major.
 rowmajor(M::Matrix{Float64}) = collect(vec(permutedims(M)))
 
@@ -119,6 +134,10 @@ function load!(h::Handle, m::BayesNet)
     check(h, ccall((:sb_model_bayesnet, LIB), Int32,
                    (Handle, Int32, Int32, Ptr{UInt32}, Ptr{Float64}, Ptr{UInt32}, Ptr{Float64}, Int32, UInt32),
                    h, D, F, m.site_parents, rowmajor(m.site_cpt), m.fac_parents, rowmajor(m.fac_logf), stride, qmask))
+end
+function load!(h::Handle, m::OpsProgram)
+    check(h, ccall((:sb_model_ops, LIB), Int32, (Handle, Int32, Ptr{OpStep}, Ptr{Float64}, Int64),
+                   h, length(m.steps), m.steps, m.obs, length(m.obs)))
 end
 load!(::Handle, comp) = error("model is not a fixed-structure descriptor: general CPS programs are not " *
                               "supported on the GPU path and there is no CPU fallback")
