@@ -324,6 +324,11 @@ def run_ours(args):
         extras["parity_vs_single_gpu"] = parity_vs_single_gpu(sb, torch, dist, args, rank, world, local, gather_strings)
         extras["strong"] = strong_scaling(sb, torch, dist, args, rank, world, local, all_max)
     extras["mh_replicas"] = mh_replicas(sb, torch, dist, rank, world, local, all_max)
+    if world > 1 and args.workload == "hmm":
+        extras["pmcmc_sharded"] = pmcmc_sharded(sb, torch, dist, rank, world, local)
+    if world == 1 and rank == 0 and args.workload == "hmm" and not args.force_shard:
+        extras["cfg3_csmc"] = cfg3_csmc(sb, local)
+        extras["ops_program"] = ops_program(sb, local)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -426,6 +431,73 @@ def strong_scaling(sb, torch, dist, args, rank, world, local, all_max, log2_tota
     e.close()
     return {"scaling": "strong", "particles_total": 1 << log2_total, "particles_per_gpu": NL, "sweeps": sweeps,
             "ms_per_sweep": ms / sweeps, "value": (1 << log2_total) * args.T * sweeps / (ms * 1e-3), "unit": UNIT, "logZ_last": lz}
+
+
+def pmcmc_sharded(sb, torch, dist, rank, world, local, log2n=14, T=16, iters=2):
+    """Iterated conditional SMC on ONE pool sharded over the GPUs (src/pmcmc.jl:59-66, 83-94: retained particle in the last
+    entry of the last GPU, history rows sharded, backward pass with peer atomics) against sb_pmcmc_run on rank 0's GPU
+    alone: per-time counts and retained trajectory must be equal bit for bit.  Outside the timed region."""
+    NL = 1 << log2n
+    N = NL * world - 1
+    A, logF, pi = workload_tables(T)
+    eng = sb.Engine(device=local, precision="fp32", resample="systematic", seed=9)
+    eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+    eng.shard(NL, history_rows=T)
+    marg, _ = eng.pmcmc_counts(iters, N)
+    xs = eng.retained()
+    dist.barrier()
+    eng.close()
+    out = None
+    if rank == 0:
+        ref = sb.Engine(device=local, precision="fp32", resample="systematic", seed=9)
+        ref.load(sb.DiscreteHMM(A, logF, pi=pi))
+        marg_ref, _ = ref.pmcmc_counts(iters, N, want_joint=False)
+        xs_ref = ref.retained()
+        ref.close()
+        out = {"particles": N, "particles_per_gpu": NL, "T": T, "iterations": iters,
+               "counts_blake2b64_sharded": digest64(marg), "counts_blake2b64_single_gpu": digest64(marg_ref),
+               "counts_total": int(marg.sum()), "retained_equal": bool(np.array_equal(xs, xs_ref)),
+               "ok": bool(np.array_equal(marg, marg_ref) and np.array_equal(xs, xs_ref))}
+    dist.barrier()
+    return out
+
+
+def cfg3_csmc(sb, local, log2n=20, T=1000, iters=3):
+    """BASELINE cfg3 as written: K = 16, T = 1000, N = 2^20, conditional SMC with history (src/pmcmc.jl:78-99): particle-steps
+    per second of whole PMCMC iterations (sweep with ancestor rows + the backward pass that counts every particle's value
+    and extracts the next retained trajectory), device time.  20 B per particle-step (16 + the ancestor row)."""
+    N = 1 << log2n
+    A, logF, pi = workload_tables(T)
+    with sb.Engine(device=local, precision="fp32", resample="systematic", seed=1) as eng:
+        eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+        eng.pmcmc_counts(1, N, want_joint=False)                       # warm-up (allocations)
+        marg, _ = eng.pmcmc_counts(iters, N, want_joint=False)
+        st = eng.stats()
+    peak, _ = measured_peak()
+    us_step = st.device_ms * 1e3 / (iters * T)
+    return {"workload": "discrete HMM K=16 T=%d, N=2^%d, %d PMCMC iterations (conditional SMC with history + backward counting)" % (T, log2n, iters),
+            "value": iters * N * T / (st.device_ms * 1e-3), "unit": UNIT, "ms_per_iteration": st.device_ms / iters,
+            "us_per_step": us_step, "kernel_launches": int(st.kernel_launches),
+            "frac_of_hbm_peak_at_20B": N * 20 / (us_step * 1e-6) / 1e9 / peak,
+            "counts_total": int(marg.sum()), "counts_expected": iters * N * T, "logZ_first": st.logZ_first}
+
+
+def ops_program(sb, local, log2n=20):
+    """An op-list program inside the sweep (sb_model_ops): p = ~Beta(2, 3), then six observe(Bernoulli(p), y1, y2, y3)
+    statements -- log-evidence estimate against the conjugate closed form."""
+    import math
+    a, b = 2.0, 3.0
+    ys = (np.random.default_rng(3).random((6, 3)) < 0.35).astype(float)
+    steps = [((("beta", a, b) if t == 0 else ("keep",)), ("bernoulli", 1.0, 0.0, list(ys[t]))) for t in range(len(ys))]
+    s, f = ys.sum(), ys.size - ys.sum()
+    lb = lambda x, y: math.lgamma(x) + math.lgamma(y) - math.lgamma(x + y)
+    with sb.Engine(device=local, precision="fp64", seed=1) as eng:
+        eng.load(sb.OpsProgram(steps))
+        eng.smc_sweep(1 << log2n)
+        lz = eng.smc_sweep(1 << log2n, it=1)
+        st = eng.stats()
+    return {"workload": "p ~ Beta(2,3); 6 x observe(Bernoulli(p), 3 observations), 2^%d particles, fp64" % log2n,
+            "logZ": lz, "logZ_exact": lb(a + s, b + f) - lb(a, b), "particle_steps_per_s": (1 << log2n) * len(ys) / (st.device_ms * 1e-3)}
 
 
 def mh_replicas(sb, torch, dist, rank, world, local, all_max, chains=65536, steps=10000):

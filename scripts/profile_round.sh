@@ -1,16 +1,29 @@
+#!/bin/bash
+# One gpurun call: the round's bench lines, launch list, ncu --set full captures of every hot kernel (reports stay in
+# /tmp on the GPU box -- gpurun_out/ carries back at most 64 MiB -- and come back as text summaries + gzipped source pages),
+# the five BASELINE configs at full size.     usage (on the box): bash scripts/profile_round.sh [tag]
 set -x
-cd $GRAFT_REPO_ROOT
+cd ${GRAFT_REPO_ROOT:-.}
+TAG=${1:-r2}
+P=/tmp/prof; mkdir -p $P gpurun_out
 NCU="ncu --set full --clock-control none --import-source on"
-timeout 300 python bench.py > gpurun_out/s4_bench.log 2> gpurun_out/s4_bench.err
-timeout 300 python bench.py --workload lg > gpurun_out/s4_bench_lg32.log 2>&1
-timeout 300 python bench.py --workload lg --precision fp64 > gpurun_out/s4_bench_lg64.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2.csv python bench.py --steps 2 --warmup 3 --T 40 > gpurun_out/ncu_launch_r2.log 2>&1
-timeout 300 $NCU -k regex:k_step_lg -s 20 -c 1 -o gpurun_out/prof_step_lg_r2 python bench.py --workload lg --steps 2 --warmup 3 --T 40 > gpurun_out/ncu_lg_r2.log 2>&1
-timeout 300 $NCU -k regex:k_mh_bnet -s 1 -c 1 -o gpurun_out/prof_mh_r2 python scripts/mh_case.py > gpurun_out/ncu_mh_r2.log 2>&1
-timeout 300 $NCU -k regex:k_tilescan -s 20 -c 1 -o gpurun_out/prof_tilescan_r2 python bench.py --steps 2 --warmup 3 --T 40 > gpurun_out/ncu_ts_r2.log 2>&1
-timeout 300 $NCU -k regex:k_sweep_hmm -s 1 -c 1 -o gpurun_out/prof_sweep_res_r2b python scripts/res_trace.py > gpurun_out/ncu_res_r2b.log 2>&1
-timeout 300 $NCU -k regex:k_count_back_all -s 1 -c 1 -o gpurun_out/prof_count_back_r2 python scripts/cfg3_split.py > gpurun_out/ncu_cb_r2.log 2>&1
-timeout 600 python scripts/run_configs.py > gpurun_out/configs_r2.log 2>&1
-timeout 60 python scripts/mh_case.py > gpurun_out/mh_case_r2.log 2>&1
-timeout 60 python scripts/cfg3_split.py > gpurun_out/cfg3_split_r2.log 2>&1
-ls -la gpurun_out/*r2* | tail -20
+cap() {   # cap <name> <kernel regex> <skip> <command...>
+  local name=$1 re=$2 skip=$3; shift 3
+  timeout 300 $NCU -k regex:$re -s $skip -c 1 -o $P/$name "$@" > gpurun_out/ncu_${name}.log 2>&1
+  python scripts/ncu_summary.py full $P/$name.ncu-rep > gpurun_out/${name}_summary.txt 2>&1
+  ncu -i $P/$name.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/${name}_source.csv.gz
+}
+timeout 300 python bench.py > gpurun_out/${TAG}_bench.log 2> gpurun_out/${TAG}_bench.err
+timeout 300 python bench.py --workload lg > gpurun_out/${TAG}_bench_lg32.log 2>&1
+timeout 300 python bench.py --workload lg --precision fp64 > gpurun_out/${TAG}_bench_lg64.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --T 40 > gpurun_out/ncu_launch_${TAG}.log 2>&1
+cap ${TAG}_step_hmm k_step_hmm 20 python bench.py --steps 2 --warmup 3 --T 40
+cap ${TAG}_step_lg k_step_lg 20 python bench.py --workload lg --steps 2 --warmup 3 --T 40
+cap ${TAG}_mh k_mh_bnet 1 python scripts/mh_case.py
+cap ${TAG}_tilescan k_tilescan 20 python bench.py --steps 2 --warmup 3 --T 40
+cap ${TAG}_sweep_resident k_sweep_hmm 1 python scripts/res_trace.py
+cap ${TAG}_count_back k_count_back_all 1 python scripts/cfg3_split.py
+timeout 600 python scripts/run_configs.py > gpurun_out/${TAG}_configs.log 2>&1
+timeout 60 python scripts/mh_case.py > gpurun_out/${TAG}_mh_case.log 2>&1
+timeout 60 python scripts/cfg3_split.py > gpurun_out/${TAG}_cfg3_split.log 2>&1
+du -sh gpurun_out; ls -la gpurun_out | tail -40

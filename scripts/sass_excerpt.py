@@ -17,7 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "stochy.jl_b200", "libstochy_b200.so")
-WATCH = ["UBLKCP", "UBLKPF", "SYNCS", "LDGSTS", "UCGABAR", "REDUX", "BAR", "MEMBAR", "ERRBAR", "ATOMG", "ATOMS", "RED",
+WATCH = ["UBLKCP", "UBLKPF", "SYNCS", "LDGSTS", "UCGABAR", "CGAERRBAR", "ACQBULK", "REDUX", "BAR", "MEMBAR", "ERRBAR", "ATOMG", "ATOMS", "RED",
          "SHFL", "VOTE", "IMAD", "DFMA", "MUFU", "HMMA", "UTCMMA", "STG", "LDG", "LDS", "STS"]
 
 
@@ -37,7 +37,9 @@ def main():
         if m and kern:
             op = m.group(1)
             total[kern] += 1
-            counts[kern][op] += 1
+            for w in WATCH:                                      # UCGABAR_ARV / UCGABAR_WAIT count as UCGABAR
+                if op == w or op.startswith(w + "_"):
+                    counts[kern][w] += 1
     print("# SASS mnemonic counts per kernel of libstochy_b200.so (%s; static instruction counts)" % arch)
     print("# %-78s %6s  %s" % ("kernel", "instr", "  ".join(WATCH[:10])))
     for k in sorted(counts, key=lambda k: -total[k]):

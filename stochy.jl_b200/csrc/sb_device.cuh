@@ -381,7 +381,7 @@ __device__ __forceinline__ void sb_split_wait() {
 // Grid-wide barrier of a cooperative launch (all CTAs resident): one release-add per CTA on a counter that only ever
 // grows, one thread per CTA spinning on an acquire-load until the counter reaches `target` = (count before the
 // launch) + (barriers so far + 1) * gridDim.x -- the host hands out the base, so nothing is reset between launches.
-// Measured against cooperative_groups' grid.sync() at 513 CTAs: see profiles/r02_notes.md.
+// (The library's own rather than cooperative_groups' grid.sync() so that it can be split into arrive / wait: sb_grid_arrive.)
 __device__ __forceinline__ void sb_grid_barrier(unsigned* counter, unsigned target) {
     __syncthreads();
     if (threadIdx.x == 0) {
