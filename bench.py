@@ -323,11 +323,21 @@ def run_ours(args):
     if world > 1:
         extras["parity_vs_single_gpu"] = parity_vs_single_gpu(sb, torch, dist, args, rank, world, local, gather_strings)
         extras["strong"] = strong_scaling(sb, torch, dist, args, rank, world, local, all_max)
+        if args.workload == "hmm":                  # BASELINE cfg4 as written: linear-Gaussian, 2^24 particles IN TOTAL, Kalman-checked
+            a4 = argparse.Namespace(**vars(args))
+            a4.workload, a4.T, a4.precision = "lg", 500, "fp32"
+            blk = strong_scaling(sb, torch, dist, a4, rank, world, local, all_max, sweeps=2)
+            blk["workload"] = "linear-Gaussian state space (BASELINE cfg4), T=500, fp32, 2^24 particles in total over the GPUs"
+            if rank == 0:
+                blk["logZ_kalman"] = exact_log_evidence(sb, a4, local)
+                blk["abs_err_vs_kalman"] = abs(blk["logZ_last"] - blk["logZ_kalman"])
+            extras["strong_cfg4_lg"] = blk
     extras["mh_replicas"] = mh_replicas(sb, torch, dist, rank, world, local, all_max)
     if world > 1 and args.workload == "hmm":
         extras["pmcmc_sharded"] = pmcmc_sharded(sb, torch, dist, rank, world, local)
     if world == 1 and rank == 0 and args.workload == "hmm" and not args.force_shard:
         extras["cfg3_csmc"] = cfg3_csmc(sb, local)
+        extras["cfg4_lg"] = cfg4_lg(sb, args, local)
         extras["ops_program"] = ops_program(sb, local)
 
     if rank == 0:
@@ -480,6 +490,24 @@ def cfg3_csmc(sb, local, log2n=20, T=1000, iters=3):
             "us_per_step": us_step, "kernel_launches": int(st.kernel_launches),
             "frac_of_hbm_peak_at_20B": N * 20 / (us_step * 1e-6) / 1e9 / peak,
             "counts_total": int(marg.sum()), "counts_expected": iters * N * T, "logZ_first": st.logZ_first}
+
+
+def cfg4_lg(sb, args, local, sweeps=2):
+    """BASELINE cfg4 on one GPU: linear-Gaussian state space, T = 500, 2^24 particles, fp32, plain SMC with systematic
+    resampling at every step; log-evidence against the Kalman filter."""
+    a4 = argparse.Namespace(**vars(args))
+    a4.workload, a4.T, a4.precision = "lg", 500, "fp32"
+    N = 1 << 24
+    with sb.Engine(device=local, precision="fp32", resample="systematic", seed=1) as eng:
+        eng.load(make_model(sb, a4))
+        eng.smc_sweep(N, it=0)
+        eng.timer_start()
+        for i in range(sweeps):
+            lz = eng.smc_sweep(N, it=1 + i)
+        ms = eng.timer_stop()
+    exact = exact_log_evidence(sb, a4, local)
+    return {"workload": "linear-Gaussian state space (BASELINE cfg4), T=500, fp32, 2^24 particles", "value": N * 500 * sweeps / (ms * 1e-3),
+            "unit": UNIT, "ms_per_sweep": ms / sweeps, "logZ_last": lz, "logZ_kalman": exact, "abs_err_vs_kalman": abs(lz - exact)}
 
 
 def ops_program(sb, local, log2n=20):
