@@ -120,6 +120,9 @@ int32_t sb_model_linear_gaussian(sb_handle* h, int32_t T, double a, double q, do
  * Distributions.jl distribution is an ERP there; these are the ones of the north star: flip, gaussian, beta, gamma,
  * uniform; poisson as a second observation family).  Replaces sample(...)/factor(...) of src/pmcmc.jl:32-46 for such
  * programs, e.g.  p = ~Beta(a, b); observe(Bernoulli(p), ys_1...); observe(Bernoulli(p), ys_2...); ...
+ * A program is either scalar (all steps draw / keep ONE real latent) or a Dirichlet program: a latent VECTOR theta of
+ * D <= 8 components drawn by SB_DRAW_DIRICHLET, kept by SB_DRAW_KEEP, scored by SB_SCORE_CATEGORICAL / SB_SCORE_ZERO
+ * (theta = ~Dir(alpha); observe(Categorical(theta), ys...); ...); sb_get_particles then returns D planes of `count`.
  * Computed in fp64 whatever the handle's precision.  Rejection samplers (Beta, Gamma: Marsaglia-Tsang) draw from the
  * particle's own Philox counter stream (particle, draw number, step, iteration). */
 #define SB_DRAW_KEEP      0   /* x_t = x_{t-1} (a statement-free step of the program between two observe calls) */
@@ -128,14 +131,18 @@ int32_t sb_model_linear_gaussian(sb_handle* h, int32_t T, double a, double q, do
 #define SB_DRAW_GAMMA     3   /* x_t ~ Gamma(shape dp[0], scale dp[1]) */
 #define SB_DRAW_UNIFORM   4   /* x_t ~ Uniform(dp[0], dp[1]) */
 #define SB_DRAW_FLIP      5   /* x_t = flip(dp[0] x_{t-1} + dp[1]) as 0.0 / 1.0 */
+#define SB_DRAW_DIRICHLET 6   /* VECTOR latent: theta_t ~ Dirichlet(par[par_off .. par_off + par_n)), 2 <= par_n <= 8 components */
 #define SB_SCORE_ZERO      0  /* factor(0.0): the step still resamples */
 #define SB_SCORE_NORMAL    1  /* observe(Normal(sp[0] x_t + sp[1], sp[2]), ys...) */
 #define SB_SCORE_BERNOULLI 2  /* observe(Bernoulli(sp[0] x_t + sp[1]), ys...), ys in {0, 1} */
 #define SB_SCORE_POISSON   3  /* observe(Poisson(sp[0] x_t + sp[1]), ys...), ys non-negative integers */
+#define SB_SCORE_CATEGORICAL 4 /* VECTOR latent: observe(Categorical(theta_t), ys...), ys in 1..D (1-based as the reference's randominteger) */
+#define SB_OPS_MAXD 8
 typedef struct sb_op_step {
     int32_t draw, score;
     double  dp[4], sp[4];
     int32_t obs_off, obs_n;   /* this step's observations: obs[obs_off .. obs_off + obs_n) */
+    int32_t par_off, par_n;   /* vector-valued parameters of the draw (Dirichlet's alpha): obs[par_off .. par_off + par_n) */
 } sb_op_step;
 int32_t sb_model_ops(sb_handle* h, int32_t T, const sb_op_step* steps, const double* obs, int64_t n_obs);
 

@@ -104,13 +104,14 @@ struct OpStep
     draw::Int32; score::Int32          # SB_DRAW_* / SB_SCORE_* codes
     dp::NTuple{4,Float64}; sp::NTuple{4,Float64}
     obs_off::Int32; obs_n::Int32
+    par_off::Int32; par_n::Int32       # Dirichlet's alpha: obs[par_off+1 : par_off+par_n]
 end
 struct OpsProgram <: Model
     steps::Vector{OpStep}
     obs::Vector{Float64}
 end
 # e.g. p = ~Beta(2, 3); observe(Bernoulli(p), ys...):
-#   OpsProgram([OpStep(2, 2, (2., 3., 0., 0.), (1., 0., 0., 0.), 0, length(ys))], Float64.(ys))
+#   OpsProgram([OpStep(2, 2, (2., 3., 0., 0.), (1., 0., 0., 0.), 0, length(ys), 0, 0)], Float64.(ys))
 # smc_logevidence(prog, n) then returns the log-evidence estimate of one sweep.
 
 # Row-major tables cross the ABI; Julia matrices are column-major.

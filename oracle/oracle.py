@@ -226,11 +226,11 @@ def lg_step(m, o, N, t, it, x_prev_gathered):
 
 class OrOpStep(C.Structure):
     _fields_ = [("draw", C.c_int32), ("score", C.c_int32), ("dp", C.c_double * 4), ("sp", C.c_double * 4),
-                ("obs_off", C.c_int32), ("obs_n", C.c_int32)]
+                ("obs_off", C.c_int32), ("obs_n", C.c_int32), ("par_off", C.c_int32), ("par_n", C.c_int32)]
 
 
 class OrOps(C.Structure):
-    _fields_ = [("T", C.c_int32), ("steps", C.c_void_p), ("obs", C.c_void_p)]
+    _fields_ = [("T", C.c_int32), ("D", C.c_int32), ("steps", C.c_void_p), ("obs", C.c_void_p)]
 
 
 class Ops:
@@ -240,33 +240,40 @@ class Ops:
         self.T = len(steps)
         self.steps = (OrOpStep * self.T)()
         obs = []
+        self.D = 1
         for t, (draw, dp, score, sp, ys) in enumerate(steps):
             st = self.steps[t]
             st.draw, st.score = int(draw), int(score)
-            for i, v in enumerate(dp):
-                st.dp[i] = float(v)
+            if int(draw) == 6:                                    # Dirichlet: dp = alpha (vector parameter, parked in obs[])
+                st.par_off, st.par_n = len(obs), len(dp)
+                obs.extend(float(v) for v in dp)
+                self.D = max(self.D, len(dp))
+            else:
+                for i, v in enumerate(dp):
+                    st.dp[i] = float(v)
             for i, v in enumerate(sp):
                 st.sp[i] = float(v)
             st.obs_off, st.obs_n = len(obs), len(ys)
             obs.extend(float(y) for y in ys)
         self.obs = np.ascontiguousarray(obs if obs else [0.0], dtype=np.float64)
-        self.c = OrOps(self.T, C.cast(self.steps, C.c_void_p), _p(self.obs))
+        self.c = OrOps(self.T, self.D, C.cast(self.steps, C.c_void_p), _p(self.obs))
 
 
 def ops_sweep(m, o, N, it=0):
-    x = np.empty(N, dtype=np.float64)
+    x = np.empty(N * m.D, dtype=np.float64)
     lw = np.empty(N, dtype=np.float64)
     lz = C.c_double(0)
     _chk(lib().or_ops_sweep(C.byref(m.c), C.byref(o), N, it, _p(x), C.byref(lz), _p(lw)))
-    return dict(x=x, lw=lw, logZ=lz.value)
+    return dict(x=x if m.D == 1 else x.reshape(m.D, N), lw=lw, logZ=lz.value)
 
 
 def ops_step(m, o, N, t, it, x_prev_gathered):
-    xp = np.ascontiguousarray(x_prev_gathered, dtype=np.float64) if x_prev_gathered is not None else np.zeros(N)
-    x = np.empty(N, dtype=np.float64)
+    """x_prev_gathered: [N] (scalar programs) or [D, N] planes (Dirichlet programs); returns x of the same shape"""
+    xp = np.ascontiguousarray(x_prev_gathered, dtype=np.float64) if x_prev_gathered is not None else np.zeros(N * m.D)
+    x = np.empty(N * m.D, dtype=np.float64)
     lw = np.empty(N, dtype=np.float64)
     lib().or_ops_step(C.byref(m.c), C.byref(o), N, t, it, _p(xp), _p(x), _p(lw))
-    return x, lw
+    return (x if m.D == 1 else x.reshape(m.D, N)), lw
 
 
 class Bnet:

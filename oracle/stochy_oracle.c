@@ -703,6 +703,29 @@ static inline double lp_poisson(double lam, double y) { return (y * log(lam) - l
 void or_ops_step(const or_ops* m, const or_opts* o, int64_t N, uint32_t t, uint32_t iter,
                  const double* xpg, double* x_out, double* lw_out) {
     const or_op_step* s = &m->steps[t];
+    const int D = m->D;
+    if (D > 1) {
+        /* Dirichlet program: theta = ~Dir(alpha) (K gammas normalised), kept by later steps,
+         * observe(Categorical(theta), ys...) = factor(sum of log theta[y]) (src/Stochy.jl:55-56) */
+        #pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < N; ++i) {
+            ops_rng g = {o->seed, (uint64_t)i, t, iter, 0u};
+            double th[8];
+            if (s->draw == 6) {
+                double sum = 0.0;
+                for (int d = 0; d < D; ++d) { th[d] = ops_gamma(&g, m->obs[s->par_off + d]); sum += th[d]; }
+                for (int d = 0; d < D; ++d) th[d] /= sum;
+            } else {
+                for (int d = 0; d < D; ++d) th[d] = (t == 0 || !xpg) ? 0.0 : xpg[(size_t)d * N + i];
+            }
+            double lw = 0.0;
+            if (s->score == 4)
+                for (int k = 0; k < s->obs_n; ++k) lw += log(th[(int)m->obs[s->obs_off + k] - 1]);
+            for (int d = 0; d < D; ++d) x_out[(size_t)d * N + i] = th[d];
+            lw_out[i] = lw;
+        }
+        return;
+    }
     #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < N; ++i) {
         ops_rng g = {o->seed, (uint64_t)i, t, iter, 0u};
@@ -731,8 +754,9 @@ void or_ops_step(const or_ops* m, const or_opts* o, int64_t N, uint32_t t, uint3
 
 int or_ops_sweep(const or_ops* m, const or_opts* o, int64_t N, uint32_t iter,
                  double* x_last, double* logZ, double* lw_last) {
-    double* x = (double*)malloc(sizeof(double) * (size_t)N);
-    double* xg = (double*)malloc(sizeof(double) * (size_t)N);
+    const size_t D = (size_t)m->D;
+    double* x = (double*)malloc(sizeof(double) * (size_t)N * D);
+    double* xg = (double*)malloc(sizeof(double) * (size_t)N * D);
     double* lw = (double*)malloc(sizeof(double) * (size_t)N);
     int64_t* anc = (int64_t*)malloc(sizeof(int64_t) * (size_t)N);
     double lz = 0.0; int rc = OR_OK;
@@ -740,7 +764,8 @@ int or_ops_sweep(const or_ops* m, const or_opts* o, int64_t N, uint32_t iter,
     for (int t = 0; t < m->T; ++t) {
         if (t) {
             #pragma omp parallel for schedule(static)
-            for (int64_t i = 0; i < N; ++i) xg[i] = x[anc[i]];       /* pmcmc.jl:51 deepcopy(particles[a]) */
+            for (int64_t i = 0; i < N; ++i)                          /* pmcmc.jl:51 deepcopy(particles[a]) */
+                for (size_t d = 0; d < D; ++d) xg[d * (size_t)N + i] = x[d * (size_t)N + anc[i]];
         }
         or_ops_step(m, &o64, N, (uint32_t)t, iter, xg, x, lw);
         double lm;
@@ -749,7 +774,7 @@ int or_ops_sweep(const or_ops* m, const or_opts* o, int64_t N, uint32_t iter,
         lz += lm;
     }
     if (rc == OR_OK) {
-        if (x_last) memcpy(x_last, x, sizeof(double) * (size_t)N);
+        if (x_last) memcpy(x_last, x, sizeof(double) * (size_t)N * D);
         if (lw_last) memcpy(lw_last, lw, sizeof(double) * (size_t)N);
         if (logZ) *logZ = lz;
     }

@@ -134,9 +134,11 @@ typedef struct {
     int32_t draw, score;
     double  dp[4], sp[4];
     int32_t obs_off, obs_n;
+    int32_t par_off, par_n;   /* Dirichlet's alpha: obs[par_off .. par_off + par_n) */
 } or_op_step;
 typedef struct {
     int32_t T;
+    int32_t D;                /* latent dimension: 1 (scalar programs) or the Dirichlet's (<= 8); x arrays are D planes of N */
     const or_op_step* steps;  /* [T] */
     const double* obs;
 } or_ops;

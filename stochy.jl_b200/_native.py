@@ -44,7 +44,7 @@ class Options(C.Structure):
 
 class OpStep(C.Structure):
     _fields_ = [("draw", C.c_int32), ("score", C.c_int32), ("dp", C.c_double * 4), ("sp", C.c_double * 4),
-                ("obs_off", C.c_int32), ("obs_n", C.c_int32)]
+                ("obs_off", C.c_int32), ("obs_n", C.c_int32), ("par_off", C.c_int32), ("par_n", C.c_int32)]
 
 
 class Stats(C.Structure):

@@ -151,23 +151,31 @@ class OpsProgram:
     `(draw, score)` where
       draw  = ("normal", a, b, sd)   x ~ Normal(a x_prev + b, sd)         | ("beta", a, b) | ("gamma", shape, scale)
               | ("uniform", lo, hi) | ("flip", a, b)  x = flip(a x_prev + b) | ("keep",)
+              | ("dirichlet", alpha_1, ..., alpha_D)  VECTOR latent theta ~ Dirichlet(alpha), D <= 8
       score = ("normal", c, d, sd, ys)  observe(Normal(c x + d, sd), ys...) | ("bernoulli", c, d, ys)
               | ("poisson", c, d, ys) | ("zero",)  factor(0.0)
+              | ("categorical", ys)  observe(Categorical(theta), ys...), ys in 1..D (vector latent)
     -- sample / observe of src/pmcmc.jl:32-46 and src/Stochy.jl:55-56 for programs such as
        p = ~Beta(2, 3); observe(Bernoulli(p), true, false, true); observe(Bernoulli(p), false, ...)."""
-    DRAWS = {"keep": 0, "normal": 1, "beta": 2, "gamma": 3, "uniform": 4, "flip": 5}
-    SCORES = {"zero": 0, "normal": 1, "bernoulli": 2, "poisson": 3}
+    DRAWS = {"keep": 0, "normal": 1, "beta": 2, "gamma": 3, "uniform": 4, "flip": 5, "dirichlet": 6}
+    SCORES = {"zero": 0, "normal": 1, "bernoulli": 2, "poisson": 3, "categorical": 4}
 
     def __init__(self, steps):
         self.T = len(steps)
         self.K = 0
+        self.D = 1
         self.steps = (nat.OpStep * self.T)()
         obs = []
         for t, (draw, score) in enumerate(steps):
             st = self.steps[t]
             st.draw = self.DRAWS[draw[0]]
-            for i, v in enumerate(draw[1:]):
-                st.dp[i] = float(v)
+            if draw[0] == "dirichlet":                            # vector parameter: parked in the observation array
+                st.par_off, st.par_n = len(obs), len(draw) - 1
+                obs.extend(float(v) for v in draw[1:])
+                self.D = max(self.D, len(draw) - 1)
+            else:
+                for i, v in enumerate(draw[1:]):
+                    st.dp[i] = float(v)
             st.score = self.SCORES[score[0]]
             ys = []
             if score[0] != "zero":
@@ -492,11 +500,12 @@ class Engine:
         """Final particle states of the last sweep.  out: optional destination array (e.g. page-locked memory,
         which the device-to-host copy then reaches at full link speed)."""
         dt = np.int32 if isinstance(self.model, DiscreteHMM) else np.float64
-        x = np.empty(count, dtype=dt) if out is None else out
-        if x.dtype != dt or x.size < count or not x.flags["C_CONTIGUOUS"]:
-            raise StochyError(nat.EINVAL, "particles: out must be a contiguous %s array of at least %d entries" % (np.dtype(dt).name, count))
+        D = getattr(self.model, "D", 1)                             # Dirichlet programs: D planes of `count` (shape [D, count])
+        x = np.empty(count * D, dtype=dt) if out is None else out
+        if x.dtype != dt or x.size < count * D or not x.flags["C_CONTIGUOUS"]:
+            raise StochyError(nat.EINVAL, "particles: out must be a contiguous %s array of at least %d entries" % (np.dtype(dt).name, count * D))
         self._chk(nat.lib().sb_get_particles(self.h, count, _ptr(x)))
-        return x
+        return x if D == 1 or out is not None else x.reshape(D, count)
 
 
 # ------------------------------------------------------------------ the reference's entry points

@@ -946,6 +946,8 @@ struct SbLgStepArgs {
     sb_op_step op;
     const double* obs;          // [n_obs] observations
     const double* obs_aux;      // [n_obs] lgamma(y + 1) (Poisson), computed on the host
+    int xdim;                   // latent dimension: 1, or D of a Dirichlet program (x arrays are D planes of xplane doubles)
+    long long xplane;
 };
 
 // Sequential draws of ONE particle at one step of an op-list program: Philox counter (particle | draw pair << 32,
@@ -1018,6 +1020,32 @@ __device__ __forceinline__ void sb_ops_particle(const sb_op_step& op, const doub
 
 #define SB_TWO_PI 6.283185307179586476925286766559
 
+// one particle of a Dirichlet program (vector latent theta of D components, D planes in memory): theta = ~Dir(alpha)
+// as D gammas normalised (src/erp.jl:18 `Dir`), or kept from the parent; observe(Categorical(theta), ys...) adds
+// log theta[y] per observation, in order.  The D logs are taken once and parked in local memory.
+__device__ __forceinline__ void sb_ops_particle_vec(const sb_op_step& op, const double* __restrict__ obs, int D, SbOpsRng& g,
+                                                    const double* __restrict__ xprev_plane0, long long plane, bool has_parent,
+                                                    double* __restrict__ xout_plane0, double* lw_out) {
+    double th[SB_OPS_MAXD];
+    if (op.draw == SB_DRAW_DIRICHLET) {
+        double sum = 0.0;
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) { th[d] = g.gamma(__ldg(obs + op.par_off + d)); sum += th[d]; }
+        for (int d = 0; d < D; ++d) th[d] /= sum;
+    } else {
+        for (int d = 0; d < D; ++d) th[d] = has_parent ? __ldg(xprev_plane0 + (size_t)d * plane) : 0.0;
+    }
+    double lw = 0.0;
+    if (op.score == SB_SCORE_CATEGORICAL) {
+        double lg[SB_OPS_MAXD];
+        for (int d = 0; d < D; ++d) lg[d] = log(th[d]);
+        const double* y = obs + op.obs_off;
+        for (int i = 0; i < op.obs_n; ++i) lw += lg[(int)__ldg(y + i) - 1];
+    }
+    for (int d = 0; d < D; ++d) xout_plane0[(size_t)d * plane] = th[d];
+    *lw_out = lw;
+}
+
 template <int ANC, bool FP32, bool PEERS, bool OPS = false>
 __global__ void __launch_bounds__(SB_THREADS, FP32 ? 5 : 3)       // fp32: 48 registers (5 CTAs per SM); fp64: 80 (3)
 k_step_lg(const __grid_constant__ SbLgStepArgs a) {
@@ -1066,7 +1094,11 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         if (ANC != SB_ANC_PULL) __syncthreads();                 // the pull has its own barrier
         if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
         REAL xpar[SB_ITEMS];
-        if (PEERS && base + SB_ITEMS <= N && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
+        const bool vec = OPS && a.xdim > 1;                       // Dirichlet program: the parents' planes are read per particle below
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) xpar[j] = (REAL)0;
+        } else if (PEERS && base + SB_ITEMS <= N && (anc[0] >> a.pool.log2n) == (anc[SB_ITEMS - 1] >> a.pool.log2n)) {
             const int g = anc[0] >> a.pool.log2n;               // ascending parents: all eight on GPU g
             const REAL* xg = reinterpret_cast<const REAL*>(a.pool.base[g] + a.pool.off_x);
             const unsigned lmask = (1u << a.pool.log2n) - 1u;
@@ -1124,7 +1156,9 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                 double xv = 0.0, lw = 0.0;
                 if (live) {
                     SbOpsRng g{a.rk, (unsigned long long)(base + j), (unsigned)a.t, a.iter, 0u};
-                    sb_ops_particle(a.op, a.obs, a.obs_aux, g, (double)xpar[j], &xv, &lw);
+                    if (vec) sb_ops_particle_vec(a.op, a.obs, a.xdim, g, reinterpret_cast<const double*>(a.pool.x) + anc[j], a.xplane, ANC != SB_ANC_NONE,
+                                                 reinterpret_cast<double*>(a.x_out) + lbase + j, &lw);
+                    else sb_ops_particle(a.op, a.obs, a.obs_aux, g, (double)xpar[j], &xv, &lw);
                 }
                 double v = live ? __dmul_rn(lw, SB_LOG2E_D) : -INFINITY;
                 if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }
@@ -1204,7 +1238,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         if (FP32) {
             reinterpret_cast<float4*>(xo)[0] = make_float4((float)x[0], (float)x[1], (float)x[2], (float)x[3]);
             reinterpret_cast<float4*>(xo)[1] = make_float4((float)x[4], (float)x[5], (float)x[6], (float)x[7]);
-        } else {
+        } else if (!vec) {                                        // (a Dirichlet program has stored its D planes already)
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; j += 2) reinterpret_cast<double2*>(xo)[j / 2] = make_double2((double)x[j], (double)x[j + 1]);
         }

@@ -99,6 +99,7 @@ struct sb_handle {
     std::vector<double> lg_y;
     // OPS (op-list program, sb_model_ops)
     std::vector<sb_op_step> ops;
+    int ops_D = 1;                    // latent dimension (Dirichlet programs: > 1)
     DevBuf ops_obs, ops_aux;
     // BNET
     int bn_D = 0, bn_F = 0, bn_stride = 0;
@@ -721,10 +722,25 @@ extern "C" int32_t sb_model_ops(sb_handle* h, int32_t T, const sb_op_step* steps
     if (!h) return SB_EINVAL;
     if (!steps || T < 1 || n_obs < 0 || (n_obs > 0 && !obs)) return fail(h, SB_EINVAL, "ops: bad arguments");
     CK(cudaSetDevice(h->opt.device));
+    int D = 1;
+    for (int t = 0; t < T; ++t)
+        if (steps[t].draw == SB_DRAW_DIRICHLET) {
+            const sb_op_step& s = steps[t];
+            if (s.par_n < 2 || s.par_n > SB_OPS_MAXD) return fail(h, SB_EUNSUPPORTED, "ops: a Dirichlet latent has 2..8 components on the GPU path (no CPU fallback)");
+            if (s.par_off < 0 || (int64_t)s.par_off + s.par_n > n_obs) return fail(h, SB_EINVAL, "ops: Dirichlet parameters outside obs[]");
+            if (D > 1 && s.par_n != D) return fail(h, SB_EINVAL, "ops: every Dirichlet statement of a program must have the same dimension");
+            for (int d = 0; d < s.par_n; ++d) if (!(obs[s.par_off + d] > 0)) return fail(h, SB_EINVAL, "ops: distribution parameter out of range");
+            D = s.par_n;
+        }
+    if (D > 1 && h->dist_ready) return fail(h, SB_EUNSUPPORTED, "ops: vector latents are not supported on sharded pools");
     for (int t = 0; t < T; ++t) {
         const sb_op_step& s = steps[t];
-        if (s.draw < SB_DRAW_KEEP || s.draw > SB_DRAW_FLIP || s.score < SB_SCORE_ZERO || s.score > SB_SCORE_POISSON)
+        if (s.draw < SB_DRAW_KEEP || s.draw > SB_DRAW_DIRICHLET || s.score < SB_SCORE_ZERO || s.score > SB_SCORE_CATEGORICAL)
             return fail(h, SB_EUNSUPPORTED, "ops: unknown draw / score statement (no CPU fallback)");
+        if (D > 1 && ((s.draw != SB_DRAW_DIRICHLET && s.draw != SB_DRAW_KEEP) || (s.score != SB_SCORE_CATEGORICAL && s.score != SB_SCORE_ZERO)))
+            return fail(h, SB_EUNSUPPORTED, "ops: a Dirichlet program draws / keeps the vector latent and observes Categorical(theta) only");
+        if (D == 1 && s.score == SB_SCORE_CATEGORICAL)
+            return fail(h, SB_EUNSUPPORTED, "ops: observe(Categorical(theta), ...) needs a Dirichlet latent");
         if (t == 0 && s.draw == SB_DRAW_KEEP) return fail(h, SB_EINVAL, "ops: the first step must draw the latent");
         if (s.obs_n < 0 || s.obs_off < 0 || (int64_t)s.obs_off + s.obs_n > n_obs) return fail(h, SB_EINVAL, "ops: observation range outside obs[]");
         bool ok = true;
@@ -742,6 +758,7 @@ extern "C" int32_t sb_model_ops(sb_handle* h, int32_t T, const sb_op_step* steps
             if (std::isnan(y)) return fail(h, SB_ENAN, "ops: NaN observation");
             if (s.score == SB_SCORE_BERNOULLI && y != 0.0 && y != 1.0) return fail(h, SB_EINVAL, "ops: Bernoulli observations must be 0 or 1");
             if (s.score == SB_SCORE_POISSON && (y < 0.0 || y != floor(y))) return fail(h, SB_EINVAL, "ops: Poisson observations must be non-negative integers");
+            if (s.score == SB_SCORE_CATEGORICAL && (y < 1.0 || y > (double)D || y != floor(y))) return fail(h, SB_EINVAL, "ops: Categorical observations must be integers in 1..D");
         }
     }
     std::vector<double> aux((size_t)(n_obs > 0 ? n_obs : 1), 0.0);
@@ -754,6 +771,7 @@ extern "C" int32_t sb_model_ops(sb_handle* h, int32_t T, const sb_op_step* steps
         CK(cudaStreamSynchronize(h->stream));
     }
     h->ops.assign(steps, steps + T);
+    h->ops_D = D;
     h->model = MODEL_OPS; h->T = T; h->K = 0;
     h->have_retained = false;
     invalidate_sweep(h);
@@ -1138,9 +1156,11 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
     const bool ops = h->model == MODEL_OPS;                         // op-list program: same sweep, fp64, its own propagate + weight
     const bool fp32 = h->opt.precision == SB_FP32 && !ops;
     const bool dist = h->dist_ready;
-    const size_t sz = fp32 ? 4 : 8;
+    const int XD = ops ? h->ops_D : 1;                              // planes of the latent (Dirichlet programs: D)
+    const size_t sz = (fp32 ? 4 : 8) * (size_t)XD;                  // bytes per particle of one pool slot
     const int64_t S = dist ? h->NL : tiles_of(N) * SB_TILE;
     const int mode = h->opt.resample_mode;
+    if (XD > 1 && dist) return fail(h, SB_EUNSUPPORTED, "ops: vector latents are not supported on sharded pools");
     if (mode == SB_RESAMPLE_LITERAL)
         return fail(h, SB_EUNSUPPORTED, "literal resampling is a parity mode of the discrete model only");
     if (dist && (mode != SB_RESAMPLE_SYSTEMATIC || h->opt.store_logw))
@@ -1182,6 +1202,7 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.N = N; a.ntiles = ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed);
+        a.xdim = XD; a.xplane = S;
         if (ops) {
             a.op = h->ops[(size_t)t]; a.obs = h->ops_obs.as<double>(); a.obs_aux = h->ops_aux.as<double>();
         } else {
@@ -1890,6 +1911,13 @@ extern "C" int32_t sb_get_particles(sb_handle* h, int64_t count, void* x_out) {
         CK(cudaMemcpy(x_out, src, (size_t)count * 4, cudaMemcpyDeviceToHost));
     } else {
         const size_t sz = (h->opt.precision == SB_FP32 && h->model != MODEL_OPS) ? 4 : 8;
+        const int XD = h->model == MODEL_OPS ? h->ops_D : 1;
+        if (XD > 1) {                                                // Dirichlet program: D planes of `count` doubles
+            const char* src = h->xbuf.as<char>() + (size_t)h->sw_slot * h->sw_S * 8 * XD;
+            for (int d = 0; d < XD; ++d)
+                CK(cudaMemcpy((double*)x_out + (size_t)d * count, src + (size_t)d * h->sw_S * 8, (size_t)count * 8, cudaMemcpyDeviceToHost));
+            return SB_OK;
+        }
         std::vector<char> tmp((size_t)count * sz);
         const char* src = h->dist_ready ? (char*)h->arena + h->off_x[h->sw_slot] : h->xbuf.as<char>() + (size_t)h->sw_slot * h->sw_S * sz;
         CK(cudaMemcpy(tmp.data(), src, tmp.size(), cudaMemcpyDeviceToHost));

@@ -3,10 +3,10 @@ import math
 
 import numpy as np
 
-D_KEEP, D_NORMAL, D_BETA, D_GAMMA, D_UNIFORM, D_FLIP = range(6)
-S_ZERO, S_NORMAL, S_BERNOULLI, S_POISSON = range(4)
-_DN = ["keep", "normal", "beta", "gamma", "uniform", "flip"]
-_SN = ["zero", "normal", "bernoulli", "poisson"]
+D_KEEP, D_NORMAL, D_BETA, D_GAMMA, D_UNIFORM, D_FLIP, D_DIRICHLET = range(7)
+S_ZERO, S_NORMAL, S_BERNOULLI, S_POISSON, S_CATEGORICAL = range(5)
+_DN = ["keep", "normal", "beta", "gamma", "uniform", "flip", "dirichlet"]
+_SN = ["zero", "normal", "bernoulli", "poisson", "categorical"]
 
 
 def beta_bernoulli(a=2.0, b=3.0, batches=6, per=3, seed=3):
@@ -28,6 +28,21 @@ def gamma_poisson(k=3.0, theta=1.5, batches=5, per=2, seed=4):
     S, n = ys.sum(), ys.size
     ev = (math.lgamma(k + S) - math.lgamma(k) - sum(math.lgamma(y + 1.0) for y in ys.ravel())
           + S * math.log(theta) - (k + S) * math.log(1.0 + n * theta))
+    return steps, ev
+
+
+def dirichlet_categorical(alpha=(0.8, 1.5, 2.0, 0.6), batches=5, per=4, seed=5):
+    """theta = ~Dir(alpha); observe(Categorical(theta), ys...) per batch (ys 1-based).  Evidence: Dirichlet-multinomial
+    Gamma(a0) / Gamma(a0 + n) * prod_k Gamma(a_k + n_k) / Gamma(a_k)."""
+    rng = np.random.default_rng(seed)
+    D = len(alpha)
+    ys = rng.choice(D, size=(batches, per), p=[0.1, 0.5, 0.3, 0.1][:D]) + 1
+    steps = [(D_DIRICHLET if t == 0 else D_KEEP, tuple(alpha) if t == 0 else (), S_CATEGORICAL, (), [float(y) for y in ys[t]]) for t in range(batches)]
+    a0, n = sum(alpha), ys.size
+    ev = math.lgamma(a0) - math.lgamma(a0 + n)
+    for k in range(D):
+        nk = int((ys == k + 1).sum())
+        ev += math.lgamma(alpha[k] + nk) - math.lgamma(alpha[k])
     return steps, ev
 
 

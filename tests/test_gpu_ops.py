@@ -27,14 +27,15 @@ def _run(sb, steps, N, seed, it=0, store_logw=True, precision="fp64"):
     return lz, x, lw
 
 
-@pytest.mark.parametrize("prog", ["beta_bernoulli", "gamma_poisson", "mix", "lg"])
+@pytest.mark.parametrize("prog", ["beta_bernoulli", "gamma_poisson", "mix", "lg", "dirichlet"])
 def test_ops_stepwise_parity(oracle, prog):
     """Every step's draw + score equals the oracle's given the SAME parents (libm vs CUDA transcendental functions
     differ in the last ulps: states 1e-11, scores 1e-9 relative); ancestors bit-exact on the GPU's own log-weights
     (the parents the GPU used are recomputed by the oracle's systematic resampler from those weights)."""
     sb = sb_mod()
     steps = {"beta_bernoulli": lambda: ou.beta_bernoulli()[0], "gamma_poisson": lambda: ou.gamma_poisson()[0],
-             "mix": ou.uniform_flip_mix, "lg": lambda: ou.lg_as_ops(cfg4_data(T=5))}[prog]()
+             "mix": ou.uniform_flip_mix, "lg": lambda: ou.lg_as_ops(cfg4_data(T=5)),
+             "dirichlet": lambda: ou.dirichlet_categorical()[0]}[prog]()
     N, seed, it = 6000, 9, 2
     o = oracle.opts(oracle.SYSTEMATIC, seed=seed)
     m = oracle.Ops(steps)
@@ -46,7 +47,7 @@ def test_ops_stepwise_parity(oracle, prog):
         else:
             u = oracle.uniform53(seed, 0, T - 2, it, 1, 0)
             anc = oracle.resample_systematic(lw[T - 2], u, N, kind=1)
-            x_ref, lw_ref = oracle.ops_step(m, o, N, T - 1, it, x_prev[anc])
+            x_ref, lw_ref = oracle.ops_step(m, o, N, T - 1, it, x_prev[..., anc])
         assert np.allclose(x_gpu, x_ref, rtol=1e-11, atol=1e-11), (prog, T, np.abs(x_gpu - x_ref).max())
         assert np.allclose(lw[T - 1], lw_ref, rtol=1e-9, atol=1e-9), (prog, T, np.abs(lw[T - 1] - lw_ref).max())
         x_prev = x_gpu
@@ -54,7 +55,7 @@ def test_ops_stepwise_parity(oracle, prog):
     assert lz == pytest.approx(ref["logZ"], rel=1e-6, abs=1e-6)
 
 
-@pytest.mark.parametrize("prog", ["beta_bernoulli", "gamma_poisson"])
+@pytest.mark.parametrize("prog", ["beta_bernoulli", "gamma_poisson", "dirichlet_categorical"])
 def test_ops_evidence_closed_form(prog):
     """Beta-Bernoulli / Gamma-Poisson programs with several observations per observe statement: the log-evidence
     estimate agrees with the conjugate closed form within 4 standard errors over 16 seeds."""
@@ -108,6 +109,12 @@ def test_ops_errors():
             eng.load(sb.OpsProgram([(("beta", 1.0, 1.0), ("bernoulli", 1.0, 0.0, [2.0]))]))
         with pytest.raises(sb.StochyError):                      # the first statement must draw
             eng.load(sb.OpsProgram([(("keep",), ("zero",))]))
+        with pytest.raises(sb.StochyError):                      # Categorical observation outside 1..D
+            eng.load(sb.OpsProgram([(("dirichlet", 1.0, 1.0, 1.0), ("categorical", [4.0]))]))
+        with pytest.raises(sb.StochyError):                      # a scalar draw inside a Dirichlet program
+            eng.load(sb.OpsProgram([(("dirichlet", 1.0, 1.0), ("categorical", [1.0])), (("beta", 1.0, 1.0), ("zero",))]))
+        with pytest.raises(sb.StochyError):                      # more than 8 components
+            eng.load(sb.OpsProgram([(("dirichlet",) + (1.0,) * 9, ("zero",))]))
         # p outside (0, 1): log of a negative number -> the reference's NaN error
         eng.load(sb.OpsProgram([(("uniform", 0.0, 1.0), ("bernoulli", 3.0, 0.0, [1.0, 0.0]))]))
         with pytest.raises(sb.StochyError) as ei:

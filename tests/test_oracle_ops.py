@@ -28,6 +28,19 @@ def test_gamma_poisson_evidence(oracle):
     assert abs(mean - exact) < 4 * se + 1e-3, (mean, exact, se)
 
 
+def test_dirichlet_categorical_evidence(oracle):
+    steps, exact = ou.dirichlet_categorical()
+    mean, se = _mean_logZ(oracle, steps, 1 << 14, 12)
+    assert abs(mean - exact) < 4 * se + 1e-3, (mean, exact, se)
+    # the draw itself: rows on the simplex with the Dirichlet's means
+    x, lw = oracle.ops_step(oracle.Ops(steps), oracle.opts(oracle.SYSTEMATIC, seed=2), 100000, 0, 0, None)
+    a = np.array([0.8, 1.5, 2.0, 0.6])
+    assert x.shape == (4, 100000) and np.allclose(x.sum(axis=0), 1.0, atol=1e-12)
+    assert np.allclose(x.mean(axis=1), a / a.sum(), atol=5e-3)
+    ys = [int(y) for y in steps[0][4]]
+    assert np.allclose(lw, sum(np.log(x[y - 1]) for y in ys), rtol=1e-12, atol=1e-12)
+
+
 def test_lg_as_ops_vs_kalman(oracle, enumref):
     from gpu_util import cfg4_data
     d = cfg4_data(T=30)
