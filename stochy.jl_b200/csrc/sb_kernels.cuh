@@ -361,6 +361,49 @@ k_pull(const SbStepInfo* __restrict__ info, const __grid_constant__ SbPool pool,
     }
 }
 
+// The same as a PERSISTENT grid (pools of many tiles: the resampling hooks at bench size): every CTA walks its children
+// tiles with the step kernels' pipeline -- candidate tiles looked up per chunk, the next tile's weights (TMA) and records
+// (cp.async) requested while this tile's markers are filled, the next tile's boundary table built by one warp -- instead
+// of paying the ramp (mbarrier init, first copies, boundary table, three dependent round trips) once per tile.
+template <bool PEERS>
+__global__ void __launch_bounds__(SB_THREADS, 5)
+k_pull_persistent(const SbStepInfo* __restrict__ info, const __grid_constant__ SbPool pool, const int* __restrict__ e,
+                  const unsigned long long* __restrict__ Pt, const int* __restrict__ child_start,
+                  const int* __restrict__ first_tile, int* __restrict__ anc_out, int ntiles) {
+    __shared__ SbPullSmem ps;
+    const SbStepInfo si = *info;
+    const int tid = threadIdx.x;
+    if (tid == 0) sb_mbar_init(&ps.bar, 1);
+    __syncthreads();
+    int k = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++k) {
+        if ((k % SB_FT_CHUNK) == 0) sb_pull_ranges<PEERS>(si, pool, e, Pt, child_start, first_tile, tile, ntiles, k == 0, ps);
+        else __syncthreads();                                    // the previous tile's markers are read and reset, this tile's boundary table is built
+        const int kk = k % SB_FT_CHUNK;
+        const int2 rng = ps.ft[kk];
+        const bool more = tile + (int)gridDim.x < ntiles;
+        const int nb = ps.ft[kk + 1].x;
+        const int c0 = pool.c_off + tile * SB_TILE;              // global child index
+        int anc[SB_ITEMS];
+        if (si.s >= 32) sb_pull_ancestors<PEERS, true>(si, pool, e, Pt, child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, ps, anc);
+        else            sb_pull_ancestors<PEERS, false>(si, pool, e, Pt, child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, ps, anc);
+        if (more && (tid >> 5) == SB_META_WARP) {
+            const int c0n = c0 + (int)gridDim.x * SB_TILE;
+            if (si.s >= 32) sb_pull_seg<true>(si, c0n, ps.ft[kk + 1], (k + 1) & 1, ps);
+            else            sb_pull_seg<false>(si, c0n, ps.ft[kk + 1], (k + 1) & 1, ps);
+        }
+        const int base = c0 + tid * SB_ITEMS;
+        int* out = anc_out + (size_t)tile * SB_TILE + tid * SB_ITEMS;      // local children row
+        if (base + SB_ITEMS <= (int)si.m) {
+            reinterpret_cast<int4*>(out)[0] = make_int4(anc[0], anc[1], anc[2], anc[3]);
+            reinterpret_cast<int4*>(out)[1] = make_int4(anc[4], anc[5], anc[6], anc[7]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < SB_ITEMS; ++j) if (base + j < (int)si.m) out[j] = anc[j];
+        }
+    }
+}
+
 // =====================================================================================
 // Multinomial on the grid: materialise the integer CDF, then one upper_bound per draw.
 // Same semantics as src/rand.jl:2-13 (first i with r < acc_i, last index as fallback).

@@ -406,12 +406,29 @@ int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, const unsigned
 
 int launch_pull(sb_handle* h, int slot, const SbStepInfo* info, int64_t m_local, int* d_anc) {
     const SbPool pool = make_pool(h, slot, nullptr);
+    const int ntiles = (int)tiles_of(m_local);
+    // many tiles: the persistent grid with the step kernels' prefetch pipeline; few: one CTA per tile (no ramp to amortise)
+    int cap = 0;
+    if (ntiles >= 4 * h->num_sms) {
+        int rc = h->dist_ready ? resident_ctas(h, k_pull_persistent<true>, 0, &cap) : resident_ctas(h, k_pull_persistent<false>, 0, &cap);
+        if (rc != SB_OK) return rc;
+    }
+    if (cap > 0 && ntiles > cap) {
+        if (h->dist_ready)
+            k_pull_persistent<true><<<(unsigned)cap, SB_THREADS, 0, h->stream>>>(info, pool, TE_pull(h, slot), h->Pt.as<unsigned long long>(),
+                                                                                 h->child_start.as<int>(), h->first_tile.as<int>(), d_anc, ntiles);
+        else
+            k_pull_persistent<false><<<(unsigned)cap, SB_THREADS, 0, h->stream>>>(info, pool, TE_pull(h, slot), h->Pt.as<unsigned long long>(),
+                                                                                  h->child_start.as<int>(), h->first_tile.as<int>(), d_anc, ntiles);
+        LAUNCH_CHECK();
+        return SB_OK;
+    }
     if (h->dist_ready)
-        k_pull<true><<<(unsigned)tiles_of(m_local), SB_THREADS, 0, h->stream>>>(info, pool, TE_pull(h, slot), h->Pt.as<unsigned long long>(),
-                                                                              h->child_start.as<int>(), h->first_tile.as<int>(), d_anc);
+        k_pull<true><<<(unsigned)ntiles, SB_THREADS, 0, h->stream>>>(info, pool, TE_pull(h, slot), h->Pt.as<unsigned long long>(),
+                                                                    h->child_start.as<int>(), h->first_tile.as<int>(), d_anc);
     else
-        k_pull<false><<<(unsigned)tiles_of(m_local), SB_THREADS, 0, h->stream>>>(info, pool, TE_pull(h, slot), h->Pt.as<unsigned long long>(),
-                                                                               h->child_start.as<int>(), h->first_tile.as<int>(), d_anc);
+        k_pull<false><<<(unsigned)ntiles, SB_THREADS, 0, h->stream>>>(info, pool, TE_pull(h, slot), h->Pt.as<unsigned long long>(),
+                                                                     h->child_start.as<int>(), h->first_tile.as<int>(), d_anc);
     LAUNCH_CHECK();
     return SB_OK;
 }

@@ -34,7 +34,8 @@ def test_systematic_bitexact(eng, oracle, n, kind):
         assert np.array_equal(got, ref)
 
 
-@pytest.mark.parametrize("n,m", [(10, 100000), (100000, 10), (5000, 3000), (3000, 5000), (2049, 2048), (1, 5000)])
+@pytest.mark.parametrize("n,m", [(10, 100000), (100000, 10), (5000, 3000), (3000, 5000), (2049, 2048), (1, 5000),
+                                 (3000000, 2500001), (2000000, 3100000)])       # the last two: persistent pull grid (many tiles per CTA)
 def test_systematic_ragged(eng, oracle, n, m):
     rng = np.random.default_rng(n + m)
     w = rng.random(n)
