@@ -48,6 +48,11 @@ def _worker(rank, world, port, q):
         ok = len(allh) == world and all(allh[r] == bytes([(r * 37 + i) % 256 for i in range(64)]) for r in range(world))
         sd.barrier()
         mx = sd.max_over_ranks(10.0 + rank)
+        # the per-rank shares of the sharded PMCMC counts (each rank counts the particles it owns) summed over the group
+        import numpy as np
+        share = np.arange(12, dtype=np.int64).reshape(3, 4) * (rank + 1)
+        tot = sd.sum_over_ranks(share)
+        ok = ok and tot.dtype == np.int64 and np.array_equal(tot, np.arange(12).reshape(3, 4) * sum(range(1, world + 1)))
         q.put((rank, ok, mx))
     finally:
         dist.destroy_process_group()

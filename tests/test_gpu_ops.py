@@ -100,6 +100,24 @@ def test_ops_fp32_handle_and_large_pool():
     assert c[0] == d[0] and np.array_equal(c[1], d[1]) and abs(c[0] - exact) < 0.05
 
 
+@pytest.mark.parametrize("prog", ["beta_bernoulli", "dirichlet_categorical"])
+def test_ops_multinomial_resampling(prog):
+    """the same programs under multinomial resampling on the weight grid (explicit ancestors: the other ancestor mode of
+    the step kernel, scalar and vector latents): evidence against the closed form"""
+    sb = sb_mod()
+    steps, exact = getattr(ou, prog)()
+    vals = []
+    for s in range(8):
+        with sb.Engine(precision="fp64", resample="multinomial", seed=40 + s) as eng:
+            eng.load(ou.to_program(sb, steps))
+            vals.append(eng.smc_sweep(1 << 16))
+            x = eng.particles(1 << 16)
+            assert np.all(np.isfinite(x)) and (x.ndim == 1 or np.allclose(x.sum(axis=0), 1.0, atol=1e-12))
+    vals = np.array(vals)
+    se = vals.std(ddof=1) / math.sqrt(len(vals))
+    assert abs(vals.mean() - exact) < 4 * se + 1e-3, (vals.mean(), exact, se)
+
+
 def test_ops_errors():
     sb = sb_mod()
     with sb.Engine(precision="fp64") as eng:
