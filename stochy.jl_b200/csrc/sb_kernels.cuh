@@ -1710,8 +1710,13 @@ k_mh_bnet(const __grid_constant__ SbBnetArgs a) {
     }
     for (int f = 0; f < F; ++f) score_old = __dadd_rn(score_old, s_fac[f * st + sb_pack_bits(state, s_fp[f])]);
     unsigned* hist = s_hist + warp * nv;
+    // The chain is a dependent sequence (state -> table lookups -> state) and only ~14 warps are resident per SM at
+    // 65536 chains: the time per step is latency, not issue slots.  The Philox block does not depend on the state: the
+    // NEXT step's is computed alongside this step's dependent part (software pipelining by hand).
+    SbU4 onext = sb_stream4(a.seed, gch, 0u, 0u, SB_P_MH);
     for (long long s = 0; s < a.steps; ++s) {
-        const SbU4 o = sb_stream4(a.seed, gch, (unsigned)s, (unsigned)(s >> 32), SB_P_MH);
+        const SbU4 o = onext;
+        onext = sb_stream4(a.seed, gch, (unsigned)(s + 1), (unsigned)((s + 1) >> 32), SB_P_MH);
         const int j = (int)__umulhi(o.x, (unsigned)D);                               // mh.jl:62
         const double up = __dmul_rn((double)o.y, 0x1p-32), ua = __dmul_rn((double)o.z, 0x1p-32);
         const unsigned prefix = state & ((1u << j) - 1u);
@@ -1771,7 +1776,9 @@ k_mh_bnet_tab(const __grid_constant__ SbBnetArgs a) {
     unsigned* s_hist = reinterpret_cast<unsigned*>(s_cs + D * NS);
     const int nq = __popc(a.query_mask), nv = 1 << nq;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    unsigned short* s_val = reinterpret_cast<unsigned short*>(s_hist + nwarps * nv);   // [NS] the program's value in every state (mh.jl:87)
     for (int i = threadIdx.x; i < nwarps * nv; i += blockDim.x) s_hist[i] = 0u;
+    for (int i = threadIdx.x; i < NS; i += blockDim.x) s_val[i] = (unsigned short)sb_pack_bits((unsigned)i, a.query_mask);
     for (int s = threadIdx.x; s < NS; s += blockDim.x) {      // choice scores and total score of every state (src/mh.jl:33,42)
         double sc = 0.0;
         for (int d = 0; d < D; ++d) {
@@ -1804,23 +1811,40 @@ k_mh_bnet_tab(const __grid_constant__ SbBnetArgs a) {
         if (__dmul_rn((double)o.x, 0x1p-32) < s_p1[d * NS + state]) state |= 1u << d;
     }
     unsigned* hist = s_hist + warp * nv;
+    const unsigned act = __ballot_sync(0xffffffffu, live);
+    unsigned long long c1 = 0;
+    // The chain is a dependent sequence (state -> table lookups -> state) and only ~14 warps are resident per SM at
+    // 65536 chains: the time per step is latency, not issue slots.  The Philox block does not depend on the state: the
+    // NEXT step's is computed alongside this step's dependent part (software pipelining by hand).
+    SbU4 onext = sb_stream4(a.seed, gch, 0u, 0u, SB_P_MH);
     for (long long s = 0; s < a.steps; ++s) {
-        const SbU4 o = sb_stream4(a.seed, gch, (unsigned)s, (unsigned)(s >> 32), SB_P_MH);
+        const SbU4 o = onext;
+        onext = sb_stream4(a.seed, gch, (unsigned)(s + 1), (unsigned)((s + 1) >> 32), SB_P_MH);
         const int j = (int)__umulhi(o.x, (unsigned)D);                               // mh.jl:62
+        // (integer thresholds ceil(p 2^32) instead of the two fp64 compares were measured: 64-bit compares, 3.56 vs 3.45 ms)
         const double up = __dmul_rn((double)o.y, 0x1p-32), ua = __dmul_rn((double)o.z, 0x1p-32);
         const int b = up < s_p1[j * NS + state] ? 1 : 0;                             // mh.jl:70-76
         if (ua < s_acc[(((j << D) + (int)state) << 1) + b]) {
             state = (state & ~(1u << j)) | ((unsigned)b << j);
             ++acc;
         }
-        const unsigned v = sb_pack_bits(state, a.query_mask);                        // mh.jl:87
-        const unsigned act = __ballot_sync(0xffffffffu, live);
+        const unsigned v = s_val[state];                                             // mh.jl:87
+        if (nv == 2) { c1 += v; continue; }                                          // one query site: a counter per chain, no histogram traffic
         if (live) {
             const unsigned peers = __match_any_sync(act, v);
             if (lane == __ffs(peers) - 1) hist[v] += __popc(peers);
         }
         __syncwarp();
         if ((s & SB_MH_FLUSH_MASK) == SB_MH_FLUSH_MASK) sb_mh_flush(s_hist, nwarps, nv, a.counts);
+    }
+    if (nv == 2) {                                               // (CTA-uniform) counts[1] = sum of the chains' counters, counts[0] = the rest
+        unsigned long long t1 = live ? c1 : 0ull, t0 = live ? (unsigned long long)a.steps - c1 : 0ull;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            t1 += ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(t1 >> 32), d) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)t1, d);
+            t0 += ((unsigned long long)__shfl_xor_sync(0xffffffffu, (unsigned)(t0 >> 32), d) << 32) | __shfl_xor_sync(0xffffffffu, (unsigned)t0, d);
+        }
+        if (lane == 0) { if (t0) atomicAdd(a.counts, t0); if (t1) atomicAdd(a.counts + 1, t1); }
     }
     sb_mh_flush(s_hist, nwarps, nv, a.counts);
     if (live && acc) atomicAdd(a.accepts, acc);

@@ -1610,14 +1610,24 @@ extern "C" int32_t sb_mh_run(sb_handle* h, int64_t chains, int64_t steps, int64_
     a.fac_parents = h->bn_fp.as<unsigned>(); a.fac_logf = h->bn_fac.as<double>();
     a.seed = h->opt.seed; a.chains = chains; a.steps = steps; a.chain0 = chain0;
     a.counts = h->bn_counts.as<unsigned long long>(); a.accepts = a.counts + nv;
-    const int threads = 128;
+    // CTA size: the one that leaves the fewest warps on the fullest SM (65536 chains on 148 SMs: 128 threads -> 4 CTAs = 16
+    // warps on some SMs, 64 threads -> 7 CTAs = 14 warps; the kernel is bound by its fullest SMs); larger CTAs on a tie
+    int threads = 128;
+    {
+        long long best = -1;
+        for (int t = 128; t >= 32; t >>= 1) {
+            const long long ctas = (chains + t - 1) / t, per_sm = (ctas + h->num_sms - 1) / h->num_sms, warps = per_sm * (t / 32);
+            if (best < 0 || warps < best) { best = warps; threads = t; }
+        }
+        if (const char* ov = getenv("SB_MH_THREADS")) { const int v = atoi(ov); if (v == 32 || v == 64 || v == 128) threads = v; }
+    }
     const size_t smem = (size_t)(3 * a.D + a.F) * a.stride * 8 + (size_t)(a.D + a.F) * 4 + (size_t)(threads / 32) * nv * 4;
     int rc;
     if ((rc = begin_timed(h)) != SB_OK) return rc;
     if (a.D <= SB_MH_TABD && !getenv("SB_MH_NOTAB")) {
         // small nets: per-(site, state) tables in shared memory (k_mh_bnet_tab); bit-identical chains
         const size_t ns = (size_t)1 << a.D;
-        const size_t smem_t = (size_t)(4 * a.D + 1) * ns * 8 + (size_t)(threads / 32) * nv * 4;
+        const size_t smem_t = (size_t)(4 * a.D + 1) * ns * 8 + (size_t)(threads / 32) * nv * 4 + ns * 2;   // + the value table (u16 per state)
         if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(k_mh_bnet_tab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
         k_mh_bnet_tab<<<(unsigned)((chains + threads - 1) / threads), threads, smem_t, h->stream>>>(a);
     } else {
