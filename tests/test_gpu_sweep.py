@@ -557,16 +557,17 @@ def test_discrete_erp_hooks(oracle):
         assert np.array_equal(eng.discrete_sample([0.5, 0.5], 4, seed=1), eng.discrete_sample([0.5, 0.5], 4, seed=1))
 
 
-@pytest.mark.parametrize("log2n", [16, 20])
-def test_tiled_conditional_smc_with_history_full_size(oracle, log2n):
+@pytest.mark.parametrize("log2n,T", [(16, 8), (20, 8), (20, 40)])
+def test_tiled_conditional_smc_with_history_full_size(oracle, log2n, T):
     """BASELINE cfg3's shape at its full particle count (K = 16 sticky HMM, N = 2^20, conditional SMC with
     history; T reduced to 8 so the oracle finishes in seconds): iteration 0 is a plain sweep, iteration 1 a
     CONDITIONAL sweep whose pool of N+1 carries the retained particle (src/pmcmc.jl:59-66).  Every history
     row (states and ancestors, including the retained slot N), the next retained trajectory (src/pmcmc.jl:89)
     and the per-time value counts over all N particles of both iterations (src/pmcmc.jl:90-92) must equal
-    the oracle's, bit for bit."""
+    the oracle's, bit for bit.  T = 40 at 2^20: the backward pass switches from its counting phase to the walks of the
+    live lineages part-way (k_count_back_all), on the resident sweep kernel's history."""
     sb = sb_mod()
-    T, N = 8, 1 << log2n
+    N = 1 << log2n
     A, logF, pi = cfg3_tables(T=T)
     om = oracle.Hmm(A, logF, pi=pi)
     oo = oracle.opts(oracle.SYSTEMATIC, fp32=True, seed=9)
