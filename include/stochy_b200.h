@@ -76,7 +76,9 @@ typedef struct {
     int32_t  resample_mode;  /* SB_RESAMPLE_* */
     int32_t  retained_pick;  /* -1 auto (index 0 for multinomial/literal as src/pmcmc.jl:89, uniform for systematic); 0; 1 */
     int32_t  store_logw;     /* 1: also keep per-step log-weights (debug / parity; costs W bytes per particle-step) */
-    int32_t  use_graph;      /* reserved, must be 0 (CUDA-graph replay of the per-sweep launch sequence is not in this version) */
+    int32_t  use_graph;      /* reserved, must be 0.  Pools whose tiles are all resident at once run a sweep as ONE persistent
+                              * cooperative launch instead (no option needed); a CUDA-graph replay of the tiled launch sequence
+                              * would save nothing: the host enqueues faster than the GPU runs at every size */
     uint64_t seed;           /* Philox4x32-10 key */
 } sb_options;
 
