@@ -42,6 +42,12 @@ def main():
     d = cfg4_data(T=20)
     cases.append(("lg fp32", lambda: sb.LinearGaussian(**d), "fp32", np.float64))
     cases.append(("lg fp64", lambda: sb.LinearGaussian(**d), "fp64", np.float64))
+    # an op-list program (Beta draw, then kept; Bernoulli observe statements with several observations; a Normal random walk
+    # at the end so that later steps draw too): the peer-addressed instantiation of the op-list step kernel
+    ys = (np.random.default_rng(3).random((6, 3)) < 0.35).astype(float)
+    prog = [((("beta", 2.0, 3.0) if t == 0 else ("keep",)), ("bernoulli", 1.0, 0.0, list(ys[t]))) for t in range(6)]
+    prog += [(("normal", 1.0, 0.0, 0.05), ("normal", 1.0, 0.0, 0.5, [0.3, 0.4])) for _ in range(5)]
+    cases.append(("ops fp64", lambda: sb.OpsProgram(prog), "fp64", np.float64))
     for name, mk, prec, dt in cases:
         eng = sb.Engine(device=local, precision=prec, resample="systematic", seed=11)
         eng.load(mk())
