@@ -68,9 +68,19 @@ def cfg3(sb, enumref, quick):
         sweeps = 3 if quick else 10
         marg, _ = eng.pmcmc_counts(1 + sweeps, N, want_joint=False)    # 1 plain + `sweeps` conditional sweeps, history on
         st = eng.stats()
+    # log Z-hat of the first (unconditional) sweep against the forward algorithm over 32 seeds
+    lzs = []
+    for seed in range(4 if quick else 32):
+        with sb.Engine(precision="fp32", resample="systematic", seed=100 + seed) as eng:
+            eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+            lzs.append(eng.smc_sweep(N, it=0))
+    lzs = np.array(lzs)
+    sd = float(lzs.std(ddof=1))
     return {"config": 3, "what": "HMM T=%d K=16 N=2^20 conditional SMC with history, %d sweeps" % (T, 1 + sweeps),
             "particle_steps_per_s": st.particle_steps / (st.device_ms * 1e-3), "device_ms": st.device_ms,
-            "logZ_first": st.logZ_first, "logZ_forward": exact, "abs_err": abs(st.logZ_first - exact)}
+            "logZ_first": st.logZ_first, "logZ_forward": exact, "abs_err": abs(st.logZ_first - exact),
+            "logZ_seeds": len(lzs), "logZ_mean": float(lzs.mean()), "logZ_sd": sd,
+            "delta_over_se": float(abs(lzs.mean() - exact) / (sd / np.sqrt(len(lzs))))}
 
 
 def cfg4(sb, enumref, quick):
@@ -80,6 +90,15 @@ def cfg4(sb, enumref, quick):
     out = {"config": 4, "what": "linear-Gaussian T=%d N=2^24 plain SMC, systematic resampling every step" % len(d["y"]),
            "logZ_kalman": exact}
     N = 1 << 24
+    # |log Z-hat - Kalman| over 16 seeds (fp32)
+    lzs = []
+    for seed in range(2 if quick else 16):
+        with sb.Engine(precision="fp32", seed=200 + seed) as eng:
+            eng.load(sb.LinearGaussian(**d))
+            lzs.append(eng.smc_sweep(N, it=0))
+    lzs = np.array(lzs)
+    out["logZ_seeds"] = len(lzs); out["logZ_mean_fp32"] = float(lzs.mean()); out["logZ_sd_fp32"] = float(lzs.std(ddof=1))
+    out["delta_over_se_fp32"] = float(abs(lzs.mean() - exact) / (lzs.std(ddof=1) / np.sqrt(len(lzs))))
     for prec in ["fp32", "fp64"]:
         with sb.Engine(precision=prec, seed=3) as eng:
             eng.load(sb.LinearGaussian(**d))
