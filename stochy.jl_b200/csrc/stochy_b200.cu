@@ -1122,6 +1122,10 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.x_out = xrow(t);
         a.w32_out = W32(h, cur);
         a.rec = make_rec(h, cur);
+        // a step without a factor statement is followed by no tile scan: its tile exponents must not enter the running
+        // maximum that the NEXT scan consumes (a stale larger exponent shifts that pool's sums right: beyond the scan's
+        // head-room of LS bits the sums lose bits, and 2^-60 of them is "zero probability mass")
+        if (!h->has_factor[t]) a.rec.emax = nullptr;
         a.sig = make_signal(h);
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;

@@ -351,6 +351,32 @@ def test_hmm_edge_models_bitexact(oracle, K, N, T, precision):
     assert lz == pytest.approx(ref["logZ"], rel=1e-9, abs=1e-12)
 
 
+@pytest.mark.parametrize("K,N", [(1, 4095), (1, 2047), (5, 30000)])
+def test_steps_without_factor_and_wide_score_range(oracle, monkeypatch, K, N):
+    """Steps without a factor statement (no resampling, src/pmcmc.jl:36-46 is simply not reached) between factor steps
+    whose scores differ by dozens of powers of two: the tile exponents of a factor-less step must not leak into the next
+    scan's running maximum (found by scripts/fuzz_sweep.py: the stale exponent shifted the next pool's sums to zero and
+    the sweep raised 'zero probability mass').  Tiled kernels (the one-tile chain kernel off) against the oracle."""
+    sb = sb_mod()
+    monkeypatch.setenv("SB_NO_SMALL", "1")
+    rng = np.random.default_rng(7 + K)
+    T = 6
+    A = rng.random((K, K)) + 0.1
+    A /= A.sum(axis=1, keepdims=True)
+    pi = np.full(K, 1.0 / K)
+    logF = rng.normal(size=(T, K)) * 0.5 + np.array([9.2, -2.0, 34.2, -14.4, -25.9, -31.9])[:, None]
+    hf = np.array([1, 0, 0, 1, 0, 1], dtype=np.uint8)
+    for prec in ["fp32", "fp64"]:
+        ref = oracle.hmm_sweep(oracle.Hmm(A, logF, pi=pi, has_factor=hf), oracle.opts(oracle.SYSTEMATIC, fp32=(prec == "fp32"), seed=3), N)
+        with sb.Engine(precision=prec, resample="systematic", seed=3) as eng:
+            eng.load(sb.DiscreteHMM(A, logF, pi=pi, has_factor=hf))
+            lz = eng.smc_sweep(N, it=0, history=True)
+            for t in range(T):
+                x, a, _ = eng.history(t, N)
+                assert np.array_equal(x, ref["x"][t, :N]) and np.array_equal(a, ref["anc"][t, :N]), (prec, t)
+        assert lz == pytest.approx(ref["logZ"], rel=1e-9)
+
+
 def test_result_independent_of_grid(monkeypatch):
     """The persistent step kernel walks tiles in an order that depends on the number of resident CTAs; the result
     must not.  One CTA per SM at 2^25 particles gives every CTA 110 tiles (the per-CTA table of candidate parent
