@@ -18,9 +18,13 @@ for c in range(cases):
     K = int(rng.choice([1, 2, 3, 5, 16, 17, 37, 64]))
     T = int(rng.integers(1, 9))
     N = int(rng.choice([1, 7, 100, 2047, 2048, 2049, 4095, 4096, 5000, 20000, 70001]))
+    if os.environ.get("FUZZ_BIG"):                                   # resident sweep kernel / many tiles per CTA of the tiled kernels
+        N = int(rng.choice([300000, 1048575, 1048577, 1212415, 1212416, 2100000, 4200001]))
     mode = str(rng.choice(["systematic", "systematic", "multinomial", "literal"]))
     if mode == "literal":
         N = min(N, 3000)
+    if mode == "multinomial":
+        N = min(N, 300000)
     prec = str(rng.choice(["fp32", "fp64"]))
     A = rng.random((K, K)) ** int(rng.choice([1, 3, 6]))
     A[rng.random((K, K)) < rng.choice([0.0, 0.2, 0.5])] = 0.0
