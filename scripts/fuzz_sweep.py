@@ -76,7 +76,10 @@ for c in range(cases):
                     x, a, _ = eng.history(t, N)
                     if not (np.array_equal(x, ref["x"][t, :N]) and np.array_equal(a, ref["anc"][t, :N])):
                         ok = False; desc["where"] = "history row %d (SB_NO_SMALL=%s)" % (t, small); break
-                if ok and not (abs(lz - ref["logZ"]) <= 1e-6 * max(1.0, abs(ref["logZ"]))):
+                # literal mode: the oracle sums exp(score) in fp64 while the GPU's log-evidence (an extension there: the
+                # reference has none) comes from the 27-bit weight grid, whose floor biases a step by ~1e-7 relative
+                tol = 1e-5 if mode == "literal" else 1e-9
+                if ok and not (abs(lz - ref["logZ"]) <= tol * max(1.0, abs(ref["logZ"]))):
                     ok = False; desc["where"] = "logZ %r vs %r" % (lz, ref["logZ"])
                 if ok:
                     marg, _ = eng.pmcmc_counts(iters, N, want_joint=False)
