@@ -37,8 +37,19 @@ def main():
     N = NL * world - 1
     fails = []
     A, logF, pi = cfg3_tables(T=T)
-    for prec in ["fp32", "fp64"]:
-        for pick in [-1, 0]:                                          # uniform pick (systematic default) / particle 1 as src/pmcmc.jl:89
+    models = [("cfg3", A, logF, pi)]
+    # SB_DIST_FUZZ=n: n more random discrete models (seeded: the same on every rank), K from 1 to 64, wide score ranges
+    frng = np.random.default_rng(int(os.environ.get("SB_DIST_FUZZ_SEED", "1")))
+    for i in range(int(os.environ.get("SB_DIST_FUZZ", "0"))):
+        K = int(frng.choice([1, 2, 5, 16, 17, 40, 64])); Tf = int(frng.integers(1, T + 1))
+        Af = frng.random((K, K)) ** int(frng.choice([1, 4])); Af[frng.random((K, K)) < 0.3] = 0.0
+        Af[np.arange(K), np.arange(K)] += 1e-3; Af /= Af.sum(axis=1, keepdims=True)
+        pif = frng.random(K) + 1e-3; pif /= pif.sum()
+        models.append(("fuzz%d K=%d T=%d" % (i, K, Tf), Af, frng.normal(size=(Tf, K)) * float(frng.choice([0.5, 5.0, 40.0])), pif))
+    for mname, A, logF, pi in models:
+      T = logF.shape[0]
+      for prec in (["fp32", "fp64"] if mname == "cfg3" else [str(frng.choice(["fp32", "fp64"]))]):
+        for pick in ([-1, 0] if mname == "cfg3" else [int(frng.choice([-1, 0]))]):   # uniform pick (systematic default) / particle 1 as src/pmcmc.jl:89
             eng = sb.Engine(device=local, precision=prec, resample="systematic", seed=5, retained_pick=pick)
             eng.load(sb.DiscreteHMM(A, logF, pi=pi))
             eng.shard(NL, history_rows=T)
@@ -63,7 +74,7 @@ def main():
                 marg_ref, _ = ref.pmcmc_counts(iters, N, want_joint=False)
                 st_ref = ref.stats()
                 xs_ref = ref.retained()
-                name = "pmcmc %s pick=%d" % (prec, pick)
+                name = "pmcmc %s %s pick=%d" % (mname, prec, pick)
                 if not np.array_equal(marg, marg_ref):
                     fails.append("%s: counts differ (%d cells)" % (name, int((marg != marg_ref).sum())))
                 if marg.sum() != iters * N * T:
@@ -81,7 +92,7 @@ def main():
                     if not np.array_equal(got[t, 1, :N], a[:N]):
                         fails.append("%s: ancestors of step %d differ" % (name, t)); break
                 ref.close()
-                print("[dist] %-22s world=%d N_local=2^%d T=%d logZ=%.6f %s" % (name, world, log2n, T, st.logZ_last,
+                print("[dist] %-34s world=%d N_local=2^%d T=%d logZ=%.6f %s" % (name, world, log2n, T, st.logZ_last,
                                                                                  "ok" if not fails else "FAIL"), flush=True)
             dist.barrier()
     if rank == 0:

@@ -48,6 +48,17 @@ def main():
     prog = [((("beta", 2.0, 3.0) if t == 0 else ("keep",)), ("bernoulli", 1.0, 0.0, list(ys[t]))) for t in range(6)]
     prog += [(("normal", 1.0, 0.0, 0.05), ("normal", 1.0, 0.0, 0.5, [0.3, 0.4])) for _ in range(5)]
     cases.append(("ops fp64", lambda: sb.OpsProgram(prog), "fp64", np.float64))
+    # SB_DIST_FUZZ=n: n more random discrete models (same on every rank: seeded), K from 1 to 64 (head markers that carry the
+    # state in 4 or 6 bits, or none), wide score ranges, zeros in the transition rows, odd and even T
+    frng = np.random.default_rng(int(os.environ.get("SB_DIST_FUZZ_SEED", "1")))
+    for i in range(int(os.environ.get("SB_DIST_FUZZ", "0"))):
+        K = int(frng.choice([1, 2, 5, 16, 17, 40, 64])); T = int(frng.integers(1, 12))
+        Af = frng.random((K, K)) ** int(frng.choice([1, 4])); Af[frng.random((K, K)) < 0.3] = 0.0
+        Af[np.arange(K), np.arange(K)] += 1e-3; Af /= Af.sum(axis=1, keepdims=True)
+        pif = frng.random(K) + 1e-3; pif /= pif.sum()
+        lf = frng.normal(size=(T, K)) * float(frng.choice([0.5, 5.0, 40.0]))
+        prec = str(frng.choice(["fp32", "fp64"]))
+        cases.append(("fuzz%d K=%d T=%d %s" % (i, K, T, prec), (lambda Af=Af, lf=lf, pif=pif: sb.DiscreteHMM(Af, lf, pi=pif)), prec, np.int32))
     for name, mk, prec, dt in cases:
         eng = sb.Engine(device=local, precision=prec, resample="systematic", seed=11)
         eng.load(mk())
@@ -78,7 +89,7 @@ def main():
             if not np.array_equal(got, x_ref):
                 fails.append("%s: %d of %d final particles differ from the single-GPU sweep"
                              % (name, int((got != x_ref).sum()), got.size))
-            print("[dist] %-9s world=%d N_local=2^%d logZ=%.6f %s" % (name, world, log2n, lz[-1],
+            print("[dist] %-22s world=%d N_local=2^%d logZ=%.6f %s" % (name, world, log2n, lz[-1],
                                                                       "ok" if not fails else "FAIL"), flush=True)
         dist.barrier()
     if rank == 0:
