@@ -17,6 +17,39 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+class Exact:
+    """Closed forms the configs are checked against, from the PRODUCT's own Enumerate on the GPU (sb_enum_hmm: exhaustive
+    joint / scaled forward-backward, itself tested against the oracle in tests/) and a scalar Kalman filter -- this script
+    does not touch oracle/."""
+
+    def __init__(self, sb):
+        self.sb = sb
+
+    def _enum(self, A, logF, want_joint, **kw):
+        with self.sb.Engine(precision="fp64") as e:
+            e.load(self.sb.DiscreteHMM(A, logF, **kw))
+            return e.enum_hmm(want_joint=want_joint)
+
+    def hmm_enumerate_joint(self, A, logF, **kw):
+        joint, _, lz = self._enum(A, logF, True, **kw)
+        return float(np.exp(lz)), joint / joint.sum()
+
+    def hmm_forward(self, A, logF, **kw):
+        return self._enum(A, logF, False, **kw)[2], None
+
+    @staticmethod
+    def kalman_loglik(a, q, c, r, m0, P0, y):
+        m, P, ll = m0, P0, 0.0
+        for t, yt in enumerate(y):
+            if t:
+                m, P = a * m, a * a * P + q
+            S = c * c * P + r
+            ll += -0.5 * (np.log(2 * np.pi * S) + (yt - c * m) ** 2 / S)
+            G = P * c / S
+            m, P = m + G * (yt - c * m), (1 - G * c) * P
+        return float(ll), None
+
+
 def tv(p, q):
     keys = set(p) | set(q)
     return 0.5 * sum(abs(p.get(k, 0.0) - q.get(k, 0.0)) for k in keys)
@@ -130,7 +163,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
     import stochy_jl_b200 as sb
-    from oracle import enumerate_ref as enumref
+    enumref = Exact(sb)
     for i, f in enumerate([cfg1, cfg2, cfg3, cfg4, cfg5], 1):
         if args.only and args.only != i:
             continue

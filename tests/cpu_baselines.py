@@ -8,7 +8,7 @@
   * cfg1: examples/hmm.jl-sized PMCMC, 100 particles x 1000 iterations, literal numerics, one thread;
   * the systematic-grid SMC sweep of the bench workload (K=16), one thread and all threads, 2^20 particles x 16 steps.
 
-  python scripts/cpu_baselines.py > profiles/rNN_cpu_baselines.jsonl        (CPU only; ~1 minute)
+  python tests/cpu_baselines.py > profiles/rNN_cpu_baselines.jsonl        (CPU only; ~1 minute)
 """
 import ctypes
 import json

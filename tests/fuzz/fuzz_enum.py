@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Randomised check of Enumerate on the GPU (sb_enum_hmm: exhaustive joint + scaled forward-backward marginals) against
 the oracle's restatement of src/enumerate.jl:36-85 on random small discrete models (zeros in the rows, hard factors,
-steps without a factor, fixed first state).  Test tooling: python scripts/fuzz_enum.py [cases] [seed]."""
+steps without a factor, fixed first state).  Test tooling: python tests/fuzz/fuzz_enum.py [cases] [seed]."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import stochy_jl_b200 as sb
 from oracle import enumerate_ref as er

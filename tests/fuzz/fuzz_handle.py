@@ -3,10 +3,10 @@
 random discrete model, plain sweeps with and without history, PMCMC runs of random pool sizes (one-tile chain kernel,
 resident sweep kernel, tiled kernels, cooperative backward pass), resampling hooks, a sweep that ends in the zero-mass
 error, log-sum-exp -- every result checked against the oracle (bit for bit where the work is integer).
-Test tooling: python scripts/fuzz_handle.py [ops] [seed]."""
+Test tooling: python tests/fuzz/fuzz_handle.py [ops] [seed]."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import stochy_jl_b200 as sb
 from oracle import oracle as orc

@@ -2,10 +2,10 @@
 """Randomised parity hunt for the resampling hooks (quantise -> tile scan -> pull / search): random pool sizes and child
 counts around tile boundaries, weight kinds (linear fp64, log fp64, log fp32), dynamic ranges from flat to 10^300, exact
 zeros / -inf, a single survivor, offsets u at 0, just below 1 and random -- GPU against the oracle, bit for bit.  Test
-tooling (uses the oracle), run by hand: python scripts/fuzz_hooks.py [cases] [seed]."""
+tooling (uses the oracle), run by hand: python tests/fuzz/fuzz_hooks.py [cases] [seed]."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import stochy_jl_b200 as sb
 from oracle import oracle as orc

@@ -3,10 +3,10 @@
 four parents, 0..3 factor statements, hard factors, probabilities at 0 and 1), query sets of 1..4 sites (one site: the
 per-chain counter path; several: the warp-aggregated histogram), chain counts that are not multiples of a warp or a CTA,
 with and without the per-(site, state) tables -- counts and accept totals against the oracle, bit for bit.
-Test tooling (uses the oracle): python scripts/fuzz_mh.py [cases] [seed]."""
+Test tooling (uses the oracle): python tests/fuzz/fuzz_mh.py [cases] [seed]."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import stochy_jl_b200 as sb
 from oracle import oracle as orc

@@ -4,10 +4,10 @@ beta / gamma / uniform / flip / keep draws, normal / bernoulli / poisson / zero 
 and Dirichlet programs, random pool sizes.  Transcendental functions differ in the last ulps between libm and CUDA, so a
 weight can differ by 1e-15 relative and -- rarely -- move a resampling boundary; the check is therefore: the first step
 (no parents) agrees to 1e-11 / 1e-9 always, the log-evidence of the whole sweep agrees to 1e-6 in at least 90 % of the cases
-and to 0.3 always.  Test tooling: python scripts/fuzz_ops.py [cases] [seed]."""
+and to 0.3 always.  Test tooling: python tests/fuzz/fuzz_ops.py [cases] [seed]."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import stochy_jl_b200 as sb
 import ops_util as ou

@@ -2,10 +2,10 @@
 """Randomised parity hunt: random discrete models (K, T, zeros / tiny probabilities, hard factors, steps without a
 factor, fixed or drawn first state), random pool sizes around tile boundaries, every resampling mode and precision,
 plain and conditional sweeps (PMCMC counts) -- GPU against the oracle, bit for bit.  Uses the oracle: test tooling, run
-by hand (python scripts/fuzz_sweep.py [cases] [seed]); prints the failing configuration and exits 1 on a mismatch."""
+by hand (python tests/fuzz/fuzz_sweep.py [cases] [seed]); prints the failing configuration and exits 1 on a mismatch."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import stochy_jl_b200 as sb
 from oracle import oracle as orc

@@ -355,7 +355,7 @@ def test_hmm_edge_models_bitexact(oracle, K, N, T, precision):
 def test_steps_without_factor_and_wide_score_range(oracle, monkeypatch, K, N):
     """Steps without a factor statement (no resampling, src/pmcmc.jl:36-46 is simply not reached) between factor steps
     whose scores differ by dozens of powers of two: the tile exponents of a factor-less step must not leak into the next
-    scan's running maximum (found by scripts/fuzz_sweep.py: the stale exponent shifted the next pool's sums to zero and
+    scan's running maximum (found by tests/fuzz/fuzz_sweep.py: the stale exponent shifted the next pool's sums to zero and
     the sweep raised 'zero probability mass').  Tiled kernels (the one-tile chain kernel off) against the oracle."""
     sb = sb_mod()
     monkeypatch.setenv("SB_NO_SMALL", "1")
