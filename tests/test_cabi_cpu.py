@@ -53,6 +53,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "stochy_oracle" not in txt, f
+    # the oracle is test infrastructure: outside tests/ only bench.py (CPU legs) and __graft_entry__.py (build + smoke) use it
+    for dp in [os.path.join(ROOT, "scripts"), os.path.join(ROOT, "julia"), os.path.join(ROOT, "include")]:
+        for f in os.listdir(dp):
+            if f.endswith((".py", ".sh", ".jl", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "stochy_oracle" not in txt, f
+    assert "oracle" not in open(os.path.join(ROOT, "stochy_jl_b200.py")).read()
 
 
 def test_host_api_rejects_general_programs(sb):
