@@ -36,9 +36,32 @@ for prec in ["fp32", "fp64"]:
         oo = orc.opts(orc.SYSTEMATIC, fp32=(prec == "fp32"), seed=seed)
         model = None
         for c in range(ops // 2):
-            op = str(rng.choice(["load", "sweep", "sweep_hist", "pmcmc", "hook", "zero", "lse"], p=[.15, .2, .2, .25, .1, .05, .05]))
+            op = str(rng.choice(["load", "sweep", "sweep_hist", "pmcmc", "hook", "zero", "lse", "lg"], p=[.15, .2, .15, .25, .1, .05, .05, .05]))
             desc = dict(prec=prec, step=c, op=op)
             try:
+                if op == "lg":                                       # another model family on the same handle, then back to a discrete one
+                    Tl = int(rng.integers(1, 6)); y = rng.normal(size=Tl) * 2
+                    par = dict(a=float(rng.uniform(-1, 1)), q=float(rng.uniform(.2, 2)), c=float(rng.uniform(.5, 2)), r=float(rng.uniform(.2, 2)),
+                               m0=float(rng.normal()), P0=float(rng.uniform(.2, 2)), y=y)
+                    Nl = int(rng.choice(SIZES[:7]))
+                    eng.load(sb.LinearGaussian(**par))
+                    lz = eng.smc_sweep(Nl, it=1)
+                    ref = orc.lg_sweep(orc.Lg(par["a"], par["q"], par["c"], par["r"], par["m0"], par["P0"], y), oo, Nl, it=1)["logZ"]
+                    # fp32: libm and CUDA's sqrt / sincos / log approximations differ at 1e-6, every weight moves a little and a
+                    # per-cent of the children change parent: the two sweeps are different Monte-Carlo runs of the same
+                    # filter.  What must hold on a reused handle: the SAME result as on a fresh handle, bit for bit.
+                    ok = abs(lz - ref) <= 1e-6 * max(1.0, abs(ref)) if prec == "fp64" else abs(lz - ref) < 1.0
+                    with sb.Engine(precision=prec, resample="systematic", seed=seed) as fresh:
+                        fresh.load(sb.LinearGaussian(**par))
+                        lz_fresh = fresh.smc_sweep(Nl, it=1)
+                    ok = ok and lz_fresh == lz
+                    if not ok:
+                        desc["where"] = "lg logZ %r (fresh handle %r) vs oracle %r (N=%d, %r)" % (lz, lz_fresh, ref, Nl, {k: (v if k != "y" else v.tolist()) for k, v in par.items()})
+                    model = None
+                    done[op] = done.get(op, 0) + 1
+                    if not ok:
+                        bad += 1; print("MISMATCH", desc, flush=True)
+                    continue
                 if op == "load" or model is None:
                     model = rand_model()
                     A, logF, pi, hf = model
