@@ -174,13 +174,11 @@ __device__ __forceinline__ uint32_t sb_q31_f32(float d) {
     p = __fmaf_rn(p, t, 1.0f);
     p = __fmaf_rn(p, t, 1.0f);
     p = __fmul_rn(p, SB_SQRT2_F);
-    // p * 2^(31+k) truncated: exact integer arithmetic on the float's 24-bit significand
-    int sh = SB_QBITS + (int)k - 23;                 // p = sig * 2^(ex-23)
-    uint32_t bits = __float_as_uint(p);
-    uint32_t sig = (bits & 0x7FFFFFu) | 0x800000u;
-    sh += (int)(bits >> 23) - 127;
-    if (sh >= 0) return sig << sh;                   // sh <= 4 because p * 2^(QBITS+k) <= 2^QBITS (+1 ulp)
-    return sh > -24 ? (sig >> (-sh)) : 0u;
+    // p * 2^(QBITS+k) truncated.  The scale is a power of two in the normal range (k > -29) and so is the product: the
+    // multiplication is exact, and the conversion truncates -- the same integer as shifting the float's 24-bit significand
+    // by hand (the oracle's C does exactly that; the hand-shifted form cost ten integer instructions per particle here).
+    const float s = __int_as_float((127 + SB_QBITS + (int)k) << 23);
+    return __float2uint_rz(__fmul_rn(p, s));
 }
 
 // Rescaled tile-local prefix: (c * R) >> rb with c <= 2^38 and a 26-bit R (product < 2^64).
