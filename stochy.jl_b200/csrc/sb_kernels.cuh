@@ -984,6 +984,9 @@ struct SbLgStepArgs {
     unsigned long long seed;
     SbRoundKeys rk;             // Philox round keys of `seed`
     double a, sq, sp, c, r, m0, y, lc;   // sq = sqrt(q), sp = sqrt(P0), lc = -0.5 log(2 pi r)
+    // the same constants rounded to float ONCE on the host (fp32 instantiations read them straight from the constant bank:
+    // eight double -> float conversions and a division per tile and thread otherwise); fhr = -0.5f / (float)r
+    float fa, fsq, fsp, fc, fy, fhr, flc, fm0;
     unsigned* err;
     // OPS instantiations (sb_model_ops): this step's draw / score statement and the observations (device memory)
     sb_op_step op;
@@ -1157,8 +1160,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         REAL mx = -INFINITY;
         bool bad = false;
         if (FP32) {
-            const float fa = (float)a.a, fsq = (float)a.sq, fsp = (float)a.sp, fc = (float)a.c, fy = (float)a.y;
-            const float hr = -0.5f / (float)a.r, flc = (float)a.lc, fm0 = (float)a.m0;
+            const float fa = a.fa, fsq = a.fsq, fsp = a.fsp, fc = a.fc, fy = a.fy, hr = a.fhr, flc = a.flc, fm0 = a.fm0;
             // Box-Muller with both branches: one Philox block per FOUR particles (two pairs)
             float z[SB_ITEMS];
 #pragma unroll
@@ -1178,19 +1180,31 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                     z[4 * p + 2 * h] = -r * cs; z[4 * p + 2 * h + 1] = -r * sn;
                 }
             }
+            // (full tiles -- all but the pool's last -- take the instantiation without the per-particle bounds predicates)
+            auto weigh = [&](auto full_c) {
+                constexpr bool FULL = decltype(full_c)::value;
 #pragma unroll
-            for (int j = 0; j < SB_ITEMS; ++j) {
-                float xv;
-                if (ANC == SB_ANC_NONE) xv = fm0 + fsp * z[j];
-                else xv = fa * (float)xpar[j] + fsq * z[j];
-                const float d = fy - fc * xv;
-                const float lw = hr * d * d + flc;
-                const bool live = base + j < N;
-                float v = live ? __fmul_rn(lw, SB_LOG2E_F) : -INFINITY;
-                if (!(v < INFINITY)) { bad = true; v = -INFINITY; }        // NaN or +Inf
-                x[j] = (REAL)xv; l2[j] = (REAL)v;
-                mx = (REAL)fmaxf((float)mx, v);
-                if (a.lw_out && live) a.lw_out[lbase + j] = (double)lw;
+                for (int j = 0; j < SB_ITEMS; ++j) {
+                    float xv;
+                    if (ANC == SB_ANC_NONE) xv = fm0 + fsp * z[j];
+                    else xv = fa * (float)xpar[j] + fsq * z[j];
+                    const float d = fy - fc * xv;
+                    const float lw = hr * d * d + flc;
+                    const bool live = FULL || base + j < N;
+                    float v = live ? __fmul_rn(lw, SB_LOG2E_F) : -INFINITY;
+                    if (!(v < INFINITY)) { bad = true; v = -INFINITY; }        // NaN or +Inf
+                    x[j] = (REAL)xv; l2[j] = (REAL)v;
+                    mx = (REAL)fmaxf((float)mx, v);
+                }
+            };
+            if (base - tid * SB_ITEMS + SB_TILE <= N) weigh(std::true_type{}); else weigh(std::false_type{});
+            if (a.lw_out) {                                       // store_logw (debug / parity): the same expression on the stored state,
+#pragma unroll                                                    // behind ONE uniform branch instead of two predicated instructions per particle
+                for (int j = 0; j < SB_ITEMS; ++j) {
+                    const float d = fy - fc * (float)x[j];
+                    const float lw = hr * d * d + flc;
+                    if (base + j < N) a.lw_out[lbase + j] = (double)lw;
+                }
             }
         } else if (OPS) {
 #pragma unroll 1
