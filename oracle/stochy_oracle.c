@@ -609,14 +609,14 @@ void or_lg_step(const or_lg* m, const or_opts* o, int64_t N, uint32_t t, uint32_
                 const double* xpg, double* x_out, double* lw_out) {
     const double lc = -0.5 * log(TWO_PI * m->r);
     if (!o->fp32) {
-        const double sq = sqrt(m->q), sp = sqrt(m->P0);
+        const double sq = sqrt(m->q), sp = sqrt(m->P0), hr = -0.5 / m->r;
         #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < N; ++i) {
             double z = normal_f64(o->seed, (uint64_t)i, t, iter);
             double x = t == 0 ? m->m0 + sp * z : m->a * xpg[i] + sq * z;
             double d = m->y[t] - m->c * x;
             x_out[i] = x;
-            lw_out[i] = -0.5 * d * d / m->r + lc;
+            lw_out[i] = hr * d * d + lc;                             /* hr = -0.5 / r: the product's operation sequence */
         }
     } else {
         const float sq = sqrtf((float)m->q), sp = sqrtf((float)m->P0);

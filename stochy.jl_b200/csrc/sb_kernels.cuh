@@ -984,6 +984,7 @@ struct SbLgStepArgs {
     unsigned long long seed;
     SbRoundKeys rk;             // Philox round keys of `seed`
     double a, sq, sp, c, r, m0, y, lc;   // sq = sqrt(q), sp = sqrt(P0), lc = -0.5 log(2 pi r)
+    double hr;                           // -0.5 / r
     // the same constants rounded to float ONCE on the host (fp32 instantiations read them straight from the constant bank:
     // eight double -> float conversions and a division per tile and thread otherwise); fhr = -0.5f / (float)r
     float fa, fsq, fsp, fc, fy, fhr, flc, fm0;
@@ -1240,7 +1241,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
                 if (ANC == SB_ANC_NONE) xv = a.m0 + a.sp * z[j];
                 else xv = a.a * (double)xpar[j] + a.sq * z[j];
                 const double d = a.y - a.c * xv;
-                const double lw = -0.5 * d * d / a.r + a.lc;
+                const double lw = a.hr * d * d + a.lc;               // hr = -0.5 / r once on the host (a division per particle before)
                 const bool live = base + j < N;
                 double v = live ? __dmul_rn(lw, SB_LOG2E_D) : -INFINITY;
                 if (isnan(v) || v == INFINITY) { bad = true; v = -INFINITY; }

@@ -1229,6 +1229,7 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         } else {
             a.a = h->lg_a; a.sq = sqrt(h->lg_q); a.sp = sqrt(h->lg_P0); a.c = h->lg_c; a.r = h->lg_r; a.m0 = h->lg_m0;
             a.y = h->lg_y[t]; a.lc = -0.5 * log(SB_TWO_PI * h->lg_r);
+            a.hr = -0.5 / a.r;
             a.fa = (float)a.a; a.fsq = (float)a.sq; a.fsp = (float)a.sp; a.fc = (float)a.c; a.fy = (float)a.y;
             a.fhr = -0.5f / (float)a.r; a.flc = (float)a.lc; a.fm0 = (float)a.m0;
         }
