@@ -323,8 +323,13 @@ k_sweep_hmm(const __grid_constant__ SbResArgs a) {
         int xp[SB_ITEMS];
         if (CARRY) {
             const int xm = (1 << xsh) - 1;
+            if (t > 0 && !tail) {                                        // (CTA-uniform: every tile but the pool's last)
 #pragma unroll
-            for (int j = 0; j < SB_ITEMS; ++j) xp[j] = (t > 0 && base + j < N) ? (anc[j] & xm) : 0;
+                for (int j = 0; j < SB_ITEMS; ++j) xp[j] = anc[j] & xm;
+            } else {
+#pragma unroll
+                for (int j = 0; j < SB_ITEMS; ++j) xp[j] = (t > 0 && base + j < N) ? (anc[j] & xm) : 0;
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) xp[j] = (t > 0 && base + j < N) ? __ldcg(xprev + anc[j]) : 0;
@@ -366,8 +371,13 @@ k_sweep_hmm(const __grid_constant__ SbResArgs a) {
         {
             const uint32_t* qtop = s_qtab + (kmax & 63u) * K;
             unsigned wm = 0u;
+            if (!tail) {
 #pragma unroll
-            for (int j = 0; j < SB_ITEMS; ++j) { q[j] = base + j < a.n_out ? qtop[x[j]] : 0u; wm = max(wm, q[j]); }
+                for (int j = 0; j < SB_ITEMS; ++j) { q[j] = qtop[x[j]]; wm = max(wm, q[j]); }
+            } else {
+#pragma unroll
+                for (int j = 0; j < SB_ITEMS; ++j) { q[j] = base + j < a.n_out ? qtop[x[j]] : 0u; wm = max(wm, q[j]); }
+            }
             wm = __reduce_max_sync(0xffffffffu, wm);
             if (wm > sm.qthr) key = kmax;
             else {
