@@ -55,7 +55,7 @@ struct SbResArgs {
     unsigned long long* dbg;                // diagnostics (SB_RES_TRACE): globaltimer stamps of CTA 0, 16 per step
 };
 
-#define SB_RES_STAMP(i) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && t < 64) { unsigned long long ts_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_)); a.dbg[t * 16 + (i)] = ts_; } } while (0)
+#define SB_RES_STAMP(i) do { if (TRACE && a.dbg && blockIdx.x == 0 && threadIdx.x == 0 && t < 64) { unsigned long long ts_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_)); a.dbg[t * 16 + (i)] = ts_; } } while (0)
 
 struct SbResSmem {
     SbPullSmem ps;
@@ -251,7 +251,9 @@ __device__ __forceinline__ void sb_res_scores(const SbResArgs& a, int t, double*
     }
 }
 
-template <bool FP32, bool MULTI, bool CARRY>
+// TRACE: the diagnostic instantiation (SB_RES_TRACE=1) with the phase stamps; without it they are not compiled in at all
+// (predicated off they still cost an issue slot each: 3 % of the kernel's instructions)
+template <bool FP32, bool MULTI, bool CARRY, bool TRACE = false>
 __global__ void __launch_bounds__(SB_THREADS, 4)
 k_sweep_hmm(const __grid_constant__ SbResArgs a) {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -427,7 +429,7 @@ k_sweep_hmm(const __grid_constant__ SbResArgs a) {
             sb_st_rec_volatile(a.rec[cur] + tile, Qt | ((unsigned long long)(epoch & 0xffffu) << 48),
                                (unsigned long long)(unsigned)e | ((unsigned long long)epoch << 32));
             sb_grid_arrive(a.bar);
-            if (a.dbg && (t == 10 || t == 11)) {                         // diagnostics: when (and where) every CTA published step 10 / 11
+            if (TRACE && a.dbg && (t == 10 || t == 11)) {                // diagnostics: when (and where) every CTA published step 10 / 11
                 unsigned long long ts_; unsigned smid_;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts_));
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));

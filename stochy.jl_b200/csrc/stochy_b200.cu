@@ -934,9 +934,10 @@ int upload_offsets(sb_handle* h, unsigned iter) {
 // The whole sweep as ONE cooperative launch (sb_resident.cuh) when every tile of the pool fits on the GPU at once.
 // *done = 0: not eligible here (too many tiles for the resident grid, no cooperative launch): the caller runs the
 // tiled kernels.  Buffers, offsets and the per-step records were prepared by sweep_hmm.
-template <bool FP32, bool MULTI, bool CARRY>
+template <bool FP32, bool MULTI, bool CARRY, bool TRACE = false>
 int sweep_hmm_resident_k(sb_handle* h, const SbResArgs& a, int* done) {
-    auto kern = k_sweep_hmm<FP32, MULTI, CARRY>;
+    if (!TRACE && a.dbg) return sweep_hmm_resident_k<FP32, MULTI, CARRY, true>(h, a, done);   // SB_RES_TRACE=1: the instantiation with the stamps
+    auto kern = k_sweep_hmm<FP32, MULTI, CARRY, TRACE>;
     const size_t smem = sb_res_smem_bytes(a.K, a.ntiles, MULTI);
     if (smem > 160 * 1024) return SB_OK;
     int cap = 0, rc;
