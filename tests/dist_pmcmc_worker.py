@@ -92,7 +92,8 @@ def main():
                     if not np.array_equal(got[t, 1, :N], a[:N]):
                         fails.append("%s: ancestors of step %d differ" % (name, t)); break
                 ref.close()
-                print("[dist] %-34s world=%d N_local=2^%d T=%d logZ=%.6f %s" % (name, world, log2n, T, st.logZ_last,
+                print("[dist] %-34s world=%d N_local=2^%d T=%d logZ=%.6f sharded %.2f ms/iteration, one GPU %.2f %s" % (
+                    name, world, log2n, T, st.logZ_last, st.device_ms / iters, st_ref.device_ms / iters,
                                                                                  "ok" if not fails else "FAIL"), flush=True)
             dist.barrier()
     if rank == 0:
