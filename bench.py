@@ -255,7 +255,10 @@ def run_ours(args):
     eng.load(model)
     if world > 1 or args.force_shard:
         eng.shard(N)                                # --force-shard: the sharded code path on one GPU (diagnostics)
-    eng.set_profile(max(1, T // 100))
+    # live kernel timing inside the timed region: a CUDA-event pair around every 50th launch of the step kernel (20 samples per
+    # sweep at T = 1000).  An event between the scan and the step kernel costs that step its programmatic overlap (~3 us), so the
+    # sampled steps are kept few: every 10th step made the whole sweep 1.2 % slower than the unprofiled one (76.0 against 75.1 ms)
+    eng.set_profile(max(1, T // 20))
 
     def barrier():
         if world > 1:
