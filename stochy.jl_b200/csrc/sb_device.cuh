@@ -326,6 +326,11 @@ __device__ __forceinline__ void sb_store8_u32(uint32_t* p, const uint32_t v[8]) 
 // serialisation: it may become resident and run its prologue (stage model tables, build the weight table)
 // while its predecessor is still running, and calls sb_grid_dep_wait() before it touches anything the
 // predecessor wrote.  Both are no-ops for a kernel launched the ordinary way.
+// CAUTION: ptxas moves ld.global.nc (__ldg) loads ABOVE griddepcontrol.wait when their address does not depend on
+// anything loaded after it (seen in k_tilescan<2>: the tile records were read while the step kernel was still writing
+// them, 2^25-particle pools).  Whatever the predecessor wrote and this kernel addresses by thread/tile index alone is
+// therefore read with __ldcg; loads whose ADDRESS comes out of such a load (or out of shared memory filled after the
+// wait) cannot be hoisted and may stay __ldg.
 __device__ __forceinline__ void sb_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void sb_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -608,7 +613,8 @@ __device__ __forceinline__ int2 sb_pull_range(const SbStepInfo& si, const int* _
     const int m = (int)si.m;
     if (c0 >= m) return make_int2(0, -1);                        // no children here: nothing is pulled
     const int cb = c0 / SB_TILE;
-    return make_int2(__ldg(first_tile + cb), (c0 + SB_TILE < m) ? __ldg(first_tile + cb + 1) : si.nt - 1);
+    // written by the scan this kernel depends on, at an address known before the wait: NOT __ldg (see sb_grid_dep_wait)
+    return make_int2(__ldcg(first_tile + cb), (c0 + SB_TILE < m) ? __ldcg(first_tile + cb + 1) : si.nt - 1);
 }
 
 // Warps 0 and SB_META_WARP (all 32 lanes each): start the copies of the two candidate parent tiles b_lo, b_lo+1 of
@@ -862,15 +868,28 @@ __device__ __forceinline__ void sb_warp_total(unsigned tsum, unsigned long long*
     const unsigned lo = __reduce_add_sync(0xffffffffu, tsum & 0xFFFFu), hi = __reduce_add_sync(0xffffffffu, tsum >> 16);
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = ((unsigned long long)hi << 16) + lo;
 }
-__device__ __forceinline__ void sb_flush_totals(const unsigned long long* sm, unsigned long long* __restrict__ wp_tile,
-                                                const SbRecOut& rec, int tile) {
+// returns the tile sum to the one thread that wrote it (lane SB_WARPS of warp SB_FLUSH_WARP), 0 to everybody else
+__device__ __forceinline__ unsigned long long sb_flush_totals(const unsigned long long* sm, unsigned long long* __restrict__ wp_tile,
+                                                              const SbRecOut& rec, int tile) {
     const int t = (int)threadIdx.x - 32 * SB_FLUSH_WARP;          // lanes 0-8 of warp SB_FLUSH_WARP
     if (t >= 0 && t <= SB_WARPS) {                               // lane w < 8: prefix of warp w; lane 8: the tile sum
         unsigned long long pre = 0;
 #pragma unroll
         for (int w = 0; w < SB_WARPS; ++w) if (w < t) pre += sm[w];
-        if (t < SB_WARPS) wp_tile[t] = pre; else sb_put_Q(rec, tile, pre);
+        if (t < SB_WARPS) wp_tile[t] = pre; else { sb_put_Q(rec, tile, pre); return pre; }
     }
+    return 0ull;
+}
+// Speculative exact total (single GPU).  The tile scan's first pass sums (Q_b << LS) >> (E - e_b) over the tiles, E = the
+// largest tile exponent -- which a step of the discrete model knows in advance whenever some tile contains a particle in
+// the best-scoring state (E_top: virtually always).  The step kernel therefore accumulates that sum at E_top on the way
+// (one thread per CTA, one 64-bit atomic per CTA at the end) into the words behind the exponent maximum:
+// emax[1] = E_top, (u64*)(emax + 2) = the sum.  The scan takes it when its E equals E_top and skips its first pass (one
+// cluster scan + barrier of its critical path, which is exposed between two step kernels); integer adds: the same bits.
+__device__ __forceinline__ unsigned long long sb_spec_term(unsigned long long Q, int e, int E_top, int LS) {
+    if (Q == 0ull || e == SB_E_EMPTY) return 0ull;
+    const int sh = E_top - e;
+    return sh >= 63 ? 0ull : ((Q << LS) >> sh);
 }
 
 // Tile sum of the weights a CTA just produced, and the exclusive prefix of its warp sums (what the

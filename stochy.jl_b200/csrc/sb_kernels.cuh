@@ -265,7 +265,7 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
                     const char* owner = sp.base[b >> sp.log2t];
                     qr[i] = __ldcv(reinterpret_cast<const unsigned long long*>(owner + sp.off_Q) + b);
                     er[i] = __ldcv(reinterpret_cast<const int*>(owner + sp.off_e) + b);
-                } else { qr[i] = __ldg(Q_g + b); er[i] = __ldg(e_g + b); }
+                } else { qr[i] = __ldcg(Q_g + b); er[i] = __ldcg(e_g + b); }   // NOT __ldg: see sb_grid_dep_wait
             }
         }
         if (PEERS) {                             // the pull reads exponents of any tile from the local array
@@ -290,11 +290,21 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     }
     const int LS = 24 - (nt <= 1 ? 0 : 32 - __clz(nt - 1));  // LS = 24 - ceil_log2(nt)
     // exact CDF of tile sums (log-evidence; multinomial resampling)
-    unsigned long long loc = 0;
-    SB_TS_FOR((void)b; if (qv != 0ull) { const int sh = E - ev; loc += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
-    unsigned long long total;
-    unsigned long long run = sb_cluster_excl_scan(loc, sm, cl, 0, &total);
-    if (!PEERS && gtid == 0) *emax = SB_E_EMPTY;              // every thread of the cluster has read it
+    // single GPU: the step kernel of the discrete model has accumulated this very sum at the exponent it expected
+    // (sb_spec_term); if that exponent is E, the first pass and its cluster scan are skipped
+    bool spec = false;
+    unsigned long long total = 0, run = 0;
+    if (!PEERS && !want_exact) {
+        const int sE = __ldcg(emax + 1);
+        const unsigned long long st = __ldcg(reinterpret_cast<const unsigned long long*>(emax + 2));
+        spec = sE == E && E != SB_E_EMPTY;
+        total = st;
+    }
+    if (!spec) {
+        unsigned long long loc = 0;
+        SB_TS_FOR((void)b; if (qv != 0ull) { const int sh = E - ev; loc += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
+        run = sb_cluster_excl_scan(loc, sm, cl, 0, &total);
+    }
     if (want_exact) {
         SB_TS_FOR(P[b] = run; if (qv != 0ull) { const int sh = E - ev; run += sh >= 63 ? 0ull : ((qv << LS) >> sh); })
         if (gtid == 0) P[nt] = total;
@@ -307,6 +317,10 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     if (si.valid) { SB_TS_FOR((void)b; if (qv != 0ull) loc2 += sb_sys_delta(qv, si.R, si.r0 + (E - ev));) }
     unsigned long long Tt;
     unsigned long long run2 = sb_cluster_excl_scan(loc2, sm, cl, 1, &Tt);
+    if (!PEERS && gtid == 0) {                                // every thread of the cluster has read them (the barrier inside the scan above)
+        emax[0] = SB_E_EMPTY; emax[1] = SB_E_EMPTY;
+        *reinterpret_cast<unsigned long long*>(emax + 2) = 0ull;
+    }
     sb_plan_offset(si, Tt, R53);
     if (gtid == 0) {
         if (!si.valid) atomicOr(err, SB_ERRBIT_ZERO);
@@ -678,10 +692,20 @@ struct SbHmmSmem {
     unsigned long long tot[2][SB_WARPS];   // warp totals of the tile just produced, by tile parity: with the split barrier a
                                            // fast warp may finish tile k+1 before the flushing warp has written out the totals of tile k
     unsigned long long bar2;    // split-phase barrier of the fused HMM kernel: one arrival per warp and children tile
+    int e_tile[2];              // exponent of the tile just produced, by tile parity (speculative total: sb_spec_term)
+    unsigned long long spec_acc;   // this CTA's share of the speculative total (one thread reads and writes it: no registers
+                                   // of the other 255 are spent on it)
     unsigned kmax;              // largest exponent key any state of this step can have
     unsigned qthr;              // largest grid weight, in kmax's row of the weight table, of a state BELOW the top exponent:
                                 // a particle weighing more proves that the tile exponent is the top one
 };
+
+// this CTA's share of the speculative exact total (sb_spec_term), by the one thread that holds a tile sum
+__device__ __forceinline__ void sb_spec_add(SbHmmSmem& sm, unsigned long long Q, int parity, int ntiles) {
+    const int E_top = (int)(sm.kmax >> 6) - SB_KEY_BIAS;
+    const int LS = 24 - (ntiles <= 1 ? 0 : 32 - __clz(ntiles - 1));
+    sm.spec_acc += sb_spec_term(Q, sm.e_tile[parity], E_top, LS);
+}
 
 // k: how many tiles this CTA has done before this one (staging slot / mbarrier parity of the pull)
 template <int ANC, bool FP32, bool PEERS, bool MULTI, bool TAIL, bool CARRY>
@@ -713,12 +737,12 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
 #endif
     } else if (ANC == SB_ANC_EXPLICIT) {
         if (!TAIL) {
-            const int4 u = __ldg(reinterpret_cast<const int4*>(a.anc_in + lbase));
-            const int4 v = __ldg(reinterpret_cast<const int4*>(a.anc_in + lbase) + 1);
+            const int4 u = __ldcg(reinterpret_cast<const int4*>(a.anc_in + lbase));
+            const int4 v = __ldcg(reinterpret_cast<const int4*>(a.anc_in + lbase) + 1);
             anc[0] = u.x; anc[1] = u.y; anc[2] = u.z; anc[3] = u.w; anc[4] = v.x; anc[5] = v.y; anc[6] = v.z; anc[7] = v.w;
         } else {
 #pragma unroll
-            for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < N) ? __ldg(a.anc_in + lbase + j) : 0;
+            for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < N) ? __ldcg(a.anc_in + lbase + j) : 0;
         }
     } else {
 #pragma unroll
@@ -810,7 +834,11 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     }
     // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
     if (ANC != SB_ANC_PULL) __syncthreads();                     // the pull has its own barrier
-    if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
+    if (k > 0) {
+        const int pt = tile - (int)gridDim.x;
+        const unsigned long long Qp = sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
+        if (Qp) sb_spec_add(sm, Qp, (k - 1) & 1, a.ntiles);       // (the one thread that wrote the tile sum)
+    }
     // (4)+(5) weight and quantise.  Only K distinct scores exist: the tile exponent is the largest
     // ceil(log2 weight) present (an integer max), and 2^(l2 - e) 2^27 comes from a K x K table.
     // The weights are looked up at once in the row of the LARGEST key the model can produce this step (sm.kmax): a
@@ -886,7 +914,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
         for (int j = 0; j < SB_ITEMS; ++j) if (base + j < a.n_out) a.wlit_out[lbase + j] = a.expF_t[x[j]];
     }
     sb_warp_total(tsum, sm.tot[k & 1]);                           // flushed after the next barrier (next tile / kernel end)
-    if (tid == 0) sb_put_e(a.rec, tile, e);
+    if (tid == 0) { sb_put_e(a.rec, tile, e); sm.e_tile[k & 1] = e; }
     // no barrier here: every shared scratch array is rewritten only after a later barrier of the next tile
 }
 
@@ -937,7 +965,7 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         unsigned qt = 0u;                                         // heaviest below-top state in the top row (0xffffffff: no shortcut)
         if (km == 0u) qt = 0xffffffffu;
         for (int i = 0; i < K; ++i) if ((s_key[i] >> 6) != (km >> 6)) qt = max(qt, s_qtab[(km & 63u) * K + i]);
-        sm.kmax = km; sm.qthr = qt;
+        sm.kmax = km; sm.qthr = qt; sm.spec_acc = 0ull;
     }
     sb_grid_dep_wait();                                           // everything above overlapped the previous scan
     SbStepInfo si;
@@ -957,7 +985,12 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
     if (k > 0) {                                                  // the last tile's totals
         __syncthreads();
         const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
-        sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
+        const unsigned long long Qp = sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
+        if (Qp) sb_spec_add(sm, Qp, (k - 1) & 1, a.ntiles);
+    }
+    if (!PEERS && a.rec.emax && (int)threadIdx.x == 32 * SB_FLUSH_WARP + SB_WARPS) {     // the thread that saw the tile sums
+        if (sm.spec_acc) atomicAdd(reinterpret_cast<unsigned long long*>(a.rec.emax + 2), sm.spec_acc);
+        if (blockIdx.x == 0) a.rec.emax[1] = (int)(sm.kmax >> 6) - SB_KEY_BIAS;
     }
     sb_signal_done(a.sig);
 }
@@ -1132,7 +1165,7 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
             else            sb_pull_ancestors<PEERS, false>(si, a.pool, a.e_prev, a.Pt, a.child_start, c0, rng, k & 1, (uint32_t)(k & 1), more, nb, sm.ps, anc);
         } else if (ANC == SB_ANC_EXPLICIT) {
 #pragma unroll
-            for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < N) ? __ldg(a.anc_in + lbase + j) : 0;
+            for (int j = 0; j < SB_ITEMS; ++j) anc[j] = (base + j < N) ? __ldcg(a.anc_in + lbase + j) : 0;
         } else {
 #pragma unroll
             for (int j = 0; j < SB_ITEMS; ++j) anc[j] = base + j;

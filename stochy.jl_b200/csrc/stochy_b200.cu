@@ -477,8 +477,8 @@ struct ProfScope {
 int begin_timed(sb_handle* h) {
     h->launches = 0;
     h->prof_used = 0;
-    static const int empty = SB_E_EMPTY;            // an aborted call may have left a partial maximum behind
-    CK(cudaMemcpyAsync(h->d_emax, &empty, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    static const int empty[4] = {SB_E_EMPTY, SB_E_EMPTY, 0, 0};   // an aborted call may have left a partial maximum / speculative total behind
+    CK(cudaMemcpyAsync(h->d_emax, empty, sizeof(empty), cudaMemcpyHostToDevice, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
     return SB_OK;
 }
@@ -543,15 +543,15 @@ extern "C" int32_t sb_create(const sb_options* o, sb_handle** out) {
         cudaEventCreate(&h->evt0) != cudaSuccess || cudaEventCreate(&h->evt1) != cudaSuccess ||
         cudaMalloc(&h->d_err, 16 * sizeof(unsigned)) != cudaSuccess ||
         cudaMemset(h->d_err, 0, 16 * sizeof(unsigned)) != cudaSuccess ||
-        cudaMalloc(&h->d_emax, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&h->d_emax, 4 * sizeof(int)) != cudaSuccess ||      // [0] exponent maximum, [1] E_top of the speculative total, [2..3] the total (u64)
         h->d_misc.ensure(64) != cudaSuccess) {
         g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(cudaGetLastError());
         sb_destroy(h);
         return SB_ECUDA;
     }
     {
-        const int empty = SB_E_EMPTY;
-        cudaMemcpy(h->d_emax, &empty, sizeof(int), cudaMemcpyHostToDevice);
+        const int empty[4] = {SB_E_EMPTY, SB_E_EMPTY, 0, 0};
+        cudaMemcpy(h->d_emax, empty, sizeof(empty), cudaMemcpyHostToDevice);
     }
     if (const char* np = getenv("SB_PDL")) h->pdl = atoi(np) & 3;
     if (const char* ns = getenv("SB_NO_SMALL")) h->use_small = atoi(ns) ? 0 : 1;

@@ -399,6 +399,24 @@ def test_result_independent_of_grid(monkeypatch):
         assert np.array_equal(outs[0][1], o[1])
 
 
+@pytest.mark.parametrize("log2n", [25, 26, 27])
+def test_large_pool_logZ_vs_forward(enumref, log2n):
+    """Pools beyond 2^24 particles use the tile-scan instantiations that keep 2, 4 and 8 tile records per thread.  Their
+    record loads once sat ABOVE the grid-dependency wait in the compiled code (ld.global.nc hoisted by ptxas: the scan
+    read tile sums the step kernel had not written yet; log-evidence off by ~0.015 at 2^26, run-to-run different).
+    The Monte-Carlo error at these sizes is far below the tolerance; two runs must agree bit for bit."""
+    sb = sb_mod()
+    A, logF, pi = cfg3_tables(T=24)
+    exact, _ = enumref.hmm_forward(A, logF, pi=pi)
+    vals = []
+    for _ in range(2):
+        with sb.Engine(precision="fp32", resample="systematic", seed=9) as eng:
+            eng.load(sb.DiscreteHMM(A, logF, pi=pi))
+            vals.append(eng.smc_sweep(1 << log2n, it=0))
+    assert vals[0] == vals[1]
+    assert abs(vals[0] - exact) < 4e-3, (vals[0], exact)
+
+
 CHAIN_KEY = 0x9E3779B97F4A7C15
 
 
