@@ -836,12 +836,21 @@ __device__ __forceinline__ void sb_put_Q(const SbRecOut& r, int tile, unsigned l
 // (weights, states, warp prefixes, tile records) is complete: one 4-byte store over NVLink into flags[self]
 // of every arena -- compute and notification in one kernel, no separate launch.  Peers wait for the flags
 // in their tile scan.  counter == nullptr: not sharded, nothing to do.
+// With the flag travels this GPU's SUMMARY of the pool share it produced (acc != nullptr; SB_REC_OFF bytes behind the
+// flags of every arena, slot [rec_slot][self]): {largest tile exponent, the exponent the speculative total was taken
+// at, the total} -- the words the single-GPU scan finds behind its exponent maximum (sb_spec_term).  Every GPU's scan
+// then has the global exponent (a max over `world` records instead of a cluster-wide reduction over all tiles) and, when
+// the exponents agree, the exact total without its first pass.  Two slots, alternating per record: a GPU can publish
+// record r + 2 only after every peer has raised the flag of record r + 1, i.e. has finished the scan that read record r.
+#define SB_REC_OFF 64
 struct SbSignal {
     unsigned* counter;                  // CTAs of this launch that have finished
     char* base[SB_MAX_PEERS];
     unsigned long long off_flags;
     int world, self;
     unsigned epoch;
+    int* acc;                           // this GPU's {emax, E_top, total (u64)} accumulators, or nullptr
+    int rec_slot;
 };
 __device__ __forceinline__ void sb_signal_done(const SbSignal& sg) {
     if (!sg.counter) return;                                     // not sharded
@@ -854,6 +863,17 @@ __device__ __forceinline__ void sb_signal_done(const SbSignal& sg) {
         const unsigned done = atomicAdd(sg.counter, 1u) + 1u;
         if (done == gridDim.x) {
             *sg.counter = 0u;                                    // next launch
+            if (sg.acc) {                                        // every CTA's atomics precede its counter increment
+                __threadfence();
+                const int em = atomicExch(sg.acc, SB_E_EMPTY), et = atomicExch(sg.acc + 1, SB_E_EMPTY);
+                const unsigned long long tot = atomicExch(reinterpret_cast<unsigned long long*>(sg.acc + 2), 0ull);
+                const unsigned long long w0 = ((unsigned long long)(unsigned)et << 32) | (unsigned)em;
+                for (int p = 0; p < sg.world; ++p) {
+                    volatile unsigned long long* r = reinterpret_cast<volatile unsigned long long*>(sg.base[p] + sg.off_flags + SB_REC_OFF) +
+                                                     2 * (sg.rec_slot * SB_MAX_PEERS + sg.self);
+                    r[0] = w0; r[1] = tot;
+                }
+            }
             __threadfence_system();
             for (int p = 0; p < sg.world; ++p)
                 *(reinterpret_cast<volatile unsigned*>(sg.base[p] + sg.off_flags) + sg.self) = sg.epoch;

@@ -215,6 +215,7 @@ struct SbScanPeers {
     int world, self;
     int log2t;                          // tiles per GPU = 2^log2t
     unsigned epoch;                     // wait until every flags[g] >= epoch
+    int rec_slot;                       // >= 0: every GPU's summary record arrived with its flag (sb_signal_done), in this slot
 };
 #define SB_SCAN_MAXPER 8
 
@@ -282,7 +283,24 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     else for (int b = b0; b < b1; ++b) { const unsigned long long qv = __ldcg(Q_g + b); const int ev = __ldcg(e_g + b); body }
     // global exponent
     int E = SB_E_EMPTY;
-    if (PEERS) {
+    bool spec = false;
+    unsigned long long total = 0, run = 0;
+    if (PEERS && sp.rec_slot >= 0) {
+        // the GPUs' summaries: the exponent maximum without a reduction and, when it is the exponent the step kernels
+        // assumed, the exact total without the first pass (sb_signal_done; integer adds: the same bits)
+        const unsigned long long* rec = reinterpret_cast<const unsigned long long*>(sp.base[sp.self] + sp.off_flags + SB_REC_OFF) +
+                                        2 * (sp.rec_slot * SB_MAX_PEERS);
+        spec = !want_exact;
+        int et0 = SB_E_EMPTY;
+        for (int g = 0; g < sp.world; ++g) {
+            const unsigned long long w0 = __ldcv(rec + 2 * g);
+            E = max(E, (int)(unsigned)w0);
+            if (g == 0) et0 = (int)(unsigned)(w0 >> 32);
+            spec = spec && (int)(unsigned)(w0 >> 32) == et0;
+            total += __ldcv(rec + 2 * g + 1);
+        }
+        spec = spec && et0 == E && E != SB_E_EMPTY;
+    } else if (PEERS) {
         SB_TS_FOR((void)b; if (qv != 0ull) E = max(E, ev);)
         E = sb_cluster_max(E, sm, cl);
     } else {
@@ -292,8 +310,6 @@ k_tilescan(const int* __restrict__ e_g, const unsigned long long* __restrict__ Q
     // exact CDF of tile sums (log-evidence; multinomial resampling)
     // single GPU: the step kernel of the discrete model has accumulated this very sum at the exponent it expected
     // (sb_spec_term); if that exponent is E, the first pass and its cluster scan are skipped
-    bool spec = false;
-    unsigned long long total = 0, run = 0;
     if (!PEERS && !want_exact) {
         const int sE = __ldcg(emax + 1);
         const unsigned long long st = __ldcg(reinterpret_cast<const unsigned long long*>(emax + 2));
@@ -678,6 +694,7 @@ struct SbHmmStepArgs {
     long long N;                // global particle count
     int n_out;                  // N (+1 with a retained particle)
     int ntiles;                 // local tiles to produce
+    int nt_pool;                // tiles of the whole pool (all GPUs): the scan's LS comes from it (sb_spec_add)
     int K, rows, t;
     int xb;                     // CARRY instantiations: state bits of a head marker ((parent << xb) | state)
     unsigned iter;
@@ -837,7 +854,7 @@ __device__ __forceinline__ void sb_hmm_tile(const SbHmmStepArgs& a, const SbStep
     if (k > 0) {
         const int pt = tile - (int)gridDim.x;
         const unsigned long long Qp = sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
-        if (Qp) sb_spec_add(sm, Qp, (k - 1) & 1, a.ntiles);       // (the one thread that wrote the tile sum)
+        if (Qp) sb_spec_add(sm, Qp, (k - 1) & 1, a.nt_pool);       // (the one thread that wrote the tile sum)
     }
     // (4)+(5) weight and quantise.  Only K distinct scores exist: the tile exponent is the largest
     // ceil(log2 weight) present (an integer max), and 2^(l2 - e) 2^27 comes from a K x K table.
@@ -986,9 +1003,9 @@ k_step_hmm(const __grid_constant__ SbHmmStepArgs a) {
         __syncthreads();
         const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
         const unsigned long long Qp = sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
-        if (Qp) sb_spec_add(sm, Qp, (k - 1) & 1, a.ntiles);
+        if (Qp) sb_spec_add(sm, Qp, (k - 1) & 1, a.nt_pool);
     }
-    if (!PEERS && a.rec.emax && (int)threadIdx.x == 32 * SB_FLUSH_WARP + SB_WARPS) {     // the thread that saw the tile sums
+    if (a.rec.emax && (int)threadIdx.x == 32 * SB_FLUSH_WARP + SB_WARPS) {     // the thread that saw the tile sums
         if (sm.spec_acc) atomicAdd(reinterpret_cast<unsigned long long*>(a.rec.emax + 2), sm.spec_acc);
         if (blockIdx.x == 0) a.rec.emax[1] = (int)(sm.kmax >> 6) - SB_KEY_BIAS;
     }

@@ -68,6 +68,8 @@ struct sb_handle {
     size_t off_w32[2] = {0, 0}, off_x[2] = {0, 0}, off_wp[2] = {0, 0}, off_e[2] = {0, 0}, off_Q[2] = {0, 0}, off_flags = 0;
     char* peer_base[SB_MAX_PEERS] = {nullptr};
     unsigned epoch = 0;
+    unsigned rec_seq = 0;             // summary records published so far (slot = parity)
+    int rec_slot_cur = -1;            // slot of the records that came with the latest step kernel's flags (-1: none)
     // sharded conditional SMC / PMCMC (sb_dist_reserve_history): state history rows, the backward pass's count
     // buffers, the retained lineage's index words and both retained trajectories live in the arena too
     int hist_rows = 0;                // rows reserved (0: plain SMC sweeps only)
@@ -189,8 +191,15 @@ inline SbRecOut make_rec(sb_handle* h, int slot) {
     SbRecOut r;
     const int tile_off = h->dist_ready ? (int)(h->rank * (h->NL / SB_TILE)) : 0;
     r.e = TE(h, slot) + tile_off; r.Q = TQ(h, slot) + tile_off;
-    r.emax = h->dist_ready ? nullptr : h->d_emax;
+    r.emax = h->d_emax;               // sharded: this GPU's share; its last CTA hands the summary to every peer (sb_signal_done)
     return r;
+}
+// sharded: the summary record travels with the flag of the step kernel that accumulates into rec.emax (call after
+// rec.emax is final); the scan that follows reads the records of all GPUs from slot h->rec_slot_cur
+inline void attach_summary(sb_handle* h, SbSignal& sg, const SbRecOut& rec) {
+    sg.acc = nullptr; sg.rec_slot = 0;
+    h->rec_slot_cur = -1;
+    if (h->dist_ready && rec.emax) { sg.acc = rec.emax; sg.rec_slot = (int)(h->rec_seq++ & 1u); h->rec_slot_cur = sg.rec_slot; }
 }
 inline unsigned long long* WP(sb_handle* h, int slot) {
     return h->dist_ready ? reinterpret_cast<unsigned long long*>((char*)h->arena + h->off_wp[slot]) : h->tile_wp[slot].as<unsigned long long>();
@@ -401,6 +410,7 @@ int launch_tilescan(sb_handle* h, int slot, int64_t n, int64_t m, const unsigned
     sp.off_flags = h->off_flags; sp.off_e = h->off_e[slot]; sp.off_Q = h->off_Q[slot];
     sp.log2t = 0; while ((1ll << sp.log2t) < h->NL / SB_TILE) ++sp.log2t;
     sp.world = h->world; sp.self = h->rank; sp.epoch = h->epoch;      // the epoch the step kernel just signalled
+    sp.rec_slot = h->rec_slot_cur;
     return launch_tilescan_t<true>(h, TE(h, slot), TQ(h, slot), nt, n, m, d_r53, info, want_exact, sp);
 }
 
@@ -1128,6 +1138,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         // head-room of LS bits the sums lose bits, and 2^-60 of them is "zero probability mass")
         if (!h->has_factor[t]) a.rec.emax = nullptr;
         a.sig = make_signal(h);
+        attach_summary(h, a.sig, a.rec);
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.wlit_out = literal ? h->wlit.as<double>() : nullptr;
@@ -1138,7 +1149,7 @@ int sweep_hmm(sb_handle* h, int64_t N, unsigned iter, bool conditional, bool his
         a.logF_t = h->hmm_logF.as<double>() + (size_t)t * K;
         a.expF_t = h->hmm_expF.as<double>() + (size_t)t * K;
         a.xstar = conditional ? (dist ? reinterpret_cast<const int*>((char*)h->arena + h->off_xstar[h->xstar_cur]) : h->xstar[h->xstar_cur].as<int>()) : nullptr;
-        a.N = N; a.n_out = n_out; a.ntiles = ntiles; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed); a.err = h->d_err;
+        a.N = N; a.n_out = n_out; a.ntiles = ntiles; a.nt_pool = dist ? ntiles * h->world : ntiles; a.K = K; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed); a.err = h->d_err;
         // head markers that carry the parent's state ((parent << xb) | state must stay below 2^31): no gather
         a.xb = 0;
         if (anc_mode == SB_ANC_PULL && h->use_carry) {
@@ -1221,6 +1232,7 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         a.w32_out = W32(h, cur);
         a.rec = make_rec(h, cur);
         a.sig = make_signal(h);
+        attach_summary(h, a.sig, a.rec);
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
         a.N = N; a.ntiles = ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed);
@@ -2006,7 +2018,7 @@ extern "C" int32_t sb_dist_ipc_export(sb_handle* h, int64_t N_local, uint8_t out
         h->off_e[sl] = take(ntl * h->world * 4);               // replicated: every rank's records, global tile index
         h->off_Q[sl] = take(ntl * h->world * 8);
     }
-    h->off_flags = take((SB_MAX_PEERS + 1) * sizeof(unsigned));     // flags[8] + the CTA counter of the step kernel
+    h->off_flags = take(SB_REC_OFF + 2 * SB_MAX_PEERS * 16);        // flags[8] + the CTA counter of the step kernel; the GPUs' summary records (2 slots)
     if (h->hist_rows > 0) {                                         // sharded conditional SMC / PMCMC (sb_dist_back.cuh)
         h->off_xh = take((size_t)h->hist_rows * (size_t)N_local * 4);
         h->off_cnt[0] = take((size_t)N_local * 4); h->off_cnt[1] = take((size_t)N_local * 4);
