@@ -22,7 +22,7 @@ def test_sharded_sweep_equals_single_gpu(log2n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,log2n", [(2, 11), (2, 13), (4, 12)])
+@pytest.mark.parametrize("world,log2n", [(2, 11), (2, 13), (4, 12), (8, 11)])
 def test_sharded_sweep_ranks_on_one_gpu(world, log2n):
     """The same parity on a ONE-GPU box: `world` rank processes, all on device 0, each with its own arena mapped into
     the others over CUDA IPC exactly as across GPUs (gloo is the host plumbing; NCCL refuses two ranks on a device).
@@ -40,7 +40,7 @@ def test_sharded_sweep_ranks_on_one_gpu(world, log2n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,log2n,T", [(2, 11, 9), (2, 13, 16), (4, 12, 7)])
+@pytest.mark.parametrize("world,log2n,T", [(2, 11, 9), (2, 13, 16), (4, 12, 7), (8, 11, 5)])
 def test_sharded_pmcmc_ranks_on_one_gpu(world, log2n, T):
     """Iterated conditional SMC on a SHARDED pool (src/pmcmc.jl:59-66, 83-94 across GPUs; retained entry in the last
     slot of the last rank, history rows sharded, the backward pass's counts and the retained lineage hopping between
