@@ -136,3 +136,36 @@ def test_product_discrete_show_order(sb):
     assert [r.split("|")[0].strip() for r in rows] == ["'long'", "'yy'", "'x'"]
     assert len({r.index("|") for r in rows}) == 1
     assert [float(r.split("|")[1]) for r in rows] == pytest.approx([0.6, 0.3, 0.1])
+
+
+def test_no_global_load_hoisted_above_grid_dependency_wait(sb):
+    """Kernels launched with programmatic stream serialisation read what their predecessor wrote only behind
+    `griddepcontrol.wait` (SASS: ACQBULK).  ptxas once moved the tile scan's `ld.global.nc` record loads in front of it
+    (wrong log-evidence beyond 2^25 particles; DESIGN.md section 4, profiles/r02_notes.md).  Static check of the built
+    library: in front of ACQBULK the tile scans may load only the host-drawn offset, the linear-Gaussian step kernels and
+    the pull kernels nothing, the discrete step kernels only their model tables (15 or 30 128-bit table loads + the scores)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", sb._native.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    pre, has, name = {}, set(), None
+    seen = False
+    for line in out.splitlines():
+        if "Function :" in line:
+            name, seen = line.split("Function :")[1].strip(), False
+        elif name and "ACQBULK" in line:
+            seen = True
+            has.add(name)
+        elif name and not seen and re.search(r"\bLDG\b|LDG\.", line):
+            pre[name] = pre.get(name, 0) + 1
+    assert any("k_tilescan" in k for k in has) and any("k_step_hmm" in k for k in has), "no ACQBULK found: check the parser"
+    for k in sorted(has):
+        n = pre.get(k, 0)
+        if "k_tilescan" in k:
+            assert n <= 1, (k, n)
+        elif "k_step_hmm" in k:
+            assert n <= 31, (k, n)
+        else:
+            assert n == 0, (k, n)
