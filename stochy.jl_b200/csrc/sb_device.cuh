@@ -824,7 +824,8 @@ __device__ __forceinline__ double sb_block_max_f64_1(double v, double* sm) {
 struct SbRecOut {
     int* e;
     unsigned long long* Q;
-    int* emax;                          // nullptr when sharded
+    int* emax;                          // {exponent maximum, E_top, speculative total (u64)} of the share this GPU produces; nullptr: the
+                                        // step has no factor statement (no scan follows, nothing may accumulate)
 };
 __device__ __forceinline__ void sb_put_e(const SbRecOut& r, int tile, int e) {
     r.e[tile] = e;

@@ -222,7 +222,8 @@ struct SbScanPeers {
 // PER > 0: every thread keeps its PER consecutive tiles in registers (PER = 1: 2^24 particles, PER = 8:
 // 2^27); PER == 0: any size, tile records re-read from global memory in every pass.
 // emax (single GPU): the largest tile exponent, accumulated with atomicMax by the kernels that produced the
-// pool; consumed and cleared here (saves one cluster-wide reduction).  Sharded pools reduce e instead.
+// pool; consumed and cleared here (saves one cluster-wide reduction).  Sharded pools take it from the GPUs' summary
+// records (sp.rec_slot >= 0: they arrived with the flags, sb_signal_done) or, without records, reduce e.
 // The cluster size is given at launch (8, or 16 for large pools).
 template <int PER, bool PEERS>
 __global__ void __launch_bounds__(SB_SCAN_THREADS)
