@@ -1030,6 +1030,7 @@ struct SbLgStepArgs {
     double* lw_out;
     long long N;                // global particle count
     int ntiles;                 // local tiles to produce
+    int nt_pool;                // tiles of the whole pool (all GPUs): LS of the speculative total (sb_spec_term)
     int t;
     unsigned iter;
     unsigned long long seed;
@@ -1165,6 +1166,13 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
     // (an op-list program has no such bound: every warp waits for the tile maximum)
     const REAL vmax = FP32 ? (REAL)__fmul_rn((float)a.lc, SB_LOG2E_F) : (REAL)__dmul_rn(a.lc, SB_LOG2E_D);
     const int e_top = OPS ? 0x7fffffff : (FP32 ? (int)ceilf((float)vmax) : (int)ceil((double)vmax));
+    // the scan's exact total, accumulated on the way at the exponent of the density's mode (as in k_step_hmm: sb_spec_term;
+    // it is taken when some tile reaches that exponent -- at these pool sizes every tile does).  fp64 only: A/B on one
+    // box, 250 steps: fp64 48.14 -> 47.88 ms per sweep; the fp32 instantiation (48 registers) lost in the kernel what the
+    // scan gained (kernel 90.3 -> 91.4 us, sweep 23.44 -> 23.41 ms)
+    constexpr bool LGSPEC = !OPS && !FP32;
+    const int LS = 24 - (a.nt_pool <= 1 ? 0 : 32 - __clz(a.nt_pool - 1));
+    if (tid == 0) sm.spec_acc = 0ull;                            // first read behind a later barrier
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
         if (ANC == SB_ANC_PULL && (k % SB_FT_CHUNK) == 0)
@@ -1190,7 +1198,11 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         }
         // the previous tile's warp totals (left in shared memory) become its warp prefixes and tile sum
         if (ANC != SB_ANC_PULL) __syncthreads();                 // the pull has its own barrier
-        if (k > 0) { const int pt = tile - (int)gridDim.x; sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt); }
+        if (k > 0) {
+            const int pt = tile - (int)gridDim.x;
+            const unsigned long long Qp = sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
+            if (LGSPEC && Qp) sm.spec_acc += sb_spec_term(Qp, sm.e_tile[(k - 1) & 1], e_top, LS);
+        }
         REAL xpar[SB_ITEMS];
         const bool vec = OPS && a.xdim > 1;                       // Dirichlet program: the parents' planes are read per particle below
         if (vec) {
@@ -1363,13 +1375,18 @@ k_step_lg(const __grid_constant__ SbLgStepArgs a) {
         }
         sb_store8_u32(a.w32_out + lbase, q);
         sb_warp_total(tsum, sm.tot[k & 1]);                       // flushed after the next barrier (next tile / kernel end)
-        if (tid == 0) sb_put_e(a.rec, tile, e);
+        if (tid == 0) { sb_put_e(a.rec, tile, e); if (LGSPEC) sm.e_tile[k & 1] = e; }
         if (bad) atomicOr(a.err, SB_ERRBIT_NAN);
     }
     if (k > 0) {
         __syncthreads();
         const int pt = (int)blockIdx.x + (k - 1) * (int)gridDim.x;
-        sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
+        const unsigned long long Qp = sb_flush_totals(sm.tot[(k - 1) & 1], a.wp_out + (size_t)pt * SB_WARPS, a.rec, pt);
+        if (LGSPEC && Qp) sm.spec_acc += sb_spec_term(Qp, sm.e_tile[(k - 1) & 1], e_top, LS);
+    }
+    if (LGSPEC && a.rec.emax && (int)threadIdx.x == 32 * SB_FLUSH_WARP + SB_WARPS) {   // the thread that saw the tile sums
+        if (sm.spec_acc) atomicAdd(reinterpret_cast<unsigned long long*>(a.rec.emax + 2), sm.spec_acc);
+        if (blockIdx.x == 0) a.rec.emax[1] = e_top;
     }
     sb_signal_done(a.sig);
 }

@@ -1235,7 +1235,7 @@ int sweep_lg(sb_handle* h, int64_t N, unsigned iter) {
         attach_summary(h, a.sig, a.rec);
         a.wp_out = WP(h, cur);
         a.lw_out = h->opt.store_logw ? h->lwbuf.as<double>() + (size_t)t * S : nullptr;
-        a.N = N; a.ntiles = ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed);
+        a.N = N; a.ntiles = ntiles; a.nt_pool = dist ? ntiles * h->world : ntiles; a.t = t; a.iter = iter; a.seed = h->opt.seed; a.rk = round_keys(h->opt.seed);
         a.xdim = XD; a.xplane = S;
         if (ops) {
             a.op = h->ops[(size_t)t]; a.obs = h->ops_obs.as<double>(); a.obs_aux = h->ops_aux.as<double>();
