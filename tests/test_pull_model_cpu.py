@@ -158,3 +158,61 @@ def test_markers_and_warp_local_fill_equal_literal_ancestors(kind):
         assert got == ref
         done += 1
     assert done >= 10
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The speculative exact total (sb_spec_term, k_step_hmm / k_step_lg -> k_tilescan) and its sharded form (the GPUs'
+# summary records, sb_signal_done): a model of the integer arithmetic.  The scan's first pass is
+#     total = sum_b (Q_b << LS) >> (E - e_b),   E = max_b e_b over tiles with Q_b != 0,   LS = 24 - ceil_log2(tiles);
+# the step kernels accumulate the same terms at the exponent E_top they expect, CTA by CTA and GPU by GPU, in any order.
+E_EMPTY = -(1 << 30)
+
+
+def scan_total(Q, e, LS):
+    live = [eb for q, eb in zip(Q, e) if q]
+    if not live:
+        return E_EMPTY, 0
+    E = max(live)
+    return E, sum(((q << LS) >> (E - eb)) if E - eb < 63 else 0 for q, eb in zip(Q, e) if q)
+
+
+def spec_term(q, eb, E_top, LS):
+    if q == 0 or eb == E_EMPTY:
+        return 0
+    sh = E_top - eb
+    return 0 if sh >= 63 else (q << LS) >> sh
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_speculative_total_equals_scan_total_or_is_refused(world):
+    rng = random.Random(20 + world)
+    for case in range(300):
+        tiles_per_gpu = rng.choice([1, 2, 8, 64])
+        nt = tiles_per_gpu * world
+        LS = 24 - (0 if nt <= 1 else (nt - 1).bit_length())
+        E_top = rng.randint(-40, 40)
+        hit = rng.random() < 0.7                      # some tile reaches the exponent the step expected
+        Q, e = [], []
+        for b in range(nt):
+            if rng.random() < 0.1:
+                Q.append(0); e.append(E_EMPTY)        # a tile of zero weights
+            else:
+                Q.append(rng.randint(1, 2048 << 27))
+                e.append(E_top - rng.choice([0, 0, 0, 1, 2, 7, 70]) - (0 if hit else 1))
+        if hit and not any(q and eb == E_top for q, eb in zip(Q, e)):
+            Q[0], e[0] = 12345, E_top
+        E, total = scan_total(Q, e, LS)
+        # per GPU: CTAs take the tiles round-robin and add their terms in any order; one record per GPU
+        records = []
+        for g in range(world):
+            mine = list(range(g * tiles_per_gpu, (g + 1) * tiles_per_gpu))
+            rng.shuffle(mine)
+            live = [e[b] for b in mine if Q[b]]
+            records.append((max(live) if live else E_EMPTY, E_top, sum(spec_term(Q[b], e[b], E_top, LS) for b in mine)))
+        E_rec = max(r[0] for r in records)
+        assert E_rec == E
+        take = all(r[1] == records[0][1] for r in records) and records[0][1] == E_rec and E_rec != E_EMPTY
+        assert take == (hit and E != E_EMPTY) or not any(Q)
+        if take:
+            assert sum(r[2] for r in records) == total
+            assert total < 1 << 62                       # the scan's head-room (LS) holds for the speculative sum too
